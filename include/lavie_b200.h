@@ -1,0 +1,137 @@
+/* lavie_b200 -- C ABI of the sm_100a kernels behind LaVie's per-step denoiser.
+ *
+ * One shared object (liblavie_b200.so), plain pointers and sizes, no torch types.  The reference is pure
+ * PyTorch and has no FFI of its own; every entry point below names the reference call it replaces
+ * (paths relative to the reference root, e.g. base/models/attention.py:209-239).  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - All activation tensors are bf16, channels-last: a feature map [B,C,F,H,W] of the reference is stored as
+ *    rows = (b, f, y, x) pixels, columns = channels, with an explicit row stride ("ld", in ELEMENTS).
+ *  - Weights are bf16 [out_features, in_features] row-major (nn.Linear layout); 3x3 conv weights are repacked by
+ *    the caller to [Cout, kh, kw, Cin].  Biases / statistics / time-embedding vectors are fp32.
+ *  - Ownership: the caller allocates every buffer (inputs, outputs, workspaces).  The library never allocates or
+ *    frees device memory and keeps no global state besides lazily configured kernel attributes.
+ *  - Every function enqueues work on `stream` and returns immediately: no host synchronisation, safe under CUDA
+ *    graph capture, re-entrant from one host thread per device.
+ *  - Return value: LAVIE_OK (0) or a negative lavie_status; lavie_last_error() gives a thread-local message.
+ *    Nothing throws, nothing calls exit().
+ */
+#ifndef LAVIE_B200_H_
+#define LAVIE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* lavie_stream_t; /* == cudaStream_t */
+
+typedef enum {
+  LAVIE_OK = 0,
+  LAVIE_ERR_SHAPE = -1,     /* unsupported / inconsistent dimensions */
+  LAVIE_ERR_ALIGN = -2,     /* pointer or leading dimension not 16-byte aligned */
+  LAVIE_ERR_WORKSPACE = -3, /* caller workspace too small */
+  LAVIE_ERR_CUDA = -4,      /* CUDA runtime / driver error (message has the code) */
+  LAVIE_ERR_DRIVER = -5     /* cuTensorMapEncodeTiled unavailable */
+} lavie_status;
+
+const char* lavie_last_error(void);
+int lavie_abi_version(void);
+
+/* Fused GEMM epilogue: out = bf16( acc + bias[n] + row_bias[row / rows_per_batch][n] + residual[row][n] ), or with
+ * geglu != 0: out[:, j] = (acc[:, j] + bias) * gelu_erf(acc[:, j + 128] + bias') per 256-column tile. */
+typedef struct {
+  const float* bias;     /* [N] or NULL */
+  const float* row_bias; /* [M / rows_per_batch, N] or NULL */
+  int rows_per_batch;
+  const void* residual;  /* bf16 [M, ld_residual] or NULL */
+  int ld_residual;
+  int geglu;
+} lavie_epilogue;
+
+/* nn.Linear / 1x1 InflatedConv3d: out[M,N] = [a0 | a1][M, k0+k1] * w[N, k0+k1]^T (+ epilogue).
+ * a1/k1 = 0 for a single source; two sources fold torch.cat([h, skip], 1) (unet_blocks.py:538,630) in front of
+ * resnet.py:202-203 conv_shortcut.  Replaces attention.py:95-104 (to_q/k/v/out), :328,356 (proj_in/out),
+ * diffusers FeedForward (mirror vsr/models/diffusers_attention.py:734-822).  block_n = 0 lets the library choose. */
+int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1, int lda1, int k1, const void* w, void* out,
+                    int ldo, int M, int N, const lavie_epilogue* ep, int block_n, lavie_stream_t stream);
+
+/* 3x3 stride-1 pad-1 InflatedConv3d (resnet.py:13-21) as implicit GEMM over a CONTIGUOUS channels-last map
+ * x[NF, H, W, C]; w is [N, 3, 3, C].  lavie_conv3x3_supported() tells whether the TMA path accepts the geometry
+ * (C % 64 == 0, W in {8,16,32,64,128}); otherwise use lavie_im2col3x3_bf16 + lavie_gemm_bf16. */
+int lavie_conv3x3_supported(int H, int W, int C);
+int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, const void* w, void* out, int ldo, int N,
+                       const lavie_epilogue* ep, int block_n, lavie_stream_t stream);
+
+/* Patch matrix for the general / strided conv (Downsample3D stride 2, resnet.py:102-110):
+ * col[NF*Ho*Wo, 9*C] with K ordered (kh, kw, c), pad 1. */
+int lavie_im2col3x3_bf16(const void* x, int NF, int H, int W, int C, int stride, void* col, lavie_stream_t stream);
+
+/* GroupNorm over channels-last rows, 32-style groups of C/groups contiguous channels.
+ * Sample s = rows [s*rows_per_sample, (s+1)*rows_per_sample): rows_per_sample = F*H*W reproduces nn.GroupNorm on the
+ * 5-D tensor (statistics across frames, resnet.py:180,191; unet.py:504), = H*W the per-frame norm of
+ * Transformer3DModel (attention.py:363-369).  The input may be the channel concat of two sources.
+ *   stats    : partial[samples, chunks, groups, 2] (sum, sum of squares), chunks = lavie_groupnorm_chunks()
+ *   finalize : scale_shift[samples, C, 2] with y = x*scale + shift  (folds gamma/beta, mean, rstd)
+ *   apply    : y = act(x*scale + shift), act = SiLU when silu != 0; writes a contiguous [rows, C] bf16 tensor */
+int lavie_groupnorm_chunks(int rows_per_sample);
+int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
+                          int rows_per_sample, int groups, float* partial, lavie_stream_t stream);
+int lavie_groupnorm_finalize(const float* partial, int samples, int chunks, int groups, int C,
+                             long long count_per_group, const float* gamma, const float* beta, float eps,
+                             float* scale_shift, lavie_stream_t stream);
+int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
+                          int rows_per_sample, const float* scale_shift, int silu, void* y, int ldy,
+                          lavie_stream_t stream);
+
+/* nn.LayerNorm over the channel dimension of every row (attention.py:444-477 norm1/norm2/norm_temp/norm3). */
+int lavie_layernorm_bf16(const void* x, int ldx, const float* gamma, const float* beta, float eps, void* y, int ldy,
+                         int rows, int C, lavie_stream_t stream);
+
+/* softmax(q k^T * scale) v per (batch, head)  (CrossAttention._attention, attention.py:209-239).
+ * q rows = batch*Sq, k/v rows = (batch / kv_batch_div)*Sk (kv_batch_div = F shares the text keys across frames,
+ * attention.py:364).  Head h occupies columns [h*head_pitch, h*head_pitch + d) of q/k/v (pitch >= d rounded up to 16,
+ * padding columns must be zero) and [h*d, (h+1)*d) of o. */
+int lavie_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
+                         int batch, int heads, int Sq, int Sk, int d, int head_pitch, int kv_batch_div, float scale,
+                         lavie_stream_t stream);
+
+/* TemporalAttention._attention (attention.py:634-667): per (b, pixel, head) attention over the F frames, with
+ * q scaled before RoPE, rotary embedding on the first 2*rot_pairs dims, + rel-pos bias[heads,F,F].
+ * qkv rows = (b, f, pixel); q at column 0, k at k_off, v at v_off (+ h*head_pitch).  rope = [F, rot_pairs, 2]
+ * (cos, sin) fp32.  o[(b,f,pixel), h*d + c]. */
+int lavie_temporal_attention_bf16(const void* qkv, int ld, int k_off, int v_off, void* o, int ldo, int B, int F,
+                                  int HW, int heads, int d, int head_pitch, float scale, const float* rope,
+                                  int rot_pairs, const float* bias, lavie_stream_t stream);
+
+/* Small-M linear for the time-embedding path (unet.py:428-434, resnet.py:187): out[m, n] = act_in(x[m,:]) . w[n,:] +
+ * bias[n], x/out fp32, w bf16 [N,K]; silu_in applies SiLU to x on load, silu_out to the result. m <= 8. */
+int lavie_linear_smallm(const float* x, int M, int K, const void* w, const float* bias, float* out, int N,
+                        int silu_in, int silu_out, lavie_stream_t stream);
+/* Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): out[b] = [cos(t w_i) | sin(t w_i)], w_i = 10000^(-i/(dim/2)). */
+int lavie_timestep_embedding(const float* t, int B, int dim, float* out, lavie_stream_t stream);
+
+/* conv_in (unet.py:454): x fp32 [B, Cin, F, H, W] -> bf16 channels-last [B*F*H*W, Cout]; w fp32 [Cout, Cin, 3, 3]. */
+int lavie_conv_in(const float* x, int B, int Cin, int F, int H, int W, const float* w, const float* bias, int Cout,
+                  void* out, int ldo, lavie_stream_t stream);
+/* conv_norm_out + SiLU + conv_out (unet.py:504-506): x bf16 [B*F*H*W, C] (raw), scale_shift from
+ * lavie_groupnorm_finalize, w fp32 [Cout, 3, 3, C]; writes fp32 [B, Cout, F, H, W]. */
+int lavie_conv_out(const void* x, int ldx, const float* scale_shift, int B, int F, int H, int W, int C,
+                   const float* w, const float* bias, int Cout, float* out, lavie_stream_t stream);
+
+/* F.interpolate(scale_factor=(1,2,2), mode="nearest") of Upsample3D (resnet.py:59-62), channels-last. */
+int lavie_upsample_nearest2x(const void* x, int NF, int H, int W, int C, void* y, lavie_stream_t stream);
+
+/* Caller-side step (pipeline_videogen.py:678-683): noise = u + g (t - u); DDIM (eta 0) latent update with the two
+ * cumulative alphas; fp32 [n] each. */
+int lavie_cfg_ddim_step(const float* noise_uncond, const float* noise_text, float guidance, float alpha_t,
+                        float alpha_prev, const float* latents, float* latents_out, long long n,
+                        lavie_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAVIE_B200_H_ */

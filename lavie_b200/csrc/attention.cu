@@ -1,0 +1,413 @@
+// Attention cores of the LaVie transformer block (sm_100a).
+//
+//  lavie_attention_bf16          flash-style softmax(q k^T * scale) v on tcgen05 / TMEM with TMA-staged Q, K, V tiles:
+//                                spatial self-attention (S = H*W tokens per frame) and CLIP cross-attention
+//                                (77 keys, shared across the frames of a batch item).
+//                                Replaces CrossAttention._attention (base/models/attention.py:209-239).
+//  lavie_temporal_attention_bf16 per-pixel attention over the F frames with fused q-scale, RoPE and rel-pos bias.
+//                                Replaces TemporalAttention._attention (attention.py:634-667) and the two
+//                                (b f) d c <-> (b d) f c transposes around it (:549-555): frames are simply read with
+//                                a row stride of H*W.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// Flash attention, one CTA = one 128-query tile of one (batch, head).  128 threads, thread t owns query row t
+// (TMEM lane t).  Per 128-key tile:  S = Q K^T (tcgen05, fp32 in TMEM) -> online softmax in registers ->
+// P (bf16, 128B-swizzled K-major in smem) -> O_tile = P V (tcgen05, V is the MN-major B operand) -> rescaled
+// accumulation in registers.  Two co-resident CTAs per SM (d = 40) overlap one CTA's softmax with the other's MMAs.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ATT_M = 128;       // queries per CTA
+constexpr int ATT_N = 128;       // keys per tile
+constexpr int CHUNK_BYTES = 128 * 128;   // one 64-column (128-byte) slab of a 128-row tile
+
+struct AttnParams {
+  int Sq, Sk, d, head_pitch, kv_batch_div, ldo;
+  float scale_log2;
+  __nv_bfloat16* o;
+};
+
+template <int DK>
+struct AttnCfg {
+  static constexpr int NC = (DK + 63) / 64;
+  static constexpr int SMEM = (3 * NC + 2) * CHUNK_BYTES + 1024 + 128;
+  static constexpr uint32_t TMEM_COLS = (ATT_N + DK) <= 256 ? 256 : 512;
+};
+
+template <int DK>
+__global__ void __launch_bounds__(128, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = AttnCfg<DK>;
+  constexpr int NC = Cfg::NC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + NC * CHUNK_BYTES;
+  uint8_t* sV = sK + NC * CHUNK_BYTES;
+  uint8_t* sP = sV + NC * CHUNK_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * CHUNK_BYTES);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int q_tile = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+  const int kv_batch = batch / p.kv_batch_div;
+  const int n_kv = (p.Sk + ATT_N - 1) / ATT_N;
+  const int col0 = head * p.head_pitch;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;             // columns [0, 128)
+  const uint32_t tmem_o = tmem_base + ATT_N;     // columns [128, 128 + DK)
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, NC * CHUNK_BYTES);
+    for (int c = 0; c < NC; ++c) tma_load_3d(sQ + c * CHUNK_BYTES, &tmap_q, bar_q, col0 + c * 64, q_tile * ATT_M, batch);
+    mbar_expect_tx(bar_k, NC * CHUNK_BYTES);
+    for (int c = 0; c < NC; ++c) tma_load_3d(sK + c * CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, 0, kv_batch);
+    mbar_expect_tx(bar_v, NC * CHUNK_BYTES);
+    for (int c = 0; c < NC; ++c) tma_load_3d(sV + c * CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, 0, kv_batch);
+  }
+
+  constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_M, ATT_N, 0, 0);
+  constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_M, DK, 0, 1);
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+
+  float m_run = -INFINITY, l_run = 0.f;
+  float acc[DK];
+#pragma unroll
+  for (int i = 0; i < DK; ++i) acc[i] = 0.f;
+
+  for (int j = 0; j < n_kv; ++j) {
+    const uint32_t ph = j & 1;
+    const int kv_len = min(ATT_N, p.Sk - j * ATT_N);
+    if (tid == 0) {
+      if (j == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < DK / 16; ++kk) {
+        const uint32_t off = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
+        umma_bf16(tmem_s, umma_desc_sw128(smem_u32(sQ) + off, 16, 1024), umma_desc_sw128(smem_u32(sK) + off, 16, 1024),
+                  idesc_qk, kk != 0);
+      }
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < n_kv) {       // K tile consumed -> prefetch the next one under the softmax
+      mbar_expect_tx(bar_k, NC * CHUNK_BYTES);
+      for (int c = 0; c < NC; ++c)
+        tma_load_3d(sK + c * CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, (j + 1) * ATT_N, kv_batch);
+    }
+    __syncwarp();
+
+    // ---- online softmax, pass 1: row maximum over the valid keys ----
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < ATT_N / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (c * 32 + e < kv_len) mx = fmaxf(mx, __uint_as_float(v[e]));
+    }
+    const float m_new = fmaxf(m_run, mx * p.scale_log2);
+    const float alpha = fast_exp2(m_run - m_new);
+    // ---- pass 2: p = exp2(s*scale - m), row sum, P -> smem (bf16, 128B swizzle, K-major) ----
+    float rs = 0.f;
+    uint8_t* p_row = sP + tid * 128;
+#pragma unroll 1
+    for (int c = 0; c < ATT_N / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
+      tmem_wait_ld();
+      uint32_t pk[16];
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        float p0 = (c * 32 + e < kv_len) ? fast_exp2(__uint_as_float(v[e]) * p.scale_log2 - m_new) : 0.f;
+        float p1 = (c * 32 + e + 1 < kv_len) ? fast_exp2(__uint_as_float(v[e + 1]) * p.scale_log2 - m_new) : 0.f;
+        rs += p0 + p1;
+        pk[e >> 1] = pack_bf16(p0, p1);
+      }
+      uint8_t* chunk = p_row + (c >> 1) * CHUNK_BYTES;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c16 = ((c & 1) * 4 + g) ^ (tid & 7);
+        *reinterpret_cast<uint4*>(chunk + c16 * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      }
+    }
+    l_run = l_run * alpha + rs;
+    m_run = m_new;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+
+    if (tid == 0) {
+      mbar_wait(bar_v, ph);
+      tc_fence_after();
+      const int nk = (kv_len + 15) >> 4;
+      for (int kk = 0; kk < nk; ++kk) {
+        const uint32_t a_off = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
+        umma_bf16(tmem_o, umma_desc_sw128(smem_u32(sP) + a_off, 16, 1024),
+                  umma_desc_sw128(smem_u32(sV) + kk * 2048, CHUNK_BYTES, 1024), idesc_pv, kk != 0);
+      }
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+    mbar_wait(bar_o, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < n_kv) {       // V tile consumed -> prefetch the next one
+      mbar_expect_tx(bar_v, NC * CHUNK_BYTES);
+      for (int c = 0; c < NC; ++c)
+        tma_load_3d(sV + c * CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, (j + 1) * ATT_N, kv_batch);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < DK / 16; ++c) {
+      uint32_t v[16];
+      tmem_ld_32x16(tmem_o + lane_base + c * 16, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[c * 16 + e] = acc[c * 16 + e] * alpha + __uint_as_float(v[e]);
+    }
+    tc_fence_before();
+  }
+
+  const int qrow = q_tile * ATT_M + tid;
+  if (qrow < p.Sq) {
+    const float inv = 1.f / l_run;
+    __nv_bfloat16* dst = p.o + (static_cast<size_t>(batch) * p.Sq + qrow) * p.ldo + head * p.d;
+#pragma unroll
+    for (int c = 0; c < DK; c += 8) {
+      if (c < p.d) {
+        uint4 o;
+        o.x = pack_bf16(acc[c] * inv, acc[c + 1] * inv);
+        o.y = pack_bf16(acc[c + 2] * inv, acc[c + 3] * inv);
+        o.z = pack_bf16(acc[c + 4] * inv, acc[c + 5] * inv);
+        o.w = pack_bf16(acc[c + 6] * inv, acc[c + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + c) = o;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int DK>
+int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, int batch,
+                int heads, cudaStream_t stream) {
+  using Cfg = AttnCfg<DK>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(attn_fwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    LAVIE_REQUIRE(e == cudaSuccess, LAVIE_ERR_CUDA, "cudaFuncSetAttribute(attn<%d>): %s", DK, cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid((p.Sq + ATT_M - 1) / ATT_M, heads, batch);
+  attn_fwd_kernel<DK><<<grid, 128, Cfg::SMEM, stream>>>(mq, mk, mv, p);
+  return lavie_check_launch("attn_fwd_kernel");
+}
+
+int make_qkv_map(CUtensorMap* map, const void* base, int ld, int cols, int S, int nbatch) {
+  const uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(S), static_cast<uint64_t>(nbatch)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(S) * ld * 2};
+  const uint32_t box[3] = {64, 128, 1};
+  return lavie_make_tmap(map, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Temporal attention: one warp per (batch item, pixel, head); F <= 64 frames.
+// ------------------------------------------------------------------------------------------------------------
+struct TempParams {
+  const __nv_bfloat16* qkv;
+  int ld, k_off, v_off;
+  __nv_bfloat16* o;
+  int ldo, B, F, HW, heads, d, head_pitch;
+  float scale;
+  const float* rope;   // [F, rot_pairs, 2]
+  int rot_pairs;
+  const float* bias;   // [heads, F, F]
+  long long items;
+};
+
+__global__ void __launch_bounds__(128)
+temporal_attn_kernel(const TempParams p) {
+  extern __shared__ float tsm[];
+  const int warp_in_blk = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int F = p.F, d = p.d;
+  const int dp = d + 1;                       // padded pitch: conflict-free column walks
+  float* base = tsm + warp_in_blk * (3 * F * dp + F * (F + 1));
+  float* sq = base;
+  float* sk = sq + F * dp;
+  float* sv = sk + F * dp;
+  float* ss = sv + F * dp;                    // [F][F+1]
+  const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long item = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp_in_blk; item < p.items;
+       item += warps_total) {
+    const int h = static_cast<int>(item % p.heads);
+    const long long bp = item / p.heads;
+    const int pix = static_cast<int>(bp % p.HW);
+    const int b = static_cast<int>(bp / p.HW);
+    // ---- load q (scaled, rotated), k (rotated), v ----
+    const int half = d >> 1;                  // bf16 pairs per head row
+    for (int idx = lane; idx < F * half; idx += 32) {
+      const int f = idx / half, pr = idx - f * half;
+      const size_t row = (static_cast<size_t>(b) * F + f) * p.HW + pix;
+      const __nv_bfloat16* src = p.qkv + row * p.ld + h * p.head_pitch + 2 * pr;
+      float2 q2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(src));
+      float2 k2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(src + p.k_off));
+      const float2 v2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(src + p.v_off));
+      q2.x *= p.scale;                        // q scaled BEFORE the rotation (attention.py:640-646)
+      q2.y *= p.scale;
+      if (pr < p.rot_pairs) {
+        const float cs = p.rope[(f * p.rot_pairs + pr) * 2], sn = p.rope[(f * p.rot_pairs + pr) * 2 + 1];
+        const float qx = q2.x * cs - q2.y * sn, qy = q2.y * cs + q2.x * sn;
+        const float kx = k2.x * cs - k2.y * sn, ky = k2.y * cs + k2.x * sn;
+        q2 = make_float2(qx, qy);
+        k2 = make_float2(kx, ky);
+      }
+      sq[f * dp + 2 * pr] = q2.x; sq[f * dp + 2 * pr + 1] = q2.y;
+      sk[f * dp + 2 * pr] = k2.x; sk[f * dp + 2 * pr + 1] = k2.y;
+      sv[f * dp + 2 * pr] = v2.x; sv[f * dp + 2 * pr + 1] = v2.y;
+    }
+    __syncwarp();
+    // ---- scores + bias ----
+    for (int idx = lane; idx < F * F; idx += 32) {
+      const int i = idx / F, jn = idx - i * F;
+      float s = 0.f;
+      for (int c = 0; c < d; ++c) s += sq[i * dp + c] * sk[jn * dp + c];
+      ss[i * (F + 1) + jn] = s + p.bias[(h * F + i) * F + jn];
+    }
+    __syncwarp();
+    // ---- softmax per query frame ----
+    for (int i = lane; i < F; i += 32) {
+      float mx = -INFINITY;
+      for (int jn = 0; jn < F; ++jn) mx = fmaxf(mx, ss[i * (F + 1) + jn]);
+      float sum = 0.f;
+      for (int jn = 0; jn < F; ++jn) {
+        const float e = __expf(ss[i * (F + 1) + jn] - mx);
+        ss[i * (F + 1) + jn] = e;
+        sum += e;
+      }
+      const float inv = 1.f / sum;
+      for (int jn = 0; jn < F; ++jn) ss[i * (F + 1) + jn] *= inv;
+    }
+    __syncwarp();
+    // ---- out = P V ----
+    for (int idx = lane; idx < F * half; idx += 32) {
+      const int i = idx / half, pr = idx - i * half;
+      float ox = 0.f, oy = 0.f;
+      for (int jn = 0; jn < F; ++jn) {
+        const float w = ss[i * (F + 1) + jn];
+        ox += w * sv[jn * dp + 2 * pr];
+        oy += w * sv[jn * dp + 2 * pr + 1];
+      }
+      const size_t row = (static_cast<size_t>(b) * F + i) * p.HW + pix;
+      *reinterpret_cast<uint32_t*>(p.o + row * p.ldo + h * d + 2 * pr) = pack_bf16(ox, oy);
+    }
+    __syncwarp();
+  }
+}
+
+bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" int lavie_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o,
+                                    int ldo, int batch, int heads, int Sq, int Sk, int d, int head_pitch,
+                                    int kv_batch_div, float scale, cudaStream_t stream) {
+  LAVIE_REQUIRE(batch > 0 && heads > 0 && Sq > 0 && Sk > 0 && kv_batch_div > 0 && batch % kv_batch_div == 0,
+                LAVIE_ERR_SHAPE, "attention: bad sizes batch=%d heads=%d Sq=%d Sk=%d div=%d", batch, heads, Sq, Sk,
+                kv_batch_div);
+  const int dk = (d + 15) & ~15;
+  LAVIE_REQUIRE(d % 8 == 0 && head_pitch >= dk && head_pitch % 8 == 0, LAVIE_ERR_SHAPE,
+                "attention: d=%d head_pitch=%d (pitch must be >= d rounded up to 16)", d, head_pitch);
+  LAVIE_REQUIRE(al16(q) && al16(k) && al16(v) && al16(o) && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 &&
+                    ldo % 8 == 0,
+                LAVIE_ERR_ALIGN, "attention: 16-byte alignment required");
+  LAVIE_REQUIRE(heads <= 65535 && batch <= 65535, LAVIE_ERR_SHAPE, "attention: grid too large");
+  AttnParams p;
+  p.Sq = Sq; p.Sk = Sk; p.d = d; p.head_pitch = head_pitch; p.kv_batch_div = kv_batch_div; p.ldo = ldo;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.o = static_cast<__nv_bfloat16*>(o);
+  CUtensorMap mq, mk, mv;
+  const int cols = heads * head_pitch;
+  int rc = make_qkv_map(&mq, q, ldq, cols, Sq, batch);
+  if (rc) return rc;
+  rc = make_qkv_map(&mk, k, ldk, cols, Sk, batch / kv_batch_div);
+  if (rc) return rc;
+  rc = make_qkv_map(&mv, v, ldv, cols, Sk, batch / kv_batch_div);
+  if (rc) return rc;
+  switch (dk) {
+    case 48: return launch_attn<48>(mq, mk, mv, p, batch, heads, stream);
+    case 64: return launch_attn<64>(mq, mk, mv, p, batch, heads, stream);
+    case 80: return launch_attn<80>(mq, mk, mv, p, batch, heads, stream);
+    case 96: return launch_attn<96>(mq, mk, mv, p, batch, heads, stream);
+    case 128: return launch_attn<128>(mq, mk, mv, p, batch, heads, stream);
+    case 160: return launch_attn<160>(mq, mk, mv, p, batch, heads, stream);
+    default:
+      lavie_set_error("attention: head dim %d (padded %d) not instantiated (48/64/80/96/128/160)", d, dk);
+      return LAVIE_ERR_SHAPE;
+  }
+}
+
+extern "C" int lavie_temporal_attention_bf16(const void* qkv, int ld, int k_off, int v_off, void* o, int ldo, int B,
+                                             int F, int HW, int heads, int d, int head_pitch, float scale,
+                                             const float* rope, int rot_pairs, const float* bias,
+                                             cudaStream_t stream) {
+  LAVIE_REQUIRE(F >= 1 && F <= 64 && d % 2 == 0 && 2 * rot_pairs <= d, LAVIE_ERR_SHAPE,
+                "temporal attention: F=%d (<=64) d=%d rot_pairs=%d", F, d, rot_pairs);
+  LAVIE_REQUIRE(ld % 2 == 0 && ldo % 2 == 0 && k_off % 2 == 0 && v_off % 2 == 0 && head_pitch % 2 == 0,
+                LAVIE_ERR_ALIGN, "temporal attention: even strides required");
+  TempParams p;
+  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.ld = ld; p.k_off = k_off; p.v_off = v_off;
+  p.o = static_cast<__nv_bfloat16*>(o);
+  p.ldo = ldo; p.B = B; p.F = F; p.HW = HW; p.heads = heads; p.d = d; p.head_pitch = head_pitch;
+  p.scale = scale; p.rope = rope; p.rot_pairs = rot_pairs; p.bias = bias;
+  p.items = static_cast<long long>(B) * HW * heads;
+  const int per_warp = (3 * F * (d + 1) + F * (F + 1)) * static_cast<int>(sizeof(float));
+  int warps = 4;
+  while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
+  const int smem = warps * per_warp;
+  LAVIE_REQUIRE(smem <= 227 * 1024, LAVIE_ERR_SHAPE, "temporal attention: F*d too large for shared memory");
+  static int configured_smem = 0;
+  if (smem > configured_smem) {
+    cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    LAVIE_REQUIRE(e == cudaSuccess, LAVIE_ERR_CUDA, "cudaFuncSetAttribute(temporal): %s", cudaGetErrorString(e));
+    configured_smem = smem;
+  }
+  long long blocks = (p.items + warps - 1) / warps;
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  temporal_attn_kernel<<<static_cast<int>(blocks), warps * 32, smem, stream>>>(p);
+  return lavie_check_launch("temporal_attn_kernel");
+}

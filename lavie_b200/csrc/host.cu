@@ -1,0 +1,72 @@
+// Host-side plumbing of the C ABI: thread-local error string, launch checking, TMA tensor-map encoding.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace {
+thread_local char g_error[512] = "";
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+EncodeTiledFn get_encode() {
+  if (g_encode) return g_encode;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return g_encode;
+}
+}  // namespace
+
+void lavie_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int lavie_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    lavie_set_error("%s: %s (%d)", what, cudaGetErrorString(e), static_cast<int>(e));
+    return LAVIE_ERR_CUDA;
+  }
+  return LAVIE_OK;
+}
+
+int lavie_make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn enc = get_encode();
+  LAVIE_REQUIRE(enc != nullptr, LAVIE_ERR_DRIVER, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                   gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    lavie_set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d, dims %llu x %llu, box %u x %u)",
+                    static_cast<int>(r), rank, static_cast<unsigned long long>(dims[0]),
+                    static_cast<unsigned long long>(rank > 1 ? dims[1] : 1), box[0], rank > 1 ? box[1] : 1);
+    return LAVIE_ERR_DRIVER;
+  }
+  return LAVIE_OK;
+}
+
+extern "C" const char* lavie_last_error(void) { return g_error; }
+extern "C" int lavie_abi_version(void) { return 1; }

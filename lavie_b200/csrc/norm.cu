@@ -1,0 +1,258 @@
+// Bandwidth-bound normalisation kernels (channels-last bf16, 16-byte vector accesses, fp32 statistics).
+//   GroupNorm  : nn.GroupNorm of resnet.py:144,160,180,191 / unet.py:288,504 (5-D: statistics span frames) and
+//                attention.py:324,369 (4-D per frame), optionally followed by SiLU (resnet.py:181,193).
+//   LayerNorm  : attention.py:444-477 (norm1 / norm2 / norm_temp / norm3).
+#include "common.cuh"
+
+namespace {
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_ROWS_PER_CHUNK = 512;
+
+__device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int ld0, int c0, const __nv_bfloat16* x1, int ld1,
+                                         size_t row, int col) {
+  const __nv_bfloat16* src = (col < c0) ? x0 + row * ld0 + col : x1 + row * ld1 + (col - c0);
+  return __ldg(reinterpret_cast<const uint4*>(src));
+}
+
+// partial[sample][chunk][group][2]
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __nv_bfloat16* __restrict__ x1, int ld1,
+                int c1, int rows_per_sample, int groups, int chunks, float* __restrict__ partial) {
+  extern __shared__ float sm[];          // [2][C]
+  const int C = c0 + c1;
+  float* s_sum = sm;
+  float* s_sq = sm + C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+
+  const int sample = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int vec_per_row = C >> 3;
+  const int r_begin = chunk * GN_ROWS_PER_CHUNK;
+  const int r_end = min(r_begin + GN_ROWS_PER_CHUNK, rows_per_sample);
+  // column slots: a thread owns one 8-channel vector per slot; narrow rows are covered by several row lanes
+  const int lanes_per_row = min(vec_per_row, static_cast<int>(blockDim.x));
+  const int row_lanes = blockDim.x / lanes_per_row;            // rows processed concurrently
+  const int my_rl = threadIdx.x / lanes_per_row;
+  for (int my_vec = threadIdx.x % lanes_per_row; my_vec < vec_per_row; my_vec += lanes_per_row) {
+    if (my_rl >= row_lanes) break;
+    float s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+    for (int r = r_begin + my_rl; r < r_end; r += row_lanes) {
+      const size_t row = static_cast<size_t>(sample) * rows_per_sample + r;
+      const uint4 v = ld_vec8(x0, ld0, c0, x1, ld1, row, my_vec * 8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        s[2 * e] += f.x; q[2 * e] += f.x * f.x;
+        s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&s_sum[my_vec * 8 + e], s[e]);
+      atomicAdd(&s_sq[my_vec * 8 + e], q[e]);
+    }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += s_sum[c]; b += s_sq[c]; }
+    float* dst = partial + ((static_cast<size_t>(sample) * chunks + chunk) * groups + g) * 2;
+    dst[0] = a;
+    dst[1] = b;
+  }
+}
+
+// one block per sample: combine chunk partials in fp64, emit per-channel (scale, shift)
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int groups, int C,
+                                   double inv_count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float* __restrict__ scale_shift) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int sample = blockIdx.x;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+      const float* src = partial + ((static_cast<size_t>(sample) * chunks + k) * groups + g) * 2;
+      a += src[0];
+      b += src[1];
+    }
+    const double mean = a * inv_count;
+    double var = b * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = s_rstd[g] * gamma[c];
+    float* dst = scale_shift + (static_cast<size_t>(sample) * C + c) * 2;
+    dst[0] = sc;
+    dst[1] = beta[c] - s_mean[g] * sc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __nv_bfloat16* __restrict__ x1, int ld1,
+                int c1, int rows_per_sample, long long total_vecs, const float* __restrict__ scale_shift, int silu,
+                __nv_bfloat16* __restrict__ y, int ldy) {
+  const int C = c0 + c1;
+  const int vec_per_row = C >> 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_vecs;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const size_t row = static_cast<size_t>(i / vec_per_row);
+    const int col = static_cast<int>(i % vec_per_row) * 8;
+    const int sample = static_cast<int>(row / rows_per_sample);
+    const uint4 v = ld_vec8(x0, ld0, c0, x1, ld1, row, col);
+    const float4* ss = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(sample) * C + col) * 2);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_bf16(w[e]);
+      const float4 p = __ldg(ss + e);        // (scale0, shift0, scale1, shift1)
+      float a = f.x * p.x + p.y;
+      float b = f.y * p.z + p.w;
+      if (silu) { a = silu_f(a); b = silu_f(b); }
+      o[e] = pack_bf16(a, b);
+    }
+    *reinterpret_cast<uint4*>(y + row * ldy + col) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// One warp per row; the row (C <= 2048) lives in registers between the two reduction passes.
+template <int MAX_VEC>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy, int rows, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = C >> 3;
+  const __nv_bfloat16* src = x + static_cast<size_t>(warp) * ldx;
+  float f[MAX_VEC][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + v * 8));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = unpack_bf16(w[e]);
+        f[i][2 * e] = t.x;
+        f[i][2 * e + 1] = t.y;
+        sum += t.x + t.y;
+      }
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(C);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[i][e] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(C) + eps);
+  __nv_bfloat16* dst = y + static_cast<size_t>(warp) * ldy;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      uint4 o;
+      o.x = pack_bf16((f[i][0] - mean) * rstd * g0.x + b0.x, (f[i][1] - mean) * rstd * g0.y + b0.y);
+      o.y = pack_bf16((f[i][2] - mean) * rstd * g0.z + b0.z, (f[i][3] - mean) * rstd * g0.w + b0.w);
+      o.z = pack_bf16((f[i][4] - mean) * rstd * g1.x + b1.x, (f[i][5] - mean) * rstd * g1.y + b1.y);
+      o.w = pack_bf16((f[i][6] - mean) * rstd * g1.z + b1.z, (f[i][7] - mean) * rstd * g1.w + b1.w);
+      *reinterpret_cast<uint4*>(dst + v * 8) = o;
+    }
+  }
+}
+
+bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int check_sources(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1) {
+  LAVIE_REQUIRE(c0 > 0 && c0 % 8 == 0 && c1 % 8 == 0 && ld0 % 8 == 0 && (c1 == 0 || ld1 % 8 == 0), LAVIE_ERR_SHAPE,
+                "groupnorm: channel counts and row strides must be multiples of 8");
+  LAVIE_REQUIRE(al16(x0) && (c1 == 0 || al16(x1)), LAVIE_ERR_ALIGN, "groupnorm: inputs must be 16-byte aligned");
+  return LAVIE_OK;
+}
+
+}  // namespace
+
+extern "C" int lavie_groupnorm_chunks(int rows_per_sample) {
+  return (rows_per_sample + GN_ROWS_PER_CHUNK - 1) / GN_ROWS_PER_CHUNK;
+}
+
+extern "C" int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
+                                     int rows_per_sample, int groups, float* partial, cudaStream_t stream) {
+  int rc = check_sources(x0, ld0, c0, x1, ld1, c1);
+  if (rc) return rc;
+  const int C = c0 + c1;
+  LAVIE_REQUIRE(C % groups == 0 && groups <= 64 && C <= 8192, LAVIE_ERR_SHAPE,
+                "groupnorm: C=%d groups=%d unsupported", C, groups);
+  const int chunks = lavie_groupnorm_chunks(rows_per_sample);
+  dim3 grid(chunks, samples);
+  gn_stats_kernel<<<grid, GN_THREADS, 2 * C * sizeof(float), stream>>>(
+      static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1,
+      rows_per_sample, groups, chunks, partial);
+  return lavie_check_launch("gn_stats_kernel");
+}
+
+extern "C" int lavie_groupnorm_finalize(const float* partial, int samples, int chunks, int groups, int C,
+                                        long long count_per_group, const float* gamma, const float* beta, float eps,
+                                        float* scale_shift, cudaStream_t stream) {
+  LAVIE_REQUIRE(groups <= 64 && C % groups == 0 && count_per_group > 0, LAVIE_ERR_SHAPE, "groupnorm_finalize: shape");
+  gn_finalize_kernel<<<samples, 256, 0, stream>>>(partial, chunks, groups, C, 1.0 / static_cast<double>(count_per_group),
+                                                  gamma, beta, eps, scale_shift);
+  return lavie_check_launch("gn_finalize_kernel");
+}
+
+extern "C" int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
+                                     int rows_per_sample, const float* scale_shift, int silu, void* y, int ldy,
+                                     cudaStream_t stream) {
+  int rc = check_sources(x0, ld0, c0, x1, ld1, c1);
+  if (rc) return rc;
+  LAVIE_REQUIRE(al16(y) && ldy % 8 == 0 && al16(scale_shift), LAVIE_ERR_ALIGN, "groupnorm_apply: output alignment");
+  const int C = c0 + c1;
+  const long long total = static_cast<long long>(samples) * rows_per_sample * (C >> 3);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  gn_apply_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1, rows_per_sample,
+      total, scale_shift, silu, static_cast<__nv_bfloat16*>(y), ldy);
+  return lavie_check_launch("gn_apply_kernel");
+}
+
+extern "C" int lavie_layernorm_bf16(const void* x, int ldx, const float* gamma, const float* beta, float eps, void* y,
+                                    int ldy, int rows, int C, cudaStream_t stream) {
+  LAVIE_REQUIRE(C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldy % 8 == 0, LAVIE_ERR_SHAPE,
+                "layernorm: C=%d must be a multiple of 8 and <= 2048", C);
+  LAVIE_REQUIRE(al16(x) && al16(y) && al16(gamma) && al16(beta), LAVIE_ERR_ALIGN, "layernorm: alignment");
+  if (rows <= 0) return LAVIE_OK;
+  const int blocks = (rows + 7) / 8;     // 8 warps (rows) per 256-thread block
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
+  const int nvec = C >> 3;
+  if (nvec <= 64) layernorm_kernel<2><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C);
+  else if (nvec <= 160) layernorm_kernel<5><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C);
+  else layernorm_kernel<8><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C);
+  return lavie_check_launch("layernorm_kernel");
+}

@@ -1,0 +1,279 @@
+"""Thin operator layer: torch CUDA tensors in, C-ABI kernel launches out.
+
+PyTorch is used only for device memory and the current stream.  Every function enqueues on
+``torch.cuda.current_stream()`` and returns the output tensor; nothing here computes with torch ops.
+Activations are bf16 channels-last ``[rows, C]`` (rows = (b, f, y, x)), see include/lavie_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Epilogue, check
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rows2d(t: torch.Tensor) -> Tuple[int, int, int]:
+    """(rows, cols, ld) of a 2-D bf16 view whose last dim is contiguous."""
+    assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == BF16 and t.is_cuda, (t.shape, t.stride(), t.dtype)
+    return t.shape[0], t.shape[1], t.stride(0)
+
+
+def _epilogue(bias=None, row_bias=None, rows_per_batch=1, residual=None, geglu=False):
+    if bias is None and row_bias is None and residual is None and not geglu:
+        return None
+    ep = Epilogue()
+    ep.bias = _ptr(bias)
+    ep.row_bias = _ptr(row_bias)
+    ep.rows_per_batch = int(rows_per_batch)
+    ep.residual = _ptr(residual)
+    ep.ld_residual = residual.stride(0) if residual is not None else 0
+    ep.geglu = 1 if geglu else 0
+    if bias is not None:
+        assert bias.dtype == F32 and bias.is_contiguous()
+    if row_bias is not None:
+        assert row_bias.dtype == F32 and row_bias.is_contiguous()
+    if residual is not None:
+        _rows2d(residual)
+    return ep
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None, bias=None, row_bias=None,
+         rows_per_batch=1, residual=None, geglu=False, out: Optional[torch.Tensor] = None, block_n: int = 0):
+    """out[M,N] = [a | a2] @ w^T (+ fused epilogue).  w: bf16 [N, K] contiguous."""
+    lib = _lib.load()
+    M, k0, lda = _rows2d(a)
+    k1, lda2 = 0, 0
+    if a2 is not None:
+        M2, k1, lda2 = _rows2d(a2)
+        assert M2 == M
+    assert w.dtype == BF16 and w.is_contiguous() and w.shape[1] == k0 + k1, (w.shape, k0, k1)
+    N = w.shape[0]
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=BF16, device=a.device)
+    Mo, No, ldo = _rows2d(out)
+    assert Mo == M and No == n_out
+    ep = _epilogue(bias, row_bias, rows_per_batch, residual, geglu)
+    rc = lib.lavie_gemm_bf16(a.data_ptr(), lda, k0, _ptr(a2), lda2, k1, w.data_ptr(), out.data_ptr(), ldo, M, N,
+                             ctypes.byref(ep) if ep is not None else None, block_n, _stream())
+    check(rc, "lavie_gemm_bf16")
+    return out
+
+
+def conv3x3_supported(H: int, W: int, C: int) -> bool:
+    return bool(_lib.load().lavie_conv3x3_supported(H, W, C))
+
+
+def im2col3x3(x: torch.Tensor, NF: int, H: int, W: int, stride: int = 1) -> torch.Tensor:
+    """x: contiguous [NF*H*W, C] -> [NF*Ho*Wo, 9*C], K ordered (kh, kw, c)."""
+    lib = _lib.load()
+    rows, C, ld = _rows2d(x)
+    assert rows == NF * H * W and ld == C
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    col = torch.empty((NF * Ho * Wo, 9 * C), dtype=BF16, device=x.device)
+    check(lib.lavie_im2col3x3_bf16(x.data_ptr(), NF, H, W, C, stride, col.data_ptr(), _stream()), "lavie_im2col3x3_bf16")
+    return col
+
+
+def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride: int = 1, bias=None, row_bias=None,
+            rows_per_batch=1, residual=None, out: Optional[torch.Tensor] = None, block_n: int = 0,
+            force_im2col: bool = False):
+    """3x3 pad-1 InflatedConv3d on a contiguous channels-last map; w: bf16 [N, 9*C] in (kh, kw, c) order."""
+    lib = _lib.load()
+    rows, C, ld = _rows2d(x)
+    assert rows == NF * H * W and ld == C, "conv3x3 needs a contiguous channels-last input"
+    N = w.shape[0]
+    assert w.dtype == BF16 and w.is_contiguous() and w.shape[1] == 9 * C
+    if stride != 1 or force_im2col or not conv3x3_supported(H, W, C):
+        col = im2col3x3(x, NF, H, W, stride)
+        return gemm(col, w, bias=bias, row_bias=row_bias, rows_per_batch=rows_per_batch, residual=residual, out=out,
+                    block_n=block_n)
+    if out is None:
+        out = torch.empty((rows, N), dtype=BF16, device=x.device)
+    Mo, No, ldo = _rows2d(out)
+    assert Mo == rows and No == N
+    ep = _epilogue(bias, row_bias, rows_per_batch, residual, False)
+    rc = lib.lavie_conv3x3_bf16(x.data_ptr(), NF, H, W, C, w.data_ptr(), out.data_ptr(), ldo, N,
+                                ctypes.byref(ep) if ep is not None else None, block_n, _stream())
+    check(rc, "lavie_conv3x3_bf16")
+    return out
+
+
+def groupnorm_scale_shift(x: torch.Tensor, samples: int, rows_per_sample: int, gamma: torch.Tensor,
+                          beta: torch.Tensor, eps: float, groups: int = 32, x2: Optional[torch.Tensor] = None):
+    """Statistics + affine folded into per-(sample, channel) (scale, shift): fp32 [samples, C, 2]."""
+    lib = _lib.load()
+    rows, c0, ld0 = _rows2d(x)
+    c1, ld1 = 0, 0
+    if x2 is not None:
+        rows2, c1, ld1 = _rows2d(x2)
+        assert rows2 == rows
+    assert rows == samples * rows_per_sample
+    C = c0 + c1
+    chunks = lib.lavie_groupnorm_chunks(rows_per_sample)
+    partial = torch.empty((samples, chunks, groups, 2), dtype=F32, device=x.device)
+    check(lib.lavie_groupnorm_stats(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample, groups,
+                                    partial.data_ptr(), _stream()), "lavie_groupnorm_stats")
+    ss = torch.empty((samples, C, 2), dtype=F32, device=x.device)
+    assert gamma.dtype == F32 and beta.dtype == F32 and gamma.numel() == C
+    check(lib.lavie_groupnorm_finalize(partial.data_ptr(), samples, chunks, groups, C,
+                                       rows_per_sample * (C // groups), gamma.data_ptr(), beta.data_ptr(), eps,
+                                       ss.data_ptr(), _stream()), "lavie_groupnorm_finalize")
+    return ss
+
+
+def groupnorm_apply(x: torch.Tensor, scale_shift: torch.Tensor, samples: int, rows_per_sample: int, silu: bool,
+                    x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    rows, c0, ld0 = _rows2d(x)
+    c1, ld1 = 0, 0
+    if x2 is not None:
+        _, c1, ld1 = _rows2d(x2)
+    C = c0 + c1
+    if out is None:
+        out = torch.empty((rows, C), dtype=BF16, device=x.device)
+    _, _, ldy = _rows2d(out)
+    check(lib.lavie_groupnorm_apply(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample,
+                                    scale_shift.data_ptr(), 1 if silu else 0, out.data_ptr(), ldy, _stream()),
+          "lavie_groupnorm_apply")
+    return out
+
+
+def groupnorm(x, samples, rows_per_sample, gamma, beta, eps, silu, groups=32, x2=None):
+    ss = groupnorm_scale_shift(x, samples, rows_per_sample, gamma, beta, eps, groups, x2)
+    return groupnorm_apply(x, ss, samples, rows_per_sample, silu, x2)
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    rows, C, ldx = _rows2d(x)
+    if out is None:
+        out = torch.empty((rows, C), dtype=BF16, device=x.device)
+    _, _, ldy = _rows2d(out)
+    assert gamma.dtype == F32 and beta.dtype == F32
+    check(lib.lavie_layernorm_bf16(x.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), ldy,
+                                   rows, C, _stream()), "lavie_layernorm_bf16")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, heads: int, Sq: int, Sk: int, d: int,
+              head_pitch: int, kv_batch_div: int = 1, scale: Optional[float] = None,
+              out: Optional[torch.Tensor] = None):
+    """q: [batch*Sq, >=heads*pitch] view, k/v: [(batch/kv_batch_div)*Sk, ...] views; returns [batch*Sq, heads*d]."""
+    lib = _lib.load()
+    rq, _, ldq = _rows2d(q)
+    rk, _, ldk = _rows2d(k)
+    rv, _, ldv = _rows2d(v)
+    assert rq == batch * Sq and rk == (batch // kv_batch_div) * Sk and rv == rk
+    if out is None:
+        out = torch.empty((rq, heads * d), dtype=BF16, device=q.device)
+    _, _, ldo = _rows2d(out)
+    if scale is None:
+        scale = d ** -0.5
+    check(lib.lavie_attention_bf16(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), ldo, batch,
+                                   heads, Sq, Sk, d, head_pitch, kv_batch_div, scale, _stream()),
+          "lavie_attention_bf16")
+    return out
+
+
+def temporal_attention(qkv: torch.Tensor, B: int, F: int, HW: int, heads: int, d: int, head_pitch: int,
+                       rope: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """qkv: [B*F*HW, 3*heads*pitch] (q | k | v); rope fp32 [F, rot_pairs, 2]; bias fp32 [heads, F, F]."""
+    lib = _lib.load()
+    rows, cols, ld = _rows2d(qkv)
+    assert rows == B * F * HW and cols == 3 * heads * head_pitch
+    if out is None:
+        out = torch.empty((rows, heads * d), dtype=BF16, device=qkv.device)
+    _, _, ldo = _rows2d(out)
+    assert rope.dtype == F32 and rope.is_contiguous() and rope.shape[0] == F
+    assert bias.dtype == F32 and bias.is_contiguous() and tuple(bias.shape) == (heads, F, F)
+    check(lib.lavie_temporal_attention_bf16(qkv.data_ptr(), ld, heads * head_pitch, 2 * heads * head_pitch,
+                                            out.data_ptr(), ldo, B, F, HW, heads, d, head_pitch, d ** -0.5,
+                                            rope.data_ptr(), rope.shape[1], bias.data_ptr(), _stream()),
+          "lavie_temporal_attention_bf16")
+    return out
+
+
+def linear_smallm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], silu_in=False, silu_out=False):
+    lib = _lib.load()
+    assert x.dtype == F32 and x.is_contiguous() and x.dim() == 2
+    M, K = x.shape
+    assert w.dtype == BF16 and w.is_contiguous() and w.shape[1] == K
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=F32, device=x.device)
+    check(lib.lavie_linear_smallm(x.data_ptr(), M, K, w.data_ptr(), _ptr(bias), out.data_ptr(), N, int(silu_in),
+                                  int(silu_out), _stream()), "lavie_linear_smallm")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int):
+    lib = _lib.load()
+    assert t.dtype == F32 and t.is_contiguous() and t.dim() == 1
+    out = torch.empty((t.shape[0], dim), dtype=F32, device=t.device)
+    check(lib.lavie_timestep_embedding(t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream()),
+          "lavie_timestep_embedding")
+    return out
+
+
+def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor):
+    """x fp32 [B,Cin,F,H,W] -> bf16 [B*F*H*W, Cout]; w fp32 [Cout,Cin,3,3]."""
+    lib = _lib.load()
+    assert x.dtype == F32 and x.is_contiguous() and x.dim() == 5
+    B, Cin, Fr, H, W = x.shape
+    Cout = w.shape[0]
+    assert w.dtype == F32 and w.is_contiguous() and bias.dtype == F32
+    out = torch.empty((B * Fr * H * W, Cout), dtype=BF16, device=x.device)
+    check(lib.lavie_conv_in(x.data_ptr(), B, Cin, Fr, H, W, w.data_ptr(), bias.data_ptr(), Cout, out.data_ptr(), Cout,
+                            _stream()), "lavie_conv_in")
+    return out
+
+
+def conv_out(x: torch.Tensor, scale_shift: torch.Tensor, B: int, Fr: int, H: int, W: int, w: torch.Tensor,
+             bias: torch.Tensor):
+    """x bf16 [B*F*H*W, C] raw; w fp32 [Cout, 3, 3, C]; returns fp32 [B, Cout, F, H, W]."""
+    lib = _lib.load()
+    rows, C, ldx = _rows2d(x)
+    assert rows == B * Fr * H * W
+    Cout = w.shape[0]
+    assert w.dtype == F32 and w.is_contiguous() and tuple(w.shape) == (Cout, 3, 3, C)
+    out = torch.empty((B, Cout, Fr, H, W), dtype=F32, device=x.device)
+    check(lib.lavie_conv_out(x.data_ptr(), ldx, scale_shift.data_ptr(), B, Fr, H, W, C, w.data_ptr(), bias.data_ptr(),
+                             Cout, out.data_ptr(), _stream()), "lavie_conv_out")
+    return out
+
+
+def upsample_nearest2x(x: torch.Tensor, NF: int, H: int, W: int):
+    lib = _lib.load()
+    rows, C, ld = _rows2d(x)
+    assert rows == NF * H * W and ld == C
+    y = torch.empty((NF * 4 * H * W, C), dtype=BF16, device=x.device)
+    check(lib.lavie_upsample_nearest2x(x.data_ptr(), NF, H, W, C, y.data_ptr(), _stream()), "lavie_upsample_nearest2x")
+    return y
+
+
+def cfg_ddim_step(noise_uncond, noise_text, guidance: float, alpha_t: float, alpha_prev: float, latents,
+                  out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    for t in (noise_uncond, noise_text, latents):
+        assert t.dtype == F32 and t.is_contiguous()
+    if out is None:
+        out = torch.empty_like(latents)
+    check(lib.lavie_cfg_ddim_step(noise_uncond.data_ptr(), noise_text.data_ptr(), guidance, alpha_t, alpha_prev,
+                                  latents.data_ptr(), out.data_ptr(), latents.numel(), _stream()),
+          "lavie_cfg_ddim_step")
+    return out

@@ -1,0 +1,285 @@
+"""Per-kernel numerics on the B200: every C-ABI entry point against a plain PyTorch fp32 reference of the same
+op, on bf16-rounded inputs.  Tolerances are stated per test (bf16 output rounding = 2^-9 relative)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from lavie_b200 import ops
+    return ops
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("block_n", [0, 64, 128, 160, 192, 256])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1000, 320, 320), (4096, 1152, 320), (300, 640, 2560)])
+def test_gemm_plain(M, N, K, block_n):
+    ops = _ops()
+    a = _bf(_rand(M, K))
+    w = _bf(_rand(N, K, scale=K ** -0.5))
+    out = ops.gemm(a, w, block_n=block_n)
+    ref = a.float() @ w.float().t()
+    assert rel_l2(out.float(), ref) < 4e-3          # bf16 output rounding only
+
+
+def test_gemm_epilogue_bias_rowbias_residual_strided():
+    ops = _ops()
+    M, N, K, B = 768, 320, 640, 3
+    a = _bf(_rand(M, K))
+    w = _bf(_rand(N, K, scale=K ** -0.5))
+    bias = _rand(N, seed=1)
+    rb = _rand(B, N, seed=2)
+    res_full = _bf(_rand(M, N + 64, seed=3))
+    res = res_full[:, 64:]                            # strided residual view
+    out_full = torch.zeros((M, 2 * N), dtype=torch.bfloat16, device=DEV)
+    out = out_full[:, N:]                             # strided output view (writes into a wider buffer)
+    ops.gemm(a, w, bias=bias, row_bias=rb, rows_per_batch=M // B, residual=res, out=out)
+    ref = a.float() @ w.float().t() + bias + rb.repeat_interleave(M // B, 0) + res.float()
+    assert rel_l2(out.float(), ref) < 4e-3
+    assert out_full[:, :N].abs().max() == 0           # nothing written outside the view
+
+
+def test_gemm_two_sources_fold_concat():
+    ops = _ops()
+    M, N, k0, k1 = 640, 320, 640, 320
+    a0 = _bf(_rand(M, k0))
+    a1 = _bf(_rand(M, k1, seed=5))
+    w = _bf(_rand(N, k0 + k1, scale=(k0 + k1) ** -0.5))
+    out = ops.gemm(a0, w, a2=a1)
+    ref = torch.cat([a0, a1], 1).float() @ w.float().t()
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+def test_gemm_geglu():
+    ops = _ops()
+    M, C = 512, 320
+    a = _bf(_rand(M, C))
+    w = _bf(_rand(8 * C, C, scale=C ** -0.5))          # reference layout: rows [0,4C) value, [4C,8C) gate
+    b = _rand(8 * C, seed=7)
+    from lavie_b200.packing import interleave_geglu
+    wi, bi = interleave_geglu(w, b)
+    out = ops.gemm(a, wi, bias=bi, geglu=True)
+    hg = a.float() @ w.float().t() + b
+    ref = hg[:, : 4 * C] * F.gelu(hg[:, 4 * C:])
+    assert out.shape == (M, 4 * C)
+    assert rel_l2(out.float(), ref) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def _conv_ref(x_nhwc, w_oihw, NF, H, W, stride=1):
+    x = x_nhwc.float().reshape(NF, H, W, -1).permute(0, 3, 1, 2)
+    y = F.conv2d(x, w_oihw.float(), None, stride=stride, padding=1)
+    return y.permute(0, 2, 3, 1).reshape(-1, w_oihw.shape[0])
+
+
+@pytest.mark.parametrize("NF,H,W,C,N", [(4, 8, 64, 64, 64), (3, 20, 32, 128, 320), (5, 10, 16, 320, 128),
+                                        (7, 5, 8, 64, 64), (2, 40, 64, 320, 320)])
+def test_conv3x3_tma(NF, H, W, C, N):
+    ops = _ops()
+    from lavie_b200.packing import pack_conv3x3
+    x = _bf(_rand(NF * H * W, C))
+    w = _bf(_rand(N, C, 3, 3, scale=(9 * C) ** -0.5))
+    assert ops.conv3x3_supported(H, W, C)
+    out = ops.conv3x3(x, NF, H, W, pack_conv3x3(w))
+    ref = _conv_ref(x, w, NF, H, W)
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+def test_conv3x3_epilogue_time_bias_and_shortcut():
+    ops = _ops()
+    from lavie_b200.packing import pack_conv3x3
+    B, Fr, H, W, C, N = 2, 3, 10, 16, 64, 128
+    NF = B * Fr
+    x = _bf(_rand(NF * H * W, C))
+    w = _bf(_rand(N, C, 3, 3, scale=(9 * C) ** -0.5))
+    bias = _rand(N, seed=3)
+    temb = _rand(B, N, seed=4)
+    res = _bf(_rand(NF * H * W, N, seed=5))
+    out = ops.conv3x3(x, NF, H, W, pack_conv3x3(w), bias=bias, row_bias=temb, rows_per_batch=Fr * H * W, residual=res)
+    ref = _conv_ref(x, w, NF, H, W) + bias + temb.repeat_interleave(Fr * H * W, 0) + res.float()
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_conv3x3_im2col_path(stride):
+    ops = _ops()
+    from lavie_b200.packing import pack_conv3x3
+    NF, H, W, C, N = 3, 12, 24, 64, 64                 # W = 24: not a TMA geometry
+    x = _bf(_rand(NF * H * W, C))
+    w = _bf(_rand(N, C, 3, 3, scale=(9 * C) ** -0.5))
+    out = ops.conv3x3(x, NF, H, W, pack_conv3x3(w), stride=stride)
+    ref = _conv_ref(x, w, NF, H, W, stride)
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("C0,C1", [(320, 0), (640, 320), (1280, 1280), (64, 0)])
+@pytest.mark.parametrize("per_frame", [False, True])
+def test_groupnorm(C0, C1, per_frame):
+    ops = _ops()
+    B, Fr, HW = 2, 3, 200
+    rows = B * Fr * HW
+    x0 = _bf(_rand(rows, C0) * 2 + 0.5)
+    x1 = _bf(_rand(rows, C1, seed=9) - 1.0) if C1 else None
+    C = C0 + C1
+    gamma = _rand(C, seed=1) * 0.1 + 1
+    beta = _rand(C, seed=2) * 0.1
+    samples, rps = (B * Fr, HW) if per_frame else (B, Fr * HW)
+    out = ops.groupnorm(x0, samples, rps, gamma, beta, 1e-5, silu=True, x2=x1)
+    xc = torch.cat([x0, x1], 1) if C1 else x0
+    ref = F.group_norm(xc.float().reshape(samples, rps, C).permute(0, 2, 1), 32, gamma, beta, 1e-5)
+    ref = F.silu(ref).permute(0, 2, 1).reshape(rows, C)
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("C", [320, 640, 1280])
+def test_layernorm(C):
+    ops = _ops()
+    rows = 1003
+    x = _bf(_rand(rows, C) * 3 + 1)
+    g = _rand(C, seed=1) * 0.1 + 1
+    b = _rand(C, seed=2) * 0.1
+    out = ops.layernorm(x, g, b, 1e-5)
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, batch, heads, Sq, Sk, d, pitch, div):
+    qh = q.float().reshape(batch, Sq, heads, pitch)[..., :d].permute(0, 2, 1, 3)
+    kh = k.float().reshape(batch // div, Sk, heads, pitch)[..., :d].permute(0, 2, 1, 3).repeat_interleave(div, 0)
+    vh = v.float().reshape(batch // div, Sk, heads, pitch)[..., :d].permute(0, 2, 1, 3).repeat_interleave(div, 0)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * d ** -0.5, -1)
+    return (p @ vh).permute(0, 2, 1, 3).reshape(batch * Sq, heads * d)
+
+
+def _padded(rows, heads, d, pitch, seed):
+    t = torch.zeros(rows, heads, pitch, device=DEV)
+    t[..., :d] = _rand(rows, heads, d, seed=seed)
+    return _bf(t.reshape(rows, heads * pitch))
+
+
+@pytest.mark.parametrize("batch,Sq,Sk,d,pitch,div", [
+    (4, 256, 256, 40, 48, 1), (2, 640, 640, 80, 80, 1), (2, 160, 160, 160, 160, 1), (3, 40, 40, 160, 160, 1),
+    (4, 200, 77, 40, 48, 2), (4, 160, 77, 80, 80, 2), (4, 40, 77, 160, 160, 4), (1, 2560, 2560, 40, 48, 1),
+    (2, 64, 154, 40, 48, 1)])
+def test_attention(batch, Sq, Sk, d, pitch, div):
+    ops = _ops()
+    heads = 8
+    q = _padded(batch * Sq, heads, d, pitch, 1)
+    k = _padded(batch // div * Sk, heads, d, pitch, 2)
+    v = _padded(batch // div * Sk, heads, d, pitch, 3)
+    out = ops.attention(q, k, v, batch, heads, Sq, Sk, d, pitch, div)
+    ref = _attn_ref(q, k, v, batch, heads, Sq, Sk, d, pitch, div)
+    assert rel_l2(out.float(), ref) < 1e-2          # P is rounded to bf16 before P V
+
+
+def test_attention_fused_qkv_views():
+    """q/k/v as column slices of one fused projection buffer (how the UNet calls it)."""
+    ops = _ops()
+    batch, S, heads, d, pitch = 2, 384, 8, 40, 48
+    hp = heads * pitch
+    parts = [_padded(batch * S, heads, d, pitch, s) for s in (1, 2, 3)]
+    qkv = torch.cat(parts, 1).contiguous()
+    out = ops.attention(qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:], batch, heads, S, S, d, pitch)
+    ref = _attn_ref(parts[0], parts[1], parts[2], batch, heads, S, S, d, pitch, 1)
+    assert rel_l2(out.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("Fr,d,pitch", [(16, 40, 48), (16, 80, 80), (5, 160, 160)])
+def test_temporal_attention(Fr, d, pitch):
+    ops = _ops()
+    from lavie_b200.packing import rope_table
+    from oracle import unet3d_oracle as O
+    B, HW, heads = 2, 37, 8
+    rows = B * Fr * HW
+    parts = [_padded(rows, heads, d, pitch, s) for s in (1, 2, 3)]
+    qkv = torch.cat(parts, 1).contiguous()
+    freqs = 1.0 / (10000.0 ** (torch.arange(0, 32, 2).float() / 32))
+    table = torch.randn(32, heads, generator=torch.Generator().manual_seed(3))
+    bias = O.rel_pos_bias(table, Fr).contiguous().to(DEV)
+    out = ops.temporal_attention(qkv, B, Fr, HW, heads, d, pitch, rope_table(freqs, Fr).to(DEV), bias)
+
+    def heads_of(t):   # [(b f hw), heads*pitch] -> [(b hw), heads, F, d]
+        return t.float().reshape(B, Fr, HW, heads, pitch)[..., :d].permute(0, 2, 3, 1, 4).reshape(B * HW, heads, Fr, d)
+    q, k, v = (heads_of(t).cpu() for t in parts)
+    q = O.rope(q * d ** -0.5, freqs)
+    k = O.rope(k, freqs)
+    s = q @ k.transpose(-1, -2) + bias.cpu()
+    o = torch.softmax(s, -1) @ v                                             # [(b hw), heads, F, d]
+    ref = o.reshape(B, HW, heads, Fr, d).permute(0, 3, 1, 2, 4).reshape(rows, heads * d)
+    assert rel_l2(out.float().cpu(), ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ small kernels
+def test_time_embedding_path():
+    ops = _ops()
+    from oracle import unet3d_oracle as O
+    t = torch.tensor([500.0, 981.0, 1.0], device=DEV)
+    emb = ops.timestep_embedding(t, 320)
+    assert torch.allclose(emb.cpu(), O.timestep_embedding(t.cpu(), 320), atol=2e-4)
+    w = _bf(_rand(1280, 320, scale=320 ** -0.5))
+    b = _rand(1280, seed=1)
+    y = ops.linear_smallm(emb, w, b, silu_in=False, silu_out=True)
+    ref = F.silu(emb @ w.float().t() + b)
+    assert rel_l2(y, ref) < 1e-4
+    y2 = ops.linear_smallm(y, _bf(_rand(640, 1280, scale=1280 ** -0.5)), None, silu_in=True)
+    ref2 = F.silu(y) @ _bf(_rand(640, 1280, scale=1280 ** -0.5)).float().t()
+    assert rel_l2(y2, ref2) < 1e-4
+
+
+def test_conv_in_and_out():
+    ops = _ops()
+    B, Fr, H, W = 2, 3, 10, 16
+    x = _rand(B, 4, Fr, H, W)
+    w = _rand(320, 4, 3, 3, scale=1 / 6.0)
+    b = _rand(320, seed=1)
+    y = ops.conv_in(x, w, b)
+    ref = F.conv2d(x.permute(0, 2, 1, 3, 4).reshape(B * Fr, 4, H, W), w, b, padding=1).permute(0, 2, 3, 1).reshape(-1, 320)
+    assert rel_l2(y.float(), ref) < 4e-3
+    # conv_norm_out + SiLU + conv_out
+    gamma = _rand(320, seed=2) * 0.1 + 1
+    beta = _rand(320, seed=3) * 0.1
+    ss = ops.groupnorm_scale_shift(y, B, Fr * H * W, gamma, beta, 1e-5)
+    wo = _rand(4, 320, 3, 3, scale=(9 * 320) ** -0.5)
+    bo = _rand(4, seed=4)
+    out = ops.conv_out(y, ss, B, Fr, H, W, wo.permute(0, 2, 3, 1).contiguous(), bo)
+    y5 = y.float().reshape(B, Fr, H, W, 320).permute(0, 4, 1, 2, 3)
+    h = F.silu(F.group_norm(y5, 32, gamma, beta, 1e-5))
+    ref = F.conv2d(h.permute(0, 2, 1, 3, 4).reshape(B * Fr, 320, H, W), wo, bo, padding=1)
+    ref = ref.reshape(B, Fr, 4, H, W).permute(0, 2, 1, 3, 4)
+    assert out.shape == (B, 4, Fr, H, W)
+    assert rel_l2(out, ref) < 2e-3
+
+
+def test_upsample_and_cfg_ddim():
+    ops = _ops()
+    NF, H, W, C = 3, 5, 8, 64
+    x = _bf(_rand(NF * H * W, C))
+    y = ops.upsample_nearest2x(x, NF, H, W)
+    ref = F.interpolate(x.float().reshape(NF, H, W, C).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    assert torch.equal(y.float(), ref.permute(0, 2, 3, 1).reshape(-1, C))
+    from oracle import unet3d_oracle as O
+    acp, ts, ratio = O.ddim_schedule(50)
+    lat, nu, nt = _rand(1, 4, 2, 8, 8), _rand(1, 4, 2, 8, 8, seed=1), _rand(1, 4, 2, 8, 8, seed=2)
+    t = int(ts[7])
+    got = ops.cfg_ddim_step(nu, nt, 7.5, float(acp[t]), float(acp[t - ratio]), lat)
+    want = O.ddim_step((nu + 7.5 * (nt - nu)).cpu(), t, lat.cpu(), acp, ratio)
+    assert torch.allclose(got.cpu(), want, atol=1e-5, rtol=1e-5)
