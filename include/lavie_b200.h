@@ -45,7 +45,8 @@ int lavie_abi_version(void);
  * geglu != 0: out[:, j] = (acc[:, j] + bias) * gelu_erf(acc[:, j + 128] + bias') per 256-column tile. */
 typedef struct {
   const float* bias;     /* [N] or NULL */
-  const float* row_bias; /* [M / rows_per_batch, N] or NULL */
+  const float* row_bias; /* [M / rows_per_batch, ld_row_bias] or NULL */
+  int ld_row_bias;       /* elements; 0 = N */
   int rows_per_batch;
   const void* residual;  /* bf16 [M, ld_residual] or NULL */
   int ld_residual;

@@ -22,6 +22,7 @@ class Epilogue(Structure):
     _fields_ = [
         ("bias", c_void_p),
         ("row_bias", c_void_p),
+        ("ld_row_bias", c_int),
         ("rows_per_batch", c_int),
         ("residual", c_void_p),
         ("ld_residual", c_int),

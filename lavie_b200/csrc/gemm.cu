@@ -45,6 +45,7 @@ struct GemmParams {
   const float* bias;         // [N] or null
   const float* row_bias;     // [M / rows_per_batch, N] or null  (time embedding add, resnet.py:187-190)
   int rows_per_batch;
+  int ld_row_bias;
   const __nv_bfloat16* residual;   // [M, ldr] or null
   int ldr;
   int geglu;                 // 1: tile columns [0,BN/2) = value, [BN/2,BN) = gate -> out = value * gelu(gate)
@@ -186,7 +187,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
       const float* rb = (p.row_bias != nullptr && row_ok)
-                            ? p.row_bias + static_cast<size_t>(row / p.rows_per_batch) * p.N
+                            ? p.row_bias + static_cast<size_t>(row / p.rows_per_batch) * p.ld_row_bias
                             : nullptr;
       if (!p.geglu) {
 #pragma unroll 1
@@ -358,18 +359,20 @@ int make_weight_map(CUtensorMap* map, const void* w, int N, int K, int bn) {
 }
 
 int fill_epilogue(GemmParams& p, const lavie_epilogue* ep, int M, int N, void* out, int ldo) {
-  p.bias = nullptr; p.row_bias = nullptr; p.rows_per_batch = 1; p.residual = nullptr; p.ldr = 0; p.geglu = 0;
+  p.bias = nullptr; p.row_bias = nullptr; p.rows_per_batch = 1; p.ld_row_bias = N; p.residual = nullptr; p.ldr = 0; p.geglu = 0;
   if (ep) {
     p.bias = ep->bias;
     p.row_bias = ep->row_bias;
     p.rows_per_batch = ep->rows_per_batch > 0 ? ep->rows_per_batch : 1;
+    p.ld_row_bias = ep->ld_row_bias > 0 ? ep->ld_row_bias : N;
     p.residual = static_cast<const __nv_bfloat16*>(ep->residual);
     p.ldr = ep->ld_residual;
     p.geglu = ep->geglu;
     LAVIE_REQUIRE(!p.residual || (aligned16(p.residual) && p.ldr % 8 == 0), LAVIE_ERR_ALIGN,
                   "gemm: residual must be 16-byte aligned with ld %% 8 == 0");
     LAVIE_REQUIRE(!p.bias || aligned16(p.bias), LAVIE_ERR_ALIGN, "gemm: bias must be 16-byte aligned");
-    LAVIE_REQUIRE(!p.row_bias || aligned16(p.row_bias), LAVIE_ERR_ALIGN, "gemm: row_bias must be 16-byte aligned");
+    LAVIE_REQUIRE(!p.row_bias || (aligned16(p.row_bias) && p.ld_row_bias % 4 == 0), LAVIE_ERR_ALIGN,
+                  "gemm: row_bias must be 16-byte aligned with ld %% 4 == 0");
     LAVIE_REQUIRE(!(p.geglu && (p.residual || p.row_bias)), LAVIE_ERR_SHAPE,
                   "gemm: GEGLU epilogue cannot be combined with residual/row_bias");
   }

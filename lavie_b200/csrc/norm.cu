@@ -19,13 +19,8 @@ __device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int ld0, int c
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __nv_bfloat16* __restrict__ x1, int ld1,
                 int c1, int rows_per_sample, int groups, int chunks, float* __restrict__ partial) {
-  extern __shared__ float sm[];          // [2][C]
+  extern __shared__ float sm[];          // [row_lanes][2][C]  (one private slot per row lane: deterministic)
   const int C = c0 + c1;
-  float* s_sum = sm;
-  float* s_sq = sm + C;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-
   const int sample = blockIdx.y;
   const int chunk = blockIdx.x;
   const int vec_per_row = C >> 3;
@@ -35,33 +30,39 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __n
   const int lanes_per_row = min(vec_per_row, static_cast<int>(blockDim.x));
   const int row_lanes = blockDim.x / lanes_per_row;            // rows processed concurrently
   const int my_rl = threadIdx.x / lanes_per_row;
-  for (int my_vec = threadIdx.x % lanes_per_row; my_vec < vec_per_row; my_vec += lanes_per_row) {
-    if (my_rl >= row_lanes) break;
-    float s[8], q[8];
+  if (my_rl < row_lanes) {
+    float* s_sum = sm + static_cast<size_t>(my_rl) * 2 * C;
+    float* s_sq = s_sum + C;
+    for (int my_vec = threadIdx.x % lanes_per_row; my_vec < vec_per_row; my_vec += lanes_per_row) {
+      float s[8], q[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
-    for (int r = r_begin + my_rl; r < r_end; r += row_lanes) {
-      const size_t row = static_cast<size_t>(sample) * rows_per_sample + r;
-      const uint4 v = ld_vec8(x0, ld0, c0, x1, ld1, row, my_vec * 8);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+      for (int r = r_begin + my_rl; r < r_end; r += row_lanes) {
+        const size_t row = static_cast<size_t>(sample) * rows_per_sample + r;
+        const uint4 v = ld_vec8(x0, ld0, c0, x1, ld1, row, my_vec * 8);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_bf16(w[e]);
-        s[2 * e] += f.x; q[2 * e] += f.x * f.x;
-        s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16(w[e]);
+          s[2 * e] += f.x; q[2 * e] += f.x * f.x;
+          s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
+        }
       }
-    }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      atomicAdd(&s_sum[my_vec * 8 + e], s[e]);
-      atomicAdd(&s_sq[my_vec * 8 + e], q[e]);
+      for (int e = 0; e < 8; ++e) {
+        s_sum[my_vec * 8 + e] = s[e];
+        s_sq[my_vec * 8 + e] = q[e];
+      }
     }
   }
   __syncthreads();
   const int cpg = C / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float a = 0.f, b = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += s_sum[c]; b += s_sq[c]; }
+    for (int rl = 0; rl < row_lanes; ++rl) {
+      const float* ps = sm + static_cast<size_t>(rl) * 2 * C;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += ps[c]; b += ps[C + c]; }
+    }
     float* dst = partial + ((static_cast<size_t>(sample) * chunks + chunk) * groups + g) * 2;
     dst[0] = a;
     dst[1] = b;
@@ -210,7 +211,9 @@ extern "C" int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void
                 "groupnorm: C=%d groups=%d unsupported", C, groups);
   const int chunks = lavie_groupnorm_chunks(rows_per_sample);
   dim3 grid(chunks, samples);
-  gn_stats_kernel<<<grid, GN_THREADS, 2 * C * sizeof(float), stream>>>(
+  const int vec_per_row = C >> 3;
+  const int row_lanes = GN_THREADS / (vec_per_row < GN_THREADS ? vec_per_row : GN_THREADS);
+  gn_stats_kernel<<<grid, GN_THREADS, static_cast<size_t>(row_lanes) * 2 * C * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1,
       rows_per_sample, groups, chunks, partial);
   return lavie_check_launch("gn_stats_kernel");

@@ -39,13 +39,14 @@ def _epilogue(bias=None, row_bias=None, rows_per_batch=1, residual=None, geglu=F
     ep.bias = _ptr(bias)
     ep.row_bias = _ptr(row_bias)
     ep.rows_per_batch = int(rows_per_batch)
+    ep.ld_row_bias = row_bias.stride(0) if row_bias is not None else 0
     ep.residual = _ptr(residual)
     ep.ld_residual = residual.stride(0) if residual is not None else 0
     ep.geglu = 1 if geglu else 0
     if bias is not None:
         assert bias.dtype == F32 and bias.is_contiguous()
     if row_bias is not None:
-        assert row_bias.dtype == F32 and row_bias.is_contiguous()
+        assert row_bias.dtype == F32 and row_bias.dim() == 2 and row_bias.stride(1) == 1
     if residual is not None:
         _rows2d(residual)
     return ep

@@ -1,0 +1,431 @@
+"""Drop-in replacement for the reference ``UNet3DConditionModel`` (base/models/unet.py:98-512).
+
+Same call signature ``forward(sample, timestep, encoder_hidden_states, ...) -> .sample``, same 830-key
+``state_dict`` (so ``lavie_base.pt`` or random-init weights of the architecture load with
+``load_state_dict(strict=True)``), same helper methods the pipelines call.  The module tree only HOLDS the
+parameters under the reference's names; the forward pass is a flat sequence of C-ABI kernel launches
+(``lavie_b200.ops``) over channels-last bf16 activations.  There is no PyTorch compute fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import ops
+from .config import BASE_CONFIG, UNetConfig, param_spec
+from .packing import (head_pitch, interleave_geglu, pack_conv1x1, pack_conv3x3, pad_heads, rel_pos_bias_table,
+                      rope_table)
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+@dataclass
+class UNet3DConditionOutput:
+    """Mirror of base/models/unet.py:93-95."""
+    sample: torch.Tensor
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]
+
+    def to_tuple(self):
+        return (self.sample,)
+
+
+class _Config(SimpleNamespace):
+    """``unet.config`` as the pipelines read it (attribute and item access, pipeline_videogen.py:141-160,606)."""
+
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+    def __contains__(self, k):
+        return hasattr(self, k)
+
+    def get(self, k, default=None):
+        return getattr(self, k, default)
+
+
+class _RotaryFreqs(nn.Module):
+    """Holds ``rotary_emb.freqs`` (rotary_embedding_torch keeps it as a frozen Parameter)."""
+
+    def __init__(self, n):
+        super().__init__()
+        self.freqs = nn.Parameter(torch.empty(n), requires_grad=False)
+
+
+def _leaf_for(key_prefix: str, names: Dict[str, Tuple[int, ...]]) -> nn.Module:
+    """A real torch module (uninitialised storage) for one parameter group, so `.modules()` probing, PEFT's
+    target_modules=["to_q","to_k","to_v","to_out.0"] (fine_tuning.py:296-308) and `.to()` behave as usual."""
+    w = names.get("weight")
+    has_bias = "bias" in names
+    last = key_prefix.rsplit(".", 1)[-1]
+    if "freqs" in names:
+        return _RotaryFreqs(names["freqs"][0])
+    if last == "relative_attention_bias":
+        return torch.nn.utils.skip_init(nn.Embedding, w[0], w[1])
+    if len(w) == 4:
+        k = w[2]
+        return torch.nn.utils.skip_init(nn.Conv2d, w[1], w[0], k, padding=k // 2, bias=has_bias)
+    if len(w) == 2:
+        return torch.nn.utils.skip_init(nn.Linear, w[1], w[0], bias=has_bias)
+    if last in ("norm1", "norm2", "norm3", "norm_temp") and ".transformer_blocks." in key_prefix:
+        return nn.LayerNorm(w[0])
+    return nn.GroupNorm(32, w[0])
+
+
+def _install(root: nn.Module, path: str, leaf: nn.Module) -> None:
+    parts = path.split(".")
+    cur = root
+    for p in parts[:-1]:
+        nxt = cur._modules.get(p)
+        if nxt is None:
+            nxt = nn.Module()
+            cur.add_module(p, nxt)
+        cur = nxt
+    cur.add_module(parts[-1], leaf)
+
+
+class UNet3DConditionModel(nn.Module):
+    """B200-native LaVie base denoiser.  ``use_cuda_graph`` replays the whole step from one captured CUDA graph per
+    input geometry (the reference launches ~1.9k kernels per step from Python)."""
+
+    def __init__(self, config: UNetConfig = BASE_CONFIG, use_cuda_graph: bool = True):
+        super().__init__()
+        self.cfg = config
+        self.config = _Config(**config.to_dict())
+        self.sample_size = config.sample_size
+        self.use_cuda_graph = use_cuda_graph
+        groups: Dict[str, Dict[str, Tuple[int, ...]]] = {}
+        for key, shape in param_spec(config).items():
+            prefix, leaf = key.rsplit(".", 1)
+            groups.setdefault(prefix, {})[leaf] = shape
+        for prefix, names in groups.items():
+            _install(self, prefix, _leaf_for(prefix, names))
+        self._packed = None
+        self._graphs: Dict[tuple, dict] = {}
+        self._tables: Dict[tuple, tuple] = {}
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    # ------------------------------------------------------------------ reference-compatible helpers
+    @property
+    def dtype(self):
+        return self.conv_in.weight.dtype
+
+    @property
+    def device(self):
+        return self.conv_in.weight.device
+
+    def set_use_memory_efficient_attention_xformers(self, valid: bool = True, attention_op=None):
+        """No-op: attention always runs in the fused tcgen05 kernel (reference hook: attention.py:482-509)."""
+
+    enable_xformers_memory_efficient_attention = set_use_memory_efficient_attention_xformers
+
+    def disable_xformers_memory_efficient_attention(self):
+        pass
+
+    def set_attention_slice(self, slice_size):
+        """No-op: the flash kernel never materialises the score matrix (reference: unet.py:297-360)."""
+
+    def _set_gradient_checkpointing(self, module, value=False):
+        pass
+
+    def _invalidate(self):
+        self._packed = None
+        self._graphs.clear()
+        self._tables.clear()
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self._invalidate()
+        return out
+
+    def init_synthetic(self, seed: int = 0):
+        """Deterministic random-init weights (lavie_b200.synthetic), loaded through the normal state_dict path."""
+        from .synthetic import synthetic_state_dict
+        sd = synthetic_state_dict(self.cfg, seed)
+        self.load_state_dict(sd, strict=True)
+        return self
+
+    # ------------------------------------------------------------------ weight packing (post-load)
+    def _pack(self):
+        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("lavie_b200.UNet3DConditionModel runs on CUDA (sm_100a) only; move it with .to('cuda')")
+        heads = self.cfg.heads
+        P: Dict[str, object] = {}
+
+        def f32(k):
+            return sd[k].to(device=dev, dtype=F32).contiguous()
+
+        def b16(t):
+            return t.to(device=dev, dtype=BF16).contiguous()
+
+        temb_w, temb_b, temb_slices = [], [], {}
+        kv_w, kv_slices = [], {}
+        temb_off = 0
+        kv_off = 0
+
+        def pack_resnet(p):
+            nonlocal temb_off
+            r = {"g1": f32(f"{p}.norm1.weight"), "b1": f32(f"{p}.norm1.bias"),
+                 "w1": b16(pack_conv3x3(sd[f"{p}.conv1.weight"])), "cb1": f32(f"{p}.conv1.bias"),
+                 "g2": f32(f"{p}.norm2.weight"), "b2": f32(f"{p}.norm2.bias"),
+                 "w2": b16(pack_conv3x3(sd[f"{p}.conv2.weight"])), "cb2": f32(f"{p}.conv2.bias")}
+            cout = sd[f"{p}.conv1.weight"].shape[0]
+            temb_w.append(sd[f"{p}.time_emb_proj.weight"])
+            temb_b.append(sd[f"{p}.time_emb_proj.bias"])
+            temb_slices[p] = (temb_off, cout)
+            temb_off += cout
+            if f"{p}.conv_shortcut.weight" in sd:
+                r["wsc"] = b16(pack_conv1x1(sd[f"{p}.conv_shortcut.weight"]))
+                r["bsc"] = f32(f"{p}.conv_shortcut.bias")
+            P[p] = r
+
+        def pack_transformer(p):
+            nonlocal kv_off
+            b = f"{p}.transformer_blocks.0"
+            C = sd[f"{p}.norm.weight"].shape[0]
+            d = C // heads
+            hp = heads * head_pitch(d)
+            t = {"C": C, "d": d, "pitch": head_pitch(d), "hp": hp,
+                 "gn_g": f32(f"{p}.norm.weight"), "gn_b": f32(f"{p}.norm.bias"),
+                 "w_in": b16(pack_conv1x1(sd[f"{p}.proj_in.weight"])), "b_in": f32(f"{p}.proj_in.bias"),
+                 "w_out": b16(pack_conv1x1(sd[f"{p}.proj_out.weight"])), "b_out": f32(f"{p}.proj_out.bias")}
+            for n in ("norm1", "norm2", "norm_temp", "norm3"):
+                t[f"{n}_g"] = f32(f"{b}.{n}.weight")
+                t[f"{n}_b"] = f32(f"{b}.{n}.bias")
+            for a in ("attn1", "attn_temp"):
+                t[f"{a}_qkv"] = b16(torch.cat([pad_heads(sd[f"{b}.{a}.to_{x}.weight"], heads) for x in "qkv"], 0))
+                t[f"{a}_wo"] = b16(sd[f"{b}.{a}.to_out.0.weight"])
+                t[f"{a}_bo"] = f32(f"{b}.{a}.to_out.0.bias")
+            t["attn2_q"] = b16(pad_heads(sd[f"{b}.attn2.to_q.weight"], heads))
+            t["attn2_wo"] = b16(sd[f"{b}.attn2.to_out.0.weight"])
+            t["attn2_bo"] = f32(f"{b}.attn2.to_out.0.bias")
+            kv_w.append(pad_heads(sd[f"{b}.attn2.to_k.weight"], heads))
+            kv_w.append(pad_heads(sd[f"{b}.attn2.to_v.weight"], heads))
+            t["kv_off"] = kv_off
+            kv_off += 2 * hp
+            wi, bi = interleave_geglu(sd[f"{b}.ff.net.0.proj.weight"], sd[f"{b}.ff.net.0.proj.bias"])
+            t["ff1_w"], t["ff1_b"] = b16(wi), bi.to(device=dev, dtype=F32).contiguous()
+            t["ff2_w"], t["ff2_b"] = b16(sd[f"{b}.ff.net.2.weight"]), f32(f"{b}.ff.net.2.bias")
+            t["rel_emb"] = f32(f"{b}.attn_temp.time_rel_pos_bias.relative_attention_bias.weight")
+            t["freqs"] = f32(f"{b}.attn_temp.rotary_emb.freqs")
+            P[p] = t
+
+        for key in self._resnet_prefixes():
+            pack_resnet(key)
+        for key in self._transformer_prefixes():
+            pack_transformer(key)
+        for i in range(len(self.cfg.block_out_channels) - 1):
+            P[f"down_blocks.{i}.downsamplers.0.conv"] = (
+                b16(pack_conv3x3(sd[f"down_blocks.{i}.downsamplers.0.conv.weight"])),
+                f32(f"down_blocks.{i}.downsamplers.0.conv.bias"))
+            P[f"up_blocks.{i}.upsamplers.0.conv"] = (
+                b16(pack_conv3x3(sd[f"up_blocks.{i}.upsamplers.0.conv.weight"])),
+                f32(f"up_blocks.{i}.upsamplers.0.conv.bias"))
+        P["conv_in"] = (f32("conv_in.weight"), f32("conv_in.bias"))
+        P["conv_out"] = (sd["conv_out.weight"].permute(0, 2, 3, 1).to(device=dev, dtype=F32).contiguous(),
+                         f32("conv_out.bias"))
+        P["norm_out"] = (f32("conv_norm_out.weight"), f32("conv_norm_out.bias"))
+        P["time1"] = (b16(sd["time_embedding.linear_1.weight"]), f32("time_embedding.linear_1.bias"))
+        P["time2"] = (b16(sd["time_embedding.linear_2.weight"]), f32("time_embedding.linear_2.bias"))
+        P["temb_w"] = b16(torch.cat(temb_w, 0))
+        P["temb_b"] = torch.cat(temb_b, 0).to(device=dev, dtype=F32).contiguous()
+        P["temb_slices"] = temb_slices
+        P["kv_w"] = b16(torch.cat(kv_w, 0))
+        self._packed = P
+        return P
+
+    def _resnet_prefixes(self) -> List[str]:
+        keys = [k[: -len(".conv1.weight")] for k in param_spec(self.cfg) if k.endswith(".conv1.weight")]
+        return keys
+
+    def _transformer_prefixes(self) -> List[str]:
+        return [k[: -len(".proj_in.weight")] for k in param_spec(self.cfg) if k.endswith(".proj_in.weight")]
+
+    def _frame_tables(self, prefix: str, frames: int):
+        key = (prefix, frames)
+        if key not in self._tables:
+            t = self._packed[prefix]
+            self._tables[key] = (rope_table(t["freqs"], frames),
+                                 rel_pos_bias_table(t["rel_emb"], frames, self.cfg.rel_pos_buckets,
+                                                    self.cfg.rel_pos_max_distance))
+        return self._tables[key]
+
+    # ------------------------------------------------------------------ blocks (kernel launch sequences)
+    def _resnet(self, p, x, x2, temb_all, B, Fr, H, W):
+        """ResnetBlock3D.forward (resnet.py:177-207); (x, x2) = folded channel concat of the up path."""
+        r = self._packed[p]
+        NF, rps = B * Fr, Fr * H * W
+        eps = self.cfg.norm_eps
+        h = ops.groupnorm(x, B, rps, r["g1"], r["b1"], eps, silu=True, x2=x2)
+        off, cout = self._packed["temb_slices"][p]
+        h = ops.conv3x3(h, NF, H, W, r["w1"], bias=r["cb1"], row_bias=temb_all[:, off:off + cout], rows_per_batch=rps)
+        h = ops.groupnorm(h, B, rps, r["g2"], r["b2"], eps, silu=True)
+        if "wsc" in r:
+            sc = ops.gemm(x, r["wsc"], a2=x2, bias=r["bsc"])
+        else:
+            assert x2 is None
+            sc = x
+        return ops.conv3x3(h, NF, H, W, r["w2"], bias=r["cb2"], residual=sc)
+
+    def _transformer(self, p, x, kv_all, B, Fr, H, W, text_len):
+        """Transformer3DModel.forward + BasicTransformerBlock.forward (attention.py:358-407, 511-560)."""
+        t = self._packed[p]
+        heads, d, pitch, hp = self.cfg.heads, t["d"], t["pitch"], t["hp"]
+        NF, HW = B * Fr, H * W
+        h = ops.groupnorm(x, NF, HW, t["gn_g"], t["gn_b"], 1e-6, silu=False)          # per-frame GN (4-D input)
+        tok = ops.gemm(h, t["w_in"], bias=t["b_in"])
+        # spatial self-attention
+        n = ops.layernorm(tok, t["norm1_g"], t["norm1_b"])
+        qkv = ops.gemm(n, t["attn1_qkv"])
+        a = ops.attention(qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:], NF, heads, HW, HW, d, pitch)
+        tok = ops.gemm(a, t["attn1_wo"], bias=t["attn1_bo"], residual=tok)
+        # text cross-attention: keys/values projected once per batch item, shared by its frames
+        n = ops.layernorm(tok, t["norm2_g"], t["norm2_b"])
+        q = ops.gemm(n, t["attn2_q"])
+        ko = t["kv_off"]
+        a = ops.attention(q, kv_all[:, ko:ko + hp], kv_all[:, ko + hp:ko + 2 * hp], NF, heads, HW, text_len, d, pitch,
+                          kv_batch_div=Fr)
+        tok = ops.gemm(a, t["attn2_wo"], bias=t["attn2_bo"], residual=tok)
+        # temporal attention: frames read in place with a row stride of HW (no (b f) d c <-> (b d) f c copies)
+        n = ops.layernorm(tok, t["norm_temp_g"], t["norm_temp_b"])
+        qkv = ops.gemm(n, t["attn_temp_qkv"])
+        rope, bias = self._frame_tables(p, Fr)
+        a = ops.temporal_attention(qkv, B, Fr, HW, heads, d, pitch, rope, bias)
+        tok = ops.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"], residual=tok)
+        # GEGLU feed-forward
+        n = ops.layernorm(tok, t["norm3_g"], t["norm3_b"])
+        g = ops.gemm(n, t["ff1_w"], bias=t["ff1_b"], geglu=True)
+        tok = ops.gemm(g, t["ff2_w"], bias=t["ff2_b"], residual=tok)
+        return ops.gemm(tok, t["w_out"], bias=t["b_out"], residual=x)
+
+    def _step(self, sample: torch.Tensor, t: torch.Tensor, text: torch.Tensor, taps: Optional[dict] = None):
+        """One denoiser evaluation.  sample fp32 [B,C,F,H,W], t fp32 [B], text bf16 [B*L, ctx] -> fp32 [B,Co,F,H,W]."""
+        P = self._packed
+        cfg = self.cfg
+        B, _, Fr, H, W = sample.shape
+        text_len = text.shape[0] // B
+        boc = cfg.block_out_channels
+
+        def tap(name, x, C, h, w):
+            if taps is not None:
+                taps[name] = x.float().reshape(B, Fr, h, w, C).permute(0, 4, 1, 2, 3).contiguous()
+
+        # time embedding (unet.py:428-434) and all 22 time_emb_proj (resnet.py:187) in three small launches
+        temb = ops.timestep_embedding(t, boc[0])
+        h1 = ops.linear_smallm(temb, P["time1"][0], P["time1"][1], silu_out=True)
+        emb = ops.linear_smallm(h1, P["time2"][0], P["time2"][1])
+        temb_all = ops.linear_smallm(emb, P["temb_w"], P["temb_b"], silu_in=True)
+        if taps is not None:
+            taps["emb"] = emb.clone()
+        # all 16 cross-attention K/V projections of the text in one GEMM
+        kv_all = ops.gemm(text, P["kv_w"])
+
+        x = ops.conv_in(sample, P["conv_in"][0], P["conv_in"][1])
+        tap("conv_in", x, boc[0], H, W)
+        skips = [(x, boc[0])]
+        h, w = H, W
+        for i, kind in enumerate(cfg.down_block_types):
+            for j in range(cfg.layers_per_block):
+                x = self._resnet(f"down_blocks.{i}.resnets.{j}", x, None, temb_all, B, Fr, h, w)
+                if i == 0 and j == 0:
+                    tap("down0_res0", x, boc[0], h, w)
+                if kind == "CrossAttnDownBlock3D":
+                    x = self._transformer(f"down_blocks.{i}.attentions.{j}", x, kv_all, B, Fr, h, w, text_len)
+                    if i == 0 and j == 0:
+                        tap("down0_attn0", x, boc[0], h, w)
+                skips.append((x, boc[i]))
+            if i != len(boc) - 1:
+                wd, bd = P[f"down_blocks.{i}.downsamplers.0.conv"]
+                x = ops.conv3x3(x, B * Fr, h, w, wd, stride=2, bias=bd)
+                h, w = h // 2, w // 2
+                skips.append((x, boc[i]))
+        x = self._resnet("mid_block.resnets.0", x, None, temb_all, B, Fr, h, w)
+        x = self._transformer("mid_block.attentions.0", x, kv_all, B, Fr, h, w, text_len)
+        x = self._resnet("mid_block.resnets.1", x, None, temb_all, B, Fr, h, w)
+        tap("mid", x, boc[-1], h, w)
+        for i, kind in enumerate(cfg.up_block_types):
+            for j in range(cfg.layers_per_block + 1):
+                skip, _ = skips.pop()
+                x = self._resnet(f"up_blocks.{i}.resnets.{j}", x, skip, temb_all, B, Fr, h, w)
+                if kind == "CrossAttnUpBlock3D":
+                    x = self._transformer(f"up_blocks.{i}.attentions.{j}", x, kv_all, B, Fr, h, w, text_len)
+            if i != len(boc) - 1:
+                wu, bu = P[f"up_blocks.{i}.upsamplers.0.conv"]
+                x = ops.upsample_nearest2x(x, B * Fr, h, w)
+                h, w = 2 * h, 2 * w
+                x = ops.conv3x3(x, B * Fr, h, w, wu, bias=bu)
+        ss = ops.groupnorm_scale_shift(x, B, Fr * h * w, P["norm_out"][0], P["norm_out"][1], cfg.norm_eps)
+        return ops.conv_out(x, ss, B, Fr, h, w, P["conv_out"][0], P["conv_out"][1])
+
+    # ------------------------------------------------------------------ public forward
+    @torch.no_grad()
+    def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
+                encoder_hidden_states: torch.Tensor = None, class_labels=None, attention_mask=None,
+                use_image_num: int = 0, return_dict: bool = True, taps: Optional[dict] = None):
+        """Same contract as base/models/unet.py:366-512.  ``attention_mask`` is accepted and ignored exactly like the
+        reference (it never reaches the blocks, unet_blocks.py:352); ``class_labels``/``use_image_num`` must be unset
+        (no class embedding in the base config; joint image-video training is out of scope)."""
+        if class_labels is not None or use_image_num:
+            raise NotImplementedError("class_labels / use_image_num are not part of the base T2V inference path")
+        if encoder_hidden_states is None:
+            raise ValueError("encoder_hidden_states is required")
+        if sample.dim() != 5:
+            raise ValueError(f"sample must be [B,C,F,H,W], got {tuple(sample.shape)}")
+        B, C, Fr, H, W = sample.shape
+        n_down = len(self.cfg.block_out_channels) - 1
+        if C != self.cfg.in_channels or H % (1 << n_down) or W % (1 << n_down):
+            raise ValueError(f"sample needs {self.cfg.in_channels} channels and H, W multiples of {1 << n_down}")
+        if encoder_hidden_states.shape[0] != B or encoder_hidden_states.shape[-1] != self.cfg.cross_attention_dim:
+            raise ValueError(f"encoder_hidden_states must be [B, L, {self.cfg.cross_attention_dim}]")
+        if self._packed is None:
+            self._pack()
+        dev = self.device
+        out_dtype = sample.dtype
+        # timestep normalisation of unet.py:413-426
+        if not torch.is_tensor(timestep):
+            t = torch.full((B,), float(timestep), dtype=F32, device=dev)
+        else:
+            t = timestep.to(device=dev, dtype=F32).reshape(-1).expand(B).contiguous()
+        if self.cfg.center_input_sample:
+            sample = 2 * sample - 1.0
+        x = sample.to(device=dev, dtype=F32, non_blocking=True).contiguous()
+        txt = encoder_hidden_states.to(device=dev, dtype=BF16, non_blocking=True).reshape(
+            -1, self.cfg.cross_attention_dim).contiguous()
+
+        if self.use_cuda_graph and taps is None:
+            out = self._graph_step(x, t, txt)
+        else:
+            out = self._step(x, t, txt, taps)
+        out = out.to(out_dtype) if out_dtype != F32 else out.clone()   # never hand out the graph's static buffer
+        if not return_dict:
+            return (out,)
+        return UNet3DConditionOutput(sample=out)
+
+    def _graph_step(self, x, t, txt):
+        key = (tuple(x.shape), tuple(txt.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            g = {"x": x.clone(), "t": t.clone(), "txt": txt.clone()}
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up run: sets kernel attributes, fills table caches
+                self._step(g["x"], g["t"], g["txt"])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g["out"] = self._step(g["x"], g["t"], g["txt"])
+            g["graph"] = graph
+            self._graphs[key] = g
+        g["x"].copy_(x, non_blocking=True)
+        g["t"].copy_(t, non_blocking=True)
+        g["txt"].copy_(txt, non_blocking=True)
+        g["graph"].replay()
+        return g["out"]
