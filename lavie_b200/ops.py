@@ -17,6 +17,33 @@ from ._lib import Epilogue, check
 BF16 = torch.bfloat16
 F32 = torch.float32
 
+# Launch accounting (bench.py's "gpu_launches") and an optional per-launch CUDA-event profiler: set
+# ``ops.PROFILE = []`` to collect (kernel, algorithmic_flops, algorithmic_bytes, start_event, end_event) per launch.
+LAUNCHES = 0
+PROFILE = None
+
+
+class _Launch:
+    """Counts one kernel launch; with ops.PROFILE set, brackets it with CUDA events on the launching stream."""
+
+    def __init__(self, kernel: str, flops: float = 0.0, nbytes: float = 0.0):
+        self.kernel, self.flops, self.nbytes = kernel, flops, nbytes
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += 1
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and exc[0] is None:
+            self.e1.record()
+            PROFILE.append((self.kernel, self.flops, self.nbytes, self.e0, self.e1))
+        return False
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -69,8 +96,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None,
     Mo, No, ldo = _rows2d(out)
     assert Mo == M and No == n_out
     ep = _epilogue(bias, row_bias, rows_per_batch, residual, geglu)
-    rc = lib.lavie_gemm_bf16(a.data_ptr(), lda, k0, _ptr(a2), lda2, k1, w.data_ptr(), out.data_ptr(), ldo, M, N,
-                             ctypes.byref(ep) if ep is not None else None, block_n, _stream())
+    with _Launch("gemm_bf16_tcgen05", 2.0 * M * N * (k0 + k1), 2.0 * (M * (k0 + k1) + N * (k0 + k1) + M * n_out)):
+        rc = lib.lavie_gemm_bf16(a.data_ptr(), lda, k0, _ptr(a2), lda2, k1, w.data_ptr(), out.data_ptr(), ldo, M, N,
+                                 ctypes.byref(ep) if ep is not None else None, block_n, _stream())
     check(rc, "lavie_gemm_bf16")
     return out
 
@@ -86,7 +114,8 @@ def im2col3x3(x: torch.Tensor, NF: int, H: int, W: int, stride: int = 1) -> torc
     assert rows == NF * H * W and ld == C
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     col = torch.empty((NF * Ho * Wo, 9 * C), dtype=BF16, device=x.device)
-    check(lib.lavie_im2col3x3_bf16(x.data_ptr(), NF, H, W, C, stride, col.data_ptr(), _stream()), "lavie_im2col3x3_bf16")
+    with _Launch("lavie_im2col3x3_bf16"):
+        check(lib.lavie_im2col3x3_bf16(x.data_ptr(), NF, H, W, C, stride, col.data_ptr(), _stream()), "lavie_im2col3x3_bf16")
     return col
 
 
@@ -108,8 +137,9 @@ def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride
     Mo, No, ldo = _rows2d(out)
     assert Mo == rows and No == N
     ep = _epilogue(bias, row_bias, rows_per_batch, residual, False)
-    rc = lib.lavie_conv3x3_bf16(x.data_ptr(), NF, H, W, C, w.data_ptr(), out.data_ptr(), ldo, N,
-                                ctypes.byref(ep) if ep is not None else None, block_n, _stream())
+    with _Launch("gemm_bf16_tcgen05", 2.0 * rows * N * 9 * C, 2.0 * (rows * C + N * 9 * C + rows * N)):
+        rc = lib.lavie_conv3x3_bf16(x.data_ptr(), NF, H, W, C, w.data_ptr(), out.data_ptr(), ldo, N,
+                                    ctypes.byref(ep) if ep is not None else None, block_n, _stream())
     check(rc, "lavie_conv3x3_bf16")
     return out
 
@@ -127,13 +157,15 @@ def groupnorm_scale_shift(x: torch.Tensor, samples: int, rows_per_sample: int, g
     C = c0 + c1
     chunks = lib.lavie_groupnorm_chunks(rows_per_sample)
     partial = torch.empty((samples, chunks, groups, 2), dtype=F32, device=x.device)
-    check(lib.lavie_groupnorm_stats(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample, groups,
-                                    partial.data_ptr(), _stream()), "lavie_groupnorm_stats")
+    with _Launch("lavie_groupnorm_stats"):
+        check(lib.lavie_groupnorm_stats(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample, groups,
+                                        partial.data_ptr(), _stream()), "lavie_groupnorm_stats")
     ss = torch.empty((samples, C, 2), dtype=F32, device=x.device)
     assert gamma.dtype == F32 and beta.dtype == F32 and gamma.numel() == C
-    check(lib.lavie_groupnorm_finalize(partial.data_ptr(), samples, chunks, groups, C,
-                                       rows_per_sample * (C // groups), gamma.data_ptr(), beta.data_ptr(), eps,
-                                       ss.data_ptr(), _stream()), "lavie_groupnorm_finalize")
+    with _Launch("lavie_groupnorm_finalize"):
+        check(lib.lavie_groupnorm_finalize(partial.data_ptr(), samples, chunks, groups, C,
+                                           rows_per_sample * (C // groups), gamma.data_ptr(), beta.data_ptr(), eps,
+                                           ss.data_ptr(), _stream()), "lavie_groupnorm_finalize")
     return ss
 
 
@@ -148,9 +180,10 @@ def groupnorm_apply(x: torch.Tensor, scale_shift: torch.Tensor, samples: int, ro
     if out is None:
         out = torch.empty((rows, C), dtype=BF16, device=x.device)
     _, _, ldy = _rows2d(out)
-    check(lib.lavie_groupnorm_apply(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample,
-                                    scale_shift.data_ptr(), 1 if silu else 0, out.data_ptr(), ldy, _stream()),
-          "lavie_groupnorm_apply")
+    with _Launch("lavie_groupnorm_apply"):
+        check(lib.lavie_groupnorm_apply(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample,
+                                        scale_shift.data_ptr(), 1 if silu else 0, out.data_ptr(), ldy, _stream()),
+              "lavie_groupnorm_apply")
     return out
 
 
@@ -167,8 +200,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         out = torch.empty((rows, C), dtype=BF16, device=x.device)
     _, _, ldy = _rows2d(out)
     assert gamma.dtype == F32 and beta.dtype == F32
-    check(lib.lavie_layernorm_bf16(x.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), ldy,
-                                   rows, C, _stream()), "lavie_layernorm_bf16")
+    with _Launch("lavie_layernorm_bf16"):
+        check(lib.lavie_layernorm_bf16(x.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), ldy,
+                                       rows, C, _stream()), "lavie_layernorm_bf16")
     return out
 
 
@@ -186,9 +220,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, hea
     _, _, ldo = _rows2d(out)
     if scale is None:
         scale = d ** -0.5
-    check(lib.lavie_attention_bf16(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), ldo, batch,
-                                   heads, Sq, Sk, d, head_pitch, kv_batch_div, scale, _stream()),
-          "lavie_attention_bf16")
+    with _Launch("lavie_attention_bf16"):
+        check(lib.lavie_attention_bf16(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), ldo, batch,
+                                       heads, Sq, Sk, d, head_pitch, kv_batch_div, scale, _stream()),
+              "lavie_attention_bf16")
     return out
 
 
@@ -203,10 +238,11 @@ def temporal_attention(qkv: torch.Tensor, B: int, F: int, HW: int, heads: int, d
     _, _, ldo = _rows2d(out)
     assert rope.dtype == F32 and rope.is_contiguous() and rope.shape[0] == F
     assert bias.dtype == F32 and bias.is_contiguous() and tuple(bias.shape) == (heads, F, F)
-    check(lib.lavie_temporal_attention_bf16(qkv.data_ptr(), ld, heads * head_pitch, 2 * heads * head_pitch,
-                                            out.data_ptr(), ldo, B, F, HW, heads, d, head_pitch, d ** -0.5,
-                                            rope.data_ptr(), rope.shape[1], bias.data_ptr(), _stream()),
-          "lavie_temporal_attention_bf16")
+    with _Launch("lavie_temporal_attention_bf16"):
+        check(lib.lavie_temporal_attention_bf16(qkv.data_ptr(), ld, heads * head_pitch, 2 * heads * head_pitch,
+                                                out.data_ptr(), ldo, B, F, HW, heads, d, head_pitch, d ** -0.5,
+                                                rope.data_ptr(), rope.shape[1], bias.data_ptr(), _stream()),
+              "lavie_temporal_attention_bf16")
     return out
 
 
@@ -217,8 +253,9 @@ def linear_smallm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     assert w.dtype == BF16 and w.is_contiguous() and w.shape[1] == K
     N = w.shape[0]
     out = torch.empty((M, N), dtype=F32, device=x.device)
-    check(lib.lavie_linear_smallm(x.data_ptr(), M, K, w.data_ptr(), _ptr(bias), out.data_ptr(), N, int(silu_in),
-                                  int(silu_out), _stream()), "lavie_linear_smallm")
+    with _Launch("lavie_linear_smallm"):
+        check(lib.lavie_linear_smallm(x.data_ptr(), M, K, w.data_ptr(), _ptr(bias), out.data_ptr(), N, int(silu_in),
+                                      int(silu_out), _stream()), "lavie_linear_smallm")
     return out
 
 
@@ -226,8 +263,9 @@ def timestep_embedding(t: torch.Tensor, dim: int):
     lib = _lib.load()
     assert t.dtype == F32 and t.is_contiguous() and t.dim() == 1
     out = torch.empty((t.shape[0], dim), dtype=F32, device=t.device)
-    check(lib.lavie_timestep_embedding(t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream()),
-          "lavie_timestep_embedding")
+    with _Launch("lavie_timestep_embedding"):
+        check(lib.lavie_timestep_embedding(t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream()),
+              "lavie_timestep_embedding")
     return out
 
 
@@ -239,8 +277,9 @@ def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor):
     Cout = w.shape[0]
     assert w.dtype == F32 and w.is_contiguous() and bias.dtype == F32
     out = torch.empty((B * Fr * H * W, Cout), dtype=BF16, device=x.device)
-    check(lib.lavie_conv_in(x.data_ptr(), B, Cin, Fr, H, W, w.data_ptr(), bias.data_ptr(), Cout, out.data_ptr(), Cout,
-                            _stream()), "lavie_conv_in")
+    with _Launch("lavie_conv_in"):
+        check(lib.lavie_conv_in(x.data_ptr(), B, Cin, Fr, H, W, w.data_ptr(), bias.data_ptr(), Cout, out.data_ptr(), Cout,
+                                _stream()), "lavie_conv_in")
     return out
 
 
@@ -253,8 +292,9 @@ def conv_out(x: torch.Tensor, scale_shift: torch.Tensor, B: int, Fr: int, H: int
     Cout = w.shape[0]
     assert w.dtype == F32 and w.is_contiguous() and tuple(w.shape) == (Cout, 3, 3, C)
     out = torch.empty((B, Cout, Fr, H, W), dtype=F32, device=x.device)
-    check(lib.lavie_conv_out(x.data_ptr(), ldx, scale_shift.data_ptr(), B, Fr, H, W, C, w.data_ptr(), bias.data_ptr(),
-                             Cout, out.data_ptr(), _stream()), "lavie_conv_out")
+    with _Launch("lavie_conv_out"):
+        check(lib.lavie_conv_out(x.data_ptr(), ldx, scale_shift.data_ptr(), B, Fr, H, W, C, w.data_ptr(), bias.data_ptr(),
+                                 Cout, out.data_ptr(), _stream()), "lavie_conv_out")
     return out
 
 
@@ -263,7 +303,8 @@ def upsample_nearest2x(x: torch.Tensor, NF: int, H: int, W: int):
     rows, C, ld = _rows2d(x)
     assert rows == NF * H * W and ld == C
     y = torch.empty((NF * 4 * H * W, C), dtype=BF16, device=x.device)
-    check(lib.lavie_upsample_nearest2x(x.data_ptr(), NF, H, W, C, y.data_ptr(), _stream()), "lavie_upsample_nearest2x")
+    with _Launch("lavie_upsample_nearest2x"):
+        check(lib.lavie_upsample_nearest2x(x.data_ptr(), NF, H, W, C, y.data_ptr(), _stream()), "lavie_upsample_nearest2x")
     return y
 
 
@@ -274,7 +315,8 @@ def cfg_ddim_step(noise_uncond, noise_text, guidance: float, alpha_t: float, alp
         assert t.dtype == F32 and t.is_contiguous()
     if out is None:
         out = torch.empty_like(latents)
-    check(lib.lavie_cfg_ddim_step(noise_uncond.data_ptr(), noise_text.data_ptr(), guidance, alpha_t, alpha_prev,
-                                  latents.data_ptr(), out.data_ptr(), latents.numel(), _stream()),
-          "lavie_cfg_ddim_step")
+    with _Launch("lavie_cfg_ddim_step"):
+        check(lib.lavie_cfg_ddim_step(noise_uncond.data_ptr(), noise_text.data_ptr(), guidance, alpha_t, alpha_prev,
+                                      latents.data_ptr(), out.data_ptr(), latents.numel(), _stream()),
+              "lavie_cfg_ddim_step")
     return out

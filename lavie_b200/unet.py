@@ -408,6 +408,10 @@ class UNet3DConditionModel(nn.Module):
             return (out,)
         return UNet3DConditionOutput(sample=out)
 
+    def launches_per_step(self) -> int:
+        """Kernel launches of this library inside the most recently replayed step graph."""
+        return getattr(self, "_last_graph_launches", 0)
+
     def _graph_step(self, x, t, txt):
         key = (tuple(x.shape), tuple(txt.shape))
         g = self._graphs.get(key)
@@ -420,10 +424,13 @@ class UNet3DConditionModel(nn.Module):
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            before = ops.LAUNCHES
             with torch.cuda.graph(graph):
                 g["out"] = self._step(g["x"], g["t"], g["txt"])
+            g["launches"] = ops.LAUNCHES - before      # kernel nodes of ours in the captured step
             g["graph"] = graph
             self._graphs[key] = g
+        self._last_graph_launches = g["launches"]
         g["x"].copy_(x, non_blocking=True)
         g["t"].copy_(t, non_blocking=True)
         g["txt"].copy_(txt, non_blocking=True)

@@ -1,0 +1,117 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the host module keeps the
+reference's state_dict contract, weight repacking is lossless, and the product path refuses to run without CUDA."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lavie_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lavie_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lavie_b200 import _lib
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/lavie_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert lib.lavie_abi_version() == 1
+    # pure host queries (no GPU work)
+    assert lib.lavie_conv3x3_supported(40, 64, 320) == 1
+    assert lib.lavie_conv3x3_supported(16, 24, 320) == 0
+    assert lib.lavie_groupnorm_chunks(16 * 40 * 64) == 80
+
+
+def test_epilogue_struct_matches_header():
+    import ctypes
+    from lavie_b200._lib import Epilogue
+    text = open(os.path.join(ROOT, "include", "lavie_b200.h")).read()
+    body = text[text.index("typedef struct {"):text.index("} lavie_epilogue;")]
+    fields = re.findall(r"\b(\w+);", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
+    assert [f for f, _ in Epilogue._fields_] == fields
+    assert ctypes.sizeof(Epilogue) == 40      # 3 pointers + 4 ints, natural alignment
+
+
+def test_param_table_is_the_reference_contract():
+    from lavie_b200.config import param_spec
+    spec = param_spec()
+    assert len(spec) == 830
+    n = 0
+    for shape in spec.values():
+        k = 1
+        for s in shape:
+            k *= s
+        n += k
+    assert n == 909_124_356
+    assert spec["conv_in.weight"] == (320, 4, 3, 3)
+    assert spec["up_blocks.0.resnets.0.conv1.weight"] == (1280, 2560, 3, 3)
+    assert spec["up_blocks.3.resnets.2.conv_shortcut.weight"] == (320, 640, 1, 1)
+    assert spec["mid_block.attentions.0.transformer_blocks.0.attn2.to_k.weight"] == (1280, 768)
+    assert spec["down_blocks.0.attentions.0.transformer_blocks.0.ff.net.0.proj.weight"] == (2560, 320)
+    assert "down_blocks.3.downsamplers.0.conv.weight" not in spec and "up_blocks.3.upsamplers.0.conv.weight" not in spec
+
+
+def test_module_state_dict_roundtrip(synthetic_sd):
+    from lavie_b200 import UNet3DConditionModel
+    m = UNet3DConditionModel()
+    assert set(m.state_dict().keys()) == set(synthetic_sd.keys())
+    missing, unexpected = m.load_state_dict(synthetic_sd, strict=True)
+    assert not missing and not unexpected
+    back = m.state_dict()
+    for k in ("conv_in.weight", "mid_block.attentions.0.transformer_blocks.0.attn_temp.rotary_emb.freqs",
+              "up_blocks.2.attentions.1.transformer_blocks.0.ff.net.2.bias"):
+        assert torch.equal(back[k], synthetic_sd[k])
+    # PEFT-style probing finds real nn.Linear projections (fine_tuning.py:296-308)
+    lin = [n for n, mod in m.named_modules() if isinstance(mod, torch.nn.Linear) and n.endswith(("to_q", "to_out.0"))]
+    assert len(lin) == 16 * 3 * 2
+    assert m.config.in_channels == 4 and m.config["sample_size"] == 64 and "_diffusers_version" in m.config
+    # no CUDA here: the product path must fail loudly, not fall back to PyTorch/CPU math
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            m(torch.zeros(1, 4, 2, 8, 8), 1, encoder_hidden_states=torch.zeros(1, 77, 768))
+
+
+def test_packing_helpers():
+    from lavie_b200 import packing as P
+    w = torch.randn(16, 8, 3, 3)
+    pk = P.pack_conv3x3(w).float()
+    assert pk.shape == (16, 72)
+    assert torch.equal(pk[:, 3 * 8:4 * 8], w[:, :, 1, 0].to(torch.bfloat16).float())   # tap (kh=1,kw=0) slab
+    q = torch.randn(8 * 40, 320)
+    qp = P.pad_heads(q, 8)
+    assert qp.shape == (8 * 48, 320) and P.head_pitch(40) == 48 and P.head_pitch(80) == 80
+    assert torch.equal(qp.reshape(8, 48, 320)[:, :40], q.reshape(8, 40, 320)) and qp.reshape(8, 48, 320)[:, 40:].abs().max() == 0
+    w8 = torch.randn(2560, 320)
+    b8 = torch.randn(2560)
+    wi, bi = P.interleave_geglu(w8, b8)
+    assert torch.equal(wi[0:128], w8[0:128]) and torch.equal(wi[128:256], w8[1280:1408]) and torch.equal(wi[256:384], w8[128:256])
+    assert torch.equal(bi[128:256], b8[1280:1408])
+    # rel-pos bias and RoPE tables agree with the oracle's restatement of the reference
+    from oracle import unet3d_oracle as O
+    emb = torch.randn(32, 8)
+    assert torch.equal(P.rel_pos_bias_table(emb, 16), O.rel_pos_bias(emb, 16))
+    freqs = 1.0 / (10000.0 ** (torch.arange(0, 32, 2).float() / 32))
+    tab = P.rope_table(freqs, 16)
+    x = torch.randn(16, 40)
+    y = O.rope(x, freqs)
+    x0, x1 = x[:, 0:32:2], x[:, 1:32:2]
+    assert torch.allclose(y[:, 0:32:2], x0 * tab[..., 0] - x1 * tab[..., 1], atol=1e-6)
+    assert torch.allclose(y[:, 1:32:2], x1 * tab[..., 0] + x0 * tab[..., 1], atol=1e-6)
+
+
+def test_ddim_schedule_matches_oracle():
+    from lavie_b200.pipeline import DDIMSchedule
+    from oracle import unet3d_oracle as O
+    s = DDIMSchedule(50)
+    acp, ts, ratio = O.ddim_schedule(50)
+    assert s.timesteps == ts.tolist() and s.ratio == ratio
+    assert torch.equal(s.alphas_cumprod, acp)
+    assert s.alphas(1) == (float(acp[1]), float(acp[0]))
