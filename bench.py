@@ -296,7 +296,7 @@ def run_b200(args):
         prof, ops.PROFILE = ops.PROFILE, None
         unet.use_cuda_graph = was
         agg = {}
-        for name, flops, nbytes, e0, e1 in prof:
+        for name, flops, nbytes, e0, e1, _tag in prof:
             a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
             a[0] += 1
             a[1] += e0.elapsed_time(e1)

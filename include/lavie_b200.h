@@ -78,7 +78,7 @@ int lavie_im2col3x3_bf16(const void* x, int NF, int H, int W, int C, int stride,
  *   stats    : partial[samples, chunks, groups, 2] (sum, sum of squares), chunks = lavie_groupnorm_chunks()
  *   finalize : scale_shift[samples, C, 2] with y = x*scale + shift  (folds gamma/beta, mean, rstd)
  *   apply    : y = act(x*scale + shift), act = SiLU when silu != 0; writes a contiguous [rows, C] bf16 tensor */
-int lavie_groupnorm_chunks(int rows_per_sample);
+int lavie_groupnorm_chunks(int samples, int rows_per_sample);
 int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
                           int rows_per_sample, int groups, float* partial, lavie_stream_t stream);
 int lavie_groupnorm_finalize(const float* partial, int samples, int chunks, int groups, int C,

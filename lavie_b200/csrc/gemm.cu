@@ -33,6 +33,7 @@ struct GemmParams {
   int M, N, K;
   int num_k_blocks;
   int k_split_blocks;        // plain mode: K blocks [0, k_split) come from A0, the rest from A1
+  int k_rot;                 // K-loop rotation stride per M tile (0 = off)
   int m_tiles, n_tiles;
   // conv3 mode
   int conv;                  // 0 plain, 1 conv3x3 stride 1 pad 1
@@ -116,7 +117,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.n_tiles;
         const int n_blk = tile % p.n_tiles;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        // K-loop rotation: CTAs start their K sweep at different blocks so that the ~74 CTAs sharing one weight
+        // tile do not hammer the same L2 lines in lockstep (the sum is order-independent up to fp32 rounding and
+        // the mapping is fixed, so results stay deterministic).
+        const int kb0 = (m_blk * p.k_rot) % p.num_k_blocks;
+        for (int it = 0; it < p.num_k_blocks; ++it) {
+          int kb = kb0 + it;
+          if (kb >= p.num_k_blocks) kb -= p.num_k_blocks;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_STAGE_BYTES;
@@ -326,6 +333,7 @@ int pick_block_n(int M, int N, int forced) {
   return best_bn;
 }
 
+int g_k_rot = 7;
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -400,6 +408,7 @@ extern "C" int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1,
   p.M = M; p.N = N; p.K = K;
   p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   p.k_split_blocks = k1 ? k0 / BLOCK_K : p.num_k_blocks;
+  p.k_rot = g_k_rot;
   p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   p.n_tiles = (N + bn - 1) / bn;
   p.conv = 0;
@@ -427,6 +436,11 @@ extern "C" int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1,
   return dispatch(bn, ma0, ma1, mb, p, stream);
 }
 
+extern "C" int lavie_debug_set(int what, int value) {
+  if (what == 0) g_k_rot = value;
+  return 0;
+}
+
 extern "C" int lavie_conv3x3_supported(int H, int W, int C) {
   if (C % BLOCK_K != 0) return 0;
   if (W > BLOCK_M || BLOCK_M % W != 0 || W % 8 != 0) return 0;
@@ -444,6 +458,7 @@ extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, co
   p.M = M; p.N = N; p.K = 9 * C;
   p.num_k_blocks = 9 * (C / BLOCK_K);
   p.k_split_blocks = p.num_k_blocks;
+  p.k_rot = g_k_rot;
   p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   p.n_tiles = (N + bn - 1) / bn;
   p.conv = 1;

@@ -7,7 +7,8 @@
 namespace {
 
 constexpr int GN_THREADS = 256;
-constexpr int GN_ROWS_PER_CHUNK = 512;
+constexpr int GN_TARGET_CTAS = 148 * 6;    // enough CTAs in flight to saturate HBM on every level of the UNet
+constexpr int GN_MIN_ROWS_PER_CHUNK = 16;
 
 __device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int ld0, int c0, const __nv_bfloat16* x1, int ld1,
                                          size_t row, int col) {
@@ -18,14 +19,14 @@ __device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int ld0, int c
 // partial[sample][chunk][group][2]
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __nv_bfloat16* __restrict__ x1, int ld1,
-                int c1, int rows_per_sample, int groups, int chunks, float* __restrict__ partial) {
+                int c1, int rows_per_sample, int rows_per_chunk, int groups, int chunks, float* __restrict__ partial) {
   extern __shared__ float sm[];          // [row_lanes][2][C]  (one private slot per row lane: deterministic)
   const int C = c0 + c1;
   const int sample = blockIdx.y;
   const int chunk = blockIdx.x;
   const int vec_per_row = C >> 3;
-  const int r_begin = chunk * GN_ROWS_PER_CHUNK;
-  const int r_end = min(r_begin + GN_ROWS_PER_CHUNK, rows_per_sample);
+  const int r_begin = chunk * rows_per_chunk;
+  const int r_end = min(r_begin + rows_per_chunk, rows_per_sample);
   // column slots: a thread owns one 8-channel vector per slot; narrow rows are covered by several row lanes
   const int lanes_per_row = min(vec_per_row, static_cast<int>(blockDim.x));
   const int row_lanes = blockDim.x / lanes_per_row;            // rows processed concurrently
@@ -37,6 +38,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __n
       float s[8], q[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+#pragma unroll 4
       for (int r = r_begin + my_rl; r < r_end; r += row_lanes) {
         const size_t row = static_cast<size_t>(sample) * rows_per_sample + r;
         const uint4 v = ld_vec8(x0, ld0, c0, x1, ld1, row, my_vec * 8);
@@ -75,18 +77,27 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks
                                    const float* __restrict__ beta, float eps, float* __restrict__ scale_shift) {
   __shared__ float s_mean[64], s_rstd[64];
   const int sample = blockIdx.x;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+  // 8 consecutive lanes share one group: each sums every 8th chunk in fp64, then a fixed-order shuffle tree
+  const int sub = threadIdx.x & 7;
+  for (int g = threadIdx.x >> 3; g < groups; g += blockDim.x >> 3) {
     double a = 0.0, b = 0.0;
-    for (int k = 0; k < chunks; ++k) {
-      const float* src = partial + ((static_cast<size_t>(sample) * chunks + k) * groups + g) * 2;
-      a += src[0];
-      b += src[1];
+    for (int k = sub; k < chunks; k += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(partial + ((static_cast<size_t>(sample) * chunks + k) * groups + g) * 2);
+      a += v.x;
+      b += v.y;
     }
-    const double mean = a * inv_count;
-    double var = b * inv_count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[g] = static_cast<float>(mean);
-    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (sub == 0) {
+      const double mean = a * inv_count;
+      double var = b * inv_count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = static_cast<float>(mean);
+      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
   }
   __syncthreads();
   const int cpg = C / groups;
@@ -198,8 +209,19 @@ int check_sources(const void* x0, int ld0, int c0, const void* x1, int ld1, int 
 
 }  // namespace
 
-extern "C" int lavie_groupnorm_chunks(int rows_per_sample) {
-  return (rows_per_sample + GN_ROWS_PER_CHUNK - 1) / GN_ROWS_PER_CHUNK;
+namespace {
+int gn_rows_per_chunk(int samples, int rows_per_sample) {
+  int chunks = (GN_TARGET_CTAS + samples - 1) / samples;
+  const int max_chunks = (rows_per_sample + GN_MIN_ROWS_PER_CHUNK - 1) / GN_MIN_ROWS_PER_CHUNK;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  return (rows_per_sample + chunks - 1) / chunks;
+}
+}  // namespace
+
+extern "C" int lavie_groupnorm_chunks(int samples, int rows_per_sample) {
+  const int rpc = gn_rows_per_chunk(samples, rows_per_sample);
+  return (rows_per_sample + rpc - 1) / rpc;
 }
 
 extern "C" int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
@@ -209,20 +231,22 @@ extern "C" int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void
   const int C = c0 + c1;
   LAVIE_REQUIRE(C % groups == 0 && groups <= 64 && C <= 8192, LAVIE_ERR_SHAPE,
                 "groupnorm: C=%d groups=%d unsupported", C, groups);
-  const int chunks = lavie_groupnorm_chunks(rows_per_sample);
+  const int rows_per_chunk = gn_rows_per_chunk(samples, rows_per_sample);
+  const int chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
   dim3 grid(chunks, samples);
   const int vec_per_row = C >> 3;
   const int row_lanes = GN_THREADS / (vec_per_row < GN_THREADS ? vec_per_row : GN_THREADS);
   gn_stats_kernel<<<grid, GN_THREADS, static_cast<size_t>(row_lanes) * 2 * C * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1,
-      rows_per_sample, groups, chunks, partial);
+      rows_per_sample, rows_per_chunk, groups, chunks, partial);
   return lavie_check_launch("gn_stats_kernel");
 }
 
 extern "C" int lavie_groupnorm_finalize(const float* partial, int samples, int chunks, int groups, int C,
                                         long long count_per_group, const float* gamma, const float* beta, float eps,
                                         float* scale_shift, cudaStream_t stream) {
-  LAVIE_REQUIRE(groups <= 64 && C % groups == 0 && count_per_group > 0, LAVIE_ERR_SHAPE, "groupnorm_finalize: shape");
+  LAVIE_REQUIRE(groups <= 64 && groups % 4 == 0 && C % groups == 0 && count_per_group > 0, LAVIE_ERR_SHAPE,
+                "groupnorm_finalize: groups must be a multiple of 4 (<= 64) dividing C");
   gn_finalize_kernel<<<samples, 256, 0, stream>>>(partial, chunks, groups, C, 1.0 / static_cast<double>(count_per_group),
                                                   gamma, beta, eps, scale_shift);
   return lavie_check_launch("gn_finalize_kernel");

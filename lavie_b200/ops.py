@@ -26,8 +26,8 @@ PROFILE = None
 class _Launch:
     """Counts one kernel launch; with ops.PROFILE set, brackets it with CUDA events on the launching stream."""
 
-    def __init__(self, kernel: str, flops: float = 0.0, nbytes: float = 0.0):
-        self.kernel, self.flops, self.nbytes = kernel, flops, nbytes
+    def __init__(self, kernel: str, flops: float = 0.0, nbytes: float = 0.0, tag: str = ""):
+        self.kernel, self.flops, self.nbytes, self.tag = kernel, flops, nbytes, tag
 
     def __enter__(self):
         global LAUNCHES
@@ -41,7 +41,7 @@ class _Launch:
     def __exit__(self, *exc):
         if PROFILE is not None and exc[0] is None:
             self.e1.record()
-            PROFILE.append((self.kernel, self.flops, self.nbytes, self.e0, self.e1))
+            PROFILE.append((self.kernel, self.flops, self.nbytes, self.e0, self.e1, self.tag))
         return False
 
 
@@ -96,7 +96,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None,
     Mo, No, ldo = _rows2d(out)
     assert Mo == M and No == n_out
     ep = _epilogue(bias, row_bias, rows_per_batch, residual, geglu)
-    with _Launch("gemm_bf16_tcgen05", 2.0 * M * N * (k0 + k1), 2.0 * (M * (k0 + k1) + N * (k0 + k1) + M * n_out)):
+    with _Launch("gemm_bf16_tcgen05", 2.0 * M * N * (k0 + k1), 2.0 * (M * (k0 + k1) + N * (k0 + k1) + M * n_out),
+                 f"gemm M={M} N={N} K={k0 + k1}{' geglu' if geglu else ''}"):
         rc = lib.lavie_gemm_bf16(a.data_ptr(), lda, k0, _ptr(a2), lda2, k1, w.data_ptr(), out.data_ptr(), ldo, M, N,
                                  ctypes.byref(ep) if ep is not None else None, block_n, _stream())
     check(rc, "lavie_gemm_bf16")
@@ -137,7 +138,8 @@ def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride
     Mo, No, ldo = _rows2d(out)
     assert Mo == rows and No == N
     ep = _epilogue(bias, row_bias, rows_per_batch, residual, False)
-    with _Launch("gemm_bf16_tcgen05", 2.0 * rows * N * 9 * C, 2.0 * (rows * C + N * 9 * C + rows * N)):
+    with _Launch("gemm_bf16_tcgen05", 2.0 * rows * N * 9 * C, 2.0 * (rows * C + N * 9 * C + rows * N),
+                 f"conv3x3 M={rows} N={N} K={9 * C} W={W}"):
         rc = lib.lavie_conv3x3_bf16(x.data_ptr(), NF, H, W, C, w.data_ptr(), out.data_ptr(), ldo, N,
                                     ctypes.byref(ep) if ep is not None else None, block_n, _stream())
     check(rc, "lavie_conv3x3_bf16")
@@ -155,9 +157,9 @@ def groupnorm_scale_shift(x: torch.Tensor, samples: int, rows_per_sample: int, g
         assert rows2 == rows
     assert rows == samples * rows_per_sample
     C = c0 + c1
-    chunks = lib.lavie_groupnorm_chunks(rows_per_sample)
+    chunks = lib.lavie_groupnorm_chunks(samples, rows_per_sample)
     partial = torch.empty((samples, chunks, groups, 2), dtype=F32, device=x.device)
-    with _Launch("lavie_groupnorm_stats"):
+    with _Launch("lavie_groupnorm_stats", 0.0, 2.0 * rows * C, f"gn_stats rows={rows} C={C} samples={samples}"):
         check(lib.lavie_groupnorm_stats(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample, groups,
                                         partial.data_ptr(), _stream()), "lavie_groupnorm_stats")
     ss = torch.empty((samples, C, 2), dtype=F32, device=x.device)
@@ -180,7 +182,7 @@ def groupnorm_apply(x: torch.Tensor, scale_shift: torch.Tensor, samples: int, ro
     if out is None:
         out = torch.empty((rows, C), dtype=BF16, device=x.device)
     _, _, ldy = _rows2d(out)
-    with _Launch("lavie_groupnorm_apply"):
+    with _Launch("lavie_groupnorm_apply", 0.0, 4.0 * rows * C, f"gn_apply rows={rows} C={C}"):
         check(lib.lavie_groupnorm_apply(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample,
                                         scale_shift.data_ptr(), 1 if silu else 0, out.data_ptr(), ldy, _stream()),
               "lavie_groupnorm_apply")
@@ -200,7 +202,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         out = torch.empty((rows, C), dtype=BF16, device=x.device)
     _, _, ldy = _rows2d(out)
     assert gamma.dtype == F32 and beta.dtype == F32
-    with _Launch("lavie_layernorm_bf16"):
+    with _Launch("lavie_layernorm_bf16", 0.0, 4.0 * rows * C, f"ln rows={rows} C={C}"):
         check(lib.lavie_layernorm_bf16(x.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), ldy,
                                        rows, C, _stream()), "lavie_layernorm_bf16")
     return out
@@ -220,7 +222,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, hea
     _, _, ldo = _rows2d(out)
     if scale is None:
         scale = d ** -0.5
-    with _Launch("lavie_attention_bf16"):
+    with _Launch("lavie_attention_bf16", 4.0 * batch * heads * Sq * Sk * d, 2.0 * (rq + 2 * rk) * heads * head_pitch + 2.0 * rq * heads * d,
+                 f"attn B={batch} Sq={Sq} Sk={Sk} d={d}"):
         check(lib.lavie_attention_bf16(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), ldo, batch,
                                        heads, Sq, Sk, d, head_pitch, kv_batch_div, scale, _stream()),
               "lavie_attention_bf16")
@@ -238,7 +241,8 @@ def temporal_attention(qkv: torch.Tensor, B: int, F: int, HW: int, heads: int, d
     _, _, ldo = _rows2d(out)
     assert rope.dtype == F32 and rope.is_contiguous() and rope.shape[0] == F
     assert bias.dtype == F32 and bias.is_contiguous() and tuple(bias.shape) == (heads, F, F)
-    with _Launch("lavie_temporal_attention_bf16"):
+    with _Launch("lavie_temporal_attention_bf16", 4.0 * B * HW * heads * F * F * d, 2.0 * rows * (cols + heads * d),
+                 f"tattn F={F} HW={HW} d={d}"):
         check(lib.lavie_temporal_attention_bf16(qkv.data_ptr(), ld, heads * head_pitch, 2 * heads * head_pitch,
                                                 out.data_ptr(), ldo, B, F, HW, heads, d, head_pitch, d ** -0.5,
                                                 rope.data_ptr(), rope.shape[1], bias.data_ptr(), _stream()),
