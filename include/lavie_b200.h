@@ -40,6 +40,8 @@ typedef enum {
 
 const char* lavie_last_error(void);
 int lavie_abi_version(void);
+/* Tuning hook for tests/benchmarks: what = 1 forces the split-K factor of the GEMM (0 = automatic). */
+int lavie_debug_set(int what, int value);
 
 /* Fused GEMM epilogue: out = bf16( acc + bias[n] + row_bias[row / rows_per_batch][n] + residual[row][n] ), or with
  * geglu != 0: out[:, j] = (acc[:, j] + bias) * gelu_erf(acc[:, j + 128] + bias') per 256-column tile. */
@@ -56,16 +58,20 @@ typedef struct {
 /* nn.Linear / 1x1 InflatedConv3d: out[M,N] = [a0 | a1][M, k0+k1] * w[N, k0+k1]^T (+ epilogue).
  * a1/k1 = 0 for a single source; two sources fold torch.cat([h, skip], 1) (unet_blocks.py:538,630) in front of
  * resnet.py:202-203 conv_shortcut.  Replaces attention.py:95-104 (to_q/k/v/out), :328,356 (proj_in/out),
- * diffusers FeedForward (mirror vsr/models/diffusers_attention.py:734-822).  block_n = 0 lets the library choose. */
+ * diffusers FeedForward (mirror vsr/models/diffusers_attention.py:734-822).  block_n = 0 lets the library choose.
+ * workspace (optional, caller-owned, fp32) enables deterministic split-K on small-M / large-K problems: the library
+ * uses at most workspace_bytes and picks splits <= workspace_bytes / (4*M*N). */
 int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1, int lda1, int k1, const void* w, void* out,
-                    int ldo, int M, int N, const lavie_epilogue* ep, int block_n, lavie_stream_t stream);
+                    int ldo, int M, int N, const lavie_epilogue* ep, int block_n, void* workspace,
+                    size_t workspace_bytes, lavie_stream_t stream);
 
 /* 3x3 stride-1 pad-1 InflatedConv3d (resnet.py:13-21) as implicit GEMM over a CONTIGUOUS channels-last map
  * x[NF, H, W, C]; w is [N, 3, 3, C].  lavie_conv3x3_supported() tells whether the TMA path accepts the geometry
  * (C % 64 == 0, W in {8,16,32,64,128}); otherwise use lavie_im2col3x3_bf16 + lavie_gemm_bf16. */
 int lavie_conv3x3_supported(int H, int W, int C);
 int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, const void* w, void* out, int ldo, int N,
-                       const lavie_epilogue* ep, int block_n, lavie_stream_t stream);
+                       const lavie_epilogue* ep, int block_n, void* workspace, size_t workspace_bytes,
+                       lavie_stream_t stream);
 
 /* Patch matrix for the general / strided conv (Downsample3D stride 2, resnet.py:102-110):
  * col[NF*Ho*Wo, 9*C] with K ordered (kh, kw, c), pad 1. */

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblavie_b200.so")
@@ -35,10 +35,12 @@ _P = c_void_p
 SIGNATURES = {
     "lavie_last_error": (c_char_p, []),
     "lavie_abi_version": (c_int, []),
+    "lavie_debug_set": (c_int, [c_int, c_int]),
     "lavie_gemm_bf16": (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(Epilogue),
-                                c_int, _P]),
+                                c_int, _P, c_size_t, _P]),
     "lavie_conv3x3_supported": (c_int, [c_int, c_int, c_int]),
-    "lavie_conv3x3_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, POINTER(Epilogue), c_int, _P]),
+    "lavie_conv3x3_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, POINTER(Epilogue), c_int, _P,
+                                   c_size_t, _P]),
     "lavie_im2col3x3_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_groupnorm_chunks": (c_int, [c_int, c_int]),
     "lavie_groupnorm_stats": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),

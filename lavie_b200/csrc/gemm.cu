@@ -1,50 +1,62 @@
-// tcgen05 GEMM / implicit-GEMM 3x3 convolution for the LaVie denoiser (sm_100a).
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for the LaVie denoiser (sm_100a), CTA-pair (cta_group::2) version.
 //
 //   D[M,N] = epilogue( A[M,K] * W[N,K]^T )        bf16 operands, fp32 accumulation in TMEM, bf16 out
 //
 // Replaces every nn.Linear / 1x1 conv / 3x3 InflatedConv3d call of the reference hot path
 // (base/models/attention.py:95-104,328,356 ; resnet.py:13-21,146,162,171-175 ; diffusers FeedForward).
 //
-// Structure: persistent, warp-specialised CTA of 192 threads, one CTA per SM.
-//   warp 0      : TMA producer   (A tile 128x64, W tile BLOCK_N x 64, 128-byte swizzle, ring of STAGES)
-//   warp 1      : MMA issuer     (one elected lane issues tcgen05.mma M=128,N=BLOCK_N,K=16) + TMEM owner
-//   warps 2..5  : epilogue       (tcgen05.ld 32 lanes x 32 columns -> bias / time-bias / GEGLU / residual -> bf16)
-// Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+// Why CTA pairs: the kernel is fed from L2, and a single-CTA 128 x BN tile needs ~70 FLOP per L2 byte, which capped
+// the first version at ~700 TFLOP/s (profiles/r1_gemm_v1_*).  A pair of SMs computes a 256 x BN tile with ONE
+// tcgen05.mma.cta_group::2 stream: each CTA stages its own 128 rows of A and HALF of the W tile, so L2 traffic per
+// FLOP drops by up to 2x.
+//
+// Structure: persistent clusters of 2 CTAs (one pair per two SMs), 320 threads per CTA:
+//   warp 0      : TMA producer   (A 128x64 slab + W (BN/2)x64 slab per stage, 128-byte swizzle, ring of STAGES;
+//                                 both CTAs' loads complete on the LEADER CTA's full barrier)
+//   warp 1      : MMA issuer     (leader CTA only: tcgen05.mma.cta_group::2 M=256, N=BN, K=16; commits are multicast
+//                                 to both CTAs' barriers) + TMEM owner (both CTAs)
+//   warps 2..9  : epilogue       (each CTA drains its own 128 accumulator rows: tcgen05.ld -> bias / time-bias /
+//                                 GEGLU / residual -> bf16, or fp32 split-K partials)
+// Two TMEM accumulator stages let the epilogue of item i overlap the main loop of item i+1.
+//
+// Work item = (m_tile, n_tile, k_split).  Split-K (deterministic: fp32 partials + ordered reduction kernel) keeps the
+// 74 pairs busy on the 5x8 / 10x16 levels where M is only 1280..5120 rows but K reaches 23040.
 //
 // A-operand modes
 //   plain : A is [M, K] row-major (row stride lda); optionally split along K over two sources
 //           (the folded torch.cat([h, skip], dim=1) in front of a 1x1 shortcut, unet_blocks.py:538,630).
 //   conv3 : A is the channels-last feature map [NF, H, W, C]; K = 9*C ordered (kh, kw, c); every K block is one
 //           (tap, 64-channel) slab fetched with 4-D TMA boxes whose out-of-bounds rows/columns are zero-filled
-//           by the hardware = the conv's zero padding.  An M tile is 128 consecutive output pixels =
-//           128/W whole image rows.
+//           by the hardware = the conv's zero padding.  128 consecutive output pixels = 128/W whole image rows.
 #include "common.cuh"
 
 namespace {
 
-constexpr int BLOCK_M = 128;
+constexpr int BLOCK_M = 128;          // rows per CTA; a pair covers 256
+constexpr int PAIR_M = 256;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_WARP0 = 2;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // 320
+constexpr int EPI_BAR_ID = 1;
 
 struct GemmParams {
   int M, N, K;
   int num_k_blocks;
   int k_split_blocks;        // plain mode: K blocks [0, k_split) come from A0, the rest from A1
-  int k_rot;                 // K-loop rotation stride per M tile (0 = off)
-  int m_tiles, n_tiles;
+  int m_tiles, n_tiles;      // m_tiles counts 256-row pair tiles
+  int splits, kb_per_split;  // split-K
   // conv3 mode
   int conv;                  // 0 plain, 1 conv3x3 stride 1 pad 1
   int c_blocks;              // Cin / 64
   int img_h, img_w;
   int box_h;                 // image rows per TMA box
-  int boxes_per_tile;        // 128 / (box_h * W)
+  int boxes_per_tile;        // 128 / (box_h * W)   (per CTA)
   int row_groups_per_img;    // H / box_h
   // epilogue
   const float* bias;         // [N] or null
-  const float* row_bias;     // [M / rows_per_batch, N] or null  (time embedding add, resnet.py:187-190)
+  const float* row_bias;     // [M / rows_per_batch, ld_row_bias] or null  (time embedding add, resnet.py:187-190)
   int rows_per_batch;
   int ld_row_bias;
   const __nv_bfloat16* residual;   // [M, ldr] or null
@@ -52,20 +64,103 @@ struct GemmParams {
   int geglu;                 // 1: tile columns [0,BN/2) = value, [BN/2,BN) = gate -> out = value * gelu(gate)
   __nv_bfloat16* out;
   int ldo;
+  float* partial;            // split-K workspace [splits, M, N] fp32 (splits > 1)
+  int k_rot;                 // K-sweep rotation stride per M tile (0 = off)
+  int debug;                 // tuning only: 1 = skip TMA (pure MMA issue rate), 2 = skip MMA (pure TMA feed rate)
 };
 
 template <int BLOCK_N>
 struct SmemLayout {
-  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int MAX_SMEM = 227 * 1024 - 2048;   // leave room for barriers + alignment slack
+  static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;   // staged bias (or the two possible row_bias rows) of the tile
+  static constexpr int MAX_SMEM = 227 * 1024 - 2048 - BIAS_BYTES;
   static constexpr int STAGES_RAW = MAX_SMEM / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// ---- cluster / cta_group::2 PTX ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this smem offset in BOTH CTAs of the pair once all prior MMAs of this thread retired
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// TMA loads whose completion bytes are credited to a barrier given by its shared::cluster address (the leader's)
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                             int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                             int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(EPI_BAR_ID), "n"(32 * NUM_EPI_WARPS) : "memory");
+}
+
+struct Item {
+  int m_blk, n_blk, kb_begin, kb_end;
+};
+__device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
+  Item it;
+  const int split = item % p.splits;
+  const int rest = item / p.splits;
+  it.n_blk = rest % p.n_tiles;
+  it.m_blk = rest / p.n_tiles;
+  it.kb_begin = split * p.kb_per_split;
+  it.kb_end = min(p.num_k_blocks, it.kb_begin + p.kb_per_split);
+  return it;
+}
+
 template <int BLOCK_N>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                   const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   using L = SmemLayout<BLOCK_N>;
@@ -76,15 +171,19 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES);          // [2][BLOCK_N]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES + L::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;     // [2]
-  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]  (only the leader's are waited on)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_items = p.m_tiles * p.n_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a0);
@@ -96,138 +195,215 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[a], 2 * NUM_EPI_WARPS);   // one arrive per epilogue warp of BOTH CTAs
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc2(tmem_slot, TMEM_COLS);
+    tmem_relinquish2();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();            // barriers of both CTAs initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.n_tiles;
-        const int n_blk = tile % p.n_tiles;
-        // K-loop rotation: CTAs start their K sweep at different blocks so that the ~74 CTAs sharing one weight
-        // tile do not hammer the same L2 lines in lockstep (the sum is order-independent up to fp32 rounding and
-        // the mapping is fixed, so results stay deterministic).
-        const int kb0 = (m_blk * p.k_rot) % p.num_k_blocks;
-        for (int it = 0; it < p.num_k_blocks; ++it) {
-          int kb = kb0 + it;
-          if (kb >= p.num_k_blocks) kb -= p.num_k_blocks;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===================================== TMA producer (both CTAs) =====================================
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses / coordinates in uniform registers);
+    // one elected lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = pair; item < num_items; item += num_pairs) {
+      const Item it = decode_item(p, item);
+      const int m_cta = it.m_blk * 2 + static_cast<int>(rank);        // this CTA's 128-row block
+      // K-sweep rotation: pairs working on different M tiles start at different K blocks, so the ~37 CTAs that share
+      // a weight slab do not request the same L2 lines in lockstep (fp32 accumulation order changes per tile, but
+      // the tile -> rotation mapping is fixed, so results stay bit-reproducible).
+      const int klen = it.kb_end - it.kb_begin;
+      const int rot = (it.m_blk * p.k_rot) % klen;
+      for (int i = 0; i < klen; ++i) {
+        int kb = it.kb_begin + i + rot;
+        if (kb >= it.kb_end) kb -= klen;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          if (p.conv) {
-            const int tap = kb / p.c_blocks;
-            const int c0 = (kb - tap * p.c_blocks) * BLOCK_K;
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            const int box_bytes = p.box_h * p.img_w * BLOCK_K * 2;
-            for (int i = 0; i < p.boxes_per_tile; ++i) {
-              const int g = m_blk * p.boxes_per_tile + i;
-              const int img = g / p.row_groups_per_img;
-              const int y0 = (g - img * p.row_groups_per_img) * p.box_h;
-              tma_load_4d(a_dst + i * box_bytes, &tmap_a0, &full_bar[stage], c0, dx, y0 + dy, img);
-            }
-          } else if (kb < p.k_split_blocks) {
-            tma_load_2d(a_dst, &tmap_a0, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (p.debug & 1) {
+            if (rank == 0) mbar_arrive(&full_bar[stage]);
           } else {
-            tma_load_2d(a_dst, &tmap_a1, &full_bar[stage], (kb - p.k_split_blocks) * BLOCK_K, m_blk * BLOCK_M);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);   // bytes landing in both CTAs
+            if (p.conv) {
+              const int tap = kb / p.c_blocks;
+              const int c0 = (kb - tap * p.c_blocks) * BLOCK_K;
+              int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              if (p.debug & 4) dx = 0;
+              if (p.debug & 8) dy = 0;
+              const int box_bytes = p.box_h * p.img_w * BLOCK_K * 2;
+              for (int i = 0; i < p.boxes_per_tile; ++i) {
+                const int g = m_cta * p.boxes_per_tile + i;
+                const int img = g / p.row_groups_per_img;
+                const int y0 = (g - img * p.row_groups_per_img) * p.box_h;
+                tma2_load_4d(a_dst + i * box_bytes, &tmap_a0, full_leader, c0, dx, y0 + dy, img);
+              }
+            } else if (kb < p.k_split_blocks) {
+              tma2_load_2d(a_dst, &tmap_a0, full_leader, kb * BLOCK_K, m_cta * BLOCK_M);
+            } else {
+              tma2_load_2d(a_dst, &tmap_a1, full_leader, (kb - p.k_split_blocks) * BLOCK_K, m_cta * BLOCK_M);
+            }
+            tma2_load_2d(b_dst, &tmap_b, full_leader, kb * BLOCK_K,
+                         it.n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2));
           }
-          tma_load_2d(b_dst, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+    // ===================================== MMA issuer (leader CTA only) =================================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR_M, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = pair; item < num_items; item += num_pairs) {
+        const Item it = decode_item(p, item);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;
           const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
           const uint64_t b_desc = umma_desc_sw128(b_addr, 16, 1024);
+          if (elect_one()) {
+            if (!(p.debug & 2)) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advancing 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the >>4 address field
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                // advancing 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the >>4 address field
+                umma2_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > it.kb_begin || k > 0) ? 1u : 0u);
+              }
+            }
+            umma2_commit_mc(&empty_bar[stage]);    // frees this smem stage in both CTAs once the MMAs retire
+            if (kb == it.kb_end - 1) umma2_commit_mc(&tmem_full[acc]);   // accumulator complete -> both epilogues
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem stage once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ===================================== epilogue =========================================
+    // ===================================== epilogue (both CTAs) =========================================
+    const int ew = warp - 2;                       // 0..7
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int chalf = ew >> 2;                     // which half of the 32-column chunks this warp drains
+    const int et = threadIdx.x - 64;               // 0..255
+    const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.n_tiles;
-      const int n_blk = tile % p.n_tiles;
+    for (int item = pair; item < num_items; item += num_pairs) {
+      const Item it = decode_item(p, item);
+      const int split = item % p.splits;
+      const int row0 = (it.m_blk * 2 + static_cast<int>(rank)) * BLOCK_M;
+      const int row = row0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int n0 = it.n_blk * BLOCK_N;
+      // ---- stage the tile's bias (and the <= 2 time-embedding rows its 128 rows can touch) in smem ----
+      const int batch0 = p.row_bias ? row0 / p.rows_per_batch : 0;
+      const int last_row = min(row0 + BLOCK_M, p.M) - 1;
+      const bool rb_smem = p.row_bias && (last_row / p.rows_per_batch - batch0) <= 1;
+      epi_bar_sync();                              // everyone is done reading the previous tile's staged bias
+      if (p.splits == 1) {
+        for (int i = et; i < 2 * BLOCK_N; i += 32 * NUM_EPI_WARPS) {
+          const int which = i / BLOCK_N, c = i - which * BLOCK_N;
+          float v = 0.f;
+          if (n0 + c < p.N) {
+            if (which == 0 && p.bias) v = p.bias[n0 + c];
+            if (rb_smem) {
+              const int b = batch0 + which;
+              if (static_cast<long long>(b) * p.rows_per_batch < p.M)
+                v += p.row_bias[static_cast<size_t>(b) * p.ld_row_bias + n0 + c] + (which == 1 && p.bias ? p.bias[n0 + c] : 0.f);
+            }
+          }
+          s_bias[i] = v;
+        }
+      }
+      epi_bar_sync();
+      const float* sb = s_bias + ((rb_smem && row_ok && (row / p.rows_per_batch) != batch0) ? BLOCK_N : 0);
+      const float* rb_glob = (p.row_bias && !rb_smem && row_ok)
+                                 ? p.row_bias + static_cast<size_t>(row / p.rows_per_batch) * p.ld_row_bias
+                                 : nullptr;
+      const bool add_bias = p.bias != nullptr || rb_smem;
+
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
-      const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-      const float* rb = (p.row_bias != nullptr && row_ok)
-                            ? p.row_bias + static_cast<size_t>(row / p.rows_per_batch) * p.ld_row_bias
-                            : nullptr;
-      if (!p.geglu) {
+
+      if (p.splits > 1) {
+        // fp32 partials for the ordered split-K reduction
+        float* dst_row = p.partial + (static_cast<size_t>(split) * p.M + row) * p.N;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        for (int c = chalf; c < BLOCK_N / 32; c += 2) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c * 32, v);
           tmem_wait_ld();
-          const int col0 = n_blk * BLOCK_N + c * 32;
+          const int col0 = n0 + c * 32;
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (col0 + j < p.N)
+                *reinterpret_cast<uint4*>(dst_row + col0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      } else if (!p.geglu) {
+        const __nv_bfloat16* res_row = (p.residual && row_ok) ? p.residual + static_cast<size_t>(row) * p.ldr : nullptr;
+        uint4 rpre[4];
+        auto prefetch_res = [&](int c) {
+          const int col0 = n0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            rpre[j] = (res_row && col0 + 8 * j < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row + col0 + 8 * j))
+                                                      : make_uint4(0, 0, 0, 0);
+        };
+        prefetch_res(chalf);
+#pragma unroll 1
+        for (int c = chalf; c < BLOCK_N / 32; c += 2) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c * 32, v);
+          uint4 rcur[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rcur[j] = rpre[j];
+          if (c + 2 < BLOCK_N / 32) prefetch_res(c + 2);        // next chunk's residual in flight under this one
+          tmem_wait_ld();
+          const int col0 = n0 + c * 32;
           if (row_ok && col0 < p.N) {
-            const __nv_bfloat16* res = p.residual ? p.residual + static_cast<size_t>(row) * p.ldr + col0 : nullptr;
             __nv_bfloat16* dst = p.out + static_cast<size_t>(row) * p.ldo + col0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < p.N) {
+            for (int j = 0; j < 4; ++j) {
+              if (col0 + 8 * j < p.N) {
                 float f[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
-                if (p.bias) {
-                  const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col0 + j);
-                  const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col0 + j + 4);
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+                if (add_bias) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(sb + c * 32 + 8 * j);
+                  const float4 b1 = *reinterpret_cast<const float4*>(sb + c * 32 + 8 * j + 4);
                   f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                   f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                 }
-                if (rb) {
-                  const float4 b0 = *reinterpret_cast<const float4*>(rb + col0 + j);
-                  const float4 b1 = *reinterpret_cast<const float4*>(rb + col0 + j + 4);
+                if (rb_glob) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(rb_glob + col0 + 8 * j);
+                  const float4 b1 = *reinterpret_cast<const float4*>(rb_glob + col0 + 8 * j + 4);
                   f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                   f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                 }
-                if (res) {
-                  const uint4 r = *reinterpret_cast<const uint4*>(res + j);
-                  const float2 r0 = unpack_bf16(r.x), r1 = unpack_bf16(r.y), r2 = unpack_bf16(r.z),
-                               r3 = unpack_bf16(r.w);
+                if (res_row) {
+                  const float2 r0 = unpack_bf16(rcur[j].x), r1 = unpack_bf16(rcur[j].y), r2 = unpack_bf16(rcur[j].z),
+                               r3 = unpack_bf16(rcur[j].w);
                   f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
                   f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
                 }
@@ -236,7 +412,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
                 o.y = pack_bf16(f[2], f[3]);
                 o.z = pack_bf16(f[4], f[5]);
                 o.w = pack_bf16(f[6], f[7]);
-                *reinterpret_cast<uint4*>(dst + j) = o;
+                *reinterpret_cast<uint4*>(dst + 8 * j) = o;
               }
             }
           }
@@ -247,13 +423,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         // vsr/models/diffusers_attention.py:811-822)
         constexpr int HALF = BLOCK_N / 2;
 #pragma unroll 1
-        for (int c = 0; c < HALF / 32; ++c) {
+        for (int c = chalf; c < HALF / 32; c += 2) {
           uint32_t v[32], g[32];
           tmem_ld_32x32(t_row + c * 32, v);
           tmem_ld_32x32(t_row + HALF + c * 32, g);
           tmem_wait_ld();
-          const int colv = n_blk * BLOCK_N + c * 32;          // column in the interleaved weight space
-          const int colo = n_blk * HALF + c * 32;             // output column
+          const int colv = n0 + c * 32;                        // column in the interleaved weight space
+          const int colo = it.n_blk * HALF + c * 32;           // output column
           if (row_ok && colv < p.N) {
             __nv_bfloat16* dst = p.out + static_cast<size_t>(row) * p.ldo + colo;
 #pragma unroll
@@ -261,12 +437,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                float val = __uint_as_float(v[j + e]);
-                float gate = __uint_as_float(g[j + e]);
-                if (p.bias) {
-                  val += p.bias[colv + j + e];
-                  gate += p.bias[colv + HALF + j + e];
-                }
+                const float val = __uint_as_float(v[j + e]) + s_bias[c * 32 + j + e];
+                const float gate = __uint_as_float(g[j + e]) + s_bias[HALF + c * 32 + j + e];
                 f[e] = val * gelu_erf_f(gate);
               }
               uint4 o;
@@ -281,16 +453,49 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();            // the peer may still be reading smem / TMEM that a cta_group::2 MMA touches
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc2(tmem_base, TMEM_COLS);
+  }
+}
+
+// Ordered split-K reduction + the same fused epilogue (bias / time-bias / residual) -> bf16
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* __restrict__ bias,
+                     const float* __restrict__ row_bias, int rows_per_batch, int ld_row_bias,
+                     const __nv_bfloat16* __restrict__ residual, int ldr, __nv_bfloat16* __restrict__ out, int ldo) {
+  const int nvec = N >> 2;
+  const long long total = static_cast<long long>(M) * nvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / nvec);
+    const int col = static_cast<int>(i % nvec) * 4;
+    float4 a = *reinterpret_cast<const float4*>(partial + static_cast<size_t>(row) * N + col);
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = *reinterpret_cast<const float4*>(partial + (static_cast<size_t>(s) * M + row) * N + col);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (bias) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + col);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (row_bias) {
+      const float4 b = *reinterpret_cast<const float4*>(row_bias + static_cast<size_t>(row / rows_per_batch) * ld_row_bias + col);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (residual) {
+      const uint2 r = *reinterpret_cast<const uint2*>(residual + static_cast<size_t>(row) * ldr + col);
+      const float2 r0 = unpack_bf16(r.x), r1 = unpack_bf16(r.y);
+      a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
+    }
+    *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * ldo + col) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
   }
 }
 
@@ -306,34 +511,27 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
                   cudaGetErrorString(e));
     configured = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_tcgen05<BLOCK_N><<<grid, NUM_THREADS, L::TOTAL, stream>>>(a0, a1, b, p);
-  return lavie_check_launch("gemm_bf16_tcgen05");
-}
-
-int pick_block_n(int M, int N, int forced) {
-  if (forced) return forced;
-  // minimise (waves x per-tile cost); per-tile cost ~ BLOCK_N (MMA time) with a small fixed overhead
-  const int cands[5] = {256, 192, 160, 128, 64};
-  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-  double best = 1e30;
-  int best_bn = 128;
-  for (int i = 0; i < 5; ++i) {
-    const int bn = cands[i];
-    const int n_tiles = (N + bn - 1) / bn;
-    const long tiles = static_cast<long>(m_tiles) * n_tiles;
-    const long waves = (tiles + 147) / 148;
-    const double cost = static_cast<double>(waves) * (bn + 24);
-    if (cost < best - 1e-9) {
-      best = cost;
-      best_bn = bn;
-    }
+  const int items = p.m_tiles * p.n_tiles * p.splits;
+  int pairs = num_sms / 2;
+  if (items < pairs) pairs = items;
+  gemm_bf16_tcgen05<BLOCK_N><<<2 * pairs, NUM_THREADS, L::TOTAL, stream>>>(a0, a1, b, p);
+  int rc = lavie_check_launch("gemm_bf16_tcgen05");
+  if (rc) return rc;
+  if (p.splits > 1) {
+    const long long total = static_cast<long long>(p.M) * (p.N >> 2);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_reduce_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p.partial, p.splits, p.M, p.N, p.bias,
+                                                                     p.row_bias, p.rows_per_batch, p.ld_row_bias,
+                                                                     p.residual, p.ldr, p.out, p.ldo);
+    rc = lavie_check_launch("splitk_reduce_kernel");
   }
-  return best_bn;
+  return rc;
 }
 
-int g_k_rot = 7;
+int g_force_splits = 0;
+int g_debug = 0;
+int g_k_rot = 0;   // measured: no effect on B200 (profiles/r1_notes.md), kept as a tuning hook only
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -343,6 +541,48 @@ int num_sms() {
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   return g_num_sms;
+}
+
+// Tile-shape / split-K choice: minimise  waves x (K blocks per item x per-block time + per-item overhead), where the
+// per-block time is the larger of the MMA time (2*BN cycles per SM) and the L2 feed time of the stage bytes.
+struct Plan {
+  int bn, splits, kb_per_split;
+};
+Plan make_plan(int M, int N, int num_k_blocks, int forced_bn, bool geglu, size_t ws_bytes) {
+  const int pairs = num_sms() / 2;
+  const int m_tiles = (M + PAIR_M - 1) / PAIR_M;
+  const int cands[5] = {256, 192, 160, 128, 64};
+  Plan best{128, 1, num_k_blocks};
+  double best_cost = 1e30;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cands[i];
+    if (forced_bn && bn != forced_bn) continue;
+    if (geglu && bn != 256) continue;
+    const int n_tiles = (N + bn - 1) / bn;
+    const long tiles = static_cast<long>(m_tiles) * n_tiles;
+    const double t_kb = fmax(2.0 * bn, (16384.0 + 64.0 * bn) / 56.0);
+    const int max_splits = geglu ? 1 : 16;
+    for (int s = 1; s <= max_splits; ++s) {
+      if (s > 1) {
+        if (static_cast<size_t>(s) * M * N * 4 > ws_bytes) break;
+        if (num_k_blocks / s < 8) break;
+        if (tiles * (s - 1) >= pairs) break;           // no point splitting once the machine is full
+      }
+      if (g_force_splits && s != g_force_splits && !geglu) continue;
+      const int kbps = (num_k_blocks + s - 1) / s;
+      const int eff_s = (num_k_blocks + kbps - 1) / kbps;
+      if (eff_s != s) continue;
+      const long items = tiles * s;
+      const long waves = (items + pairs - 1) / pairs;
+      double cost = static_cast<double>(waves) * (kbps * t_kb + 1500.0 + 6.0 * bn);
+      if (s > 1) cost += 4000.0 + 0.0013 * (s + 0.5) * static_cast<double>(M) * N;      // reduction pass (HBM)
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = Plan{bn, s, kbps};
+      }
+    }
+  }
+  return best;
 }
 
 int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
@@ -362,12 +602,13 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 int make_weight_map(CUtensorMap* map, const void* w, int N, int K, int bn) {
   const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
   const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
-  const uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(bn)};
+  const uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(bn / 2)};     // each CTA of the pair stages half the tile
   return lavie_make_tmap(map, w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-int fill_epilogue(GemmParams& p, const lavie_epilogue* ep, int M, int N, void* out, int ldo) {
-  p.bias = nullptr; p.row_bias = nullptr; p.rows_per_batch = 1; p.ld_row_bias = N; p.residual = nullptr; p.ldr = 0; p.geglu = 0;
+int fill_epilogue(GemmParams& p, const lavie_epilogue* ep, int N, void* out, int ldo) {
+  p.bias = nullptr; p.row_bias = nullptr; p.rows_per_batch = 1; p.ld_row_bias = N; p.residual = nullptr; p.ldr = 0;
+  p.geglu = 0;
   if (ep) {
     p.bias = ep->bias;
     p.row_bias = ep->row_bias;
@@ -387,32 +628,48 @@ int fill_epilogue(GemmParams& p, const lavie_epilogue* ep, int M, int N, void* o
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   LAVIE_REQUIRE(aligned16(out) && ldo % 8 == 0, LAVIE_ERR_ALIGN, "gemm: out must be 16-byte aligned, ldo %% 8 == 0");
-  (void)M; (void)N;
   return LAVIE_OK;
+}
+
+void apply_plan(GemmParams& p, const Plan& plan, void* workspace) {
+  p.m_tiles = (p.M + PAIR_M - 1) / PAIR_M;
+  p.n_tiles = (p.N + plan.bn - 1) / plan.bn;
+  p.splits = plan.splits;
+  p.kb_per_split = plan.kb_per_split;
+  p.partial = static_cast<float*>(workspace);
+  p.debug = g_debug;
+  p.k_rot = g_k_rot;
 }
 
 }  // namespace
 
+extern "C" int lavie_debug_set(int what, int value) {
+  if (what == 1) g_force_splits = value;
+  if (what == 2) g_debug = value;
+  if (what == 0) g_k_rot = value;
+  return 0;
+}
+
 extern "C" int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1, int lda1, int k1, const void* w,
                                void* out, int ldo, int M, int N, const lavie_epilogue* ep, int block_n,
-                               cudaStream_t stream) {
+                               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const int K = k0 + k1;
   LAVIE_REQUIRE(M > 0 && N > 0 && K > 0, LAVIE_ERR_SHAPE, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   LAVIE_REQUIRE(N % 8 == 0 && k0 % 8 == 0 && k1 % 8 == 0, LAVIE_ERR_SHAPE, "gemm: N, K must be multiples of 8");
   LAVIE_REQUIRE(k1 == 0 || k0 % BLOCK_K == 0, LAVIE_ERR_SHAPE, "gemm: split-K source boundary must be a multiple of 64");
   LAVIE_REQUIRE(aligned16(a0) && aligned16(w) && lda0 % 8 == 0 && (k1 == 0 || (aligned16(a1) && lda1 % 8 == 0)),
                 LAVIE_ERR_ALIGN, "gemm: operands must be 16-byte aligned with ld %% 8 == 0");
+  LAVIE_REQUIRE(workspace == nullptr || aligned16(workspace), LAVIE_ERR_ALIGN, "gemm: workspace alignment");
   GemmParams p{};
-  int bn = ep && ep->geglu ? 256 : pick_block_n(M, N, block_n);
-  LAVIE_REQUIRE(!(ep && ep->geglu) || N % 256 == 0, LAVIE_ERR_SHAPE, "gemm: GEGLU needs N %% 256 == 0");
+  const bool geglu = ep && ep->geglu;
+  LAVIE_REQUIRE(!geglu || N % 256 == 0, LAVIE_ERR_SHAPE, "gemm: GEGLU needs N %% 256 == 0");
   p.M = M; p.N = N; p.K = K;
   p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   p.k_split_blocks = k1 ? k0 / BLOCK_K : p.num_k_blocks;
-  p.k_rot = g_k_rot;
-  p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-  p.n_tiles = (N + bn - 1) / bn;
   p.conv = 0;
-  int rc = fill_epilogue(p, ep, M, N, out, ldo);
+  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, geglu, workspace ? workspace_bytes : 0);
+  apply_plan(p, plan, workspace);
+  int rc = fill_epilogue(p, ep, N, out, ldo);
   if (rc) return rc;
   CUtensorMap ma0, ma1, mb;
   {
@@ -431,40 +688,37 @@ extern "C" int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1,
   } else {
     ma1 = ma0;
   }
-  rc = make_weight_map(&mb, w, N, K, bn);
+  rc = make_weight_map(&mb, w, N, K, plan.bn);
   if (rc) return rc;
-  return dispatch(bn, ma0, ma1, mb, p, stream);
-}
-
-extern "C" int lavie_debug_set(int what, int value) {
-  if (what == 0) g_k_rot = value;
-  return 0;
+  return dispatch(plan.bn, ma0, ma1, mb, p, stream);
 }
 
 extern "C" int lavie_conv3x3_supported(int H, int W, int C) {
   if (C % BLOCK_K != 0) return 0;
   if (W > BLOCK_M || BLOCK_M % W != 0 || W % 8 != 0) return 0;
+  (void)H;
   return 1;
 }
 
 extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, const void* w, void* out, int ldo,
-                                  int N, const lavie_epilogue* ep, int block_n, cudaStream_t stream) {
+                                  int N, const lavie_epilogue* ep, int block_n, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream) {
   LAVIE_REQUIRE(lavie_conv3x3_supported(H, W, C), LAVIE_ERR_SHAPE,
                 "conv3x3: TMA path needs C %% 64 == 0 and W in {8,16,32,64,128} (got H=%d W=%d C=%d)", H, W, C);
   LAVIE_REQUIRE(N % 8 == 0 && aligned16(x) && aligned16(w), LAVIE_ERR_ALIGN, "conv3x3: alignment");
+  LAVIE_REQUIRE(workspace == nullptr || aligned16(workspace), LAVIE_ERR_ALIGN, "conv3x3: workspace alignment");
+  LAVIE_REQUIRE(!(ep && ep->geglu), LAVIE_ERR_SHAPE, "conv3x3: GEGLU epilogue not supported");
   const int M = NF * H * W;
   GemmParams p{};
-  const int bn = pick_block_n(M, N, block_n);
   p.M = M; p.N = N; p.K = 9 * C;
   p.num_k_blocks = 9 * (C / BLOCK_K);
   p.k_split_blocks = p.num_k_blocks;
-  p.k_rot = g_k_rot;
-  p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-  p.n_tiles = (N + bn - 1) / bn;
   p.conv = 1;
   p.c_blocks = C / BLOCK_K;
   p.img_h = H; p.img_w = W;
-  // largest number of whole image rows per TMA box that divides both H and the 128/W rows of an M tile
+  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, false, workspace ? workspace_bytes : 0);
+  apply_plan(p, plan, workspace);
+  // largest number of whole image rows per TMA box that divides both H and the 128/W rows of a CTA's M block
   const int rows_per_tile = BLOCK_M / W;
   int box_h = 1;
   for (int h = rows_per_tile; h >= 1; --h) {
@@ -473,9 +727,8 @@ extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, co
   p.box_h = box_h;
   p.boxes_per_tile = rows_per_tile / box_h;
   p.row_groups_per_img = H / box_h;
-  int rc = fill_epilogue(p, ep, M, N, out, ldo);
+  int rc = fill_epilogue(p, ep, N, out, ldo);
   if (rc) return rc;
-  LAVIE_REQUIRE(!(ep && ep->geglu), LAVIE_ERR_SHAPE, "conv3x3: GEGLU epilogue not supported");
   CUtensorMap ma, mb;
   {
     const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
@@ -486,7 +739,7 @@ extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, co
     rc = lavie_make_tmap(&ma, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  rc = make_weight_map(&mb, w, N, 9 * C, bn);
+  rc = make_weight_map(&mb, w, N, 9 * C, plan.bn);
   if (rc) return rc;
-  return dispatch(bn, ma, ma, mb, p, stream);
+  return dispatch(plan.bn, ma, ma, mb, p, stream);
 }

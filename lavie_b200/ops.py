@@ -45,6 +45,20 @@ class _Launch:
         return False
 
 
+WORKSPACE_BYTES = 128 << 20
+_workspaces = {}
+
+
+def _workspace(device) -> torch.Tensor:
+    """Caller-owned split-K scratch (fp32 partials), one per device, reused by every GEMM on the stream."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -96,10 +110,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None,
     Mo, No, ldo = _rows2d(out)
     assert Mo == M and No == n_out
     ep = _epilogue(bias, row_bias, rows_per_batch, residual, geglu)
+    ws = _workspace(a.device)
     with _Launch("gemm_bf16_tcgen05", 2.0 * M * N * (k0 + k1), 2.0 * (M * (k0 + k1) + N * (k0 + k1) + M * n_out),
                  f"gemm M={M} N={N} K={k0 + k1}{' geglu' if geglu else ''}"):
         rc = lib.lavie_gemm_bf16(a.data_ptr(), lda, k0, _ptr(a2), lda2, k1, w.data_ptr(), out.data_ptr(), ldo, M, N,
-                                 ctypes.byref(ep) if ep is not None else None, block_n, _stream())
+                                 ctypes.byref(ep) if ep is not None else None, block_n, ws.data_ptr(), ws.numel(),
+                                 _stream())
     check(rc, "lavie_gemm_bf16")
     return out
 
@@ -138,10 +154,12 @@ def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride
     Mo, No, ldo = _rows2d(out)
     assert Mo == rows and No == N
     ep = _epilogue(bias, row_bias, rows_per_batch, residual, False)
+    ws = _workspace(x.device)
     with _Launch("gemm_bf16_tcgen05", 2.0 * rows * N * 9 * C, 2.0 * (rows * C + N * 9 * C + rows * N),
                  f"conv3x3 M={rows} N={N} K={9 * C} W={W}"):
         rc = lib.lavie_conv3x3_bf16(x.data_ptr(), NF, H, W, C, w.data_ptr(), out.data_ptr(), ldo, N,
-                                    ctypes.byref(ep) if ep is not None else None, block_n, _stream())
+                                    ctypes.byref(ep) if ep is not None else None, block_n, ws.data_ptr(),
+                                    ws.numel(), _stream())
     check(rc, "lavie_conv3x3_bf16")
     return out
 

@@ -283,3 +283,38 @@ def test_upsample_and_cfg_ddim():
     got = ops.cfg_ddim_step(nu, nt, 7.5, float(acp[t]), float(acp[t - ratio]), lat)
     want = O.ddim_step((nu + 7.5 * (nt - nu)).cpu(), t, lat.cpu(), acp, ratio)
     assert torch.allclose(got.cpu(), want, atol=1e-5, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ split-K
+@pytest.mark.parametrize("splits", [0, 1, 2, 5])
+def test_gemm_splitk_matches(splits):
+    """Small-M / large-K problems (the 5x8 level: 1280 rows, K = 11520) take the deterministic split-K path."""
+    ops = _ops()
+    from lavie_b200 import _lib
+    lib = _lib.load()
+    M, N, K = 1280, 1280, 11520
+    a = _bf(_rand(M, K))
+    w = _bf(_rand(N, K, scale=K ** -0.5))
+    bias = _rand(N, seed=1)
+    res = _bf(_rand(M, N, seed=2))
+    lib.lavie_debug_set(1, splits)
+    try:
+        out = ops.gemm(a, w, bias=bias, residual=res)
+        out2 = ops.gemm(a, w, bias=bias, residual=res)
+    finally:
+        lib.lavie_debug_set(1, 0)
+    ref = a.float() @ w.float().t() + bias + res.float()
+    assert rel_l2(out.float(), ref) < 4e-3
+    assert torch.equal(out, out2)                      # ordered reduction: bit-reproducible
+
+
+def test_conv3x3_small_m_large_k():
+    ops = _ops()
+    from lavie_b200.packing import pack_conv3x3
+    NF, H, W, C, N = 32, 5, 8, 1280, 1280
+    x = _bf(_rand(NF * H * W, C))
+    w = _bf(_rand(N, C, 3, 3, scale=(9 * C) ** -0.5))
+    temb = _rand(2, N, seed=4)
+    out = ops.conv3x3(x, NF, H, W, pack_conv3x3(w), row_bias=temb, rows_per_batch=16 * H * W)
+    ref = _conv_ref(x, w, NF, H, W) + temb.repeat_interleave(16 * H * W, 0)
+    assert rel_l2(out.float(), ref) < 4e-3

