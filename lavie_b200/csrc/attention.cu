@@ -19,8 +19,9 @@ namespace {
 // accumulation in registers.  Two co-resident CTAs per SM (d = 40) overlap one CTA's softmax with the other's MMAs.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int ATT_M = 128;       // queries per CTA
-constexpr int ATT_N = 128;       // keys per tile
-constexpr int CHUNK_BYTES = 128 * 128;   // one 64-column (128-byte) slab of a 128-row tile
+constexpr int ATT_N = 64;        // keys per tile: small tiles -> 4 co-resident CTAs per SM hide the MMA round trips
+constexpr int CHUNK_BYTES = 128 * 128;      // one 64-column (128-byte) slab of a 128-row tile (Q, P)
+constexpr int KV_CHUNK_BYTES = ATT_N * 128;  // the same slab of a K / V tile
 
 struct AttnParams {
   int Sq, Sk, d, head_pitch, kv_batch_div, ldo;
@@ -31,12 +32,14 @@ struct AttnParams {
 template <int DK>
 struct AttnCfg {
   static constexpr int NC = (DK + 63) / 64;
-  static constexpr int SMEM = (3 * NC + 2) * CHUNK_BYTES + 1024 + 128;
-  static constexpr uint32_t TMEM_COLS = (ATT_N + DK) <= 256 ? 256 : 512;
+  static constexpr int P_CHUNKS = (ATT_N + 63) / 64;
+  static constexpr int SMEM = NC * CHUNK_BYTES + 2 * NC * KV_CHUNK_BYTES + P_CHUNKS * CHUNK_BYTES + 1024 + 128;
+  static constexpr uint32_t TMEM_COLS = (ATT_N + DK) <= 128 ? 128 : (ATT_N + DK) <= 256 ? 256 : 512;
+  static constexpr int MIN_BLOCKS = DK <= 64 ? 4 : (DK <= 96 ? 2 : 1);
 };
 
 template <int DK>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, AttnCfg<DK>::MIN_BLOCKS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   using Cfg = AttnCfg<DK>;
@@ -45,9 +48,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + NC * CHUNK_BYTES;
-  uint8_t* sV = sK + NC * CHUNK_BYTES;
-  uint8_t* sP = sV + NC * CHUNK_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * CHUNK_BYTES);
+  uint8_t* sV = sK + NC * KV_CHUNK_BYTES;
+  uint8_t* sP = sV + NC * KV_CHUNK_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_CHUNKS * CHUNK_BYTES);
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_k = bars + 1;
   uint64_t* bar_v = bars + 2;
@@ -77,16 +80,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;             // columns [0, 128)
-  const uint32_t tmem_o = tmem_base + ATT_N;     // columns [128, 128 + DK)
+  const uint32_t tmem_s = tmem_base;             // columns [0, ATT_N)
+  const uint32_t tmem_o = tmem_base + ATT_N;     // columns [ATT_N, ATT_N + DK)
 
   if (tid == 0) {
     mbar_expect_tx(bar_q, NC * CHUNK_BYTES);
     for (int c = 0; c < NC; ++c) tma_load_3d(sQ + c * CHUNK_BYTES, &tmap_q, bar_q, col0 + c * 64, q_tile * ATT_M, batch);
-    mbar_expect_tx(bar_k, NC * CHUNK_BYTES);
-    for (int c = 0; c < NC; ++c) tma_load_3d(sK + c * CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, 0, kv_batch);
-    mbar_expect_tx(bar_v, NC * CHUNK_BYTES);
-    for (int c = 0; c < NC; ++c) tma_load_3d(sV + c * CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, 0, kv_batch);
+    mbar_expect_tx(bar_k, NC * KV_CHUNK_BYTES);
+    for (int c = 0; c < NC; ++c) tma_load_3d(sK + c * KV_CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, 0, kv_batch);
+    mbar_expect_tx(bar_v, NC * KV_CHUNK_BYTES);
+    for (int c = 0; c < NC; ++c) tma_load_3d(sV + c * KV_CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, 0, kv_batch);
   }
 
   constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_M, ATT_N, 0, 0);
@@ -107,9 +110,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < DK / 16; ++kk) {
-        const uint32_t off = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
-        umma_bf16(tmem_s, umma_desc_sw128(smem_u32(sQ) + off, 16, 1024), umma_desc_sw128(smem_u32(sK) + off, 16, 1024),
-                  idesc_qk, kk != 0);
+        const uint32_t qoff = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
+        const uint32_t koff = (kk >> 2) * KV_CHUNK_BYTES + (kk & 3) * 32;
+        umma_bf16(tmem_s, umma_desc_sw128(smem_u32(sQ) + qoff, 16, 1024),
+                  umma_desc_sw128(smem_u32(sK) + koff, 16, 1024), idesc_qk, kk != 0);
       }
       umma_commit(bar_s);
     }
@@ -117,40 +121,62 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_wait(bar_s, ph);
     tc_fence_after();
     if (tid == 0 && j + 1 < n_kv) {       // K tile consumed -> prefetch the next one under the softmax
-      mbar_expect_tx(bar_k, NC * CHUNK_BYTES);
+      mbar_expect_tx(bar_k, NC * KV_CHUNK_BYTES);
       for (int c = 0; c < NC; ++c)
-        tma_load_3d(sK + c * CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, (j + 1) * ATT_N, kv_batch);
+        tma_load_3d(sK + c * KV_CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, (j + 1) * ATT_N, kv_batch);
     }
     __syncwarp();
 
-    // ---- online softmax, pass 1: row maximum over the valid keys ----
-    float mx = -INFINITY;
+    // ---- online softmax (full tiles take an unmasked path: ~2x fewer issue slots, this loop is issue-bound) ----
+    const bool full = (kv_len == ATT_N);           // CTA-uniform
+    float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll 1
     for (int c = 0; c < ATT_N / 32; ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
       tmem_wait_ld();
+      if (full) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if (c * 32 + e < kv_len) mx = fmaxf(mx, __uint_as_float(v[e]));
+        for (int e = 0; e < 32; e += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (c * 32 + e < kv_len) mx0 = fmaxf(mx0, __uint_as_float(v[e]));
+      }
     }
-    const float m_new = fmaxf(m_run, mx * p.scale_log2);
+    const float m_new = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
     const float alpha = fast_exp2(m_run - m_new);
     // ---- pass 2: p = exp2(s*scale - m), row sum, P -> smem (bf16, 128B swizzle, K-major) ----
-    float rs = 0.f;
+    float rs0 = 0.f, rs1 = 0.f;
     uint8_t* p_row = sP + tid * 128;
+    const float sc = p.scale_log2;
 #pragma unroll 1
     for (int c = 0; c < ATT_N / 32; ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
       tmem_wait_ld();
       uint32_t pk[16];
+      if (full) {
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        float p0 = (c * 32 + e < kv_len) ? fast_exp2(__uint_as_float(v[e]) * p.scale_log2 - m_new) : 0.f;
-        float p1 = (c * 32 + e + 1 < kv_len) ? fast_exp2(__uint_as_float(v[e + 1]) * p.scale_log2 - m_new) : 0.f;
-        rs += p0 + p1;
-        pk[e >> 1] = pack_bf16(p0, p1);
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sc, -m_new));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sc, -m_new));
+          rs0 += p0;
+          rs1 += p1;
+          pk[e >> 1] = pack_bf16(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = (c * 32 + e < kv_len) ? fast_exp2(fmaf(__uint_as_float(v[e]), sc, -m_new)) : 0.f;
+          const float p1 = (c * 32 + e + 1 < kv_len) ? fast_exp2(fmaf(__uint_as_float(v[e + 1]), sc, -m_new)) : 0.f;
+          rs0 += p0;
+          rs1 += p1;
+          pk[e >> 1] = pack_bf16(p0, p1);
+        }
       }
       uint8_t* chunk = p_row + (c >> 1) * CHUNK_BYTES;
 #pragma unroll
@@ -159,6 +185,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         *reinterpret_cast<uint4*>(chunk + c16 * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
       }
     }
+    const float rs = rs0 + rs1;
     l_run = l_run * alpha + rs;
     m_run = m_new;
     fence_proxy_async_smem();
@@ -172,7 +199,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int kk = 0; kk < nk; ++kk) {
         const uint32_t a_off = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
         umma_bf16(tmem_o, umma_desc_sw128(smem_u32(sP) + a_off, 16, 1024),
-                  umma_desc_sw128(smem_u32(sV) + kk * 2048, CHUNK_BYTES, 1024), idesc_pv, kk != 0);
+                  umma_desc_sw128(smem_u32(sV) + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv, kk != 0);
       }
       umma_commit(bar_o);
     }
@@ -180,9 +207,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_wait(bar_o, ph);
     tc_fence_after();
     if (tid == 0 && j + 1 < n_kv) {       // V tile consumed -> prefetch the next one
-      mbar_expect_tx(bar_v, NC * CHUNK_BYTES);
+      mbar_expect_tx(bar_v, NC * KV_CHUNK_BYTES);
       for (int c = 0; c < NC; ++c)
-        tma_load_3d(sV + c * CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, (j + 1) * ATT_N, kv_batch);
+        tma_load_3d(sV + c * KV_CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, (j + 1) * ATT_N, kv_batch);
     }
     __syncwarp();
 #pragma unroll
@@ -236,10 +263,10 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
   return lavie_check_launch("attn_fwd_kernel");
 }
 
-int make_qkv_map(CUtensorMap* map, const void* base, int ld, int cols, int S, int nbatch) {
+int make_qkv_map(CUtensorMap* map, const void* base, int ld, int cols, int S, int nbatch, int box_rows) {
   const uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(S), static_cast<uint64_t>(nbatch)};
   const uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(S) * ld * 2};
-  const uint32_t box[3] = {64, 128, 1};
+  const uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
   return lavie_make_tmap(map, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -361,11 +388,11 @@ extern "C" int lavie_attention_bf16(const void* q, int ldq, const void* k, int l
   p.o = static_cast<__nv_bfloat16*>(o);
   CUtensorMap mq, mk, mv;
   const int cols = heads * head_pitch;
-  int rc = make_qkv_map(&mq, q, ldq, cols, Sq, batch);
+  int rc = make_qkv_map(&mq, q, ldq, cols, Sq, batch, ATT_M);
   if (rc) return rc;
-  rc = make_qkv_map(&mk, k, ldk, cols, Sk, batch / kv_batch_div);
+  rc = make_qkv_map(&mk, k, ldk, cols, Sk, batch / kv_batch_div, ATT_N);
   if (rc) return rc;
-  rc = make_qkv_map(&mv, v, ldv, cols, Sk, batch / kv_batch_div);
+  rc = make_qkv_map(&mv, v, ldv, cols, Sk, batch / kv_batch_div, ATT_N);
   if (rc) return rc;
   switch (dk) {
     case 48: return launch_attn<48>(mq, mk, mv, p, batch, heads, stream);
