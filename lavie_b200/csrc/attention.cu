@@ -365,6 +365,205 @@ temporal_attn_kernel(const TempParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Temporal attention, F <= 16 frames: one warp per (batch item, pixel, head) on mma.sync m16n8k16 (the 16x16xd problem
+// is far below the 64-row minimum of tcgen05; the kernel is bound by streaming q/k/v once from HBM).
+// Q and K are loaded straight from global memory into the A / B fragment layouts; the contraction index is permuted
+// (identically for Q and K, so the dot products are unchanged) such that every lane reads 16 contiguous bytes.
+// The exp(S) registers are re-used as the A operand of P.V (accumulator layout == A layout); V goes through shared
+// memory for the transposing ldmatrix.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_addr));
+}
+// scale (q only) and rotate one bf16 pair; pair index pr < rot_pairs is rotated by the frame's angle
+__device__ __forceinline__ uint32_t scale_rope_pair(uint32_t w, float scale, bool rotate, const float* cs) {
+  float2 f = unpack_bf16(w);
+  f.x *= scale;
+  f.y *= scale;
+  if (rotate) {
+    const float c = cs[0], sn = cs[1];
+    const float x = f.x * c - f.y * sn, y = f.y * c + f.x * sn;
+    f.x = x;
+    f.y = y;
+  }
+  return pack_bf16(f.x, f.y);
+}
+
+template <int DP>   // head pitch (d rounded up to 16): 48, 64, 80, 96, 128, 160
+__global__ void __launch_bounds__(128)
+temporal_attn_mma_kernel(const TempParams p) {
+  constexpr int VP = DP + 8;                      // smem V row pitch (elements): conflict-free ldmatrix rows
+  constexpr int NB32 = DP / 32;                   // 32-column blocks (two k-steps each)
+  constexpr bool TAIL16 = (DP % 32) != 0;         // one trailing 16-column block
+  constexpr int KSTEPS = DP / 16;
+  __shared__ __align__(16) __nv_bfloat16 s_v[4][16 * VP];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int F = p.F;
+  __nv_bfloat16* sv = s_v[wib];
+  const long long warps_total = static_cast<long long>(gridDim.x) * 4;
+  for (long long item = static_cast<long long>(blockIdx.x) * 4 + wib; item < p.items; item += warps_total) {
+    const int h = static_cast<int>(item % p.heads);
+    const long long bp = item / p.heads;
+    const int pix = static_cast<int>(bp % p.HW);
+    const int b = static_cast<int>(bp / p.HW);
+    const size_t row0 = static_cast<size_t>(b) * F * p.HW + pix;             // frame f lives at row0 + f*HW
+    const __nv_bfloat16* base = p.qkv + row0 * p.ld + h * p.head_pitch;
+    const size_t fstride = static_cast<size_t>(p.HW) * p.ld;
+    const bool lo_ok = g < F, hi_ok = g + 8 < F;
+    const __nv_bfloat16* r_lo = base + static_cast<size_t>(g) * fstride;
+    const __nv_bfloat16* r_hi = base + static_cast<size_t>(g + 8) * fstride;
+
+    // ---- V tile -> shared memory (row-major [frame][DP], 16-byte vectors) ----
+    __syncwarp();
+    for (int i = lane; i < 16 * (DP / 8); i += 32) {
+      const int f = i / (DP / 8), vc = i - f * (DP / 8);
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (f < F) val = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(f) * fstride + p.v_off + vc * 8));
+      *reinterpret_cast<uint4*>(sv + f * VP + vc * 8) = val;
+    }
+
+    // ---- S = (scale * rope(Q)) . rope(K)^T ----
+    float s[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[nt][e] = 0.f;
+    const float* cs_lo = p.rope + static_cast<size_t>(g) * p.rot_pairs * 2;
+    const float* cs_hi = p.rope + static_cast<size_t>(g + 8) * p.rot_pairs * 2;
+#pragma unroll
+    for (int blk = 0; blk < NB32; ++blk) {
+      const int col = blk * 32 + t * 8;           // this lane's 8 contiguous channels of the 32-wide block
+      uint4 q_lo = make_uint4(0, 0, 0, 0), q_hi = q_lo, k_lo = q_lo, k_hi = q_lo;
+      if (lo_ok) {
+        q_lo = __ldg(reinterpret_cast<const uint4*>(r_lo + col));
+        k_lo = __ldg(reinterpret_cast<const uint4*>(r_lo + p.k_off + col));
+      }
+      if (hi_ok) {
+        q_hi = __ldg(reinterpret_cast<const uint4*>(r_hi + col));
+        k_hi = __ldg(reinterpret_cast<const uint4*>(r_hi + p.k_off + col));
+      }
+      uint32_t ql[4] = {q_lo.x, q_lo.y, q_lo.z, q_lo.w}, qh[4] = {q_hi.x, q_hi.y, q_hi.z, q_hi.w};
+      uint32_t kl[4] = {k_lo.x, k_lo.y, k_lo.z, k_lo.w}, kh[4] = {k_hi.x, k_hi.y, k_hi.z, k_hi.w};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int pr = (col >> 1) + w;            // bf16-pair index inside the head
+        const bool rot = pr < p.rot_pairs;
+        ql[w] = scale_rope_pair(ql[w], p.scale, rot && lo_ok, cs_lo + 2 * (rot ? pr : 0));
+        qh[w] = scale_rope_pair(qh[w], p.scale, rot && hi_ok, cs_hi + 2 * (rot ? pr : 0));
+        kl[w] = scale_rope_pair(kl[w], 1.f, rot && lo_ok, cs_lo + 2 * (rot ? pr : 0));
+        kh[w] = scale_rope_pair(kh[w], 1.f, rot && hi_ok, cs_hi + 2 * (rot ? pr : 0));
+      }
+      // words (0,1) form one k-step, words (2,3) the next: a0/a2 = row g, a1/a3 = row g+8; b0/b1 = key frame g (+8)
+      const uint32_t a_first[4] = {ql[0], qh[0], ql[1], qh[1]};
+      const uint32_t a_second[4] = {ql[2], qh[2], ql[3], qh[3]};
+      mma_bf16_16816(s[0], a_first, kl[0], kl[1]);
+      mma_bf16_16816(s[1], a_first, kh[0], kh[1]);
+      mma_bf16_16816(s[0], a_second, kl[2], kl[3]);
+      mma_bf16_16816(s[1], a_second, kh[2], kh[3]);
+    }
+    if (TAIL16) {
+      const int col = NB32 * 32 + t * 4;          // 4 contiguous channels of the trailing 16-wide block
+      uint2 q_lo = make_uint2(0, 0), q_hi = q_lo, k_lo = q_lo, k_hi = q_lo;
+      if (lo_ok) {
+        q_lo = __ldg(reinterpret_cast<const uint2*>(r_lo + col));
+        k_lo = __ldg(reinterpret_cast<const uint2*>(r_lo + p.k_off + col));
+      }
+      if (hi_ok) {
+        q_hi = __ldg(reinterpret_cast<const uint2*>(r_hi + col));
+        k_hi = __ldg(reinterpret_cast<const uint2*>(r_hi + p.k_off + col));
+      }
+      uint32_t ql[2] = {q_lo.x, q_lo.y}, qh[2] = {q_hi.x, q_hi.y}, kl[2] = {k_lo.x, k_lo.y}, kh[2] = {k_hi.x, k_hi.y};
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int pr = (col >> 1) + w;
+        const bool rot = pr < p.rot_pairs;
+        ql[w] = scale_rope_pair(ql[w], p.scale, rot && lo_ok, cs_lo + 2 * (rot ? pr : 0));
+        qh[w] = scale_rope_pair(qh[w], p.scale, rot && hi_ok, cs_hi + 2 * (rot ? pr : 0));
+        kl[w] = scale_rope_pair(kl[w], 1.f, rot && lo_ok, cs_lo + 2 * (rot ? pr : 0));
+        kh[w] = scale_rope_pair(kh[w], 1.f, rot && hi_ok, cs_hi + 2 * (rot ? pr : 0));
+      }
+      const uint32_t a_tail[4] = {ql[0], qh[0], ql[1], qh[1]};
+      mma_bf16_16816(s[0], a_tail, kl[0], kl[1]);
+      mma_bf16_16816(s[1], a_tail, kh[0], kh[1]);
+    }
+    (void)KSTEPS;
+
+    // ---- + rel-pos bias, mask padded frames, softmax over the key frames (a row lives in one lane quad) ----
+    const float* bias_h = p.bias + static_cast<size_t>(h) * F * F;
+    float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int jn = nt * 8 + 2 * t + e;
+        const bool jok = jn < F;
+        s[nt][e] = (jok && lo_ok) ? s[nt][e] + __ldg(bias_h + g * F + jn) : -INFINITY;
+        s[nt][2 + e] = (jok && hi_ok) ? s[nt][2 + e] + __ldg(bias_h + (g + 8) * F + jn) : -INFINITY;
+        mx_lo = fmaxf(mx_lo, s[nt][e]);
+        mx_hi = fmaxf(mx_hi, s[nt][2 + e]);
+      }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    if (!lo_ok) mx_lo = 0.f;
+    if (!hi_ok) mx_hi = 0.f;
+    float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[nt][e] = __expf(s[nt][e] - mx_lo);
+        s[nt][2 + e] = __expf(s[nt][2 + e] - mx_hi);
+        sum_lo += s[nt][e];
+        sum_hi += s[nt][2 + e];
+      }
+    sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
+    sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+    sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
+    sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+    const float inv_lo = lo_ok ? 1.f / sum_lo : 0.f, inv_hi = hi_ok ? 1.f / sum_hi : 0.f;
+    // probabilities -> A fragment of P.V (row g: a0 / a2, row g+8: a1 / a3)
+    const uint32_t pa[4] = {pack_bf16(s[0][0] * inv_lo, s[0][1] * inv_lo), pack_bf16(s[0][2] * inv_hi, s[0][3] * inv_hi),
+                            pack_bf16(s[1][0] * inv_lo, s[1][1] * inv_lo), pack_bf16(s[1][2] * inv_hi, s[1][3] * inv_hi)};
+
+    // ---- O = P . V, 8 output channels per mma ----
+    __syncwarp();                                   // V tile visible to the whole warp
+    const uint32_t sv_addr = smem_u32(sv) + ((lane & 15) * VP) * 2;   // ldmatrix row address: key frame (lane & 15)
+    __nv_bfloat16* o_lo = p.o + (row0 + static_cast<size_t>(g) * p.HW) * p.ldo + h * p.d;
+    __nv_bfloat16* o_hi = p.o + (row0 + static_cast<size_t>(g + 8) * p.HW) * p.ldo + h * p.d;
+#pragma unroll
+    for (int nt = 0; nt < DP / 8; ++nt) {
+      if (nt * 8 < p.d) {
+        uint32_t b0, b1;
+        ldmatrix_x2_trans(b0, b1, sv_addr + nt * 16);
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_16816(o, pa, b0, b1);
+        const int c = nt * 8 + 2 * t;
+        if (lo_ok) *reinterpret_cast<uint32_t*>(o_lo + c) = pack_bf16(o[0], o[1]);
+        if (hi_ok) *reinterpret_cast<uint32_t*>(o_hi + c) = pack_bf16(o[2], o[3]);
+      }
+    }
+  }
+}
+
+template <int DP>
+int launch_temporal_mma(const TempParams& p, cudaStream_t stream) {
+  long long blocks = (p.items + 3) / 4;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  temporal_attn_mma_kernel<DP><<<static_cast<int>(blocks), 128, 0, stream>>>(p);
+  return lavie_check_launch("temporal_attn_mma_kernel");
+}
+
 bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -422,6 +621,18 @@ extern "C" int lavie_temporal_attention_bf16(const void* qkv, int ld, int k_off,
   p.ldo = ldo; p.B = B; p.F = F; p.HW = HW; p.heads = heads; p.d = d; p.head_pitch = head_pitch;
   p.scale = scale; p.rope = rope; p.rot_pairs = rot_pairs; p.bias = bias;
   p.items = static_cast<long long>(B) * HW * heads;
+  if (F <= 16 && d % 8 == 0 && head_pitch == ((d + 15) & ~15) && ld % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0 &&
+      al16(qkv)) {
+    switch (head_pitch) {
+      case 48: return launch_temporal_mma<48>(p, stream);
+      case 64: return launch_temporal_mma<64>(p, stream);
+      case 80: return launch_temporal_mma<80>(p, stream);
+      case 96: return launch_temporal_mma<96>(p, stream);
+      case 128: return launch_temporal_mma<128>(p, stream);
+      case 160: return launch_temporal_mma<160>(p, stream);
+      default: break;     // fall through to the general kernel
+    }
+  }
   const int per_warp = (3 * F * (d + 1) + F * (F + 1)) * static_cast<int>(sizeof(float));
   int warps = 4;
   while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
