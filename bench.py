@@ -190,23 +190,35 @@ def run_b200(args):
     sched = DDIMSchedule(50)
     timesteps = sched.timesteps
 
-    # ---- partitioning ----
-    # N = 1: both CFG halves on one GPU.  N >= 2: the uncond / cond halves never interact inside the UNet, so each
-    # GPU pair splits them and exchanges the two noise predictions (2 x 655 KB) for the guidance combine.  Pairs beyond
-    # the first denoise independent videos (replicas of the 2-GPU path) until frame sharding lands.
+    # ---- partitioning: ONE video, strong scaling ----
+    # N = 1: both CFG halves on one GPU.  N >= 2: rank = half * P + shard.  The uncond / cond halves never interact
+    # inside the UNet, so they go to the two halves of the ranks; each half shards the 16 frames over P = N/2 GPUs
+    # (all-to-all around every temporal attention, all-reduce of the 5-D GroupNorm sums).  The latents stay
+    # frame-sharded across steps: after the forward the two ranks holding the same frames exchange their noise
+    # predictions (all_gather of 2 x 655/P KB) and each applies the fused guidance + DDIM update to its frames.
+    jobs, scaling = 1, "strong"
     if world == 1:
-        parallelism, scaling, jobs = "single", "strong", 1
-        pair_group, half = None, None
+        parallelism = "single"
+        pair_group, half, P, shard_idx = None, None, 1, 0
     else:
-        jobs = world // 2
-        parallelism = "cfg2" if world == 2 else f"cfg2 x {jobs} replicas"
-        scaling = "strong" if world == 2 else "weak"
-        half = rank % 2
+        if world % 2 or FRAMES % (world // 2):
+            raise SystemExit("--gpus must be 1, 2, 4 or 8")
+        P = world // 2
+        half, shard_idx = rank // P, rank % P
+        parallelism = "cfg2" if P == 1 else f"cfg2 x frames{P}"
+        frame_group = None
+        for hh in range(2):
+            g = dist.new_group(list(range(hh * P, hh * P + P)))
+            if hh == half:
+                frame_group = g
         pair_group = None
-        for j in range(jobs):
-            g = dist.new_group([2 * j, 2 * j + 1])
-            if rank // 2 == j:
+        for ss in range(P):
+            g = dist.new_group([ss, P + ss])
+            if ss == shard_idx:
                 pair_group = g
+        unet.set_frame_sharding(frame_group)
+        fl = FRAMES // P
+        latents0 = latents0[:, :, shard_idx * fl:(shard_idx + 1) * fl].contiguous()
 
     lat = latents0.to(dev)
     txt = text.to(dev)
@@ -282,19 +294,20 @@ def run_b200(args):
     d2h = out_host.numel() * 4
 
     # ---- roofline of the dominant kernel: per-launch CUDA events over one eager (un-graphed) step ----
+    # (every rank runs the eager pass: with frame sharding its collectives need the whole group; rank 0 reports)
     roofline, kernels = None, None
+    was = unet.use_cuda_graph
+    unet.use_cuda_graph = False
+    model_in = torch.cat([lat, lat]) if world == 1 else lat
+    text_in = txt if world == 1 else txt[half:half + 1]
+    unet(model_in, 500, encoder_hidden_states=text_in)                # eager warm-up
+    ops.PROFILE = []
+    unet(model_in, 500, encoder_hidden_states=text_in)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    unet.use_cuda_graph = was
     if rank == 0:
         peaks = measured_peaks()
-        was = unet.use_cuda_graph
-        unet.use_cuda_graph = False
-        model_in = torch.cat([lat, lat]) if world == 1 else lat
-        text_in = txt if world == 1 else txt[half:half + 1]
-        unet(model_in, 500, encoder_hidden_states=text_in)            # eager warm-up
-        ops.PROFILE = []
-        unet(model_in, 500, encoder_hidden_states=text_in)
-        torch.cuda.synchronize()
-        prof, ops.PROFILE = ops.PROFILE, None
-        unet.use_cuda_graph = was
         agg = {}
         for name, flops, nbytes, e0, e1, _tag in prof:
             a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
@@ -333,13 +346,16 @@ def run_b200(args):
                            "weights": "random-init (seeded), 909.1 M params", "cuda_graph": bool(unet.use_cuda_graph),
                            "l2": "no flush: one step streams 1.8 GB of weights and several GB of activations, "
                                  ">> 126 MB L2"},
-                "step_tflops": STEP_GFLOP * jobs / ms_per_step / 1e3 if world <= 2 else None,
+                "step_tflops": STEP_GFLOP / ms_per_step / 1e3,
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)        # captured NCCL graphs make process-group teardown hang; nothing left to clean up
 
 
 def main():

@@ -98,6 +98,24 @@ int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void* x1, int l
 int lavie_layernorm_bf16(const void* x, int ldx, const float* gamma, const float* beta, float eps, void* y, int ldy,
                          int rows, int C, lavie_stream_t stream);
 
+/* Frame sharding (one CFG half spread over P GPUs, F/P frames each).
+ *  - lavie_groupnorm_reduce: ordered sum of the stats partials -> sums[samples, groups, 2] (fp64); the caller
+ *    all-reduces `sums` across the frame shards (NCCL) and calls lavie_groupnorm_finalize_sums with the GLOBAL count.
+ *  - lavie_layernorm_scatter_bf16: LayerNorm whose output row (f, pixel) lands at (pixel / hwp, f, pixel % hwp):
+ *    the send buffer of the all-to-all that switches from frame sharding to pixel sharding before the temporal
+ *    attention (replaces the in-memory transpose attention.py:549-550).
+ *  - lavie_add_gathered_bf16: out[(f, pixel)] = res[(f, pixel)] + z[(pixel / hwp, f, pixel % hwp)]: residual add over
+ *    the receive buffer of the all-to-all back (attention.py:554-555). */
+int lavie_groupnorm_reduce(const float* partial, int samples, int chunks, int groups, double* sums,
+                           lavie_stream_t stream);
+int lavie_groupnorm_finalize_sums(const double* sums, int samples, int groups, int C, long long count_per_group,
+                                  const float* gamma, const float* beta, float eps, float* scale_shift,
+                                  lavie_stream_t stream);
+int lavie_layernorm_scatter_bf16(const void* x, int ldx, const float* gamma, const float* beta, float eps, void* y,
+                                 int ldy, int rows, int C, int hw, int hwp, lavie_stream_t stream);
+int lavie_add_gathered_bf16(const void* res, int ldr, const void* z, int ldz, void* out, int ldo, int rows, int C,
+                            int hw, int hwp, lavie_stream_t stream);
+
 /* softmax(q k^T * scale) v per (batch, head)  (CrossAttention._attention, attention.py:209-239).
  * q rows = batch*Sq, k/v rows = (batch / kv_batch_div)*Sk (kv_batch_div = F shares the text keys across frames,
  * attention.py:364).  Head h occupies columns [h*head_pitch, h*head_pitch + d) of q/k/v (pitch >= d rounded up to 16,

@@ -142,7 +142,8 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __n
 template <int MAX_VEC>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy, int rows, int C) {
+                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy, int rows, int C,
+                 int perm_hw, int perm_hwp) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -179,7 +180,16 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __re
     }
   }
   const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(C) + eps);
-  __nv_bfloat16* dst = y + static_cast<size_t>(warp) * ldy;
+  // Optional scatter for frame sharding: source row (f, pixel) of a [F_loc, HW] shard goes to row
+  // (pixel_block * F_loc + f) * HWp + pixel_in_block, i.e. the send buffer of the all-to-all that turns frame
+  // sharding into pixel sharding around the temporal attention.
+  int drow = warp;
+  if (perm_hw > 0) {
+    const int f = warp / perm_hw, pix = warp - f * perm_hw;
+    const int blk = pix / perm_hwp;
+    drow = (blk * (rows / perm_hw) + f) * perm_hwp + (pix - blk * perm_hwp);
+  }
+  __nv_bfloat16* dst = y + static_cast<size_t>(drow) * ldy;
 #pragma unroll
   for (int i = 0; i < MAX_VEC; ++i) {
     const int v = lane + i * 32;
@@ -268,8 +278,9 @@ extern "C" int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void
   return lavie_check_launch("gn_apply_kernel");
 }
 
-extern "C" int lavie_layernorm_bf16(const void* x, int ldx, const float* gamma, const float* beta, float eps, void* y,
-                                    int ldy, int rows, int C, cudaStream_t stream) {
+namespace {
+int layernorm_impl(const void* x, int ldx, const float* gamma, const float* beta, float eps, void* y, int ldy, int rows,
+                   int C, int perm_hw, int perm_hwp, cudaStream_t stream) {
   LAVIE_REQUIRE(C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldy % 8 == 0, LAVIE_ERR_SHAPE,
                 "layernorm: C=%d must be a multiple of 8 and <= 2048", C);
   LAVIE_REQUIRE(al16(x) && al16(y) && al16(gamma) && al16(beta), LAVIE_ERR_ALIGN, "layernorm: alignment");
@@ -278,8 +289,123 @@ extern "C" int lavie_layernorm_bf16(const void* x, int ldx, const float* gamma, 
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   const int nvec = C >> 3;
-  if (nvec <= 64) layernorm_kernel<2><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C);
-  else if (nvec <= 160) layernorm_kernel<5><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C);
-  else layernorm_kernel<8><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C);
+  if (nvec <= 64)
+    layernorm_kernel<2><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C, perm_hw, perm_hwp);
+  else if (nvec <= 160)
+    layernorm_kernel<5><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C, perm_hw, perm_hwp);
+  else
+    layernorm_kernel<8><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C, perm_hw, perm_hwp);
   return lavie_check_launch("layernorm_kernel");
 }
+
+// out[(f, blk*HWp + j)] = res[(f, blk*HWp + j)] + z[(blk, f, j)]: the receive side of the all-to-all back to frame sharding
+__global__ void __launch_bounds__(256)
+add_gathered_kernel(const __nv_bfloat16* __restrict__ res, int ldr, const __nv_bfloat16* __restrict__ z, int ldz,
+                    __nv_bfloat16* __restrict__ out, int ldo, int rows, int C, int hw, int hwp) {
+  const int nvec = C >> 3;
+  const int f_loc = rows / hw;
+  const long long total = static_cast<long long>(rows) * nvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / nvec), v = static_cast<int>(i % nvec);
+    const int f = row / hw, pix = row - f * hw;
+    const int blk = pix / hwp;
+    const size_t zrow = (static_cast<size_t>(blk) * f_loc + f) * hwp + (pix - blk * hwp);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(res + static_cast<size_t>(row) * ldr + v * 8));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(z + zrow * ldz + v * 8));
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x = unpack_bf16(aw[e]), y = unpack_bf16(bw[e]);
+      o[e] = pack_bf16(x.x + y.x, x.y + y.y);
+    }
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ldo + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// sums[sample][group][2] (fp64) = ordered sum of the chunk partials: what gets all-reduced across frame shards
+__global__ void gn_reduce_kernel(const float* __restrict__ partial, int chunks, int groups, double* __restrict__ sums) {
+  const int sample = blockIdx.x;
+  const int sub = threadIdx.x & 7;
+  for (int g = threadIdx.x >> 3; g < groups; g += blockDim.x >> 3) {
+    double a = 0.0, b = 0.0;
+    for (int k = sub; k < chunks; k += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(partial + ((static_cast<size_t>(sample) * chunks + k) * groups + g) * 2);
+      a += v.x;
+      b += v.y;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (sub == 0) {
+      sums[(static_cast<size_t>(sample) * groups + g) * 2] = a;
+      sums[(static_cast<size_t>(sample) * groups + g) * 2 + 1] = b;
+    }
+  }
+}
+
+__global__ void gn_finalize_sums_kernel(const double* __restrict__ sums, int groups, int C, double inv_count,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                        float* __restrict__ scale_shift) {
+  const int sample = blockIdx.x;
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double mean = sums[(static_cast<size_t>(sample) * groups + g) * 2] * inv_count;
+    double var = sums[(static_cast<size_t>(sample) * groups + g) * 2 + 1] * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = rstd * gamma[c];
+    float* dst = scale_shift + (static_cast<size_t>(sample) * C + c) * 2;
+    dst[0] = sc;
+    dst[1] = beta[c] - static_cast<float>(mean) * sc;
+  }
+}
+}  // namespace
+
+extern "C" int lavie_layernorm_bf16(const void* x, int ldx, const float* gamma, const float* beta, float eps, void* y,
+                                    int ldy, int rows, int C, cudaStream_t stream) {
+  return layernorm_impl(x, ldx, gamma, beta, eps, y, ldy, rows, C, 0, 0, stream);
+}
+
+extern "C" int lavie_layernorm_scatter_bf16(const void* x, int ldx, const float* gamma, const float* beta, float eps,
+                                            void* y, int ldy, int rows, int C, int hw, int hwp, cudaStream_t stream) {
+  LAVIE_REQUIRE(hw > 0 && hwp > 0 && hw % hwp == 0 && rows % hw == 0, LAVIE_ERR_SHAPE,
+                "layernorm_scatter: rows=%d must be whole frames of hw=%d, hw %% hwp=%d == 0", rows, hw, hwp);
+  return layernorm_impl(x, ldx, gamma, beta, eps, y, ldy, rows, C, hw, hwp, stream);
+}
+
+extern "C" int lavie_add_gathered_bf16(const void* res, int ldr, const void* z, int ldz, void* out, int ldo, int rows,
+                                       int C, int hw, int hwp, cudaStream_t stream) {
+  LAVIE_REQUIRE(C % 8 == 0 && ldr % 8 == 0 && ldz % 8 == 0 && ldo % 8 == 0 && hw > 0 && hwp > 0 && hw % hwp == 0 &&
+                    rows % hw == 0,
+                LAVIE_ERR_SHAPE, "add_gathered: bad shape rows=%d C=%d hw=%d hwp=%d", rows, C, hw, hwp);
+  LAVIE_REQUIRE(al16(res) && al16(z) && al16(out), LAVIE_ERR_ALIGN, "add_gathered: alignment");
+  const long long total = static_cast<long long>(rows) * (C >> 3);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  add_gathered_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(res), ldr, static_cast<const __nv_bfloat16*>(z), ldz,
+      static_cast<__nv_bfloat16*>(out), ldo, rows, C, hw, hwp);
+  return lavie_check_launch("add_gathered_kernel");
+}
+
+extern "C" int lavie_groupnorm_reduce(const float* partial, int samples, int chunks, int groups, double* sums,
+                                      cudaStream_t stream) {
+  LAVIE_REQUIRE(groups <= 64 && groups % 4 == 0 && samples > 0 && chunks > 0, LAVIE_ERR_SHAPE, "groupnorm_reduce: shape");
+  gn_reduce_kernel<<<samples, 256, 0, stream>>>(partial, chunks, groups, sums);
+  return lavie_check_launch("gn_reduce_kernel");
+}
+
+extern "C" int lavie_groupnorm_finalize_sums(const double* sums, int samples, int groups, int C,
+                                             long long count_per_group, const float* gamma, const float* beta,
+                                             float eps, float* scale_shift, cudaStream_t stream) {
+  LAVIE_REQUIRE(groups <= 64 && C % groups == 0 && count_per_group > 0, LAVIE_ERR_SHAPE, "groupnorm_finalize_sums: shape");
+  gn_finalize_sums_kernel<<<samples, 256, 0, stream>>>(sums, groups, C, 1.0 / static_cast<double>(count_per_group), gamma,
+                                                       beta, eps, scale_shift);
+  return lavie_check_launch("gn_finalize_sums_kernel");
+}
+

@@ -189,6 +189,64 @@ def groupnorm_scale_shift(x: torch.Tensor, samples: int, rows_per_sample: int, g
     return ss
 
 
+def groupnorm_sums(x: torch.Tensor, samples: int, rows_per_sample: int, groups: int = 32,
+                   x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Local (sum, sum of squares) per (sample, group) as fp64 [samples, groups, 2]: the quantity frame shards all-reduce."""
+    lib = _lib.load()
+    rows, c0, ld0 = _rows2d(x)
+    c1, ld1 = 0, 0
+    if x2 is not None:
+        _, c1, ld1 = _rows2d(x2)
+    assert rows == samples * rows_per_sample
+    chunks = lib.lavie_groupnorm_chunks(samples, rows_per_sample)
+    partial = torch.empty((samples, chunks, groups, 2), dtype=F32, device=x.device)
+    with _Launch("lavie_groupnorm_stats", 0.0, 2.0 * rows * (c0 + c1), f"gn_stats rows={rows} C={c0 + c1} samples={samples}"):
+        check(lib.lavie_groupnorm_stats(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample, groups,
+                                        partial.data_ptr(), _stream()), "lavie_groupnorm_stats")
+    sums = torch.empty((samples, groups, 2), dtype=torch.float64, device=x.device)
+    with _Launch("lavie_groupnorm_reduce"):
+        check(lib.lavie_groupnorm_reduce(partial.data_ptr(), samples, chunks, groups, sums.data_ptr(), _stream()),
+              "lavie_groupnorm_reduce")
+    return sums
+
+
+def groupnorm_finalize_sums(sums: torch.Tensor, C: int, count_per_group: int, gamma: torch.Tensor, beta: torch.Tensor,
+                            eps: float) -> torch.Tensor:
+    lib = _lib.load()
+    samples, groups, _ = sums.shape
+    assert sums.dtype == torch.float64 and sums.is_contiguous()
+    ss = torch.empty((samples, C, 2), dtype=F32, device=sums.device)
+    with _Launch("lavie_groupnorm_finalize_sums"):
+        check(lib.lavie_groupnorm_finalize_sums(sums.data_ptr(), samples, groups, C, count_per_group, gamma.data_ptr(),
+                                                beta.data_ptr(), eps, ss.data_ptr(), _stream()),
+              "lavie_groupnorm_finalize_sums")
+    return ss
+
+
+def layernorm_scatter(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, hw: int, hwp: int, eps: float = 1e-5):
+    """LayerNorm + scatter rows (f, pixel) -> (pixel // hwp, f, pixel % hwp) (all-to-all send layout)."""
+    lib = _lib.load()
+    rows, C, ldx = _rows2d(x)
+    out = torch.empty((rows, C), dtype=BF16, device=x.device)
+    with _Launch("lavie_layernorm_bf16", 0.0, 4.0 * rows * C, f"ln_scatter rows={rows} C={C}"):
+        check(lib.lavie_layernorm_scatter_bf16(x.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(),
+                                               C, rows, C, hw, hwp, _stream()), "lavie_layernorm_scatter_bf16")
+    return out
+
+
+def add_gathered(res: torch.Tensor, z: torch.Tensor, hw: int, hwp: int):
+    """res[(f, pixel)] + z[(pixel // hwp, f, pixel % hwp)] (all-to-all receive layout) -> new tensor."""
+    lib = _lib.load()
+    rows, C, ldr = _rows2d(res)
+    rz, Cz, ldz = _rows2d(z)
+    assert rz == rows and Cz == C
+    out = torch.empty((rows, C), dtype=BF16, device=res.device)
+    with _Launch("lavie_add_gathered_bf16", 0.0, 6.0 * rows * C):
+        check(lib.lavie_add_gathered_bf16(res.data_ptr(), ldr, z.data_ptr(), ldz, out.data_ptr(), C, rows, C, hw, hwp,
+                                          _stream()), "lavie_add_gathered_bf16")
+    return out
+
+
 def groupnorm_apply(x: torch.Tensor, scale_shift: torch.Tensor, samples: int, rows_per_sample: int, silu: bool,
                     x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
     lib = _lib.load()

@@ -106,6 +106,7 @@ class UNet3DConditionModel(nn.Module):
         for prefix, names in groups.items():
             _install(self, prefix, _leaf_for(prefix, names))
         self._packed = None
+        self._shard = None            # (process group, P, index) when the frames of one CFG half span P GPUs
         self._graphs: Dict[tuple, dict] = {}
         self._tables: Dict[tuple, tuple] = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
@@ -142,6 +143,37 @@ class UNet3DConditionModel(nn.Module):
         out = super()._apply(fn, *a, **kw)
         self._invalidate()
         return out
+
+    def set_frame_sharding(self, group=None):
+        """Frame sharding: this rank holds F/P consecutive frames of the video; `group` is the
+        torch.distributed process group of the P ranks that share one CFG half (rank order = frame order).
+        Per-frame work (convs, per-frame GroupNorm, LayerNorm, spatial / cross attention, FF) runs shard-local;
+        5-D GroupNorm statistics are all-reduced and the tokens are exchanged all-to-all around every temporal
+        attention.  `None` switches it off."""
+        if group is None:
+            self._shard = None
+        else:
+            import torch.distributed as dist
+            P = dist.get_world_size(group)
+            self._shard = None if P == 1 else (group, P, dist.get_rank(group))
+        self._graphs.clear()
+
+    def _gn5(self, x, x2, B, rows_local, gamma, beta, eps, silu):
+        """nn.GroupNorm on the 5-D tensor: statistics span ALL frames (resnet.py:180,191; unet.py:504)."""
+        if self._shard is None:
+            return ops.groupnorm(x, B, rows_local, gamma, beta, eps, silu=silu, x2=x2)
+        ss = self._gn5_scale_shift(x, x2, B, rows_local, gamma, beta, eps)
+        return ops.groupnorm_apply(x, ss, B, rows_local, silu, x2=x2)
+
+    def _gn5_scale_shift(self, x, x2, B, rows_local, gamma, beta, eps):
+        if self._shard is None:
+            return ops.groupnorm_scale_shift(x, B, rows_local, gamma, beta, eps, x2=x2)
+        import torch.distributed as dist
+        group, P, _ = self._shard
+        C = x.shape[1] + (x2.shape[1] if x2 is not None else 0)
+        sums = ops.groupnorm_sums(x, B, rows_local, x2=x2)                  # fp64 [B, 32, 2]
+        dist.all_reduce(sums, group=group)                                   # 512 B per call
+        return ops.groupnorm_finalize_sums(sums, C, rows_local * P * (C // 32), gamma, beta, eps)
 
     def init_synthetic(self, seed: int = 0):
         """Deterministic random-init weights (lavie_b200.synthetic), loaded through the normal state_dict path."""
@@ -263,10 +295,10 @@ class UNet3DConditionModel(nn.Module):
         r = self._packed[p]
         NF, rps = B * Fr, Fr * H * W
         eps = self.cfg.norm_eps
-        h = ops.groupnorm(x, B, rps, r["g1"], r["b1"], eps, silu=True, x2=x2)
+        h = self._gn5(x, x2, B, rps, r["g1"], r["b1"], eps, True)
         off, cout = self._packed["temb_slices"][p]
         h = ops.conv3x3(h, NF, H, W, r["w1"], bias=r["cb1"], row_bias=temb_all[:, off:off + cout], rows_per_batch=rps)
-        h = ops.groupnorm(h, B, rps, r["g2"], r["b2"], eps, silu=True)
+        h = self._gn5(h, None, B, rps, r["g2"], r["b2"], eps, True)
         if "wsc" in r:
             sc = ops.gemm(x, r["wsc"], a2=x2, bias=r["bsc"])
         else:
@@ -294,11 +326,28 @@ class UNet3DConditionModel(nn.Module):
                           kv_batch_div=Fr)
         tok = ops.gemm(a, t["attn2_wo"], bias=t["attn2_bo"], residual=tok)
         # temporal attention: frames read in place with a row stride of HW (no (b f) d c <-> (b d) f c copies)
-        n = ops.layernorm(tok, t["norm_temp_g"], t["norm_temp_b"])
-        qkv = ops.gemm(n, t["attn_temp_qkv"])
-        rope, bias = self._frame_tables(p, Fr)
-        a = ops.temporal_attention(qkv, B, Fr, HW, heads, d, pitch, rope, bias)
-        tok = ops.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"], residual=tok)
+        if self._shard is None:
+            n = ops.layernorm(tok, t["norm_temp_g"], t["norm_temp_b"])
+            qkv = ops.gemm(n, t["attn_temp_qkv"])
+            rope, bias = self._frame_tables(p, Fr)
+            a = ops.temporal_attention(qkv, B, Fr, HW, heads, d, pitch, rope, bias)
+            tok = ops.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"], residual=tok)
+        else:
+            # frame-sharded: all-to-all to pixel sharding (every rank gets ALL frames of HW/P pixels), attend, and back
+            import torch.distributed as dist
+            group, P, _ = self._shard
+            assert B == 1 and HW % P == 0, "frame sharding runs one CFG half per rank and needs H*W divisible by P"
+            hwp = HW // P
+            send = ops.layernorm_scatter(tok, t["norm_temp_g"], t["norm_temp_b"], HW, hwp)   # [P, F_loc, hwp, C]
+            recv = torch.empty_like(send)                                                     # [F, hwp, C]
+            dist.all_to_all_single(recv, send, group=group)
+            qkv = ops.gemm(recv, t["attn_temp_qkv"])
+            rope, bias = self._frame_tables(p, Fr * P)
+            a = ops.temporal_attention(qkv, 1, Fr * P, hwp, heads, d, pitch, rope, bias)
+            y = ops.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"])                        # [F, hwp, C] = P chunks
+            back = torch.empty_like(y)                                                        # [P, F_loc, hwp, C]
+            dist.all_to_all_single(back, y, group=group)
+            tok = ops.add_gathered(tok, back, HW, hwp)
         # GEGLU feed-forward
         n = ops.layernorm(tok, t["norm3_g"], t["norm3_b"])
         g = ops.gemm(n, t["ff1_w"], bias=t["ff1_b"], geglu=True)
@@ -361,7 +410,7 @@ class UNet3DConditionModel(nn.Module):
                 x = ops.upsample_nearest2x(x, B * Fr, h, w)
                 h, w = 2 * h, 2 * w
                 x = ops.conv3x3(x, B * Fr, h, w, wu, bias=bu)
-        ss = ops.groupnorm_scale_shift(x, B, Fr * h * w, P["norm_out"][0], P["norm_out"][1], cfg.norm_eps)
+        ss = self._gn5_scale_shift(x, None, B, Fr * h * w, P["norm_out"][0], P["norm_out"][1], cfg.norm_eps)
         return ops.conv_out(x, ss, B, Fr, h, w, P["conv_out"][0], P["conv_out"][1])
 
     # ------------------------------------------------------------------ public forward
@@ -425,6 +474,7 @@ class UNet3DConditionModel(nn.Module):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             before = ops.LAUNCHES
+            # with frame sharding the NCCL collectives of the step are captured too (same sequence on every rank)
             with torch.cuda.graph(graph):
                 g["out"] = self._step(g["x"], g["t"], g["txt"])
             g["launches"] = ops.LAUNCHES - before      # kernel nodes of ours in the captured step
