@@ -73,11 +73,12 @@ template <int BLOCK_N>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;   // staged bias (or the two possible row_bias rows) of the tile
-  static constexpr int MAX_SMEM = 227 * 1024 - 2048 - BIAS_BYTES;
+  static constexpr int BIAS_BYTES = 0;
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * 32 * 36 * 4;   // per-warp 32x32 fp32 transpose buffers (pitch 36)
+  static constexpr int MAX_SMEM = 227 * 1024 - 2048 - BIAS_BYTES - EPI_BYTES;
   static constexpr int STAGES_RAW = MAX_SMEM / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BIAS_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // ---- cluster / cta_group::2 PTX ----
@@ -171,8 +172,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_bias = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES);          // [2][BLOCK_N]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES + L::BIAS_BYTES);
+  float* s_epi = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES + L::BIAS_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES + L::BIAS_BYTES + L::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]  (only the leader's are waited on)
@@ -313,36 +314,64 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       const int row = row0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       const int n0 = it.n_blk * BLOCK_N;
-      // ---- stage the tile's bias (and the <= 2 time-embedding rows its 128 rows can touch) in smem ----
-      const int batch0 = p.row_bias ? row0 / p.rows_per_batch : 0;
-      const int last_row = min(row0 + BLOCK_M, p.M) - 1;
-      const bool rb_smem = p.row_bias && (last_row / p.rows_per_batch - batch0) <= 1;
-      epi_bar_sync();                              // everyone is done reading the previous tile's staged bias
-      if (p.splits == 1) {
-        for (int i = et; i < 2 * BLOCK_N; i += 32 * NUM_EPI_WARPS) {
-          const int which = i / BLOCK_N, c = i - which * BLOCK_N;
-          float v = 0.f;
-          if (n0 + c < p.N) {
-            if (which == 0 && p.bias) v = p.bias[n0 + c];
-            if (rb_smem) {
-              const int b = batch0 + which;
-              if (static_cast<long long>(b) * p.rows_per_batch < p.M)
-                v += p.row_bias[static_cast<size_t>(b) * p.ld_row_bias + n0 + c] + (which == 1 && p.bias ? p.bias[n0 + c] : 0.f);
-            }
-          }
-          s_bias[i] = v;
-        }
-      }
-      epi_bar_sync();
-      const float* sb = s_bias + ((rb_smem && row_ok && (row / p.rows_per_batch) != batch0) ? BLOCK_N : 0);
-      const float* rb_glob = (p.row_bias && !rb_smem && row_ok)
-                                 ? p.row_bias + static_cast<size_t>(row / p.rows_per_batch) * p.ld_row_bias
-                                 : nullptr;
-      const bool add_bias = p.bias != nullptr || rb_smem;
+      // bias / time-embedding rows are read straight from global memory in the quad mapping (8 values per lane and
+      // chunk, L1-resident): no shared-memory staging and no block-wide barrier per tile
+      const int n_out_limit = p.geglu ? p.N / 2 : p.N;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+
+      // Coalescing: tcgen05.ld hands every lane one accumulator ROW; storing it directly would touch 32 different
+      // 128-byte lines per instruction.  Each warp therefore transposes its 32x32 fp32 chunk through a private
+      // shared-memory buffer (pitch 36 words: conflict-free both ways) into a "quad" mapping -- lane = (row r8 =
+      // lane/4, 8-column piece = lane%4) -- where one instruction covers 8 rows x 64 contiguous bytes, for the
+      // residual loads as well as the bf16 stores.
+      float* stage_buf = s_epi + ew * (32 * 36);
+      const int qrow = lane >> 2, piece = lane & 3;
+      auto emit_chunk = [&](const float (&f)[32], int col_out0, bool add_b, const uint4 (&rq)[4], bool has_res) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stage_buf + lane * 36 + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int r = 8 * s4 + qrow;
+          const int grow = row0 + q * 32 + r;
+          const int col = col_out0 + piece * 8;
+          const float4 v0 = *reinterpret_cast<const float4*>(stage_buf + r * 36 + piece * 8);
+          const float4 v1 = *reinterpret_cast<const float4*>(stage_buf + r * 36 + piece * 8 + 4);
+          float o[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          if (grow < p.M && col < n_out_limit && !(p.debug & 16)) {
+            if (add_b && p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+              o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+            }
+            if (add_b && p.row_bias) {
+              const float* rbp = p.row_bias + static_cast<size_t>(grow / p.rows_per_batch) * p.ld_row_bias + col;
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(rbp));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
+              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+              o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+            }
+            if (has_res) {
+              const float2 r0 = unpack_bf16(rq[s4].x), r1 = unpack_bf16(rq[s4].y), r2 = unpack_bf16(rq[s4].z),
+                           r3 = unpack_bf16(rq[s4].w);
+              o[0] += r0.x; o[1] += r0.y; o[2] += r1.x; o[3] += r1.y;
+              o[4] += r2.x; o[5] += r2.y; o[6] += r3.x; o[7] += r3.y;
+            }
+            uint4 pk;
+            pk.x = pack_bf16(o[0], o[1]);
+            pk.y = pack_bf16(o[2], o[3]);
+            pk.z = pack_bf16(o[4], o[5]);
+            pk.w = pack_bf16(o[6], o[7]);
+            *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(grow) * p.ldo + col) = pk;
+          }
+        }
+        __syncwarp();
+      };
 
       if (p.splits > 1) {
         // fp32 partials for the ordered split-K reduction
@@ -361,18 +390,21 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
           }
         }
       } else if (!p.geglu) {
-        const __nv_bfloat16* res_row = (p.residual && row_ok) ? p.residual + static_cast<size_t>(row) * p.ldr : nullptr;
         uint4 rpre[4];
         auto prefetch_res = [&](int c) {
-          const int col0 = n0 + c * 32;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            rpre[j] = (res_row && col0 + 8 * j < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row + col0 + 8 * j))
-                                                      : make_uint4(0, 0, 0, 0);
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int grow = row0 + q * 32 + 8 * s4 + qrow;
+            const int col = n0 + c * 32 + piece * 8;
+            rpre[s4] = (p.residual && grow < p.M && col < p.N && !(p.debug & 64))
+                           ? __ldg(reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(grow) * p.ldr + col))
+                           : make_uint4(0, 0, 0, 0);
+          }
         };
         prefetch_res(chalf);
 #pragma unroll 1
         for (int c = chalf; c < BLOCK_N / 32; c += 2) {
+          if (p.debug & 256) continue;
           uint32_t v[32];
           tmem_ld_32x32(t_row + c * 32, v);
           uint4 rcur[4];
@@ -380,75 +412,32 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
           for (int j = 0; j < 4; ++j) rcur[j] = rpre[j];
           if (c + 2 < BLOCK_N / 32) prefetch_res(c + 2);        // next chunk's residual in flight under this one
           tmem_wait_ld();
-          const int col0 = n0 + c * 32;
-          if (row_ok && col0 < p.N) {
-            __nv_bfloat16* dst = p.out + static_cast<size_t>(row) * p.ldo + col0;
+          if (p.debug & 128) continue;
+          float f[32];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (col0 + 8 * j < p.N) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
-                if (add_bias) {
-                  const float4 b0 = *reinterpret_cast<const float4*>(sb + c * 32 + 8 * j);
-                  const float4 b1 = *reinterpret_cast<const float4*>(sb + c * 32 + 8 * j + 4);
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                }
-                if (rb_glob) {
-                  const float4 b0 = *reinterpret_cast<const float4*>(rb_glob + col0 + 8 * j);
-                  const float4 b1 = *reinterpret_cast<const float4*>(rb_glob + col0 + 8 * j + 4);
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                }
-                if (res_row) {
-                  const float2 r0 = unpack_bf16(rcur[j].x), r1 = unpack_bf16(rcur[j].y), r2 = unpack_bf16(rcur[j].z),
-                               r3 = unpack_bf16(rcur[j].w);
-                  f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
-                  f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
-                }
-                uint4 o;
-                o.x = pack_bf16(f[0], f[1]);
-                o.y = pack_bf16(f[2], f[3]);
-                o.z = pack_bf16(f[4], f[5]);
-                o.w = pack_bf16(f[6], f[7]);
-                *reinterpret_cast<uint4*>(dst + 8 * j) = o;
-              }
-            }
-          }
+          for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+          emit_chunk(f, n0 + c * 32, true, rcur, p.residual != nullptr);
         }
       } else {
         // GEGLU: value columns [0, BN/2), gate columns [BN/2, BN) of the same tile (weights interleaved on the
         // host); out[:, n_blk*BN/2 + j] = (value + b) * gelu_erf(gate + b')   (diffusers GEGLU, mirror at
         // vsr/models/diffusers_attention.py:811-822)
         constexpr int HALF = BLOCK_N / 2;
+        const uint4 nores[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
 #pragma unroll 1
         for (int c = chalf; c < HALF / 32; c += 2) {
           uint32_t v[32], g[32];
           tmem_ld_32x32(t_row + c * 32, v);
           tmem_ld_32x32(t_row + HALF + c * 32, g);
           tmem_wait_ld();
-          const int colv = n0 + c * 32;                        // column in the interleaved weight space
-          const int colo = it.n_blk * HALF + c * 32;           // output column
-          if (row_ok && colv < p.N) {
-            __nv_bfloat16* dst = p.out + static_cast<size_t>(row) * p.ldo + colo;
+          float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float val = __uint_as_float(v[j + e]) + s_bias[c * 32 + j + e];
-                const float gate = __uint_as_float(g[j + e]) + s_bias[HALF + c * 32 + j + e];
-                f[e] = val * gelu_erf_f(gate);
-              }
-              uint4 o;
-              o.x = pack_bf16(f[0], f[1]);
-              o.y = pack_bf16(f[2], f[3]);
-              o.z = pack_bf16(f[4], f[5]);
-              o.w = pack_bf16(f[6], f[7]);
-              *reinterpret_cast<uint4*>(dst + j) = o;
-            }
+          for (int e = 0; e < 32; ++e) {
+            const float val = __uint_as_float(v[e]) + (p.bias ? __ldg(p.bias + n0 + c * 32 + e) : 0.f);
+            const float gate = __uint_as_float(g[e]) + (p.bias ? __ldg(p.bias + n0 + HALF + c * 32 + e) : 0.f);
+            f[e] = val * gelu_erf_f(gate);
           }
+          emit_chunk(f, it.n_blk * HALF + c * 32, false, nores, false);
         }
       }
       tc_fence_before();
