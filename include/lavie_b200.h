@@ -65,11 +65,12 @@ int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1, int lda1, 
                     int ldo, int M, int N, const lavie_epilogue* ep, int block_n, void* workspace,
                     size_t workspace_bytes, lavie_stream_t stream);
 
-/* 3x3 stride-1 pad-1 InflatedConv3d (resnet.py:13-21) as implicit GEMM over a CONTIGUOUS channels-last map
- * x[NF, H, W, C]; w is [N, 3, 3, C].  lavie_conv3x3_supported() tells whether the TMA path accepts the geometry
- * (C % 64 == 0, W in {8,16,32,64,128}); otherwise use lavie_im2col3x3_bf16 + lavie_gemm_bf16. */
+/* 3x3 pad-1 InflatedConv3d, stride 1 or 2 (resnet.py:13-21; Downsample3D :102-110) as implicit GEMM over a CONTIGUOUS
+ * channels-last map x[NF, H, W, C]; w is [N, 3, 3, C]; out has NF*Ho*Wo rows.  The A operand is fetched with
+ * im2col-mode TMA (the hardware walks the output pixels and zero-fills the halo), so any H, W works;
+ * lavie_conv3x3_supported() only asks for C % 64 == 0 (otherwise: lavie_im2col3x3_bf16 + lavie_gemm_bf16). */
 int lavie_conv3x3_supported(int H, int W, int C);
-int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, const void* w, void* out, int ldo, int N,
+int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, int stride, const void* w, void* out, int ldo, int N,
                        const lavie_epilogue* ep, int block_n, void* workspace, size_t workspace_bytes,
                        lavie_stream_t stream);
 

@@ -39,7 +39,7 @@ SIGNATURES = {
     "lavie_gemm_bf16": (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(Epilogue),
                                 c_int, _P, c_size_t, _P]),
     "lavie_conv3x3_supported": (c_int, [c_int, c_int, c_int]),
-    "lavie_conv3x3_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, POINTER(Epilogue), c_int, _P,
+    "lavie_conv3x3_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, POINTER(Epilogue), c_int, _P,
                                    c_size_t, _P]),
     "lavie_im2col3x3_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_groupnorm_chunks": (c_int, [c_int, c_int]),

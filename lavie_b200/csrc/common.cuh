@@ -29,6 +29,9 @@ int lavie_make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t
                     const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box,
                     CUtensorMapSwizzle swizzle);
 
+int lavie_make_tmap_im2col(CUtensorMap* map, const void* base, int N, int H, int W, int C, int channels, int pixels,
+                           int stride);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // Small device utilities

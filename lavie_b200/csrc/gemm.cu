@@ -54,6 +54,7 @@ struct GemmParams {
   int box_h;                 // image rows per TMA box
   int boxes_per_tile;        // 128 / (box_h * W)   (per CTA)
   int row_groups_per_img;    // H / box_h
+  int out_h, out_w, conv_stride;   // im2col-mode conv (conv == 2): output geometry and stride
   // epilogue
   const float* bias;         // [N] or null
   const float* row_bias;     // [M / rows_per_batch, ld_row_bias] or null  (time embedding add, resnet.py:187-190)
@@ -140,6 +141,16 @@ __device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, ui
       "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
       "%5, %6}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// im2col-mode TMA (conv halo handled by the hardware): coordinates = first output pixel of the tile in the bounding box
+// (w = x - pad, h = y - pad, n), offsets = filter tap (s, r)
+__device__ __forceinline__ void tma2_load_im2col(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c,
+                                                 int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync() {
@@ -235,7 +246,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
             if (rank == 0) mbar_arrive(&full_bar[stage]);
           } else {
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);   // bytes landing in both CTAs
-            if (p.conv) {
+            if (p.conv == 2) {
+              // one request: 128 consecutive output pixels x 64 channels of filter tap (r, s)
+              const int tap = kb / p.c_blocks;
+              const int c0 = (kb - tap * p.c_blocks) * BLOCK_K;
+              const int m0 = m_cta * BLOCK_M;
+              const int img = m0 / (p.out_h * p.out_w);
+              const int rem = m0 - img * (p.out_h * p.out_w);
+              const int oy = rem / p.out_w, ox = rem - oy * p.out_w;
+              tma2_load_im2col(a_dst, &tmap_a0, full_leader, c0, ox * p.conv_stride - 1, oy * p.conv_stride - 1, img,
+                               static_cast<uint16_t>(tap % 3), static_cast<uint16_t>(tap / 3));
+            } else if (p.conv) {
               const int tap = kb / p.c_blocks;
               const int c0 = (kb - tap * p.c_blocks) * BLOCK_K;
               int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -683,51 +704,58 @@ extern "C" int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1,
 }
 
 extern "C" int lavie_conv3x3_supported(int H, int W, int C) {
-  if (C % BLOCK_K != 0) return 0;
-  if (W > BLOCK_M || BLOCK_M % W != 0 || W % 8 != 0) return 0;
-  (void)H;
-  return 1;
+  (void)H; (void)W;
+  return C % BLOCK_K == 0 ? 1 : 0;      // im2col-mode TMA handles any image geometry; channels come in 64-wide slabs
 }
 
-extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, const void* w, void* out, int ldo,
-                                  int N, const lavie_epilogue* ep, int block_n, void* workspace,
+namespace {
+bool tiled_geometry_ok(int W) { return W <= BLOCK_M && BLOCK_M % W == 0 && W % 8 == 0; }
+}  // namespace
+
+extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, int stride, const void* w, void* out,
+                                  int ldo, int N, const lavie_epilogue* ep, int block_n, void* workspace,
                                   size_t workspace_bytes, cudaStream_t stream) {
-  LAVIE_REQUIRE(lavie_conv3x3_supported(H, W, C), LAVIE_ERR_SHAPE,
-                "conv3x3: TMA path needs C %% 64 == 0 and W in {8,16,32,64,128} (got H=%d W=%d C=%d)", H, W, C);
+  LAVIE_REQUIRE(lavie_conv3x3_supported(H, W, C), LAVIE_ERR_SHAPE, "conv3x3: C=%d must be a multiple of 64", C);
+  LAVIE_REQUIRE(stride == 1 || stride == 2, LAVIE_ERR_SHAPE, "conv3x3: stride must be 1 or 2");
   LAVIE_REQUIRE(N % 8 == 0 && aligned16(x) && aligned16(w), LAVIE_ERR_ALIGN, "conv3x3: alignment");
   LAVIE_REQUIRE(workspace == nullptr || aligned16(workspace), LAVIE_ERR_ALIGN, "conv3x3: workspace alignment");
   LAVIE_REQUIRE(!(ep && ep->geglu), LAVIE_ERR_SHAPE, "conv3x3: GEGLU epilogue not supported");
-  const int M = NF * H * W;
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int M = NF * Ho * Wo;
   GemmParams p{};
   p.M = M; p.N = N; p.K = 9 * C;
   p.num_k_blocks = 9 * (C / BLOCK_K);
   p.k_split_blocks = p.num_k_blocks;
-  p.conv = 1;
   p.c_blocks = C / BLOCK_K;
   p.img_h = H; p.img_w = W;
+  p.out_h = Ho; p.out_w = Wo; p.conv_stride = stride;
+  const bool tiled = (g_debug & 1024) && stride == 1 && tiled_geometry_ok(W);   // first-generation path, for A/B timing
+  p.conv = tiled ? 1 : 2;
   const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, false, workspace ? workspace_bytes : 0);
   apply_plan(p, plan, workspace);
-  // largest number of whole image rows per TMA box that divides both H and the 128/W rows of a CTA's M block
-  const int rows_per_tile = BLOCK_M / W;
-  int box_h = 1;
-  for (int h = rows_per_tile; h >= 1; --h) {
-    if (H % h == 0 && rows_per_tile % h == 0) { box_h = h; break; }
-  }
-  p.box_h = box_h;
-  p.boxes_per_tile = rows_per_tile / box_h;
-  p.row_groups_per_img = H / box_h;
   int rc = fill_epilogue(p, ep, N, out, ldo);
   if (rc) return rc;
   CUtensorMap ma, mb;
-  {
+  if (tiled) {
+    // largest number of whole image rows per TMA box that divides both H and the 128/W rows of a CTA's M block
+    const int rows_per_tile = BLOCK_M / W;
+    int box_h = 1;
+    for (int h = rows_per_tile; h >= 1; --h) {
+      if (H % h == 0 && rows_per_tile % h == 0) { box_h = h; break; }
+    }
+    p.box_h = box_h;
+    p.boxes_per_tile = rows_per_tile / box_h;
+    p.row_groups_per_img = H / box_h;
     const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                               static_cast<uint64_t>(NF)};
     const uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(W) * C * 2,
                                  static_cast<uint64_t>(H) * W * C * 2};
     const uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(W), static_cast<uint32_t>(box_h), 1};
     rc = lavie_make_tmap(&ma, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
+  } else {
+    rc = lavie_make_tmap_im2col(&ma, x, NF, H, W, C, BLOCK_K, BLOCK_M, stride);
   }
+  if (rc) return rc;
   rc = make_weight_map(&mb, w, N, 9 * C, plan.bn);
   if (rc) return rc;
   return dispatch(plan.bn, ma, ma, mb, p, stream);

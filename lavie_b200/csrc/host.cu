@@ -12,6 +12,25 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeIm2colFn g_encode_im2col = nullptr;
+
+EncodeIm2colFn get_encode_im2col() {
+  if (g_encode_im2col) return g_encode_im2col;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  return g_encode_im2col;
+}
+
 EncodeTiledFn get_encode() {
   if (g_encode) return g_encode;
   void* fn = nullptr;
@@ -63,6 +82,31 @@ int lavie_make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t
     lavie_set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d, dims %llu x %llu, box %u x %u)",
                     static_cast<int>(r), rank, static_cast<unsigned long long>(dims[0]),
                     static_cast<unsigned long long>(rank > 1 ? dims[1] : 1), box[0], rank > 1 ? box[1] : 1);
+    return LAVIE_ERR_DRIVER;
+  }
+  return LAVIE_OK;
+}
+
+// im2col-mode tensor map over a channels-last feature map [N, H, W, C] for a 3x3 pad-1 convolution: one TMA request
+// fetches `pixels` consecutive OUTPUT pixels x `channels` input channels for one filter tap, walking the (W, H, N)
+// bounding box and zero-filling the halo (PTX ISA "im2col mode"; same corner convention as CUTLASS:
+// lower = -pad, upper = pad - (filter - 1)).
+int lavie_make_tmap_im2col(CUtensorMap* map, const void* base, int N, int H, int W, int C, int channels, int pixels,
+                           int stride) {
+  EncodeIm2colFn enc = get_encode_im2col();
+  LAVIE_REQUIRE(enc != nullptr, LAVIE_ERR_DRIVER, "cuTensorMapEncodeIm2col is not available from the driver");
+  const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                              static_cast<cuuint64_t>(N)};
+  const cuuint64_t gstr[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                              static_cast<cuuint64_t>(H) * W * C * 2};
+  const int lower[2] = {-1, -1};
+  const int upper[2] = {-1, -1};
+  const cuuint32_t es[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, lower, upper,
+                   static_cast<cuuint32_t>(channels), static_cast<cuuint32_t>(pixels), es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    lavie_set_error("cuTensorMapEncodeIm2col failed: CUresult %d (N=%d H=%d W=%d C=%d)", static_cast<int>(r), N, H, W, C);
     return LAVIE_ERR_DRIVER;
   }
   return LAVIE_OK;

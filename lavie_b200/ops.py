@@ -145,19 +145,21 @@ def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride
     assert rows == NF * H * W and ld == C, "conv3x3 needs a contiguous channels-last input"
     N = w.shape[0]
     assert w.dtype == BF16 and w.is_contiguous() and w.shape[1] == 9 * C
-    if stride != 1 or force_im2col or not conv3x3_supported(H, W, C):
+    if force_im2col or not conv3x3_supported(H, W, C):
         col = im2col3x3(x, NF, H, W, stride)
         return gemm(col, w, bias=bias, row_bias=row_bias, rows_per_batch=rows_per_batch, residual=residual, out=out,
                     block_n=block_n)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    m_out = NF * Ho * Wo
     if out is None:
-        out = torch.empty((rows, N), dtype=BF16, device=x.device)
+        out = torch.empty((m_out, N), dtype=BF16, device=x.device)
     Mo, No, ldo = _rows2d(out)
-    assert Mo == rows and No == N
+    assert Mo == m_out and No == N
     ep = _epilogue(bias, row_bias, rows_per_batch, residual, False)
     ws = _workspace(x.device)
-    with _Launch("gemm_bf16_tcgen05", 2.0 * rows * N * 9 * C, 2.0 * (rows * C + N * 9 * C + rows * N),
-                 f"conv3x3 M={rows} N={N} K={9 * C} W={W}"):
-        rc = lib.lavie_conv3x3_bf16(x.data_ptr(), NF, H, W, C, w.data_ptr(), out.data_ptr(), ldo, N,
+    with _Launch("gemm_bf16_tcgen05", 2.0 * m_out * N * 9 * C, 2.0 * (rows * C + N * 9 * C + m_out * N),
+                 f"conv3x3 M={m_out} N={N} K={9 * C} W={W} s={stride}"):
+        rc = lib.lavie_conv3x3_bf16(x.data_ptr(), NF, H, W, C, stride, w.data_ptr(), out.data_ptr(), ldo, N,
                                     ctypes.byref(ep) if ep is not None else None, block_n, ws.data_ptr(),
                                     ws.numel(), _stream())
     check(rc, "lavie_conv3x3_bf16")

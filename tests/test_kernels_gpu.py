@@ -90,7 +90,8 @@ def _conv_ref(x_nhwc, w_oihw, NF, H, W, stride=1):
 
 
 @pytest.mark.parametrize("NF,H,W,C,N", [(4, 8, 64, 64, 64), (3, 20, 32, 128, 320), (5, 10, 16, 320, 128),
-                                        (7, 5, 8, 64, 64), (2, 40, 64, 320, 320)])
+                                        (7, 5, 8, 64, 64), (2, 40, 64, 320, 320), (3, 12, 24, 64, 64),
+                                        (2, 5, 7, 64, 64), (3, 3, 3, 128, 64), (1, 1, 1, 64, 64)])
 def test_conv3x3_tma(NF, H, W, C, N):
     ops = _ops()
     from lavie_b200.packing import pack_conv3x3
@@ -118,14 +119,18 @@ def test_conv3x3_epilogue_time_bias_and_shortcut():
 
 
 @pytest.mark.parametrize("stride", [1, 2])
-def test_conv3x3_im2col_path(stride):
+@pytest.mark.parametrize("explicit", [False, True])
+@pytest.mark.parametrize("NF,H,W,C,N", [(3, 12, 24, 64, 64), (2, 40, 64, 320, 320), (2, 5, 7, 128, 64)])
+def test_conv3x3_stride_and_explicit_im2col(NF, H, W, C, N, stride, explicit):
+    """stride-2 Downsample3D through im2col-mode TMA, and the explicit patch-matrix path (kept for C % 64 != 0)."""
     ops = _ops()
     from lavie_b200.packing import pack_conv3x3
-    NF, H, W, C, N = 3, 12, 24, 64, 64                 # W = 24: not a TMA geometry
     x = _bf(_rand(NF * H * W, C))
     w = _bf(_rand(N, C, 3, 3, scale=(9 * C) ** -0.5))
-    out = ops.conv3x3(x, NF, H, W, pack_conv3x3(w), stride=stride)
-    ref = _conv_ref(x, w, NF, H, W, stride)
+    bias = _rand(N, seed=2)
+    out = ops.conv3x3(x, NF, H, W, pack_conv3x3(w), stride=stride, bias=bias, force_im2col=explicit)
+    ref = _conv_ref(x, w, NF, H, W, stride) + bias
+    assert out.shape == ref.shape
     assert rel_l2(out.float(), ref) < 4e-3
 
 
