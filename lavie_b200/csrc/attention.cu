@@ -101,31 +101,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
   for (int i = 0; i < DK; ++i) acc[i] = 0.f;
 
+  // One MMA round trip per key tile: batch j = { O_tile = P(j-1) V(j-1),  S = Q K(j)^T } is committed to ONE barrier.
+  // While it runs, nothing in this CTA can proceed -- the other co-resident CTAs fill the SM.
+  auto issue_qk = [&]() {
+#pragma unroll
+    for (int kk = 0; kk < DK / 16; ++kk) {
+      const uint32_t qoff = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
+      const uint32_t koff = (kk >> 2) * KV_CHUNK_BYTES + (kk & 3) * 32;
+      umma_bf16(tmem_s, umma_desc_sw128(smem_u32(sQ) + qoff, 16, 1024),
+                umma_desc_sw128(smem_u32(sK) + koff, 16, 1024), idesc_qk, kk != 0);
+    }
+  };
+  if (tid == 0) {
+    mbar_wait(bar_q, 0);
+    mbar_wait(bar_k, 0);
+    tc_fence_after();
+    issue_qk();
+    umma_commit(bar_s);
+  }
+  __syncwarp();
+  float alpha_prev = 1.f;
+
   for (int j = 0; j < n_kv; ++j) {
     const uint32_t ph = j & 1;
     const int kv_len = min(ATT_N, p.Sk - j * ATT_N);
-    if (tid == 0) {
-      if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_k, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int kk = 0; kk < DK / 16; ++kk) {
-        const uint32_t qoff = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
-        const uint32_t koff = (kk >> 2) * KV_CHUNK_BYTES + (kk & 3) * 32;
-        umma_bf16(tmem_s, umma_desc_sw128(smem_u32(sQ) + qoff, 16, 1024),
-                  umma_desc_sw128(smem_u32(sK) + koff, 16, 1024), idesc_qk, kk != 0);
-      }
-      umma_commit(bar_s);
-    }
-    __syncwarp();
-    mbar_wait(bar_s, ph);
+    mbar_wait(bar_s, ph);                    // S(j) ready; for j >= 1 also O_tile(j-1)
     tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {       // K tile consumed -> prefetch the next one under the softmax
-      mbar_expect_tx(bar_k, NC * KV_CHUNK_BYTES);
-      for (int c = 0; c < NC; ++c)
-        tma_load_3d(sK + c * KV_CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, (j + 1) * ATT_N, kv_batch);
+    if (tid == 0) {
+      if (j + 1 < n_kv) {                    // K buffer is free (QK(j) retired): prefetch K(j+1) under the softmax
+        mbar_expect_tx(bar_k, NC * KV_CHUNK_BYTES);
+        for (int c = 0; c < NC; ++c)
+          tma_load_3d(sK + c * KV_CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, (j + 1) * ATT_N, kv_batch);
+      }
+      if (j >= 1) {                          // V buffer is free (PV(j-1) retired): fetch V(j)
+        mbar_expect_tx(bar_v, NC * KV_CHUNK_BYTES);
+        for (int c = 0; c < NC; ++c)
+          tma_load_3d(sV + c * KV_CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, j * ATT_N, kv_batch);
+      }
     }
     __syncwarp();
+    if (j >= 1) {                            // fold the previous tile's P V into the running output
+#pragma unroll
+      for (int c = 0; c < DK / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_o + lane_base + c * 16, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[c * 16 + e] = acc[c * 16 + e] * alpha_prev + __uint_as_float(v[e]);
+      }
+    }
 
     // ---- online softmax (full tiles take an unmasked path: ~2x fewer issue slots, this loop is issue-bound) ----
     const bool full = (kv_len == ATT_N);           // CTA-uniform
@@ -188,12 +212,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const float rs = rs0 + rs1;
     l_run = l_run * alpha + rs;
     m_run = m_new;
+    alpha_prev = alpha;
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();                         // P(j) complete in smem, S(j) and O_tile(j-1) fully read
 
     if (tid == 0) {
-      mbar_wait(bar_v, ph);
+      mbar_wait(bar_v, ph);                  // V(j) landed (j = 0: prologue load)
+      if (j + 1 < n_kv) mbar_wait(bar_k, ph ^ 1);
       tc_fence_after();
       const int nk = (kv_len + 15) >> 4;
       for (int kk = 0; kk < nk; ++kk) {
@@ -201,27 +227,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         umma_bf16(tmem_o, umma_desc_sw128(smem_u32(sP) + a_off, 16, 1024),
                   umma_desc_sw128(smem_u32(sV) + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv, kk != 0);
       }
-      umma_commit(bar_o);
+      if (j + 1 < n_kv) issue_qk();          // S(j+1) in the same batch: one round trip per tile
+      umma_commit(bar_s);
     }
     __syncwarp();
-    mbar_wait(bar_o, ph);
-    tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {       // V tile consumed -> prefetch the next one
-      mbar_expect_tx(bar_v, NC * KV_CHUNK_BYTES);
-      for (int c = 0; c < NC; ++c)
-        tma_load_3d(sV + c * KV_CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, (j + 1) * ATT_N, kv_batch);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < DK / 16; ++c) {
-      uint32_t v[16];
-      tmem_ld_32x16(tmem_o + lane_base + c * 16, v);
-      tmem_wait_ld();
-#pragma unroll
-      for (int e = 0; e < 16; ++e) acc[c * 16 + e] = acc[c * 16 + e] * alpha + __uint_as_float(v[e]);
-    }
-    tc_fence_before();
   }
+  // last batch: O_tile(n_kv - 1)
+  mbar_wait(bar_s, n_kv & 1);
+  tc_fence_after();
+#pragma unroll
+  for (int c = 0; c < DK / 16; ++c) {
+    uint32_t v[16];
+    tmem_ld_32x16(tmem_o + lane_base + c * 16, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[c * 16 + e] = acc[c * 16 + e] * alpha_prev + __uint_as_float(v[e]);
+  }
+  tc_fence_before();
 
   const int qrow = q_tile * ATT_M + tid;
   if (qrow < p.Sq) {
