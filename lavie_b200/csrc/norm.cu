@@ -7,7 +7,7 @@
 namespace {
 
 constexpr int GN_THREADS = 256;
-constexpr int GN_TARGET_CTAS = 148 * 6;    // enough CTAs in flight to saturate HBM on every level of the UNet
+constexpr int GN_TARGET_CTAS = 148 * 8;    // enough CTAs in flight to saturate HBM on every level of the UNet
 constexpr int GN_MIN_ROWS_PER_CHUNK = 16;
 
 __device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int ld0, int c0, const __nv_bfloat16* x1, int ld1,
@@ -38,16 +38,26 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __n
       float s[8], q[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
-#pragma unroll 4
-      for (int r = r_begin + my_rl; r < r_end; r += row_lanes) {
-        const size_t row = static_cast<size_t>(sample) * rows_per_sample + r;
-        const uint4 v = ld_vec8(x0, ld0, c0, x1, ld1, row, my_vec * 8);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      constexpr int U = 8;                     // independent 16-byte loads in flight per thread
+      for (int r = r_begin + my_rl; r < r_end; r += row_lanes * U) {
+        uint4 v[U];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack_bf16(w[e]);
-          s[2 * e] += f.x; q[2 * e] += f.x * f.x;
-          s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
+        for (int u = 0; u < U; ++u) {
+          const int rr = r + u * row_lanes;
+          const size_t row = static_cast<size_t>(sample) * rows_per_sample + (rr < r_end ? rr : r);
+          v[u] = ld_vec8(x0, ld0, c0, x1, ld1, row, my_vec * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (r + u * row_lanes < r_end) {
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16(w[e]);
+              s[2 * e] += f.x; q[2 * e] += f.x * f.x;
+              s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
+            }
+          }
         }
       }
 #pragma unroll
@@ -110,31 +120,128 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks
   }
 }
 
+// y = act(x * scale + shift).  A thread owns one 8-channel column vector and walks down the rows of ONE sample, so the
+// 16 (scale, shift) floats stay in registers (they are 4x the bytes of the data they apply to); 4 independent 16-byte
+// loads are in flight per thread.  grid = (row chunks, samples).
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __nv_bfloat16* __restrict__ x1, int ld1,
-                int c1, int rows_per_sample, long long total_vecs, const float* __restrict__ scale_shift, int silu,
+                int c1, int rows_per_sample, int rows_per_chunk, const float* __restrict__ scale_shift, int silu,
                 __nv_bfloat16* __restrict__ y, int ldy) {
   const int C = c0 + c1;
   const int vec_per_row = C >> 3;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total_vecs;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const size_t row = static_cast<size_t>(i / vec_per_row);
-    const int col = static_cast<int>(i % vec_per_row) * 8;
-    const int sample = static_cast<int>(row / rows_per_sample);
-    const uint4 v = ld_vec8(x0, ld0, c0, x1, ld1, row, col);
+  const int sample = blockIdx.y;
+  const int r_begin = blockIdx.x * rows_per_chunk;
+  const int r_end = min(r_begin + rows_per_chunk, rows_per_sample);
+  const int lanes_per_row = min(vec_per_row, static_cast<int>(blockDim.x));
+  const int row_lanes = blockDim.x / lanes_per_row;
+  const int my_rl = threadIdx.x / lanes_per_row;
+  if (my_rl >= row_lanes) return;
+  constexpr int U = 4;
+  for (int my_vec = threadIdx.x % lanes_per_row; my_vec < vec_per_row; my_vec += lanes_per_row) {
+    const int col = my_vec * 8;
+    float sc[8], sh[8];
     const float4* ss = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(sample) * C + col) * 2);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack_bf16(w[e]);
-      const float4 p = __ldg(ss + e);        // (scale0, shift0, scale1, shift1)
-      float a = f.x * p.x + p.y;
-      float b = f.y * p.z + p.w;
-      if (silu) { a = silu_f(a); b = silu_f(b); }
-      o[e] = pack_bf16(a, b);
+      const float4 p = __ldg(ss + e);
+      sc[2 * e] = p.x; sh[2 * e] = p.y; sc[2 * e + 1] = p.z; sh[2 * e + 1] = p.w;
     }
-    *reinterpret_cast<uint4*>(y + row * ldy + col) = make_uint4(o[0], o[1], o[2], o[3]);
+    for (int r = r_begin + my_rl; r < r_end; r += row_lanes * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int rr = r + u * row_lanes;
+        const size_t row = static_cast<size_t>(sample) * rows_per_sample + (rr < r_end ? rr : r);
+        v[u] = ld_vec8(x0, ld0, c0, x1, ld1, row, col);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int rr = r + u * row_lanes;
+        if (rr >= r_end) break;
+        const size_t row = static_cast<size_t>(sample) * rows_per_sample + rr;
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16(w[e]);
+          float a = f.x * sc[2 * e] + sh[2 * e];
+          float b = f.y * sc[2 * e + 1] + sh[2 * e + 1];
+          if (silu) { a = silu_f(a); b = silu_f(b); }
+          o[e] = pack_bf16(a, b);
+        }
+        *reinterpret_cast<uint4*>(y + row * ldy + col) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// LayerNorm for C = 40*L (320 / 640 / 1280): L lanes share a row (5 independent 16-byte loads per lane), so a warp
+// keeps 32/L rows = 2.5 KB in flight instead of one row.  Same arithmetic (two-pass, fp32) as layernorm_kernel.
+template <int L>
+__global__ void __launch_bounds__(256)
+layernorm_grouped_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy, int rows,
+                         int perm_hw, int perm_hwp) {
+  constexpr int VPL = 5;
+  constexpr int C = 40 * L;
+  constexpr int RPW = 32 / L;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % L;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long row = warp * RPW + lane / L;
+  const bool ok = row < rows;
+  const __nv_bfloat16* src = x + static_cast<size_t>(ok ? row : 0) * ldx;
+  uint4 u[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(src + (sub + i * L) * 8));
+  float f[VPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = unpack_bf16(w[e]);
+      f[i][2 * e] = t.x;
+      f[i][2 * e + 1] = t.y;
+      sum += t.x + t.y;
+    }
+  }
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(C);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float d = f[i][e] - mean;
+      sq += d * d;
+    }
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / static_cast<float>(C) + eps);
+  if (!ok) return;
+  long long drow = row;
+  if (perm_hw > 0) {
+    const long long fr = row / perm_hw, pix = row - fr * perm_hw;
+    const long long blk = pix / perm_hwp;
+    drow = (blk * (rows / perm_hw) + fr) * perm_hwp + (pix - blk * perm_hwp);
+  }
+  __nv_bfloat16* dst = y + static_cast<size_t>(drow) * ldy;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = sub + i * L;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+    uint4 o;
+    o.x = pack_bf16((f[i][0] - mean) * rstd * g0.x + b0.x, (f[i][1] - mean) * rstd * g0.y + b0.y);
+    o.y = pack_bf16((f[i][2] - mean) * rstd * g0.z + b0.z, (f[i][3] - mean) * rstd * g0.w + b0.w);
+    o.z = pack_bf16((f[i][4] - mean) * rstd * g1.x + b1.x, (f[i][5] - mean) * rstd * g1.y + b1.y);
+    o.w = pack_bf16((f[i][6] - mean) * rstd * g1.z + b1.z, (f[i][7] - mean) * rstd * g1.w + b1.w);
+    *reinterpret_cast<uint4*>(dst + v * 8) = o;
   }
 }
 
@@ -268,13 +375,12 @@ extern "C" int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void
   int rc = check_sources(x0, ld0, c0, x1, ld1, c1);
   if (rc) return rc;
   LAVIE_REQUIRE(al16(y) && ldy % 8 == 0 && al16(scale_shift), LAVIE_ERR_ALIGN, "groupnorm_apply: output alignment");
-  const int C = c0 + c1;
-  const long long total = static_cast<long long>(samples) * rows_per_sample * (C >> 3);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
-  gn_apply_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+  const int rows_per_chunk = gn_rows_per_chunk(samples, rows_per_sample);
+  const int chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
+  dim3 grid(chunks, samples);
+  gn_apply_kernel<<<grid, 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1, rows_per_sample,
-      total, scale_shift, silu, static_cast<__nv_bfloat16*>(y), ldy);
+      rows_per_chunk, scale_shift, silu, static_cast<__nv_bfloat16*>(y), ldy);
   return lavie_check_launch("gn_apply_kernel");
 }
 
@@ -289,6 +395,19 @@ int layernorm_impl(const void* x, int ldx, const float* gamma, const float* beta
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   const int nvec = C >> 3;
+  if (C == 320 || C == 640 || C == 1280) {
+    const int lanes = C / 40;
+    const int rpw = 32 / lanes;
+    const long long warps = (static_cast<long long>(rows) + rpw - 1) / rpw;
+    const int gblocks = static_cast<int>((warps + 7) / 8);
+    if (lanes == 8)
+      layernorm_grouped_kernel<8><<<gblocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, perm_hw, perm_hwp);
+    else if (lanes == 16)
+      layernorm_grouped_kernel<16><<<gblocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, perm_hw, perm_hwp);
+    else
+      layernorm_grouped_kernel<32><<<gblocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, perm_hw, perm_hwp);
+    return lavie_check_launch("layernorm_grouped_kernel");
+  }
   if (nvec <= 64)
     layernorm_kernel<2><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C, perm_hw, perm_hwp);
   else if (nvec <= 160)
