@@ -117,6 +117,29 @@ int lavie_layernorm_scatter_bf16(const void* x, int ldx, const float* gamma, con
 int lavie_add_gathered_bf16(const void* res, int ldr, const void* z, int ldz, void* out, int ldo, int rows, int C,
                             int hw, int hwp, lavie_stream_t stream);
 
+/* The same three exchanges fused into the compute kernels over NVLink PEER MEMORY (no NCCL on the data path).
+ * `*_ptrs` are HOST arrays of P device pointers, entry r = rank r's buffer as mapped into this process (CUDA IPC /
+ * symmetric memory, set up by the caller); flag_ptrs[r] -> uint32[P] (zero-initialised), slot_ptrs[r] ->
+ * double[2][P][samples*groups*2]; epoch_counter is a device uint32 owned by this rank (zero-initialised).  All ranks of
+ * the frame group must issue the same sequence of these calls.
+ *  - lavie_gn_exchange_finalize: local reduce -> store my sums into every peer -> flag barrier -> ordered sum ->
+ *    (scale, shift).  Replaces lavie_groupnorm_reduce + all-reduce + lavie_groupnorm_finalize_sums.
+ *  - lavie_layernorm_scatter_p2p: LayerNorm whose rows are stored into the peers' receive buffers
+ *    (recv_ptrs[r] -> bf16 [F, hw/P, C] on rank r); follow with lavie_rank_barrier before reading the local one.
+ *  - lavie_add_gathered_p2p: out = res + rows loaded from the peers' y buffers (y_ptrs[r] -> bf16 [F, hw/P, C]);
+ *    precede with lavie_rank_barrier (every rank's y complete).
+ *  - lavie_rank_barrier: "everything I launched before this is done and visible" handshake among the P ranks. */
+int lavie_rank_barrier(void* const* flag_ptrs, unsigned int* epoch_counter, int P, int my_rank, lavie_stream_t stream);
+int lavie_gn_exchange_finalize(const float* partial, int samples, int chunks, int groups, int C,
+                               long long count_per_group_global, const float* gamma, const float* beta, float eps,
+                               float* scale_shift, void* const* slot_ptrs, void* const* flag_ptrs,
+                               unsigned int* epoch_counter, int P, int my_rank, lavie_stream_t stream);
+int lavie_layernorm_scatter_p2p(const void* x, int ldx, const float* gamma, const float* beta, float eps,
+                                void* const* recv_ptrs, int rows, int C, int hw, int hwp, int P, int my_rank,
+                                lavie_stream_t stream);
+int lavie_add_gathered_p2p(const void* res, int ldr, void* const* y_ptrs, void* out, int ldo, int rows, int C, int hw,
+                           int hwp, int P, int my_rank, lavie_stream_t stream);
+
 /* softmax(q k^T * scale) v per (batch, head)  (CrossAttention._attention, attention.py:209-239).
  * q rows = batch*Sq, k/v rows = (batch / kv_batch_div)*Sk (kv_batch_div = F shares the text keys across frames,
  * attention.py:364).  Head h occupies columns [h*head_pitch, h*head_pitch + d) of q/k/v (pitch >= d rounded up to 16,

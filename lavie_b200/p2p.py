@@ -1,0 +1,106 @@
+"""Peer-memory plumbing for the fused frame-sharding kernels (csrc/p2p.cu).
+
+torch's symmetric-memory allocator is used ONLY to obtain buffers that every rank of the frame group can address
+(CUDA IPC mappings) and their peer pointers; all loads / stores / flags on those buffers are issued by this repo's
+kernels.  One `PeerContext` per frame group.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check
+from .ops import _Launch, _rows2d, _stream, BF16, F32
+
+
+class PeerContext:
+    """Symmetric buffers of one frame group: flags, GroupNorm slots, and the two token exchange buffers."""
+
+    def __init__(self, group, token_bytes: int, device: torch.device):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group
+        self.P = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = device
+        flags_b = 256                                     # uint32[P], padded
+        slots_b = 2 * self.P * (2 * 64 * 2) * 8           # double[2][P][samples<=2 * groups<=64 * 2]
+        tok_b = (token_bytes + 255) // 256 * 256
+        self.layout = {"flags": 0, "slots": flags_b, "recv": flags_b + slots_b, "y": flags_b + slots_b + tok_b}
+        total = flags_b + slots_b + 2 * tok_b
+        self.buf = symm.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm.rendezvous(self.buf, group)
+        self.peer_base: List[int] = [int(p) for p in self.handle.buffer_ptrs]
+        assert len(self.peer_base) == self.P and self.peer_base[self.rank] == self.buf.data_ptr()
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.token_bytes = tok_b
+        dist.barrier(group)                               # everybody has zeroed flags before the first kernel
+
+    def ptrs(self, what: str):
+        off = self.layout[what]
+        return (ctypes.c_void_p * self.P)(*[b + off for b in self.peer_base])
+
+    def local(self, what: str, rows: int, cols: int) -> torch.Tensor:
+        """bf16 [rows, cols] view of this rank's `recv` / `y` buffer."""
+        off = self.layout[what]
+        n = rows * cols * 2
+        assert n <= self.token_bytes, (n, self.token_bytes)
+        return self.buf[off:off + n].view(BF16).view(rows, cols)
+
+    # ---- fused kernels ----
+    def barrier(self):
+        lib = _lib.load()
+        with _Launch("lavie_rank_barrier"):
+            check(lib.lavie_rank_barrier(self.ptrs("flags"), self.epoch.data_ptr(), self.P, self.rank, _stream()),
+                  "lavie_rank_barrier")
+
+    def gn_scale_shift(self, x, x2, samples, rows_local, gamma, beta, eps, groups=32):
+        lib = _lib.load()
+        rows, c0, ld0 = _rows2d(x)
+        c1, ld1 = 0, 0
+        if x2 is not None:
+            _, c1, ld1 = _rows2d(x2)
+        C = c0 + c1
+        chunks = lib.lavie_groupnorm_chunks(samples, rows_local)
+        partial = torch.empty((samples, chunks, groups, 2), dtype=F32, device=x.device)
+        with _Launch("lavie_groupnorm_stats", 0.0, 2.0 * rows * C, f"gn_stats rows={rows} C={C} samples={samples}"):
+            check(lib.lavie_groupnorm_stats(x.data_ptr(), ld0, c0, x2.data_ptr() if x2 is not None else None, ld1, c1,
+                                            samples, rows_local, groups, partial.data_ptr(), _stream()),
+                  "lavie_groupnorm_stats")
+        ss = torch.empty((samples, C, 2), dtype=F32, device=x.device)
+        with _Launch("lavie_gn_exchange_finalize"):
+            check(lib.lavie_gn_exchange_finalize(partial.data_ptr(), samples, chunks, groups, C,
+                                                 rows_local * self.P * (C // groups), gamma.data_ptr(), beta.data_ptr(),
+                                                 eps, ss.data_ptr(), self.ptrs("slots"), self.ptrs("flags"),
+                                                 self.epoch.data_ptr(), self.P, self.rank, _stream()),
+                  "lavie_gn_exchange_finalize")
+        return ss
+
+    def layernorm_scatter(self, x, gamma, beta, hw, eps=1e-5):
+        """LayerNorm + all-to-all (store side).  Returns this rank's receive buffer [F, hw/P, C] (valid after barrier)."""
+        lib = _lib.load()
+        rows, C, ldx = _rows2d(x)
+        hwp = hw // self.P
+        with _Launch("lavie_layernorm_scatter_p2p", 0.0, 4.0 * rows * C, f"ln_scatter_p2p rows={rows} C={C}"):
+            check(lib.lavie_layernorm_scatter_p2p(x.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), eps,
+                                                  self.ptrs("recv"), rows, C, hw, hwp, self.P, self.rank, _stream()),
+                  "lavie_layernorm_scatter_p2p")
+        self.barrier()
+        return self.local("recv", rows, C)
+
+    def add_gathered(self, res, hw):
+        """res + all-to-all back (load side) of the peers' `y` buffers."""
+        lib = _lib.load()
+        rows, C, ldr = _rows2d(res)
+        hwp = hw // self.P
+        self.barrier()                                    # every rank's y is complete
+        out = torch.empty((rows, C), dtype=BF16, device=res.device)
+        with _Launch("lavie_add_gathered_p2p", 0.0, 6.0 * rows * C):
+            check(lib.lavie_add_gathered_p2p(res.data_ptr(), ldr, self.ptrs("y"), out.data_ptr(), C, rows, C, hw, hwp,
+                                             self.P, self.rank, _stream()), "lavie_add_gathered_p2p")
+        return out

@@ -107,6 +107,8 @@ class UNet3DConditionModel(nn.Module):
             _install(self, prefix, _leaf_for(prefix, names))
         self._packed = None
         self._shard = None            # (process group, P, index) when the frames of one CFG half span P GPUs
+        self._shard_backend = "p2p"
+        self._peer = None
         self._graphs: Dict[tuple, dict] = {}
         self._tables: Dict[tuple, tuple] = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
@@ -144,19 +146,31 @@ class UNet3DConditionModel(nn.Module):
         self._invalidate()
         return out
 
-    def set_frame_sharding(self, group=None):
+    def set_frame_sharding(self, group=None, backend: str = "p2p"):
         """Frame sharding: this rank holds F/P consecutive frames of the video; `group` is the
         torch.distributed process group of the P ranks that share one CFG half (rank order = frame order).
         Per-frame work (convs, per-frame GroupNorm, LayerNorm, spatial / cross attention, FF) runs shard-local;
         5-D GroupNorm statistics are all-reduced and the tokens are exchanged all-to-all around every temporal
-        attention.  `None` switches it off."""
+        attention.  backend "p2p" (default) runs those exchanges inside this library's kernels over NVLink peer memory
+        (csrc/p2p.cu); "nccl" keeps the exchanges in torch.distributed collectives.  `None` switches sharding off."""
+        if backend not in ("p2p", "nccl"):
+            raise ValueError("backend must be 'p2p' or 'nccl'")
         if group is None:
             self._shard = None
         else:
             import torch.distributed as dist
             P = dist.get_world_size(group)
             self._shard = None if P == 1 else (group, P, dist.get_rank(group))
+        self._shard_backend = backend
+        self._peer = None
         self._graphs.clear()
+
+    def _peer_ctx(self, token_bytes: int):
+        """Symmetric buffers of the frame group, created at the first sharded forward (collective call)."""
+        if self._peer is None or self._peer.token_bytes < token_bytes:
+            from .p2p import PeerContext
+            self._peer = PeerContext(self._shard[0], token_bytes, self.device)
+        return self._peer
 
     def _gn5(self, x, x2, B, rows_local, gamma, beta, eps, silu):
         """nn.GroupNorm on the 5-D tensor: statistics span ALL frames (resnet.py:180,191; unet.py:504)."""
@@ -168,6 +182,8 @@ class UNet3DConditionModel(nn.Module):
     def _gn5_scale_shift(self, x, x2, B, rows_local, gamma, beta, eps):
         if self._shard is None:
             return ops.groupnorm_scale_shift(x, B, rows_local, gamma, beta, eps, x2=x2)
+        if self._shard_backend == "p2p":
+            return self._peer.gn_scale_shift(x, x2, B, rows_local, gamma, beta, eps)
         import torch.distributed as dist
         group, P, _ = self._shard
         C = x.shape[1] + (x2.shape[1] if x2 is not None else 0)
@@ -338,17 +354,29 @@ class UNet3DConditionModel(nn.Module):
             group, P, _ = self._shard
             assert B == 1 and HW % P == 0, "frame sharding runs one CFG half per rank and needs H*W divisible by P"
             hwp = HW // P
+            rope, bias = self._frame_tables(p, Fr * P)
+            if self._shard_backend == "p2p":
+                # the all-to-alls are the store side of the LayerNorm and the load side of the residual add
+                ctx = self._peer
+                recv = ctx.layernorm_scatter(tok, t["norm_temp_g"], t["norm_temp_b"], HW)     # [F, hwp, C]
+                qkv = ops.gemm(recv, t["attn_temp_qkv"])
+                a = ops.temporal_attention(qkv, 1, Fr * P, hwp, heads, d, pitch, rope, bias)
+                ops.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"], out=ctx.local("y", Fr * P * hwp, t["C"]))
+                tok = ctx.add_gathered(tok, HW)
+                return self._ff_and_out(t, tok, x)
             send = ops.layernorm_scatter(tok, t["norm_temp_g"], t["norm_temp_b"], HW, hwp)   # [P, F_loc, hwp, C]
             recv = torch.empty_like(send)                                                     # [F, hwp, C]
             dist.all_to_all_single(recv, send, group=group)
             qkv = ops.gemm(recv, t["attn_temp_qkv"])
-            rope, bias = self._frame_tables(p, Fr * P)
             a = ops.temporal_attention(qkv, 1, Fr * P, hwp, heads, d, pitch, rope, bias)
             y = ops.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"])                        # [F, hwp, C] = P chunks
             back = torch.empty_like(y)                                                        # [P, F_loc, hwp, C]
             dist.all_to_all_single(back, y, group=group)
             tok = ops.add_gathered(tok, back, HW, hwp)
-        # GEGLU feed-forward
+        return self._ff_and_out(t, tok, x)
+
+    def _ff_and_out(self, t, tok, x):
+        # GEGLU feed-forward, then proj_out + the block's residual (attention.py:558, 394-401)
         n = ops.layernorm(tok, t["norm3_g"], t["norm3_b"])
         g = ops.gemm(n, t["ff1_w"], bias=t["ff1_b"], geglu=True)
         tok = ops.gemm(g, t["ff2_w"], bias=t["ff2_b"], residual=tok)
@@ -361,6 +389,8 @@ class UNet3DConditionModel(nn.Module):
         B, _, Fr, H, W = sample.shape
         text_len = text.shape[0] // B
         boc = cfg.block_out_channels
+        if self._shard is not None and self._shard_backend == "p2p":
+            self._peer_ctx(B * Fr * H * W * boc[0] * 2)        # largest token tensor = level 0
 
         def tap(name, x, C, h, w):
             if taps is not None:

@@ -31,7 +31,8 @@ def main():
     sample, t, text = synthetic_inputs(2, F, H, W, seed=0)
     sample, text = sample.to(dev), text.to(dev)
     ref = unet(sample, t, encoder_hidden_states=text).sample                       # single-GPU answer, all frames
-    unet.set_frame_sharding(frame_groups[c])
+    backend = sys.argv[4] if len(sys.argv) > 4 else "p2p"
+    unet.set_frame_sharding(frame_groups[c], backend=backend)
     fl = F // P
     shard = sample[c:c + 1, :, s * fl:(s + 1) * fl].contiguous()
     out = unet(shard, t, encoder_hidden_states=text[c:c + 1]).sample
@@ -53,7 +54,7 @@ def main():
         for r in errs:
             print(f"rank {r[0]} (cfg half {r[1]}, frame shard {r[2]}/{P}): rel-L2 vs single GPU = {r[3]:.3e}, {r[4]:.2f} ms/forward")
         worst = max(r[3] for r in errs)
-        print(f"RESULT world={world} P={P} graph={graph} worst_rel_l2={worst:.3e} {'OK' if worst < 2e-2 else 'FAIL'}")
+        print(f"RESULT world={world} P={P} graph={graph} backend={backend} worst_rel_l2={worst:.3e} {'OK' if worst < 2e-2 else 'FAIL'}")
     torch.cuda.synchronize(); dist.barrier(); sys.stdout.flush()
     os._exit(0)     # process-group teardown hangs with captured NCCL graphs
 
