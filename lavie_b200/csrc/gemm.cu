@@ -40,6 +40,8 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // 320
 constexpr int EPI_BAR_ID = 1;
+constexpr int EPI_CHUNK_BYTES = 32 * 32 * 2;      // one 32-row x 32-column bf16 chunk (TMA box, 64-byte swizzle)
+constexpr int EPI_CHUNKS_PER_WARP = 4;            // BLOCK_N <= 256 -> at most 8 chunks per row quarter, 2 warps share them
 
 struct GemmParams {
   int M, N, K;
@@ -75,11 +77,11 @@ struct SmemLayout {
   static constexpr int B_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BIAS_BYTES = 0;
-  static constexpr int EPI_BYTES = NUM_EPI_WARPS * 32 * 36 * 4;   // per-warp 32x32 fp32 transpose buffers (pitch 36)
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_CHUNKS_PER_WARP * EPI_CHUNK_BYTES;   // per-warp bf16 staging chunks
   static constexpr int MAX_SMEM = 227 * 1024 - 2048 - BIAS_BYTES - EPI_BYTES;
   static constexpr int STAGES_RAW = MAX_SMEM / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BIAS_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BIAS_BYTES + EPI_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 // ---- cluster / cta_group::2 PTX ----
@@ -174,7 +176,8 @@ __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
-                  const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+                  const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
+                  const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
   using L = SmemLayout<BLOCK_N>;
   constexpr int STAGES = L::STAGES;
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
@@ -183,12 +186,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_epi = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES + L::BIAS_BYTES);
+  uint8_t* s_epi = smem + STAGES * L::STAGE_BYTES + L::BIAS_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES + L::BIAS_BYTES + L::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]  (only the leader's are waited on)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;           // [NUM_EPI_WARPS] residual-prefetch barriers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + NUM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -201,6 +205,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
     tma_prefetch_desc(&tmap_a0);
     tma_prefetch_desc(&tmap_a1);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    tma_prefetch_desc(&tmap_res);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -209,6 +215,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 2 * NUM_EPI_WARPS);   // one arrive per epilogue warp of BOTH CTAs
     }
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&res_bar[w], 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -321,77 +328,83 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
     }
   } else {
     // ===================================== epilogue (both CTAs) =========================================
+    // tcgen05.ld hands every lane one accumulator ROW; writing rows straight to global memory would touch 32
+    // different 128-byte lines per instruction.  Each warp instead stages its 32x32 bf16 chunks in shared memory
+    // (64-byte-swizzled, conflict-free) and lets the TMA move them: the residual tile is PREFETCHED into the same
+    // buffers with TMA loads while the MMAs of the tile are still running, the sum is written back in place and
+    // leaves with a TMA store (which also clips the M / N tails).
     const int ew = warp - 2;                       // 0..7
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int chalf = ew >> 2;                     // which half of the 32-column chunks this warp drains
-    const int et = threadIdx.x - 64;               // 0..255
     const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    uint8_t* my_stage = s_epi + ew * (EPI_CHUNKS_PER_WARP * EPI_CHUNK_BYTES);
+    uint64_t* my_res_bar = &res_bar[ew];
+    uint32_t res_phase = 0;
+    const int swz = (lane >> 1) & 3;               // 64-byte swizzle: 16-byte unit j of row r lives at unit j ^ ((r>>1)&3)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = pair; item < num_items; item += num_pairs) {
       const Item it = decode_item(p, item);
       const int split = item % p.splits;
       const int row0 = (it.m_blk * 2 + static_cast<int>(rank)) * BLOCK_M;
-      const int row = row0 + q * 32 + lane;
+      const int wrow0 = row0 + q * 32;             // first row of this warp's 32-row slab
+      const int row = wrow0 + lane;
       const bool row_ok = row < p.M;
       const int n0 = it.n_blk * BLOCK_N;
-      // bias / time-embedding rows are read straight from global memory in the quad mapping (8 values per lane and
-      // chunk, L1-resident): no shared-memory staging and no block-wide barrier per tile
-      const int n_out_limit = p.geglu ? p.N / 2 : p.N;
+      const bool staged = p.splits == 1;
+      const bool has_res = staged && p.residual != nullptr;
+      if (staged) {
+        // buffers are free once the previous tile's stores have finished READING them
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        if (has_res && lane == 0 && !(p.debug & 64)) {
+          int nch = 0;
+          for (int c = chalf; c < BLOCK_N / 32; c += 2) ++nch;
+          mbar_expect_tx(my_res_bar, nch * EPI_CHUNK_BYTES);
+          int k = 0;
+          for (int c = chalf; c < BLOCK_N / 32; c += 2, ++k)
+            tma_load_2d(my_stage + k * EPI_CHUNK_BYTES, &tmap_res, my_res_bar, n0 + c * 32, wrow0);
+        }
+      }
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      if (has_res && !(p.debug & 64)) {
+        mbar_wait(my_res_bar, res_phase);
+        res_phase ^= 1;
+      }
+      const float* rb_row = (p.row_bias && row_ok) ? p.row_bias + static_cast<size_t>(row / p.rows_per_batch) * p.ld_row_bias
+                                                    : nullptr;
 
-      // Coalescing: tcgen05.ld hands every lane one accumulator ROW; storing it directly would touch 32 different
-      // 128-byte lines per instruction.  Each warp therefore transposes its 32x32 fp32 chunk through a private
-      // shared-memory buffer (pitch 36 words: conflict-free both ways) into a "quad" mapping -- lane = (row r8 =
-      // lane/4, 8-column piece = lane%4) -- where one instruction covers 8 rows x 64 contiguous bytes, for the
-      // residual loads as well as the bf16 stores.
-      float* stage_buf = s_epi + ew * (32 * 36);
-      const int qrow = lane >> 2, piece = lane & 3;
-      auto emit_chunk = [&](const float (&f)[32], int col_out0, bool add_b, const uint4 (&rq)[4], bool has_res) {
+      // packs f[32] (+ residual already in the buffer) into the warp's chunk buffer k and hands it to the TMA
+      auto stage_and_store = [&](float (&f)[32], int k, int col_out0, bool add_res) {
+        uint8_t* buf = my_stage + k * EPI_CHUNK_BYTES + lane * 64;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stage_buf + lane * 36 + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-          const int r = 8 * s4 + qrow;
-          const int grow = row0 + q * 32 + r;
-          const int col = col_out0 + piece * 8;
-          const float4 v0 = *reinterpret_cast<const float4*>(stage_buf + r * 36 + piece * 8);
-          const float4 v1 = *reinterpret_cast<const float4*>(stage_buf + r * 36 + piece * 8 + 4);
-          float o[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          if (grow < p.M && col < n_out_limit && !(p.debug & 16)) {
-            if (add_b && p.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-              o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-            }
-            if (add_b && p.row_bias) {
-              const float* rbp = p.row_bias + static_cast<size_t>(grow / p.rows_per_batch) * p.ld_row_bias + col;
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(rbp));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
-              o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-              o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-            }
-            if (has_res) {
-              const float2 r0 = unpack_bf16(rq[s4].x), r1 = unpack_bf16(rq[s4].y), r2 = unpack_bf16(rq[s4].z),
-                           r3 = unpack_bf16(rq[s4].w);
-              o[0] += r0.x; o[1] += r0.y; o[2] += r1.x; o[3] += r1.y;
-              o[4] += r2.x; o[5] += r2.y; o[6] += r3.x; o[7] += r3.y;
-            }
-            uint4 pk;
-            pk.x = pack_bf16(o[0], o[1]);
-            pk.y = pack_bf16(o[2], o[3]);
-            pk.z = pack_bf16(o[4], o[5]);
-            pk.w = pack_bf16(o[6], o[7]);
-            *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(grow) * p.ldo + col) = pk;
+        for (int j = 0; j < 4; ++j) {
+          uint4* slot = reinterpret_cast<uint4*>(buf + ((j ^ swz) << 4));
+          if (add_res) {
+            const uint4 r = *slot;
+            const float2 r0 = unpack_bf16(r.x), r1 = unpack_bf16(r.y), r2 = unpack_bf16(r.z), r3 = unpack_bf16(r.w);
+            f[8 * j] += r0.x; f[8 * j + 1] += r0.y; f[8 * j + 2] += r1.x; f[8 * j + 3] += r1.y;
+            f[8 * j + 4] += r2.x; f[8 * j + 5] += r2.y; f[8 * j + 6] += r3.x; f[8 * j + 7] += r3.y;
           }
+          uint4 o;
+          o.x = pack_bf16(f[8 * j], f[8 * j + 1]);
+          o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+          o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+          o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+          *slot = o;
         }
+        fence_proxy_async_smem();
         __syncwarp();
+        if (lane == 0 && !(p.debug & 16)) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmap_out)),
+                       "r"(smem_u32(my_stage + k * EPI_CHUNK_BYTES)), "r"(col_out0), "r"(wrow0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       };
 
       if (p.splits > 1) {
@@ -411,54 +424,60 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
           }
         }
       } else if (!p.geglu) {
-        uint4 rpre[4];
-        auto prefetch_res = [&](int c) {
-#pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4) {
-            const int grow = row0 + q * 32 + 8 * s4 + qrow;
-            const int col = n0 + c * 32 + piece * 8;
-            rpre[s4] = (p.residual && grow < p.M && col < p.N && !(p.debug & 64))
-                           ? __ldg(reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(grow) * p.ldr + col))
-                           : make_uint4(0, 0, 0, 0);
-          }
-        };
-        prefetch_res(chalf);
+        int k = 0;
 #pragma unroll 1
-        for (int c = chalf; c < BLOCK_N / 32; c += 2) {
-          if (p.debug & 256) continue;
+        for (int c = chalf; c < BLOCK_N / 32; c += 2, ++k) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c * 32, v);
-          uint4 rcur[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rcur[j] = rpre[j];
-          if (c + 2 < BLOCK_N / 32) prefetch_res(c + 2);        // next chunk's residual in flight under this one
           tmem_wait_ld();
-          if (p.debug & 128) continue;
+          const int col0 = n0 + c * 32;
           float f[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-          emit_chunk(f, n0 + c * 32, true, rcur, p.residual != nullptr);
+          if (col0 < p.N) {
+            if (p.bias) {                          // warp-uniform addresses: broadcast loads
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + e));
+                f[e] += b4.x; f[e + 1] += b4.y; f[e + 2] += b4.z; f[e + 3] += b4.w;
+              }
+            }
+            if (rb_row) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb_row + col0 + e));
+                f[e] += b4.x; f[e + 1] += b4.y; f[e + 2] += b4.z; f[e + 3] += b4.w;
+              }
+            }
+          }
+          stage_and_store(f, k, col0, has_res && !(p.debug & 64));
         }
       } else {
         // GEGLU: value columns [0, BN/2), gate columns [BN/2, BN) of the same tile (weights interleaved on the
         // host); out[:, n_blk*BN/2 + j] = (value + b) * gelu_erf(gate + b')   (diffusers GEGLU, mirror at
         // vsr/models/diffusers_attention.py:811-822)
         constexpr int HALF = BLOCK_N / 2;
-        const uint4 nores[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        int k = 0;
 #pragma unroll 1
-        for (int c = chalf; c < HALF / 32; c += 2) {
+        for (int c = chalf; c < HALF / 32; c += 2, ++k) {
           uint32_t v[32], g[32];
           tmem_ld_32x32(t_row + c * 32, v);
           tmem_ld_32x32(t_row + HALF + c * 32, g);
           tmem_wait_ld();
           float f[32];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float val = __uint_as_float(v[e]) + (p.bias ? __ldg(p.bias + n0 + c * 32 + e) : 0.f);
-            const float gate = __uint_as_float(g[e]) + (p.bias ? __ldg(p.bias + n0 + HALF + c * 32 + e) : 0.f);
-            f[e] = val * gelu_erf_f(gate);
+          for (int e = 0; e < 32; e += 4) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+            if (p.bias) {                                   // warp-uniform addresses: one broadcast transaction each
+              bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + e));
+              bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + HALF + c * 32 + e));
+            }
+            f[e] = (__uint_as_float(v[e]) + bv.x) * gelu_erf_f(__uint_as_float(g[e]) + bg.x);
+            f[e + 1] = (__uint_as_float(v[e + 1]) + bv.y) * gelu_erf_f(__uint_as_float(g[e + 1]) + bg.y);
+            f[e + 2] = (__uint_as_float(v[e + 2]) + bv.z) * gelu_erf_f(__uint_as_float(g[e + 2]) + bg.z);
+            f[e + 3] = (__uint_as_float(v[e + 3]) + bv.w) * gelu_erf_f(__uint_as_float(g[e + 3]) + bg.w);
           }
-          emit_chunk(f, it.n_blk * HALF + c * 32, false, nores, false);
+          stage_and_store(f, k, it.n_blk * HALF + c * 32, false);
         }
       }
       tc_fence_before();
@@ -468,6 +487,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
     }
   }
 
+  if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // output stores complete
   tc_fence_before();
   cluster_sync_all();            // the peer may still be reading smem / TMEM that a cta_group::2 MMA touches
   if (warp == 1) {
@@ -510,7 +530,8 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N
 }
 
 template <int BLOCK_N>
-int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
+int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& mo,
+                const CUtensorMap& mr, const GemmParams& p,
                 int num_sms, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N>;
   static bool configured = false;
@@ -524,7 +545,7 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   const int items = p.m_tiles * p.n_tiles * p.splits;
   int pairs = num_sms / 2;
   if (items < pairs) pairs = items;
-  gemm_bf16_tcgen05<BLOCK_N><<<2 * pairs, NUM_THREADS, L::TOTAL, stream>>>(a0, a1, b, p);
+  gemm_bf16_tcgen05<BLOCK_N><<<2 * pairs, NUM_THREADS, L::TOTAL, stream>>>(a0, a1, b, mo, mr, p);
   int rc = lavie_check_launch("gemm_bf16_tcgen05");
   if (rc) return rc;
   if (p.splits > 1) {
@@ -595,14 +616,33 @@ Plan make_plan(int M, int N, int num_k_blocks, int forced_bn, bool geglu, size_t
   return best;
 }
 
+// TMA maps of the epilogue: 32x32 bf16 boxes, 64-byte swizzle, over the output and (optionally) the residual
+int make_epilogue_maps(const GemmParams& p, CUtensorMap* mo, CUtensorMap* mr) {
+  const uint32_t box[2] = {32, 32};
+  const uint64_t odims[2] = {static_cast<uint64_t>(p.geglu ? p.N / 2 : p.N), static_cast<uint64_t>(p.M)};
+  const uint64_t ostr[1] = {static_cast<uint64_t>(p.ldo) * 2};
+  int rc = lavie_make_tmap(mo, p.out, 2, odims, ostr, box, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  if (p.residual) {
+    const uint64_t rdims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};
+    const uint64_t rstr[1] = {static_cast<uint64_t>(p.ldr) * 2};
+    return lavie_make_tmap(mr, p.residual, 2, rdims, rstr, box, CU_TENSOR_MAP_SWIZZLE_64B);
+  }
+  *mr = *mo;
+  return LAVIE_OK;
+}
+
 int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
              cudaStream_t stream) {
+  CUtensorMap mo, mr;
+  int rc = make_epilogue_maps(p, &mo, &mr);
+  if (rc) return rc;
   switch (bn) {
-    case 64: return launch_gemm<64>(a0, a1, b, p, num_sms(), stream);
-    case 128: return launch_gemm<128>(a0, a1, b, p, num_sms(), stream);
-    case 160: return launch_gemm<160>(a0, a1, b, p, num_sms(), stream);
-    case 192: return launch_gemm<192>(a0, a1, b, p, num_sms(), stream);
-    case 256: return launch_gemm<256>(a0, a1, b, p, num_sms(), stream);
+    case 64: return launch_gemm<64>(a0, a1, b, mo, mr, p, num_sms(), stream);
+    case 128: return launch_gemm<128>(a0, a1, b, mo, mr, p, num_sms(), stream);
+    case 160: return launch_gemm<160>(a0, a1, b, mo, mr, p, num_sms(), stream);
+    case 192: return launch_gemm<192>(a0, a1, b, mo, mr, p, num_sms(), stream);
+    case 256: return launch_gemm<256>(a0, a1, b, mo, mr, p, num_sms(), stream);
     default: lavie_set_error("unsupported BLOCK_N %d", bn); return LAVIE_ERR_SHAPE;
   }
 }

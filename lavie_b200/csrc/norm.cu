@@ -91,10 +91,20 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks
   const int sub = threadIdx.x & 7;
   for (int g = threadIdx.x >> 3; g < groups; g += blockDim.x >> 3) {
     double a = 0.0, b = 0.0;
-    for (int k = sub; k < chunks; k += 8) {
-      const float2 v = *reinterpret_cast<const float2*>(partial + ((static_cast<size_t>(sample) * chunks + k) * groups + g) * 2);
-      a += v.x;
-      b += v.y;
+    for (int k0 = sub; k0 < chunks; k0 += 64) {          // 8 independent loads in flight, summed in a fixed order
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + 8 * u;
+        v[u] = k < chunks ? *reinterpret_cast<const float2*>(
+                                partial + ((static_cast<size_t>(sample) * chunks + k) * groups + g) * 2)
+                          : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a += v[u].x;
+        b += v[u].y;
+      }
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
@@ -449,10 +459,20 @@ __global__ void gn_reduce_kernel(const float* __restrict__ partial, int chunks, 
   const int sub = threadIdx.x & 7;
   for (int g = threadIdx.x >> 3; g < groups; g += blockDim.x >> 3) {
     double a = 0.0, b = 0.0;
-    for (int k = sub; k < chunks; k += 8) {
-      const float2 v = *reinterpret_cast<const float2*>(partial + ((static_cast<size_t>(sample) * chunks + k) * groups + g) * 2);
-      a += v.x;
-      b += v.y;
+    for (int k0 = sub; k0 < chunks; k0 += 64) {          // 8 independent loads in flight, summed in a fixed order
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + 8 * u;
+        v[u] = k < chunks ? *reinterpret_cast<const float2*>(
+                                partial + ((static_cast<size_t>(sample) * chunks + k) * groups + g) * 2)
+                          : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a += v[u].x;
+        b += v[u].y;
+      }
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
