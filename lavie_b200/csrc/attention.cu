@@ -97,6 +97,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
 
   float m_run = -INFINITY, l_run = 0.f;
+  // d < DK (d = 40 in a 48-wide head slot): a padded V column is set to 1.0 so that the P.V MMA itself produces the
+  // softmax denominator (sum of the bf16-rounded probabilities) in accumulator column d -- no per-element FADD.
+  const bool ones_col = p.d < DK;
   float acc[DK];
 #pragma unroll
   for (int i = 0; i < DK; ++i) acc[i] = 0.f;
@@ -112,14 +115,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 umma_desc_sw128(smem_u32(sK) + koff, 16, 1024), idesc_qk, kk != 0);
     }
   };
-  if (tid == 0) {
+  // MMA / TMA issue runs warp-uniformly in warp 0 (descriptors stay in uniform registers; with a divergent
+  // `if (tid == 0)` every tcgen05.mma needed ~5 R2UR moves and cost ~150 cycles to issue) -- one elected lane issues.
+  if (warp == 0) {
     mbar_wait(bar_q, 0);
     mbar_wait(bar_k, 0);
     tc_fence_after();
-    issue_qk();
-    umma_commit(bar_s);
+    if (elect_one()) {
+      issue_qk();
+      umma_commit(bar_s);
+    }
+    __syncwarp();
   }
-  __syncwarp();
   float alpha_prev = 1.f;
 
   for (int j = 0; j < n_kv; ++j) {
@@ -127,7 +134,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int kv_len = min(ATT_N, p.Sk - j * ATT_N);
     mbar_wait(bar_s, ph);                    // S(j) ready; for j >= 1 also O_tile(j-1)
     tc_fence_after();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       if (j + 1 < n_kv) {                    // K buffer is free (QK(j) retired): prefetch K(j+1) under the softmax
         mbar_expect_tx(bar_k, NC * KV_CHUNK_BYTES);
         for (int c = 0; c < NC; ++c)
@@ -154,7 +161,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ---- online softmax (full tiles take an unmasked path: ~2x fewer issue slots, this loop is issue-bound) ----
     const bool full = (kv_len == ATT_N);           // CTA-uniform
     float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < ATT_N / 32; ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
@@ -177,7 +184,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     float rs0 = 0.f, rs1 = 0.f;
     uint8_t* p_row = sP + tid * 128;
     const float sc = p.scale_log2;
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < ATT_N / 32; ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
@@ -188,8 +195,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int e = 0; e < 32; e += 2) {
           const float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sc, -m_new));
           const float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sc, -m_new));
-          rs0 += p0;
-          rs1 += p1;
+          if (!ones_col) {
+            rs0 += p0;
+            rs1 += p1;
+          }
           pk[e >> 1] = pack_bf16(p0, p1);
         }
       } else {
@@ -213,24 +222,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     l_run = l_run * alpha + rs;
     m_run = m_new;
     alpha_prev = alpha;
+    if (ones_col && tid < ATT_N) {           // V(j)[key = tid][column d] = 1.0 (bf16), 128-byte-swizzled address
+      mbar_wait(bar_v, ph);
+      const int unit = ((p.d >> 3) & 7) ^ (tid & 7);
+      *reinterpret_cast<uint16_t*>(sV + (p.d >> 6) * KV_CHUNK_BYTES + tid * 128 + unit * 16 + (p.d & 7) * 2) = 0x3F80;
+    }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();                         // P(j) complete in smem, S(j) and O_tile(j-1) fully read
 
-    if (tid == 0) {
+    if (warp == 0) {
       mbar_wait(bar_v, ph);                  // V(j) landed (j = 0: prologue load)
       if (j + 1 < n_kv) mbar_wait(bar_k, ph ^ 1);
       tc_fence_after();
       const int nk = (kv_len + 15) >> 4;
-      for (int kk = 0; kk < nk; ++kk) {
-        const uint32_t a_off = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
-        umma_bf16(tmem_o, umma_desc_sw128(smem_u32(sP) + a_off, 16, 1024),
-                  umma_desc_sw128(smem_u32(sV) + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv, kk != 0);
+      if (elect_one()) {
+        for (int kk = 0; kk < nk; ++kk) {
+          const uint32_t a_off = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
+          umma_bf16(tmem_o, umma_desc_sw128(smem_u32(sP) + a_off, 16, 1024),
+                    umma_desc_sw128(smem_u32(sV) + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv, kk != 0);
+        }
+        if (j + 1 < n_kv) issue_qk();        // S(j+1) in the same batch: one round trip per tile
+        umma_commit(bar_s);
       }
-      if (j + 1 < n_kv) issue_qk();          // S(j+1) in the same batch: one round trip per tile
-      umma_commit(bar_s);
+      __syncwarp();
     }
-    __syncwarp();
   }
   // last batch: O_tile(n_kv - 1)
   mbar_wait(bar_s, n_kv & 1);
@@ -247,7 +263,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   const int qrow = q_tile * ATT_M + tid;
   if (qrow < p.Sq) {
-    const float inv = 1.f / l_run;
+    float denom = l_run;
+    if (ones_col) {
+#pragma unroll
+      for (int c = 0; c < DK; ++c)
+        if (c == p.d) denom = acc[c];
+    }
+    const float inv = 1.f / denom;
     __nv_bfloat16* dst = p.o + (static_cast<size_t>(batch) * p.Sq + qrow) * p.ldo + head * p.d;
 #pragma unroll
     for (int c = 0; c < DK; c += 8) {
