@@ -42,6 +42,7 @@ template <int DK>
 __global__ void __launch_bounds__(128, AttnCfg<DK>::MIN_BLOCKS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  pdl_launch_dependents();
   using Cfg = AttnCfg<DK>;
   constexpr int NC = Cfg::NC;
   extern __shared__ uint8_t smem_raw[];
@@ -79,6 +80,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                    // prologue above overlaps the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;             // columns [0, ATT_N)
   const uint32_t tmem_o = tmem_base + ATT_N;     // columns [ATT_N, ATT_N + DK)
@@ -303,7 +305,7 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
     configured = true;
   }
   dim3 grid((p.Sq + ATT_M - 1) / ATT_M, heads, batch);
-  attn_fwd_kernel<DK><<<grid, 128, Cfg::SMEM, stream>>>(mq, mk, mv, p);
+  launch_pdl(attn_fwd_kernel<DK>, grid, 128, Cfg::SMEM, stream, mq, mk, mv, p);
   return lavie_check_launch("attn_fwd_kernel");
 }
 
@@ -331,6 +333,7 @@ struct TempParams {
 
 __global__ void __launch_bounds__(128)
 temporal_attn_kernel(const TempParams p) {
+  pdl_prologue();
   extern __shared__ float tsm[];
   const int warp_in_blk = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -444,6 +447,7 @@ __device__ __forceinline__ uint32_t scale_rope_pair(uint32_t w, float scale, boo
 template <int DP>   // head pitch (d rounded up to 16): 48, 64, 80, 96, 128, 160
 __global__ void __launch_bounds__(128)
 temporal_attn_mma_kernel(const TempParams p) {
+  pdl_prologue();
   constexpr int VP = DP + 8;                      // smem V row pitch (elements): conflict-free ldmatrix rows
   constexpr int NB32 = DP / 32;                   // 32-column blocks (two k-steps each)
   constexpr bool TAIL16 = (DP % 32) != 0;         // one trailing 16-column block
@@ -604,7 +608,7 @@ template <int DP>
 int launch_temporal_mma(const TempParams& p, cudaStream_t stream) {
   long long blocks = (p.items + 3) / 4;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
-  temporal_attn_mma_kernel<DP><<<static_cast<int>(blocks), 128, 0, stream>>>(p);
+  launch_pdl(temporal_attn_mma_kernel<DP>, static_cast<int>(blocks), 128, 0, stream, p);
   return lavie_check_launch("temporal_attn_mma_kernel");
 }
 
@@ -690,6 +694,6 @@ extern "C" int lavie_temporal_attention_bf16(const void* qkv, int ld, int k_off,
   }
   long long blocks = (p.items + warps - 1) / warps;
   if (blocks > 148LL * 8) blocks = 148LL * 8;
-  temporal_attn_kernel<<<static_cast<int>(blocks), warps * 32, smem, stream>>>(p);
+  launch_pdl(temporal_attn_kernel, static_cast<int>(blocks), warps * 32, smem, stream, p);
   return lavie_check_launch("temporal_attn_kernel");
 }

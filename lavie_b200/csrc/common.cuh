@@ -32,7 +32,38 @@ int lavie_make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t
 int lavie_make_tmap_im2col(CUtensorMap* map, const void* base, int N, int H, int W, int C, int channels, int pixels,
                            int stride);
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, calls griddepcontrol.launch_dependents at its very start and
+// griddepcontrol.wait before it touches memory a predecessor may have written.  The next kernel's CTAs can therefore
+// be scheduled, set up barriers / TMEM / descriptors and park at the wait while the current kernel drains, instead of
+// paying launch latency + prologue after it (~2-4 us per launch x ~550 launches per step).
+// ---------------------------------------------------------------------------------------------
+extern int g_lavie_pdl;       // 1 = on (default); lavie_debug_set(3, 0) turns it off for A/B timing
+
 #ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_lavie_pdl;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// start of every kernel: let the dependent grid begin its prologue, then wait for our own predecessors
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
 // ---------------------------------------------------------------------------------------------
 // Small device utilities
 // ---------------------------------------------------------------------------------------------
@@ -81,6 +112,23 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-form (erf) GELU at 7 FMA-pipe instructions + 1 MUFU, for epilogues that run it on every accumulator element:
+//   Phi(-t) = erfc(t / sqrt 2) / 2 = 2^-q(t),  q(t) = 1 + t * Q(t),  Q = degree-4 minimax fit on t in [0, 6]
+//   (leading coefficient > 0, so q keeps growing and 2^-q -> 0 for any larger t);
+//   gelu(x) = x * Phi(x) = max(x, 0) - |x| * Phi(-|x|).
+// |gelu_fast - gelu_erf| <= 1.6e-6 over the whole real line (fit + fp32 evaluation, tools/fit_gelu.py), i.e. three
+// orders of magnitude below the bf16 rounding of the result.
+__device__ __forceinline__ float gelu_fast_f(float x) {
+  const float t = fabsf(x);
+  float q = fmaf(t, 0.0005355844041332603f, -0.007474260404706001f);
+  q = fmaf(q, t, 0.052688680589199066f);
+  q = fmaf(q, t, 0.4591757357120514f);
+  q = fmaf(q, t, 1.1511057615280151f);
+  q = fmaf(q, t, 1.0f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q));
+  return fmaf(-t, e, fmaxf(x, 0.0f));
+}
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier

@@ -37,11 +37,12 @@ constexpr int PAIR_M = 256;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 8;                  // 2 per TMEM lane quarter (16 measured: no faster, GEGLU slower)
+constexpr int EPI_SPLIT = NUM_EPI_WARPS / 4;      // warps sharing one 32-row slab take every EPI_SPLIT-th 32-column chunk
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // 320
 constexpr int EPI_BAR_ID = 1;
 constexpr int EPI_CHUNK_BYTES = 32 * 32 * 2;      // one 32-row x 32-column bf16 chunk (TMA box, 64-byte swizzle)
-constexpr int EPI_CHUNKS_PER_WARP = 4;            // BLOCK_N <= 256 -> at most 8 chunks per row quarter, 2 warps share them
+constexpr int EPI_CHUNKS_PER_WARP = (8 + EPI_SPLIT - 1) / EPI_SPLIT;   // BLOCK_N <= 256 -> at most 8 chunks per row quarter
 
 struct GemmParams {
   int M, N, K;
@@ -99,7 +100,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // .relaxed: the only thing this arrive publishes is "my tcgen05.ld's have completed", which tcgen05.wait::ld +
+  // tcgen05.fence::before_thread_sync already order.  The default .release.cluster compiles to MEMBAR.ALL.GPU +
+  // CCTL.IVALL and cost 3000-4000 cycles per tile while TMA stores were in flight (tools/gemm_timeline.py).
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
@@ -178,6 +182,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                   const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
                   const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
+  pdl_launch_dependents();
   using L = SmemLayout<BLOCK_N>;
   constexpr int STAGES = L::STAGES;
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
@@ -225,6 +230,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
   tc_fence_before();
   cluster_sync_all();            // barriers of both CTAs initialised before any remote arrive / multicast commit
   tc_fence_after();
+  pdl_wait();                    // everything above overlapped the previous kernel's tail; its data is visible from here
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -299,12 +305,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       uint32_t acc_phase = 0;
       for (int item = pair; item < num_items; item += num_pairs) {
         const Item it = decode_item(p, item);
+        const bool tl = (p.debug & 512) && blockIdx.x == 0 && lane == 0;    // debug timeline (tools/gemm_timeline.py)
+        long long* tl_row = reinterpret_cast<long long*>(p.partial) + 8192 + ((item - pair) / num_pairs) * 8;
+        if (tl) tl_row[0] = clock64();
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (tl) tl_row[1] = clock64();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (tl && kb == it.kb_begin) tl_row[2] = clock64();
+          if (tl && kb == it.kb_end - 1) tl_row[3] = clock64();
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;
           const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024);
@@ -323,6 +335,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (tl) tl_row[4] = clock64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -333,9 +346,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
     // (64-byte-swizzled, conflict-free) and lets the TMA move them: the residual tile is PREFETCHED into the same
     // buffers with TMA loads while the MMAs of the tile are still running, the sum is written back in place and
     // leaves with a TMA store (which also clips the M / N tails).
-    const int ew = warp - 2;                       // 0..7
+    const int ew = warp - 2;                       // 0..NUM_EPI_WARPS-1
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    const int chalf = ew >> 2;                     // which half of the 32-column chunks this warp drains
+    const int chalf = ew >> 2;                     // which share of the 32-column chunks this warp drains
     const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     uint8_t* my_stage = s_epi + ew * (EPI_CHUNKS_PER_WARP * EPI_CHUNK_BYTES);
     uint64_t* my_res_bar = &res_bar[ew];
@@ -353,22 +366,27 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       const int n0 = it.n_blk * BLOCK_N;
       const bool staged = p.splits == 1;
       const bool has_res = staged && p.residual != nullptr;
+      const bool tl = (p.debug & 512) && blockIdx.x == 0 && ew == 0 && lane == 0;
+      long long* tl_row = reinterpret_cast<long long*>(p.partial) + ((item - pair) / num_pairs) * 8;
+      if (tl) tl_row[0] = clock64();
       if (staged) {
         // buffers are free once the previous tile's stores have finished READING them
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
         if (has_res && lane == 0 && !(p.debug & 64)) {
           int nch = 0;
-          for (int c = chalf; c < BLOCK_N / 32; c += 2) ++nch;
+          for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT) ++nch;
           mbar_expect_tx(my_res_bar, nch * EPI_CHUNK_BYTES);
           int k = 0;
-          for (int c = chalf; c < BLOCK_N / 32; c += 2, ++k)
+          for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT, ++k)
             tma_load_2d(my_stage + k * EPI_CHUNK_BYTES, &tmap_res, my_res_bar, n0 + c * 32, wrow0);
         }
       }
 
+      if (tl) tl_row[1] = clock64();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (tl) tl_row[2] = clock64();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
       if (has_res && !(p.debug & 64)) {
         mbar_wait(my_res_bar, res_phase);
@@ -411,7 +429,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         // fp32 partials for the ordered split-K reduction
         float* dst_row = p.partial + (static_cast<size_t>(split) * p.M + row) * p.N;
 #pragma unroll 1
-        for (int c = chalf; c < BLOCK_N / 32; c += 2) {
+        for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c * 32, v);
           tmem_wait_ld();
@@ -426,10 +444,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       } else if (!p.geglu) {
         int k = 0;
 #pragma unroll 1
-        for (int c = chalf; c < BLOCK_N / 32; c += 2, ++k) {
+        for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT, ++k) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c * 32, v);
           tmem_wait_ld();
+          if (tl && k == 0) tl_row[3] = clock64();
           const int col0 = n0 + c * 32;
           float f[32];
 #pragma unroll
@@ -459,7 +478,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         constexpr int HALF = BLOCK_N / 2;
         int k = 0;
 #pragma unroll 1
-        for (int c = chalf; c < HALF / 32; c += 2, ++k) {
+        for (int c = chalf; c < HALF / 32; c += EPI_SPLIT, ++k) {
           uint32_t v[32], g[32];
           tmem_ld_32x32(t_row + c * 32, v);
           tmem_ld_32x32(t_row + HALF + c * 32, g);
@@ -472,17 +491,19 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
               bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + e));
               bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + HALF + c * 32 + e));
             }
-            f[e] = (__uint_as_float(v[e]) + bv.x) * gelu_erf_f(__uint_as_float(g[e]) + bg.x);
-            f[e + 1] = (__uint_as_float(v[e + 1]) + bv.y) * gelu_erf_f(__uint_as_float(g[e + 1]) + bg.y);
-            f[e + 2] = (__uint_as_float(v[e + 2]) + bv.z) * gelu_erf_f(__uint_as_float(g[e + 2]) + bg.z);
-            f[e + 3] = (__uint_as_float(v[e + 3]) + bv.w) * gelu_erf_f(__uint_as_float(g[e + 3]) + bg.w);
+            f[e] = (__uint_as_float(v[e]) + bv.x) * gelu_fast_f(__uint_as_float(g[e]) + bg.x);
+            f[e + 1] = (__uint_as_float(v[e + 1]) + bv.y) * gelu_fast_f(__uint_as_float(g[e + 1]) + bg.y);
+            f[e + 2] = (__uint_as_float(v[e + 2]) + bv.z) * gelu_fast_f(__uint_as_float(g[e + 2]) + bg.z);
+            f[e + 3] = (__uint_as_float(v[e + 3]) + bv.w) * gelu_fast_f(__uint_as_float(g[e + 3]) + bg.w);
           }
           stage_and_store(f, k, it.n_blk * HALF + c * 32, false);
         }
       }
+      if (tl) tl_row[4] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
+      if (tl) tl_row[5] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -501,6 +522,7 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* __restrict__ bias,
                      const float* __restrict__ row_bias, int rows_per_batch, int ld_row_bias,
                      const __nv_bfloat16* __restrict__ residual, int ldr, __nv_bfloat16* __restrict__ out, int ldo) {
+  pdl_prologue();
   const int nvec = N >> 2;
   const long long total = static_cast<long long>(M) * nvec;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -545,14 +567,14 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   const int items = p.m_tiles * p.n_tiles * p.splits;
   int pairs = num_sms / 2;
   if (items < pairs) pairs = items;
-  gemm_bf16_tcgen05<BLOCK_N><<<2 * pairs, NUM_THREADS, L::TOTAL, stream>>>(a0, a1, b, mo, mr, p);
+  launch_pdl(gemm_bf16_tcgen05<BLOCK_N>, 2 * pairs, NUM_THREADS, L::TOTAL, stream, a0, a1, b, mo, mr, p);
   int rc = lavie_check_launch("gemm_bf16_tcgen05");
   if (rc) return rc;
   if (p.splits > 1) {
     const long long total = static_cast<long long>(p.M) * (p.N >> 2);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_reduce_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p.partial, p.splits, p.M, p.N, p.bias,
+    launch_pdl(splitk_reduce_kernel, static_cast<int>(blocks), 256, 0, stream, p.partial, p.splits, p.M, p.N, p.bias,
                                                                      p.row_bias, p.rows_per_batch, p.ld_row_bias,
                                                                      p.residual, p.ldr, p.out, p.ldo);
     rc = lavie_check_launch("splitk_reduce_kernel");
@@ -697,6 +719,7 @@ extern "C" int lavie_debug_set(int what, int value) {
   if (what == 1) g_force_splits = value;
   if (what == 2) g_debug = value;
   if (what == 0) g_k_rot = value;
+  if (what == 3) g_lavie_pdl = value ? 1 : 0;
   return 0;
 }
 

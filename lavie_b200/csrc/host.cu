@@ -112,5 +112,7 @@ int lavie_make_tmap_im2col(CUtensorMap* map, const void* base, int N, int H, int
   return LAVIE_OK;
 }
 
+int g_lavie_pdl = 1;
+
 extern "C" const char* lavie_last_error(void) { return g_error; }
 extern "C" int lavie_abi_version(void) { return 1; }

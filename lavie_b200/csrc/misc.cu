@@ -10,6 +10,7 @@ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 // Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): [cos | sin]   (unet.py:153,428; diffusers 0.16)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, float* __restrict__ out) {
+  pdl_prologue();
   const int half = dim >> 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -27,6 +28,7 @@ template <int MAXM>
 __global__ void __launch_bounds__(256)
 linear_smallm_kernel(const float* __restrict__ x, int M, int K, const __nv_bfloat16* __restrict__ w,
                      const float* __restrict__ bias, float* __restrict__ out, int N, int silu_in, int silu_out) {
+  pdl_prologue();
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -75,6 +77,7 @@ linear_smallm_kernel(const float* __restrict__ x, int M, int K, const __nv_bfloa
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x, int B, int Cin, int F, int H, int W, const float* __restrict__ w,
                const float* __restrict__ bias, int Cout, __nv_bfloat16* __restrict__ out, int ldo) {
+  pdl_prologue();
   extern __shared__ float s_w[];     // transposed to [Cin*9][Cout]: a warp reads 1 KiB contiguous per tap
   const int kk = Cin * 9;
   for (int i = threadIdx.x; i < Cout * kk; i += blockDim.x) {
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(256)
 conv_out_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ scale_shift, int B, int F,
                 int H, int W, int C, const float* __restrict__ w, const float* __restrict__ bias,
                 float* __restrict__ out) {
+  pdl_prologue();
   extern __shared__ float s_w[];     // [COUT][9][C]
   for (int i = threadIdx.x; i < COUT * 9 * C; i += blockDim.x) s_w[i] = w[i];
   __syncthreads();
@@ -190,6 +194,7 @@ conv_out_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __res
 __global__ void __launch_bounds__(256)
 im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, int NF, int H, int W, int C, int stride, int Ho, int Wo,
                  __nv_bfloat16* __restrict__ col) {
+  pdl_prologue();
   const int nvec = C >> 3;
   const long long total = static_cast<long long>(NF) * Ho * Wo * 9 * nvec;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -210,6 +215,7 @@ im2col3x3_kernel(const __nv_bfloat16* __restrict__ x, int NF, int H, int W, int 
 
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int NF, int H, int W, int C, __nv_bfloat16* __restrict__ y) {
+  pdl_prologue();
   const int nvec = C >> 3;
   const int Ho = 2 * H, Wo = 2 * W;
   const long long total = static_cast<long long>(NF) * Ho * Wo * nvec;
@@ -229,6 +235,7 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int NF, int H, int W, int
 __global__ void cfg_ddim_kernel(const float* __restrict__ nu, const float* __restrict__ nt, float g, float sa_t,
                                 float s1a_t, float sa_p, float s1a_p, const float* __restrict__ lat,
                                 float* __restrict__ out, long long n) {
+  pdl_prologue();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float eps = nu[i] + g * (nt[i] - nu[i]);
@@ -249,7 +256,7 @@ int grid_for(long long total, int threads) {
 extern "C" int lavie_timestep_embedding(const float* t, int B, int dim, float* out, cudaStream_t stream) {
   LAVIE_REQUIRE(B > 0 && dim > 0 && dim % 2 == 0, LAVIE_ERR_SHAPE, "timestep_embedding: dim must be even");
   const int total = B * (dim / 2);
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, stream>>>(t, B, dim, out);
+  launch_pdl(timestep_embedding_kernel, (total + 127) / 128, 128, 0, stream, t, B, dim, out);
   return lavie_check_launch("timestep_embedding_kernel");
 }
 
@@ -259,8 +266,8 @@ extern "C" int lavie_linear_smallm(const float* x, int M, int K, const void* w, 
   LAVIE_REQUIRE(al16(x) && al16(w), LAVIE_ERR_ALIGN, "linear_smallm: alignment");
   const int blocks = (N + 7) / 8;
   const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w);
-  if (M <= 2) linear_smallm_kernel<2><<<blocks, 256, 0, stream>>>(x, M, K, wp, bias, out, N, silu_in, silu_out);
-  else linear_smallm_kernel<8><<<blocks, 256, 0, stream>>>(x, M, K, wp, bias, out, N, silu_in, silu_out);
+  if (M <= 2) launch_pdl(linear_smallm_kernel<2>, blocks, 256, 0, stream, x, M, K, wp, bias, out, N, silu_in, silu_out);
+  else launch_pdl(linear_smallm_kernel<8>, blocks, 256, 0, stream, x, M, K, wp, bias, out, N, silu_in, silu_out);
   return lavie_check_launch("linear_smallm_kernel");
 }
 
@@ -278,7 +285,7 @@ extern "C" int lavie_conv_in(const float* x, int B, int Cin, int F, int H, int W
   const long long total = static_cast<long long>(B) * F * H * W * (Cout / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
-  conv_in_kernel<<<static_cast<int>(blocks), 256, smem, stream>>>(x, B, Cin, F, H, W, w, bias, Cout,
+  launch_pdl(conv_in_kernel, static_cast<int>(blocks), 256, smem, stream, x, B, Cin, F, H, W, w, bias, Cout,
                                                                   static_cast<__nv_bfloat16*>(out), ldo);
   return lavie_check_launch("conv_in_kernel");
 }
@@ -298,7 +305,7 @@ extern "C" int lavie_conv_out(const void* x, int ldx, const float* scale_shift, 
   const long long total = static_cast<long long>(B) * F * H * W;
   long long blocks = (total + 7) / 8;
   if (blocks > 148 * 4) blocks = 148 * 4;
-  conv_out_kernel<4><<<static_cast<int>(blocks), 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+  launch_pdl(conv_out_kernel<4>, static_cast<int>(blocks), 256, smem, stream, static_cast<const __nv_bfloat16*>(x), ldx,
                                                                       scale_shift, B, F, H, W, C, w, bias, out);
   return lavie_check_launch("conv_out_kernel");
 }
@@ -309,7 +316,7 @@ extern "C" int lavie_im2col3x3_bf16(const void* x, int NF, int H, int W, int C, 
   LAVIE_REQUIRE(al16(x) && al16(col), LAVIE_ERR_ALIGN, "im2col: alignment");
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long total = static_cast<long long>(NF) * Ho * Wo * 9 * (C / 8);
-  im2col3x3_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), NF, H, W, C, stride,
+  launch_pdl(im2col3x3_kernel, grid_for(total, 256), 256, 0, stream, static_cast<const __nv_bfloat16*>(x), NF, H, W, C, stride,
                                                              Ho, Wo, static_cast<__nv_bfloat16*>(col));
   return lavie_check_launch("im2col3x3_kernel");
 }
@@ -318,7 +325,7 @@ extern "C" int lavie_upsample_nearest2x(const void* x, int NF, int H, int W, int
   LAVIE_REQUIRE(C % 8 == 0, LAVIE_ERR_SHAPE, "upsample: C %% 8 == 0");
   LAVIE_REQUIRE(al16(x) && al16(y), LAVIE_ERR_ALIGN, "upsample: alignment");
   const long long total = static_cast<long long>(NF) * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), NF, H, W, C,
+  launch_pdl(upsample2x_kernel, grid_for(total, 256), 256, 0, stream, static_cast<const __nv_bfloat16*>(x), NF, H, W, C,
                                                               static_cast<__nv_bfloat16*>(y));
   return lavie_check_launch("upsample2x_kernel");
 }
@@ -328,7 +335,7 @@ extern "C" int lavie_cfg_ddim_step(const float* noise_uncond, const float* noise
                                    cudaStream_t stream) {
   LAVIE_REQUIRE(n > 0 && alpha_t > 0.f && alpha_t <= 1.f && alpha_prev > 0.f && alpha_prev <= 1.f, LAVIE_ERR_SHAPE,
                 "cfg_ddim_step: bad arguments");
-  cfg_ddim_kernel<<<grid_for(n, 256), 256, 0, stream>>>(noise_uncond, noise_text, guidance, sqrtf(alpha_t),
+  launch_pdl(cfg_ddim_kernel, grid_for(n, 256), 256, 0, stream, noise_uncond, noise_text, guidance, sqrtf(alpha_t),
                                                         sqrtf(1.f - alpha_t), sqrtf(alpha_prev),
                                                         sqrtf(1.f - alpha_prev), latents, latents_out, n);
   return lavie_check_launch("cfg_ddim_kernel");

@@ -20,6 +20,7 @@ __device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int ld0, int c
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __nv_bfloat16* __restrict__ x1, int ld1,
                 int c1, int rows_per_sample, int rows_per_chunk, int groups, int chunks, float* __restrict__ partial) {
+  pdl_prologue();
   extern __shared__ float sm[];          // [row_lanes][2][C]  (one private slot per row lane: deterministic)
   const int C = c0 + c1;
   const int sample = blockIdx.y;
@@ -85,6 +86,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __n
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int groups, int C,
                                    double inv_count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float* __restrict__ scale_shift) {
+  pdl_prologue();
   __shared__ float s_mean[64], s_rstd[64];
   const int sample = blockIdx.x;
   // 8 consecutive lanes share one group: each sums every 8th chunk in fp64, then a fixed-order shuffle tree
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __nv_bfloat16* __restrict__ x1, int ld1,
                 int c1, int rows_per_sample, int rows_per_chunk, const float* __restrict__ scale_shift, int silu,
                 __nv_bfloat16* __restrict__ y, int ldy) {
+  pdl_prologue();
   const int C = c0 + c1;
   const int vec_per_row = C >> 3;
   const int sample = blockIdx.y;
@@ -192,6 +195,7 @@ __global__ void __launch_bounds__(256)
 layernorm_grouped_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gamma,
                          const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy, int rows,
                          int perm_hw, int perm_hwp) {
+  pdl_prologue();
   constexpr int VPL = 5;
   constexpr int C = 40 * L;
   constexpr int RPW = 32 / L;
@@ -261,6 +265,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy, int rows, int C,
                  int perm_hw, int perm_hwp) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -363,8 +368,7 @@ extern "C" int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void
   dim3 grid(chunks, samples);
   const int vec_per_row = C >> 3;
   const int row_lanes = GN_THREADS / (vec_per_row < GN_THREADS ? vec_per_row : GN_THREADS);
-  gn_stats_kernel<<<grid, GN_THREADS, static_cast<size_t>(row_lanes) * 2 * C * sizeof(float), stream>>>(
-      static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1,
+  launch_pdl(gn_stats_kernel, grid, GN_THREADS, static_cast<size_t>(row_lanes) * 2 * C * sizeof(float), stream, static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1,
       rows_per_sample, rows_per_chunk, groups, chunks, partial);
   return lavie_check_launch("gn_stats_kernel");
 }
@@ -374,7 +378,7 @@ extern "C" int lavie_groupnorm_finalize(const float* partial, int samples, int c
                                         float* scale_shift, cudaStream_t stream) {
   LAVIE_REQUIRE(groups <= 64 && groups % 4 == 0 && C % groups == 0 && count_per_group > 0, LAVIE_ERR_SHAPE,
                 "groupnorm_finalize: groups must be a multiple of 4 (<= 64) dividing C");
-  gn_finalize_kernel<<<samples, 256, 0, stream>>>(partial, chunks, groups, C, 1.0 / static_cast<double>(count_per_group),
+  launch_pdl(gn_finalize_kernel, samples, 256, 0, stream, partial, chunks, groups, C, 1.0 / static_cast<double>(count_per_group),
                                                   gamma, beta, eps, scale_shift);
   return lavie_check_launch("gn_finalize_kernel");
 }
@@ -388,8 +392,7 @@ extern "C" int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void
   const int rows_per_chunk = gn_rows_per_chunk(samples, rows_per_sample);
   const int chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
   dim3 grid(chunks, samples);
-  gn_apply_kernel<<<grid, 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1, rows_per_sample,
+  launch_pdl(gn_apply_kernel, grid, 256, 0, stream, static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1, rows_per_sample,
       rows_per_chunk, scale_shift, silu, static_cast<__nv_bfloat16*>(y), ldy);
   return lavie_check_launch("gn_apply_kernel");
 }
@@ -411,19 +414,19 @@ int layernorm_impl(const void* x, int ldx, const float* gamma, const float* beta
     const long long warps = (static_cast<long long>(rows) + rpw - 1) / rpw;
     const int gblocks = static_cast<int>((warps + 7) / 8);
     if (lanes == 8)
-      layernorm_grouped_kernel<8><<<gblocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, perm_hw, perm_hwp);
+      launch_pdl(layernorm_grouped_kernel<8>, gblocks, 256, 0, stream, xp, ldx, gamma, beta, eps, yp, ldy, rows, perm_hw, perm_hwp);
     else if (lanes == 16)
-      layernorm_grouped_kernel<16><<<gblocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, perm_hw, perm_hwp);
+      launch_pdl(layernorm_grouped_kernel<16>, gblocks, 256, 0, stream, xp, ldx, gamma, beta, eps, yp, ldy, rows, perm_hw, perm_hwp);
     else
-      layernorm_grouped_kernel<32><<<gblocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, perm_hw, perm_hwp);
+      launch_pdl(layernorm_grouped_kernel<32>, gblocks, 256, 0, stream, xp, ldx, gamma, beta, eps, yp, ldy, rows, perm_hw, perm_hwp);
     return lavie_check_launch("layernorm_grouped_kernel");
   }
   if (nvec <= 64)
-    layernorm_kernel<2><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C, perm_hw, perm_hwp);
+    launch_pdl(layernorm_kernel<2>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, yp, ldy, rows, C, perm_hw, perm_hwp);
   else if (nvec <= 160)
-    layernorm_kernel<5><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C, perm_hw, perm_hwp);
+    launch_pdl(layernorm_kernel<5>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, yp, ldy, rows, C, perm_hw, perm_hwp);
   else
-    layernorm_kernel<8><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, yp, ldy, rows, C, perm_hw, perm_hwp);
+    launch_pdl(layernorm_kernel<8>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, yp, ldy, rows, C, perm_hw, perm_hwp);
   return lavie_check_launch("layernorm_kernel");
 }
 
@@ -431,6 +434,7 @@ int layernorm_impl(const void* x, int ldx, const float* gamma, const float* beta
 __global__ void __launch_bounds__(256)
 add_gathered_kernel(const __nv_bfloat16* __restrict__ res, int ldr, const __nv_bfloat16* __restrict__ z, int ldz,
                     __nv_bfloat16* __restrict__ out, int ldo, int rows, int C, int hw, int hwp) {
+  pdl_prologue();
   const int nvec = C >> 3;
   const int f_loc = rows / hw;
   const long long total = static_cast<long long>(rows) * nvec;
@@ -455,6 +459,7 @@ add_gathered_kernel(const __nv_bfloat16* __restrict__ res, int ldr, const __nv_b
 
 // sums[sample][group][2] (fp64) = ordered sum of the chunk partials: what gets all-reduced across frame shards
 __global__ void gn_reduce_kernel(const float* __restrict__ partial, int chunks, int groups, double* __restrict__ sums) {
+  pdl_prologue();
   const int sample = blockIdx.x;
   const int sub = threadIdx.x & 7;
   for (int g = threadIdx.x >> 3; g < groups; g += blockDim.x >> 3) {
@@ -489,6 +494,7 @@ __global__ void gn_reduce_kernel(const float* __restrict__ partial, int chunks, 
 __global__ void gn_finalize_sums_kernel(const double* __restrict__ sums, int groups, int C, double inv_count,
                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                         float* __restrict__ scale_shift) {
+  pdl_prologue();
   const int sample = blockIdx.x;
   const int cpg = C / groups;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -526,8 +532,7 @@ extern "C" int lavie_add_gathered_bf16(const void* res, int ldr, const void* z, 
   const long long total = static_cast<long long>(rows) * (C >> 3);
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
-  add_gathered_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(res), ldr, static_cast<const __nv_bfloat16*>(z), ldz,
+  launch_pdl(add_gathered_kernel, static_cast<int>(blocks), 256, 0, stream, static_cast<const __nv_bfloat16*>(res), ldr, static_cast<const __nv_bfloat16*>(z), ldz,
       static_cast<__nv_bfloat16*>(out), ldo, rows, C, hw, hwp);
   return lavie_check_launch("add_gathered_kernel");
 }
@@ -535,7 +540,7 @@ extern "C" int lavie_add_gathered_bf16(const void* res, int ldr, const void* z, 
 extern "C" int lavie_groupnorm_reduce(const float* partial, int samples, int chunks, int groups, double* sums,
                                       cudaStream_t stream) {
   LAVIE_REQUIRE(groups <= 64 && groups % 4 == 0 && samples > 0 && chunks > 0, LAVIE_ERR_SHAPE, "groupnorm_reduce: shape");
-  gn_reduce_kernel<<<samples, 256, 0, stream>>>(partial, chunks, groups, sums);
+  launch_pdl(gn_reduce_kernel, samples, 256, 0, stream, partial, chunks, groups, sums);
   return lavie_check_launch("gn_reduce_kernel");
 }
 
@@ -543,7 +548,7 @@ extern "C" int lavie_groupnorm_finalize_sums(const double* sums, int samples, in
                                              long long count_per_group, const float* gamma, const float* beta,
                                              float eps, float* scale_shift, cudaStream_t stream) {
   LAVIE_REQUIRE(groups <= 64 && C % groups == 0 && count_per_group > 0, LAVIE_ERR_SHAPE, "groupnorm_finalize_sums: shape");
-  gn_finalize_sums_kernel<<<samples, 256, 0, stream>>>(sums, groups, C, 1.0 / static_cast<double>(count_per_group), gamma,
+  launch_pdl(gn_finalize_sums_kernel, samples, 256, 0, stream, sums, groups, C, 1.0 / static_cast<double>(count_per_group), gamma,
                                                        beta, eps, scale_shift);
   return lavie_check_launch("gn_finalize_sums_kernel");
 }

@@ -54,6 +54,7 @@ __device__ __forceinline__ void block_rank_barrier(const PeerPtrs& flags, int P,
 }
 
 __global__ void rank_barrier_kernel(PeerPtrs flags, uint32_t* epoch_counter, int P, int my_rank) {
+  pdl_prologue();
   const uint32_t epoch = *epoch_counter + 1;
   block_rank_barrier(flags, P, my_rank, epoch);
   if (threadIdx.x == 0) *epoch_counter = epoch;
@@ -66,6 +67,7 @@ gn_exchange_finalize_kernel(const float* __restrict__ partial, int samples, int 
                             double inv_count, const float* __restrict__ gamma, const float* __restrict__ beta,
                             float eps, float* __restrict__ scale_shift, PeerPtrs slots, PeerPtrs flags,
                             uint32_t* epoch_counter, int P, int my_rank) {
+  pdl_prologue();
   __shared__ double s_sums[2 * 64 * 2];          // [samples <= 2][groups <= 64][2]
   __shared__ float s_mean[2 * 64], s_rstd[2 * 64];
   const uint32_t epoch = *epoch_counter + 1;
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(256)
 layernorm_scatter_p2p_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gamma,
                              const float* __restrict__ beta, float eps, PeerPtrs recv, int rows, int hw, int hwp,
                              int my_rank) {
+  pdl_prologue();
   constexpr int VPL = 5;
   constexpr int C = 40 * L;
   constexpr int RPW = 32 / L;
@@ -205,6 +208,7 @@ layernorm_scatter_p2p_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const
 __global__ void __launch_bounds__(256)
 add_gathered_p2p_kernel(const __nv_bfloat16* __restrict__ res, int ldr, PeerPtrs ybuf, __nv_bfloat16* __restrict__ out,
                         int ldo, int rows, int C, int hw, int hwp, int my_rank) {
+  pdl_prologue();
   const int nvec = C >> 3;
   const int f_loc = rows / hw;
   const long long total = static_cast<long long>(rows) * nvec;
@@ -256,7 +260,7 @@ extern "C" int lavie_rank_barrier(void* const* flag_ptrs, unsigned int* epoch_co
   PeerPtrs f;
   int rc = fill_peers(f, flag_ptrs, P);
   if (rc) return rc;
-  rank_barrier_kernel<<<1, 32, 0, stream>>>(f, epoch_counter, P, my_rank);
+  launch_pdl(rank_barrier_kernel, 1, 32, 0, stream, f, epoch_counter, P, my_rank);
   return lavie_check_launch("rank_barrier_kernel");
 }
 
@@ -272,7 +276,7 @@ extern "C" int lavie_gn_exchange_finalize(const float* partial, int samples, int
   if (rc) return rc;
   rc = fill_peers(f, flag_ptrs, P);
   if (rc) return rc;
-  gn_exchange_finalize_kernel<<<1, 256, 0, stream>>>(partial, samples, chunks, groups, C,
+  launch_pdl(gn_exchange_finalize_kernel, 1, 256, 0, stream, partial, samples, chunks, groups, C,
                                                      1.0 / static_cast<double>(count_per_group_global), gamma, beta, eps,
                                                      scale_shift, s, f, epoch_counter, P, my_rank);
   return lavie_check_launch("gn_exchange_finalize_kernel");
@@ -294,11 +298,11 @@ extern "C" int lavie_layernorm_scatter_p2p(const void* x, int ldx, const float* 
   const int blocks = static_cast<int>((warps + 7) / 8);
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   if (lanes == 8)
-    layernorm_scatter_p2p_kernel<8><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, r, rows, hw, hwp, my_rank);
+    launch_pdl(layernorm_scatter_p2p_kernel<8>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, my_rank);
   else if (lanes == 16)
-    layernorm_scatter_p2p_kernel<16><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, r, rows, hw, hwp, my_rank);
+    launch_pdl(layernorm_scatter_p2p_kernel<16>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, my_rank);
   else
-    layernorm_scatter_p2p_kernel<32><<<blocks, 256, 0, stream>>>(xp, ldx, gamma, beta, eps, r, rows, hw, hwp, my_rank);
+    launch_pdl(layernorm_scatter_p2p_kernel<32>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, my_rank);
   return lavie_check_launch("layernorm_scatter_p2p_kernel");
 }
 
@@ -314,7 +318,6 @@ extern "C" int lavie_add_gathered_p2p(const void* res, int ldr, void* const* y_p
   long long blocks = (total + 1023) / 1024;
   if (blocks > 148LL * 8) blocks = 148LL * 8;
   if (blocks < 1) blocks = 1;
-  add_gathered_p2p_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(res), ldr, y, static_cast<__nv_bfloat16*>(out), ldo, rows, C, hw, hwp, my_rank);
+  launch_pdl(add_gathered_p2p_kernel, static_cast<int>(blocks), 256, 0, stream, static_cast<const __nv_bfloat16*>(res), ldr, y, static_cast<__nv_bfloat16*>(out), ldo, rows, C, hw, hwp, my_rank);
   return lavie_check_launch("add_gathered_p2p_kernel");
 }
