@@ -40,8 +40,12 @@ typedef enum {
 
 const char* lavie_last_error(void);
 int lavie_abi_version(void);
-/* Tuning hook for tests/benchmarks: what = 1 forces the split-K factor of the GEMM (0 = automatic). */
+/* Tuning hooks for tests/benchmarks (never needed for correct results): what = 1 forces the split-K factor of the
+ * GEMM (0 = automatic); 2 = debug bit mask (512: GEMM per-tile clock64 timeline into the workspace); 3 = programmatic
+ * dependent launch on/off; 4 = attention: every n-th exp2 on the FMA pipe (0 = all on the MUFU). */
 int lavie_debug_set(int what, int value);
+/* Device scratch (>= 64 KB) that the attention kernel fills with a per-tile clock64 timeline of one CTA; NULL = off. */
+int lavie_debug_buffer(void* device_ptr);
 
 /* Fused GEMM epilogue: out = bf16( acc + bias[n] + row_bias[row / rows_per_batch][n] + residual[row][n] ), or with
  * geglu != 0: out[:, j] = (acc[:, j] + bias) * gelu_erf(acc[:, j + 128] + bias') per 256-column tile. */

@@ -27,6 +27,7 @@ struct AttnParams {
   int Sq, Sk, d, head_pitch, kv_batch_div, ldo;
   float scale_log2;
   __nv_bfloat16* o;
+  long long* timeline;   // debug (tools/attn_timeline.py): clock64 stamps of one mid-grid CTA, else nullptr
 };
 
 template <int DK>
@@ -38,7 +39,7 @@ struct AttnCfg {
   static constexpr int MIN_BLOCKS = DK <= 64 ? 4 : (DK <= 96 ? 2 : 1);
 };
 
-template <int DK>
+template <int DK, int POLY, bool ONES>
 __global__ void __launch_bounds__(128, AttnCfg<DK>::MIN_BLOCKS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -90,31 +91,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int c = 0; c < NC; ++c) tma_load_3d(sQ + c * CHUNK_BYTES, &tmap_q, bar_q, col0 + c * 64, q_tile * ATT_M, batch);
     mbar_expect_tx(bar_k, NC * KV_CHUNK_BYTES);
     for (int c = 0; c < NC; ++c) tma_load_3d(sK + c * KV_CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, 0, kv_batch);
-    mbar_expect_tx(bar_v, NC * KV_CHUNK_BYTES);
-    for (int c = 0; c < NC; ++c) tma_load_3d(sV + c * KV_CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, 0, kv_batch);
   }
 
   constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_M, ATT_N, 0, 0);
   constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_M, DK, 0, 1);
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
 
-  float m_run = -INFINITY, l_run = 0.f;
+  // Softmax state per query row (one row per thread).  The output accumulator stays in TMEM across key tiles
+  // (P.V accumulates with use_acc); m_used is the exponent offset currently baked into it.  It is only moved -- and O
+  // rescaled in TMEM -- when the running maximum has grown by more than 2^8 since (lazy rescale): probabilities are
+  // then at most 256, harmless in bf16 / fp32, and the result O / l is unchanged because both use the same offset.
+  float m_used = -INFINITY, l_run = 0.f;
   // d < DK (d = 40 in a 48-wide head slot): a padded V column is set to 1.0 so that the P.V MMA itself produces the
   // softmax denominator (sum of the bf16-rounded probabilities) in accumulator column d -- no per-element FADD.
-  const bool ones_col = p.d < DK;
-  float acc[DK];
-#pragma unroll
-  for (int i = 0; i < DK; ++i) acc[i] = 0.f;
+  constexpr bool ones_col = ONES;              // host: p.d < DK
 
-  // One MMA round trip per key tile: batch j = { O_tile = P(j-1) V(j-1),  S = Q K(j)^T } is committed to ONE barrier.
+  // One MMA round trip per key tile: batch j = { O += P(j-1) V(j-1),  S = Q K(j)^T } is committed to ONE barrier.
   // While it runs, nothing in this CTA can proceed -- the other co-resident CTAs fill the SM.
+  // Operand descriptors are built once; a K-step only adds (byte offset >> 4) to the 14-bit start-address field.
+  const uint64_t desc_q = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+  const uint64_t desc_k = umma_desc_sw128(smem_u32(sK), 16, 1024);
+  const uint64_t desc_p = umma_desc_sw128(smem_u32(sP), 16, 1024);
+  const uint64_t desc_v = umma_desc_sw128(smem_u32(sV), KV_CHUNK_BYTES, 1024);
   auto issue_qk = [&]() {
 #pragma unroll
     for (int kk = 0; kk < DK / 16; ++kk) {
       const uint32_t qoff = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
       const uint32_t koff = (kk >> 2) * KV_CHUNK_BYTES + (kk & 3) * 32;
-      umma_bf16(tmem_s, umma_desc_sw128(smem_u32(sQ) + qoff, 16, 1024),
-                umma_desc_sw128(smem_u32(sK) + koff, 16, 1024), idesc_qk, kk != 0);
+      umma_bf16(tmem_s, desc_q + (qoff >> 4), desc_k + (koff >> 4), idesc_qk, kk != 0);
     }
   };
   // MMA / TMA issue runs warp-uniformly in warp 0 (descriptors stay in uniform registers; with a divergent
@@ -129,74 +133,89 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     __syncwarp();
   }
-  float alpha_prev = 1.f;
+  const float sc = p.scale_log2;
+  uint8_t* p_row = sP + tid * 128;
 
+  const bool tl = p.timeline != nullptr && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2 &&
+                  blockIdx.z == gridDim.z / 2;
   for (int j = 0; j < n_kv; ++j) {
     const uint32_t ph = j & 1;
     const int kv_len = min(ATT_N, p.Sk - j * ATT_N);
-    mbar_wait(bar_s, ph);                    // S(j) ready; for j >= 1 also O_tile(j-1)
+    long long* tl_row = p.timeline + j * 8;
+    if (tl) tl_row[0] = clock64();
+    mbar_wait(bar_s, ph);                    // S(j) ready; for j >= 1 also P(j-1) V(j-1) accumulated
     tc_fence_after();
+    if (tl) tl_row[1] = clock64();
     if (warp == 0 && elect_one()) {
-      if (j + 1 < n_kv) {                    // K buffer is free (QK(j) retired): prefetch K(j+1) under the softmax
-        mbar_expect_tx(bar_k, NC * KV_CHUNK_BYTES);
+      // Both buffers are free (QK(j) and PV(j-1) retired): K(j+1) and V(j) stream in under the softmax and complete
+      // ONE barrier -- every mbarrier wait on the issuing thread's path costs ~130 cycles even when already complete.
+      const bool more = j + 1 < n_kv;
+      mbar_expect_tx(bar_v, (more ? 2 : 1) * NC * KV_CHUNK_BYTES);
+      for (int c = 0; c < NC; ++c)
+        tma_load_3d(sV + c * KV_CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, j * ATT_N, kv_batch);
+      if (more)
         for (int c = 0; c < NC; ++c)
-          tma_load_3d(sK + c * KV_CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, (j + 1) * ATT_N, kv_batch);
-      }
-      if (j >= 1) {                          // V buffer is free (PV(j-1) retired): fetch V(j)
-        mbar_expect_tx(bar_v, NC * KV_CHUNK_BYTES);
-        for (int c = 0; c < NC; ++c)
-          tma_load_3d(sV + c * KV_CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, j * ATT_N, kv_batch);
-      }
+          tma_load_3d(sK + c * KV_CHUNK_BYTES, &tmap_k, bar_v, col0 + c * 64, (j + 1) * ATT_N, kv_batch);
     }
     __syncwarp();
-    if (j >= 1) {                            // fold the previous tile's P V into the running output
+
+    // ---- S(j) -> registers, read once ----
+    uint32_t s0[32], s1[32];
+    tmem_ld_32x32(tmem_s + lane_base, s0);
+    tmem_ld_32x32(tmem_s + lane_base + 32, s1);
+    tmem_wait_ld();
+    if (tl) tl_row[2] = clock64();
+    const bool full = (kv_len == ATT_N);           // CTA-uniform
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+    if (full) {
+      float mx2 = -INFINITY, mx3 = -INFINITY;      // four short FMNMX3 chains instead of two long ones
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        mx0 = fmax3(mx0, __uint_as_float(s0[e]), __uint_as_float(s0[e + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s1[e]), __uint_as_float(s1[e + 1]));
+        mx2 = fmax3(mx2, __uint_as_float(s0[e + 2]), __uint_as_float(s0[e + 3]));
+        mx3 = fmax3(mx3, __uint_as_float(s1[e + 2]), __uint_as_float(s1[e + 3]));
+      }
+      mx0 = fmaxf(mx0, mx2);
+      mx1 = fmaxf(mx1, mx3);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        if (e < kv_len) mx0 = fmaxf(mx0, __uint_as_float(s0[e]));
+        if (32 + e < kv_len) mx1 = fmaxf(mx1, __uint_as_float(s1[e]));
+      }
+    }
+    const float m_tile = fmaxf(mx0, mx1) * sc;     // sc > 0
+    const bool grow = m_tile > m_used + 8.0f;      // always true for j == 0 (m_used = -inf)
+    if (j > 0 && __any_sync(0xffffffffu, grow)) {
+      const float alpha = grow ? fast_exp2(m_used - m_tile) : 1.0f;
 #pragma unroll
       for (int c = 0; c < DK / 16; ++c) {
         uint32_t v[16];
         tmem_ld_32x16(tmem_o + lane_base + c * 16, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) acc[c * 16 + e] = acc[c * 16 + e] * alpha_prev + __uint_as_float(v[e]);
+        for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+        tmem_st_32x16(tmem_o + lane_base + c * 16, v);
       }
+      tmem_wait_st();
+      l_run *= alpha;
     }
+    if (grow) m_used = m_tile;
+    const float neg_m = -m_used;
 
-    // ---- online softmax (full tiles take an unmasked path: ~2x fewer issue slots, this loop is issue-bound) ----
-    const bool full = (kv_len == ATT_N);           // CTA-uniform
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < ATT_N / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
-      tmem_wait_ld();
-      if (full) {
-#pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          mx0 = fmax3(mx0, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (c * 32 + e < kv_len) mx0 = fmaxf(mx0, __uint_as_float(v[e]));
-      }
-    }
-    const float m_new = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
-    const float alpha = fast_exp2(m_run - m_new);
-    // ---- pass 2: p = exp2(s*scale - m), row sum, P -> smem (bf16, 128B swizzle, K-major) ----
+    // ---- p = exp2(s*scale - m_used), P -> smem (bf16, 128B swizzle, K-major) ----
+    // Full tiles: every POLY-th exponential runs on the FMA pipe (exp2_poly), the rest on the MUFU.
     float rs0 = 0.f, rs1 = 0.f;
-    uint8_t* p_row = sP + tid * 128;
-    const float sc = p.scale_log2;
-#pragma unroll
-    for (int c = 0; c < ATT_N / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
-      tmem_wait_ld();
+    auto soft_half = [&](uint32_t (&sv)[32], int c) {
       uint32_t pk[16];
       if (full) {
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sc, -m_new));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sc, -m_new));
+          const float x0 = fmaf(__uint_as_float(sv[e]), sc, neg_m);
+          const float x1 = fmaf(__uint_as_float(sv[e + 1]), sc, neg_m);
+          const float p0 = (POLY > 0 && (e % POLY) == POLY - 1) ? exp2_poly(x0) : fast_exp2(x0);
+          const float p1 = (POLY > 0 && ((e + 1) % POLY) == POLY - 1) ? exp2_poly(x1) : fast_exp2(x1);
           if (!ones_col) {
             rs0 += p0;
             rs1 += p1;
@@ -206,8 +225,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       } else {
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float p0 = (c * 32 + e < kv_len) ? fast_exp2(fmaf(__uint_as_float(v[e]), sc, -m_new)) : 0.f;
-          const float p1 = (c * 32 + e + 1 < kv_len) ? fast_exp2(fmaf(__uint_as_float(v[e + 1]), sc, -m_new)) : 0.f;
+          const float p0 = (c * 32 + e < kv_len) ? fast_exp2(fmaf(__uint_as_float(sv[e]), sc, neg_m)) : 0.f;
+          const float p1 = (c * 32 + e + 1 < kv_len) ? fast_exp2(fmaf(__uint_as_float(sv[e + 1]), sc, neg_m)) : 0.f;
           rs0 += p0;
           rs1 += p1;
           pk[e >> 1] = pack_bf16(p0, p1);
@@ -219,69 +238,76 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int c16 = ((c & 1) * 4 + g) ^ (tid & 7);
         *reinterpret_cast<uint4*>(chunk + c16 * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
       }
-    }
-    const float rs = rs0 + rs1;
-    l_run = l_run * alpha + rs;
-    m_run = m_new;
-    alpha_prev = alpha;
+    };
+    soft_half(s0, 0);
+    soft_half(s1, 1);
+    l_run += rs0 + rs1;
     if (ones_col && tid < ATT_N) {           // V(j)[key = tid][column d] = 1.0 (bf16), 128-byte-swizzled address
       mbar_wait(bar_v, ph);
       const int unit = ((p.d >> 3) & 7) ^ (tid & 7);
       *reinterpret_cast<uint16_t*>(sV + (p.d >> 6) * KV_CHUNK_BYTES + tid * 128 + unit * 16 + (p.d & 7) * 2) = 0x3F80;
     }
+    if (tl) tl_row[3] = clock64();
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();                         // P(j) complete in smem, S(j) and O_tile(j-1) fully read
+    __syncthreads();                         // P(j) complete in smem, S(j) fully read, O rescaled where needed
+    if (tl) tl_row[4] = clock64();
 
     if (warp == 0) {
-      mbar_wait(bar_v, ph);                  // V(j) landed (j = 0: prologue load)
-      if (j + 1 < n_kv) mbar_wait(bar_k, ph ^ 1);
+      mbar_wait(bar_v, ph);                  // V(j) and K(j+1) landed
       tc_fence_after();
+      if (tl) tl_row[5] = clock64();
       const int nk = (kv_len + 15) >> 4;
       if (elect_one()) {
-        for (int kk = 0; kk < nk; ++kk) {
-          const uint32_t a_off = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
-          umma_bf16(tmem_o, umma_desc_sw128(smem_u32(sP) + a_off, 16, 1024),
-                    umma_desc_sw128(smem_u32(sV) + kk * 2048, KV_CHUNK_BYTES, 1024), idesc_pv, kk != 0);
+        if (full) {
+#pragma unroll
+          for (int kk = 0; kk < ATT_N / 16; ++kk)
+            umma_bf16(tmem_o, desc_p + (((kk >> 2) * CHUNK_BYTES + (kk & 3) * 32) >> 4), desc_v + ((kk * 2048) >> 4),
+                      idesc_pv, (j > 0 || kk != 0));
+        } else {
+          for (int kk = 0; kk < nk; ++kk)
+            umma_bf16(tmem_o, desc_p + (((kk >> 2) * CHUNK_BYTES + (kk & 3) * 32) >> 4), desc_v + ((kk * 2048) >> 4),
+                      idesc_pv, (j > 0 || kk != 0));
         }
+        if (tl) tl_row[7] = clock64();
         if (j + 1 < n_kv) issue_qk();        // S(j+1) in the same batch: one round trip per tile
         umma_commit(bar_s);
       }
       __syncwarp();
+      if (tl) tl_row[6] = clock64();
     }
   }
-  // last batch: O_tile(n_kv - 1)
+  // last batch: O complete
   mbar_wait(bar_s, n_kv & 1);
   tc_fence_after();
+  float denom = l_run;
+  if (ones_col) {                            // the ones column of V accumulated the denominator in O[:, d]
+    uint32_t v[16];
+    tmem_ld_32x16(tmem_o + lane_base + (p.d >> 4) * 16, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      if (e == (p.d & 15)) denom = __uint_as_float(v[e]);
+  }
+  const float inv = 1.f / denom;
+  const int qrow = q_tile * ATT_M + tid;
+  __nv_bfloat16* dst = p.o + (static_cast<size_t>(batch) * p.Sq + qrow) * p.ldo + head * p.d;
 #pragma unroll
   for (int c = 0; c < DK / 16; ++c) {
     uint32_t v[16];
     tmem_ld_32x16(tmem_o + lane_base + c * 16, v);
     tmem_wait_ld();
+    if (qrow < p.Sq) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) acc[c * 16 + e] = acc[c * 16 + e] * alpha_prev + __uint_as_float(v[e]);
-  }
-  tc_fence_before();
-
-  const int qrow = q_tile * ATT_M + tid;
-  if (qrow < p.Sq) {
-    float denom = l_run;
-    if (ones_col) {
-#pragma unroll
-      for (int c = 0; c < DK; ++c)
-        if (c == p.d) denom = acc[c];
-    }
-    const float inv = 1.f / denom;
-    __nv_bfloat16* dst = p.o + (static_cast<size_t>(batch) * p.Sq + qrow) * p.ldo + head * p.d;
-#pragma unroll
-    for (int c = 0; c < DK; c += 8) {
-      if (c < p.d) {
-        uint4 o;
-        o.x = pack_bf16(acc[c] * inv, acc[c + 1] * inv);
-        o.y = pack_bf16(acc[c + 2] * inv, acc[c + 3] * inv);
-        o.z = pack_bf16(acc[c + 4] * inv, acc[c + 5] * inv);
-        o.w = pack_bf16(acc[c + 6] * inv, acc[c + 7] * inv);
-        *reinterpret_cast<uint4*>(dst + c) = o;
+      for (int h = 0; h < 2; ++h) {
+        if (c * 16 + h * 8 < p.d) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(v[8 * h]) * inv, __uint_as_float(v[8 * h + 1]) * inv);
+          o.y = pack_bf16(__uint_as_float(v[8 * h + 2]) * inv, __uint_as_float(v[8 * h + 3]) * inv);
+          o.z = pack_bf16(__uint_as_float(v[8 * h + 4]) * inv, __uint_as_float(v[8 * h + 5]) * inv);
+          o.w = pack_bf16(__uint_as_float(v[8 * h + 6]) * inv, __uint_as_float(v[8 * h + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 16 + h * 8) = o;
+        }
       }
     }
   }
@@ -293,20 +319,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-template <int DK>
-int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, int batch,
-                int heads, cudaStream_t stream) {
+template <int DK, int POLY, bool ONES>
+int launch_attn_inst(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, int batch,
+                     int heads, cudaStream_t stream) {
   using Cfg = AttnCfg<DK>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
-        cudaFuncSetAttribute(attn_fwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaFuncSetAttribute(attn_fwd_kernel<DK, POLY, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     LAVIE_REQUIRE(e == cudaSuccess, LAVIE_ERR_CUDA, "cudaFuncSetAttribute(attn<%d>): %s", DK, cudaGetErrorString(e));
     configured = true;
   }
   dim3 grid((p.Sq + ATT_M - 1) / ATT_M, heads, batch);
-  launch_pdl(attn_fwd_kernel<DK>, grid, 128, Cfg::SMEM, stream, mq, mk, mv, p);
+  launch_pdl(attn_fwd_kernel<DK, POLY, ONES>, grid, 128, Cfg::SMEM, stream, mq, mk, mv, p);
   return lavie_check_launch("attn_fwd_kernel");
+}
+
+// every g_lavie_attn_poly-th exponential of a full key tile is evaluated on the FMA pipe (0: all on the MUFU)
+template <int DK>
+int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, int batch,
+                int heads, cudaStream_t stream) {
+  if (p.d < DK) {                 // a spare padded column carries the softmax denominator through the P.V MMA
+    if (g_lavie_attn_poly == 4) return launch_attn_inst<DK, 4, true>(mq, mk, mv, p, batch, heads, stream);
+    return launch_attn_inst<DK, 0, true>(mq, mk, mv, p, batch, heads, stream);
+  }
+  if (g_lavie_attn_poly == 4) return launch_attn_inst<DK, 4, false>(mq, mk, mv, p, batch, heads, stream);
+  return launch_attn_inst<DK, 0, false>(mq, mk, mv, p, batch, heads, stream);
 }
 
 int make_qkv_map(CUtensorMap* map, const void* base, int ld, int cols, int S, int nbatch, int box_rows) {
@@ -633,6 +671,7 @@ extern "C" int lavie_attention_bf16(const void* q, int ldq, const void* k, int l
   p.Sq = Sq; p.Sk = Sk; p.d = d; p.head_pitch = head_pitch; p.kv_batch_div = kv_batch_div; p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.o = static_cast<__nv_bfloat16*>(o);
+  p.timeline = static_cast<long long*>(g_lavie_debug_buf);
   CUtensorMap mq, mk, mv;
   const int cols = heads * head_pitch;
   int rc = make_qkv_map(&mq, q, ldq, cols, Sq, batch, ATT_M);

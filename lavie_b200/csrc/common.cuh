@@ -40,6 +40,8 @@ int lavie_make_tmap_im2col(CUtensorMap* map, const void* base, int N, int H, int
 // paying launch latency + prologue after it (~2-4 us per launch x ~550 launches per step).
 // ---------------------------------------------------------------------------------------------
 extern int g_lavie_pdl;       // 1 = on (default); lavie_debug_set(3, 0) turns it off for A/B timing
+extern void* g_lavie_debug_buf; // device scratch for the clock64 timelines (lavie_debug_buffer), nullptr = off
+extern int g_lavie_attn_poly; // attention: every n-th exp2 on the FMA pipe (0 = none); lavie_debug_set(4, n)
 
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
@@ -104,6 +106,19 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 polynomial for
+// 2^f, exponent n added into the float's exponent field.  Relative error <= 2.3e-4 -- an order of magnitude under the
+// bf16 rounding the attention probabilities get anyway.  The softmax loop is bound by the 16-lane/clk MUFU unit;
+// evaluating a fraction of the exponentials here balances the two pipes (the trick FlashAttention-4 uses on Blackwell).
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;            // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05485820025205612f, 0.24183107912540436f);
+  p = fmaf(p, f, 0.6932342052459717f);
+  p = fmaf(p, f, 0.9999654293060303f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
@@ -260,6 +275,18 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

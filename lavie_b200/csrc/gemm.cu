@@ -42,7 +42,6 @@ constexpr int EPI_SPLIT = NUM_EPI_WARPS / 4;      // warps sharing one 32-row sl
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // 320
 constexpr int EPI_BAR_ID = 1;
 constexpr int EPI_CHUNK_BYTES = 32 * 32 * 2;      // one 32-row x 32-column bf16 chunk (TMA box, 64-byte swizzle)
-constexpr int EPI_CHUNKS_PER_WARP = (8 + EPI_SPLIT - 1) / EPI_SPLIT;   // BLOCK_N <= 256 -> at most 8 chunks per row quarter
 
 struct GemmParams {
   int M, N, K;
@@ -75,10 +74,18 @@ struct GemmParams {
 
 template <int BLOCK_N>
 struct SmemLayout {
-  static constexpr int B_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;
+  // One tcgen05.mma covers at most N = 256.  A 320-wide tile is two 160-wide MMAs per K step that share the A stage:
+  // the activation operand is fetched from L2 once per 320 output columns instead of once per 160, which is what
+  // bounds the N = 320 / 640 layers (tools/bench_feedtheory.py: throughput follows L2->SM bytes per flop).
+  static constexpr int N_MMA = BLOCK_N > 256 ? 2 : 1;
+  static constexpr int UMMA_N = BLOCK_N / N_MMA;
+  static constexpr int ACC_STAGES = 2 * BLOCK_N <= 512 ? 2 : 1;     // TMEM has 512 columns
+  static constexpr int B_HALF_BYTES = (UMMA_N / 2) * BLOCK_K * 2;   // this CTA's rows of one MMA's B operand
+  static constexpr int B_STAGE_BYTES = N_MMA * B_HALF_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BIAS_BYTES = 0;
-  static constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_CHUNKS_PER_WARP * EPI_CHUNK_BYTES;   // per-warp bf16 staging chunks
+  static constexpr int EPI_CHUNKS = (BLOCK_N / 32 + EPI_SPLIT - 1) / EPI_SPLIT;   // 32-column chunks per epilogue warp
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_CHUNKS * EPI_CHUNK_BYTES;  // per-warp bf16 staging chunks
   static constexpr int MAX_SMEM = 227 * 1024 - 2048 - BIAS_BYTES - EPI_BYTES;
   static constexpr int STAGES_RAW = MAX_SMEM / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -185,9 +192,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
   pdl_launch_dependents();
   using L = SmemLayout<BLOCK_N>;
   constexpr int STAGES = L::STAGES;
-  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
-                                 : (2 * BLOCK_N <= 256) ? 256 : 512;
-  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
+  constexpr int ACC_STAGES = L::ACC_STAGES;
+  constexpr int ACC_COLS = ACC_STAGES * BLOCK_N;
+  constexpr uint32_t TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128
+                                 : (ACC_COLS <= 256) ? 256 : 512;
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && ACC_COLS <= 512 && L::UMMA_N % 16 == 0 && L::UMMA_N <= 256,
+                "BLOCK_N");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -287,8 +297,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
             } else {
               tma2_load_2d(a_dst, &tmap_a1, full_leader, (kb - p.k_split_blocks) * BLOCK_K, m_cta * BLOCK_M);
             }
-            tma2_load_2d(b_dst, &tmap_b, full_leader, kb * BLOCK_K,
-                         it.n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2));
+#pragma unroll
+            for (int h = 0; h < L::N_MMA; ++h)       // this CTA's half of each MMA's weight rows
+              tma2_load_2d(b_dst + h * L::B_HALF_BYTES, &tmap_b, full_leader, kb * BLOCK_K,
+                           it.n_blk * BLOCK_N + h * L::UMMA_N + static_cast<int>(rank) * (L::UMMA_N / 2));
           }
         }
         __syncwarp();
@@ -298,7 +310,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) =================================
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(PAIR_M, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR_M, L::UMMA_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -326,7 +338,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                 // advancing 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the >>4 address field
-                umma2_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > it.kb_begin || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int h = 0; h < L::N_MMA; ++h)
+                  umma2_bf16(d_tmem + h * L::UMMA_N, a_desc + 2 * k, b_desc + h * (L::B_HALF_BYTES >> 4) + 2 * k, idesc,
+                             (kb > it.kb_begin || k > 0) ? 1u : 0u);
               }
             }
             umma2_commit_mc(&empty_bar[stage]);    // frees this smem stage in both CTAs once the MMAs retire
@@ -336,7 +351,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (tl) tl_row[4] = clock64();
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -350,7 +365,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int chalf = ew >> 2;                     // which share of the 32-column chunks this warp drains
     const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&tmem_empty[0]), 0);
-    uint8_t* my_stage = s_epi + ew * (EPI_CHUNKS_PER_WARP * EPI_CHUNK_BYTES);
+    uint8_t* my_stage = s_epi + ew * (L::EPI_CHUNKS * EPI_CHUNK_BYTES);
     uint64_t* my_res_bar = &res_bar[ew];
     uint32_t res_phase = 0;
     const int swz = (lane >> 1) & 3;               // 64-byte swizzle: 16-byte unit j of row r lives at unit j ^ ((r>>1)&3)
@@ -504,7 +519,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
       if (tl) tl_row[5] = clock64();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -601,19 +616,22 @@ int num_sms() {
 struct Plan {
   int bn, splits, kb_per_split;
 };
-Plan make_plan(int M, int N, int num_k_blocks, int forced_bn, bool geglu, size_t ws_bytes) {
+Plan make_plan(int M, int N, int num_k_blocks, int forced_bn, bool geglu, bool conv, size_t ws_bytes) {
   const int pairs = num_sms() / 2;
   const int m_tiles = (M + PAIR_M - 1) / PAIR_M;
-  const int cands[5] = {256, 192, 160, 128, 64};
+  const int cands[6] = {320, 256, 192, 160, 128, 64};
   Plan best{128, 1, num_k_blocks};
   double best_cost = 1e30;
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; i < 6; ++i) {
     const int bn = cands[i];
     if (forced_bn && bn != forced_bn) continue;
     if (geglu && bn != 256) continue;
     const int n_tiles = (N + bn - 1) / bn;
     const long tiles = static_cast<long>(m_tiles) * n_tiles;
-    const double t_kb = fmax(2.0 * bn, (16384.0 + 64.0 * bn) / 56.0);
+    // measured L2->SM feed per SM and clock with all SMs pulling (tools/bench_feedtheory.py): ~47 B dense, ~38 B through
+    // the im2col-mode TMA; a 64-deep K block needs 16 KiB of A plus 64*bn bytes of B per CTA
+    const double t_kb = fmax(2.0 * bn, (16384.0 + 64.0 * bn) / (conv ? 38.0 : 47.0));
+    const double t_epi = bn > 256 ? 5000.0 : 0.0;      // single accumulator stage: the epilogue is not overlapped
     const int max_splits = geglu ? 1 : 16;
     for (int s = 1; s <= max_splits; ++s) {
       if (s > 1) {
@@ -627,7 +645,7 @@ Plan make_plan(int M, int N, int num_k_blocks, int forced_bn, bool geglu, size_t
       if (eff_s != s) continue;
       const long items = tiles * s;
       const long waves = (items + pairs - 1) / pairs;
-      double cost = static_cast<double>(waves) * (kbps * t_kb + 1500.0 + 6.0 * bn);
+      double cost = static_cast<double>(waves) * (kbps * t_kb + 1500.0 + 6.0 * bn + t_epi);
       if (s > 1) cost += 4000.0 + 0.0013 * (s + 0.5) * static_cast<double>(M) * N;      // reduction pass (HBM)
       if (cost < best_cost) {
         best_cost = cost;
@@ -665,6 +683,7 @@ int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtenso
     case 160: return launch_gemm<160>(a0, a1, b, mo, mr, p, num_sms(), stream);
     case 192: return launch_gemm<192>(a0, a1, b, mo, mr, p, num_sms(), stream);
     case 256: return launch_gemm<256>(a0, a1, b, mo, mr, p, num_sms(), stream);
+    case 320: return launch_gemm<320>(a0, a1, b, mo, mr, p, num_sms(), stream);
     default: lavie_set_error("unsupported BLOCK_N %d", bn); return LAVIE_ERR_SHAPE;
   }
 }
@@ -674,7 +693,8 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 int make_weight_map(CUtensorMap* map, const void* w, int N, int K, int bn) {
   const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
   const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
-  const uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(bn / 2)};     // each CTA of the pair stages half the tile
+  // each CTA of the pair stages half of the weight rows of one MMA (a 320-wide tile is two 160-wide MMAs)
+  const uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>((bn > 256 ? bn / 2 : bn) / 2)};
   return lavie_make_tmap(map, w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -720,6 +740,7 @@ extern "C" int lavie_debug_set(int what, int value) {
   if (what == 2) g_debug = value;
   if (what == 0) g_k_rot = value;
   if (what == 3) g_lavie_pdl = value ? 1 : 0;
+  if (what == 4) g_lavie_attn_poly = value;
   return 0;
 }
 
@@ -740,7 +761,7 @@ extern "C" int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1,
   p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   p.k_split_blocks = k1 ? k0 / BLOCK_K : p.num_k_blocks;
   p.conv = 0;
-  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, geglu, workspace ? workspace_bytes : 0);
+  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, geglu, false, workspace ? workspace_bytes : 0);
   apply_plan(p, plan, workspace);
   int rc = fill_epilogue(p, ep, N, out, ldo);
   if (rc) return rc;
@@ -794,7 +815,7 @@ extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, in
   p.out_h = Ho; p.out_w = Wo; p.conv_stride = stride;
   const bool tiled = (g_debug & 1024) && stride == 1 && tiled_geometry_ok(W);   // first-generation path, for A/B timing
   p.conv = tiled ? 1 : 2;
-  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, false, workspace ? workspace_bytes : 0);
+  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, false, true, workspace ? workspace_bytes : 0);
   apply_plan(p, plan, workspace);
   int rc = fill_epilogue(p, ep, N, out, ldo);
   if (rc) return rc;

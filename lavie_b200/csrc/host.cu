@@ -113,6 +113,13 @@ int lavie_make_tmap_im2col(CUtensorMap* map, const void* base, int N, int H, int
 }
 
 int g_lavie_pdl = 1;
+int g_lavie_attn_poly = 0;
+void* g_lavie_debug_buf = nullptr;
+
+extern "C" int lavie_debug_buffer(void* device_ptr) {
+  g_lavie_debug_buf = device_ptr;
+  return 0;
+}
 
 extern "C" const char* lavie_last_error(void) { return g_error; }
 extern "C" int lavie_abi_version(void) { return 1; }

@@ -28,7 +28,7 @@ def _rand(*shape, scale=1.0, seed=0):
 
 
 # ------------------------------------------------------------------------------------------------ GEMM
-@pytest.mark.parametrize("block_n", [0, 64, 128, 160, 192, 256])
+@pytest.mark.parametrize("block_n", [0, 64, 128, 160, 192, 256, 320])
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1000, 320, 320), (4096, 1152, 320), (300, 640, 2560)])
 def test_gemm_plain(M, N, K, block_n):
     ops = _ops()
@@ -54,6 +54,31 @@ def test_gemm_epilogue_bias_rowbias_residual_strided():
     ref = a.float() @ w.float().t() + bias + rb.repeat_interleave(M // B, 0) + res.float()
     assert rel_l2(out.float(), ref) < 4e-3
     assert out_full[:, :N].abs().max() == 0           # nothing written outside the view
+
+
+@pytest.mark.parametrize("N", [320, 640, 200])
+def test_gemm_wide_tile_epilogue(N):
+    """BLOCK_N = 320: two 160-wide MMAs per K step share the activation stage, single accumulator stage, five
+    staging chunks per epilogue warp; several tiles per CTA pair so the accumulator hand-back is exercised."""
+    ops = _ops()
+    M, K = 256 * 150 + 77, 192
+    a = _bf(_rand(M, K))
+    w = _bf(_rand(N, K, scale=K ** -0.5))
+    bias = _rand(N, seed=1)
+    res = _bf(_rand(M, N, seed=3))
+    out = ops.gemm(a, w, bias=bias, residual=res, block_n=320)
+    ref = a.float() @ w.float().t() + bias + res.float()
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+def test_conv3x3_wide_tile():
+    ops = _ops()
+    from lavie_b200.packing import pack_conv3x3
+    NF, H, W, C, N = 3, 20, 32, 128, 640
+    x = _bf(_rand(NF * H * W, C))
+    w = _bf(_rand(N, C, 3, 3, scale=(9 * C) ** -0.5))
+    out = ops.conv3x3(x, NF, H, W, pack_conv3x3(w), block_n=320)
+    assert rel_l2(out.float(), _conv_ref(x, w, NF, H, W)) < 4e-3
 
 
 def test_gemm_two_sources_fold_concat():

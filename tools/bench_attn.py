@@ -1,6 +1,7 @@
 import sys, torch
 sys.path.insert(0, ".")
-from lavie_b200 import ops
+from lavie_b200 import ops, _lib
+lib = _lib.load()
 dev = "cuda"
 def timeit(fn, n=10):
     for _ in range(3): fn()
@@ -18,6 +19,9 @@ for batch, Sq, Sk, d, pitch, div in [(32, 2560, 2560, 40, 48, 1), (32, 640, 640,
         t = torch.zeros(rows, heads, pitch, device=dev); t[..., :d] = torch.randn(rows, heads, d, device=dev)
         return t.reshape(rows, hp).to(torch.bfloat16)
     q, k, v = mk(batch * Sq), mk(batch // div * Sk), mk(batch // div * Sk)
-    ms = timeit(lambda: ops.attention(q, k, v, batch, heads, Sq, Sk, d, pitch, div))
     fl = 4.0 * batch * heads * Sq * Sk * d
-    print(f"attn B={batch} Sq={Sq} Sk={Sk} d={d}: {ms*1e3:8.1f} us {fl/ms/1e9:7.1f} TF/s")
+    for poly in (0, 4):
+        lib.lavie_debug_set(4, poly)
+        ms = timeit(lambda: ops.attention(q, k, v, batch, heads, Sq, Sk, d, pitch, div))
+        print(f"attn B={batch} Sq={Sq} Sk={Sk} d={d} poly={poly}: {ms*1e3:8.1f} us {fl/ms/1e9:7.1f} TF/s")
+    lib.lavie_debug_set(4, 0)
