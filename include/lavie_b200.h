@@ -95,6 +95,11 @@ int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void* x1, int l
 int lavie_groupnorm_finalize(const float* partial, int samples, int chunks, int groups, int C,
                              long long count_per_group, const float* gamma, const float* beta, float eps,
                              float* scale_shift, lavie_stream_t stream);
+/* stats + finalize in ONE launch: the last block of each sample to publish its partials (atomic ticket) folds them
+ * into scale_shift with the arithmetic of lavie_groupnorm_finalize.  tickets: int[samples], zero on entry, left zero. */
+int lavie_groupnorm_scale_shift(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
+                                int rows_per_sample, int groups, const float* gamma, const float* beta, float eps,
+                                float* partial, int* tickets, float* scale_shift, lavie_stream_t stream);
 int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
                           int rows_per_sample, const float* scale_shift, int silu, void* y, int ldy,
                           lavie_stream_t stream);

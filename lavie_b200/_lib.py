@@ -46,6 +46,8 @@ SIGNATURES = {
     "lavie_groupnorm_chunks": (c_int, [c_int, c_int]),
     "lavie_groupnorm_stats": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_groupnorm_finalize": (c_int, [_P, c_int, c_int, c_int, c_int, c_longlong, _P, _P, c_float, _P, _P]),
+    "lavie_groupnorm_scale_shift": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float,
+                                            _P, _P, _P, _P]),
     "lavie_groupnorm_apply": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),
     "lavie_layernorm_bf16": (c_int, [_P, c_int, _P, _P, c_float, _P, c_int, c_int, c_int, _P]),
     "lavie_layernorm_scatter_bf16": (c_int, [_P, c_int, _P, _P, c_float, _P, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -72,8 +72,11 @@ linear_smallm_kernel(const float* __restrict__ x, int M, int K, const __nv_bfloa
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// conv_in: fp32 [B,Cin,F,H,W] -> bf16 channels-last [B*F*H*W, Cout]; thread = (pixel, 8 output channels)
+// conv_in: fp32 [B,Cin,F,H,W] -> bf16 channels-last [B*F*H*W, Cout].
+// thread = (strip of 4 pixels along x, 8 output channels): every weight vector fetched from shared memory feeds
+// 4 pixels (32 FMAs per 2 LDS.128), the 6 input values of a filter row are loaded once per (channel, dy).
 // ---------------------------------------------------------------------------------------------------------
+constexpr int CIN_P = 4;
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x, int B, int Cin, int F, int H, int W, const float* __restrict__ w,
                const float* __restrict__ bias, int Cout, __nv_bfloat16* __restrict__ out, int ldo) {
@@ -86,104 +89,144 @@ conv_in_kernel(const float* __restrict__ x, int B, int Cin, int F, int H, int W,
   }
   __syncthreads();
   const int groups = Cout >> 3;
-  const long long total = static_cast<long long>(B) * F * H * W * groups;
+  const int strips = (W + CIN_P - 1) / CIN_P;
+  const long long total = static_cast<long long>(B) * F * H * strips * groups;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int g = static_cast<int>(i % groups);
-    const long long pix = i / groups;
-    const int xw = static_cast<int>(pix % W);
-    const int yh = static_cast<int>((pix / W) % H);
-    const int f = static_cast<int>((pix / (static_cast<long long>(W) * H)) % F);
-    const int b = static_cast<int>(pix / (static_cast<long long>(W) * H * F));
-    float acc[8];
+    const long long sidx = i / groups;
+    const int xs = static_cast<int>(sidx % strips) * CIN_P;
+    const int yh = static_cast<int>((sidx / strips) % H);
+    const int f = static_cast<int>((sidx / (static_cast<long long>(strips) * H)) % F);
+    const int b = static_cast<int>(sidx / (static_cast<long long>(strips) * H * F));
+    float acc[CIN_P][8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + g * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias + g * 8 + 4);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = bias[g * 8 + e];
+      for (int pp = 0; pp < CIN_P; ++pp) {
+        acc[pp][0] = b0.x; acc[pp][1] = b0.y; acc[pp][2] = b0.z; acc[pp][3] = b0.w;
+        acc[pp][4] = b1.x; acc[pp][5] = b1.y; acc[pp][6] = b1.z; acc[pp][7] = b1.w;
+      }
+    }
     for (int c = 0; c < Cin; ++c) {
       const float* plane = x + ((static_cast<size_t>(b) * Cin + c) * F + f) * H * W;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-          const float v = __ldg(plane + yy * W + xx);
-          const float4* wp = reinterpret_cast<const float4*>(s_w + (c * 9 + t) * Cout + g * 8);
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yy = yh + dy - 1;
+        if (yy < 0 || yy >= H) continue;
+        float xv[CIN_P + 2];
+#pragma unroll
+        for (int j = 0; j < CIN_P + 2; ++j) {
+          const int xx = xs - 1 + j;
+          xv[j] = (xx >= 0 && xx < W) ? __ldg(plane + yy * W + xx) : 0.f;
+        }
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4* wp = reinterpret_cast<const float4*>(s_w + (c * 9 + dy * 3 + dx) * Cout + g * 8);
           const float4 w0 = wp[0], w1 = wp[1];
-          acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
-          acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
+#pragma unroll
+          for (int pp = 0; pp < CIN_P; ++pp) {
+            const float v = xv[pp + dx];
+            acc[pp][0] += v * w0.x; acc[pp][1] += v * w0.y; acc[pp][2] += v * w0.z; acc[pp][3] += v * w0.w;
+            acc[pp][4] += v * w1.x; acc[pp][5] += v * w1.y; acc[pp][6] += v * w1.z; acc[pp][7] += v * w1.w;
+          }
         }
       }
     }
-    uint4 o;
-    o.x = pack_bf16(acc[0], acc[1]);
-    o.y = pack_bf16(acc[2], acc[3]);
-    o.z = pack_bf16(acc[4], acc[5]);
-    o.w = pack_bf16(acc[6], acc[7]);
-    *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * ldo + g * 8) = o;
+    const size_t pix0 = ((static_cast<size_t>(b) * F + f) * H + yh) * W + xs;
+#pragma unroll
+    for (int pp = 0; pp < CIN_P; ++pp) {
+      if (xs + pp < W) {
+        uint4 o;
+        o.x = pack_bf16(acc[pp][0], acc[pp][1]);
+        o.y = pack_bf16(acc[pp][2], acc[pp][3]);
+        o.z = pack_bf16(acc[pp][4], acc[pp][5]);
+        o.w = pack_bf16(acc[pp][6], acc[pp][7]);
+        *reinterpret_cast<uint4*>(out + (pix0 + pp) * ldo + g * 8) = o;
+      }
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// conv_norm_out -> SiLU -> conv_out, fused: one warp per output pixel, lanes split the channel vectors.
-// Zero padding applies to the ACTIVATED map, so out-of-image taps are simply skipped.
+// conv_norm_out -> SiLU -> conv_out, fused.  One warp per strip of 4 output pixels; lane l owns the channel pairs
+// {l, l+32, ...} (coalesced 128-byte reads of the activation rows).  For each pair and filter row the 6 input pixels
+// are normalised + activated once and feed 3 taps x 4 pixels x COUT outputs; every weight pair read from shared
+// memory feeds 8 FMAs.  Zero padding applies to the ACTIVATED map, so out-of-image taps contribute 0.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int COUT_P = 4;
 template <int COUT>
 __global__ void __launch_bounds__(256)
 conv_out_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ scale_shift, int B, int F,
                 int H, int W, int C, const float* __restrict__ w, const float* __restrict__ bias,
                 float* __restrict__ out) {
   pdl_prologue();
-  extern __shared__ float s_w[];     // [COUT][9][C]
-  for (int i = threadIdx.x; i < COUT * 9 * C; i += blockDim.x) s_w[i] = w[i];
+  extern __shared__ float s_w[];     // [9][COUT][C]   (source layout [COUT][9][C])
+  for (int i = threadIdx.x; i < COUT * 9 * C; i += blockDim.x) {
+    const int c = i % C, ot = i / C;
+    const int o = ot / 9, t = ot - o * 9;
+    s_w[(t * COUT + o) * C + c] = w[i];
+  }
   __syncthreads();
+  const float2* s_w2 = reinterpret_cast<const float2*>(s_w);
   const int lane = threadIdx.x & 31;
-  const int nvec = C >> 3;
-  const long long total = static_cast<long long>(B) * F * H * W;
+  const int npairs = C >> 1;
+  const int strips = (W + COUT_P - 1) / COUT_P;
+  const long long total = static_cast<long long>(B) * F * H * strips;
   const long long warps_total = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  for (long long pix = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < total;
-       pix += warps_total) {
-    const int xw = static_cast<int>(pix % W);
-    const int yh = static_cast<int>((pix / W) % H);
-    const long long bf = pix / (static_cast<long long>(W) * H);
+  for (long long task = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); task < total;
+       task += warps_total) {
+    const int xs = static_cast<int>(task % strips) * COUT_P;
+    const int yh = static_cast<int>((task / strips) % H);
+    const long long bf = task / (static_cast<long long>(strips) * H);
     const int b = static_cast<int>(bf / F);
     const int f = static_cast<int>(bf % F);
-    float acc[COUT];
+    float acc[COUT_P][COUT];
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
-    for (int v = lane; v < nvec; v += 32) {
-      float sc[8], sh[8];
-      const float4* ss = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(b) * C + v * 8) * 2);
+    for (int pp = 0; pp < COUT_P; ++pp)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float4 p = __ldg(ss + e);
-        sc[2 * e] = p.x; sh[2 * e] = p.y; sc[2 * e + 1] = p.z; sh[2 * e + 1] = p.w;
-      }
+      for (int o = 0; o < COUT; ++o) acc[pp][o] = 0.f;
+    for (int p = lane; p < npairs; p += 32) {
+      const float4 ss = __ldg(reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(b) * C + 2 * p) * 2));
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        const size_t row = (static_cast<size_t>(bf) * H + yy) * W + xx;
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + v * 8));
-        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-        float a[8];
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yy = yh + dy - 1;
+        const bool row_ok = yy >= 0 && yy < H;       // out-of-image rows contribute zeros (no divergent control flow)
+        // first tap column of the strip (may be x = -1: only dereferenced when inside the image)
+        const __nv_bfloat16* xp = x + (((static_cast<long long>(bf) * H + yy) * W) + xs - 1) * ldx + 2 * p;
+        float a0[COUT_P + 2], a1[COUT_P + 2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 t2 = unpack_bf16(uw[e]);
-          a[2 * e] = silu_f(t2.x * sc[2 * e] + sh[2 * e]);
-          a[2 * e + 1] = silu_f(t2.y * sc[2 * e + 1] + sh[2 * e + 1]);
+        for (int i = 0; i < COUT_P + 2; ++i) {
+          const int xx = xs - 1 + i;
+          if (row_ok && xx >= 0 && xx < W) {
+            const float2 t2 = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(xp + i * ldx)));
+            a0[i] = silu_f(t2.x * ss.x + ss.y);
+            a1[i] = silu_f(t2.y * ss.z + ss.w);
+          } else {
+            a0[i] = 0.f;
+            a1[i] = 0.f;
+          }
         }
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-          const float4* wp = reinterpret_cast<const float4*>(s_w + (o * 9 + t) * C + v * 8);
-          const float4 w0 = wp[0], w1 = wp[1];
-          acc[o] += a[0] * w0.x + a[1] * w0.y + a[2] * w0.z + a[3] * w0.w + a[4] * w1.x + a[5] * w1.y + a[6] * w1.z +
-                    a[7] * w1.w;
+        for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+          for (int o = 0; o < COUT; ++o) {
+            const float2 wv = s_w2[((dy * 3 + dx) * COUT + o) * npairs + p];
+#pragma unroll
+            for (int pp = 0; pp < COUT_P; ++pp) acc[pp][o] = fmaf(a1[pp + dx], wv.y, fmaf(a0[pp + dx], wv.x, acc[pp][o]));
+          }
         }
       }
     }
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) {
-      const float s = warp_sum(acc[o]);
-      if (lane == 0)
-        out[(((static_cast<size_t>(b) * COUT + o) * F + f) * H + yh) * W + xw] = s + bias[o];
+    for (int pp = 0; pp < COUT_P; ++pp) {
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const float s = warp_sum(acc[pp][o]);
+        if (lane == 0 && xs + pp < W)
+          out[(((static_cast<size_t>(b) * COUT + o) * F + f) * H + yh) * W + xs + pp] = s + bias[o];
+      }
     }
   }
 }
@@ -282,7 +325,8 @@ extern "C" int lavie_conv_in(const float* x, int B, int Cin, int F, int H, int W
     LAVIE_REQUIRE(e == cudaSuccess, LAVIE_ERR_CUDA, "cudaFuncSetAttribute(conv_in): %s", cudaGetErrorString(e));
     configured = smem;
   }
-  const long long total = static_cast<long long>(B) * F * H * W * (Cout / 8);
+  LAVIE_REQUIRE(al16(bias), LAVIE_ERR_ALIGN, "conv_in: bias must be 16-byte aligned");
+  const long long total = static_cast<long long>(B) * F * H * ((W + CIN_P - 1) / CIN_P) * (Cout / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   launch_pdl(conv_in_kernel, static_cast<int>(blocks), 256, smem, stream, x, B, Cin, F, H, W, w, bias, Cout,
@@ -302,9 +346,9 @@ extern "C" int lavie_conv_out(const void* x, int ldx, const float* scale_shift, 
     LAVIE_REQUIRE(e == cudaSuccess, LAVIE_ERR_CUDA, "cudaFuncSetAttribute(conv_out): %s", cudaGetErrorString(e));
     configured = smem;
   }
-  const long long total = static_cast<long long>(B) * F * H * W;
+  const long long total = static_cast<long long>(B) * F * H * ((W + COUT_P - 1) / COUT_P);
   long long blocks = (total + 7) / 8;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 2) blocks = 148 * 2;        // 2 resident blocks per SM (registers): one wave, one weight fill each
   launch_pdl(conv_out_kernel<4>, static_cast<int>(blocks), 256, smem, stream, static_cast<const __nv_bfloat16*>(x), ldx,
                                                                       scale_shift, B, F, H, W, C, w, bias, out);
   return lavie_check_launch("conv_out_kernel");

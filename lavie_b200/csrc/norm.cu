@@ -16,10 +16,79 @@ __device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int ld0, int c
   return __ldg(reinterpret_cast<const uint4*>(src));
 }
 
+// combine the chunk partials of one sample in fp64 (fixed order) and emit per-channel (scale, shift); whole block
+__device__ __forceinline__ void gn_finalize_sample(const float* __restrict__ partial, int sample, int chunks, int groups,
+                                                   int C, double inv_count, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, float eps,
+                                                   float* __restrict__ scale_shift) {
+  __shared__ float s_mean[64], s_rstd[64];
+  // 8 consecutive lanes share one group: each sums every 8th chunk in fp64, then a fixed-order shuffle tree
+  const int sub = threadIdx.x & 7;
+  for (int g = threadIdx.x >> 3; g < groups; g += blockDim.x >> 3) {
+    double a = 0.0, b = 0.0;
+    for (int k0 = sub; k0 < chunks; k0 += 64) {          // 8 independent loads in flight, summed in a fixed order
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + 8 * u;
+        v[u] = k < chunks ? __ldcg(reinterpret_cast<const float2*>(
+                                partial + ((static_cast<size_t>(sample) * chunks + k) * groups + g) * 2))
+                          : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a += v[u].x;
+        b += v[u].y;
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (sub == 0) {
+      const double mean = a * inv_count;
+      double var = b * inv_count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = static_cast<float>(mean);
+      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = s_rstd[g] * gamma[c];
+    float* dst = scale_shift + (static_cast<size_t>(sample) * C + c) * 2;
+    dst[0] = sc;
+    dst[1] = beta[c] - s_mean[g] * sc;
+  }
+}
+
+// one block per sample
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int groups, int C,
+                                   double inv_count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float* __restrict__ scale_shift) {
+  pdl_prologue();
+  gn_finalize_sample(partial, blockIdx.x, chunks, groups, C, inv_count, gamma, beta, eps, scale_shift);
+}
+
+// Optional fused finalize: the LAST block of a sample to publish its partials (atomic ticket) folds all of them into
+// (scale, shift) -- same arithmetic and order as gn_finalize_kernel, one launch less per GroupNorm.
+struct GnFused {
+  int* tickets;            // [samples], zero on entry, reset to zero by the finalizing block; nullptr = stats only
+  double inv_count;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float* scale_shift;
+};
+
 // partial[sample][chunk][group][2]
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __nv_bfloat16* __restrict__ x1, int ld1,
-                int c1, int rows_per_sample, int rows_per_chunk, int groups, int chunks, float* __restrict__ partial) {
+                int c1, int rows_per_sample, int rows_per_chunk, int groups, int chunks, float* __restrict__ partial,
+                const GnFused fused) {
   pdl_prologue();
   extern __shared__ float sm[];          // [row_lanes][2][C]  (one private slot per row lane: deterministic)
   const int C = c0 + c1;
@@ -80,56 +149,17 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __n
     dst[0] = a;
     dst[1] = b;
   }
-}
-
-// one block per sample: combine chunk partials in fp64, emit per-channel (scale, shift)
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int groups, int C,
-                                   double inv_count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float eps, float* __restrict__ scale_shift) {
-  pdl_prologue();
-  __shared__ float s_mean[64], s_rstd[64];
-  const int sample = blockIdx.x;
-  // 8 consecutive lanes share one group: each sums every 8th chunk in fp64, then a fixed-order shuffle tree
-  const int sub = threadIdx.x & 7;
-  for (int g = threadIdx.x >> 3; g < groups; g += blockDim.x >> 3) {
-    double a = 0.0, b = 0.0;
-    for (int k0 = sub; k0 < chunks; k0 += 64) {          // 8 independent loads in flight, summed in a fixed order
-      float2 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int k = k0 + 8 * u;
-        v[u] = k < chunks ? *reinterpret_cast<const float2*>(
-                                partial + ((static_cast<size_t>(sample) * chunks + k) * groups + g) * 2)
-                          : make_float2(0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        a += v[u].x;
-        b += v[u].y;
-      }
-    }
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-    if (sub == 0) {
-      const double mean = a * inv_count;
-      double var = b * inv_count - mean * mean;
-      if (var < 0.0) var = 0.0;
-      s_mean[g] = static_cast<float>(mean);
-      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    }
-  }
+  if (fused.tickets == nullptr) return;
+  __shared__ int s_last;
+  __threadfence();                                 // partials visible device-wide before the ticket
   __syncthreads();
-  const int cpg = C / groups;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float sc = s_rstd[g] * gamma[c];
-    float* dst = scale_shift + (static_cast<size_t>(sample) * C + c) * 2;
-    dst[0] = sc;
-    dst[1] = beta[c] - s_mean[g] * sc;
-  }
+  if (threadIdx.x == 0) s_last = (atomicAdd(fused.tickets + sample, 1) == chunks - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  gn_finalize_sample(partial, sample, chunks, groups, C, fused.inv_count, fused.gamma, fused.beta, fused.eps,
+                     fused.scale_shift);
+  if (threadIdx.x == 0) fused.tickets[sample] = 0;
 }
 
 // y = act(x * scale + shift).  A thread owns one 8-channel column vector and walks down the rows of ONE sample, so the
@@ -369,7 +399,7 @@ extern "C" int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void
   const int vec_per_row = C >> 3;
   const int row_lanes = GN_THREADS / (vec_per_row < GN_THREADS ? vec_per_row : GN_THREADS);
   launch_pdl(gn_stats_kernel, grid, GN_THREADS, static_cast<size_t>(row_lanes) * 2 * C * sizeof(float), stream, static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1,
-      rows_per_sample, rows_per_chunk, groups, chunks, partial);
+      rows_per_sample, rows_per_chunk, groups, chunks, partial, GnFused{});
   return lavie_check_launch("gn_stats_kernel");
 }
 
@@ -381,6 +411,35 @@ extern "C" int lavie_groupnorm_finalize(const float* partial, int samples, int c
   launch_pdl(gn_finalize_kernel, samples, 256, 0, stream, partial, chunks, groups, C, 1.0 / static_cast<double>(count_per_group),
                                                   gamma, beta, eps, scale_shift);
   return lavie_check_launch("gn_finalize_kernel");
+}
+
+extern "C" int lavie_groupnorm_scale_shift(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1,
+                                           int samples, int rows_per_sample, int groups, const float* gamma,
+                                           const float* beta, float eps, float* partial, int* tickets,
+                                           float* scale_shift, cudaStream_t stream) {
+  int rc = check_sources(x0, ld0, c0, x1, ld1, c1);
+  if (rc) return rc;
+  const int C = c0 + c1;
+  LAVIE_REQUIRE(C % groups == 0 && groups <= 64 && groups % 4 == 0 && C <= 8192, LAVIE_ERR_SHAPE,
+                "groupnorm: C=%d groups=%d unsupported", C, groups);
+  LAVIE_REQUIRE(tickets != nullptr && partial != nullptr && scale_shift != nullptr, LAVIE_ERR_SHAPE,
+                "groupnorm_scale_shift: null buffer");
+  const int rows_per_chunk = gn_rows_per_chunk(samples, rows_per_sample);
+  const int chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
+  dim3 grid(chunks, samples);
+  const int vec_per_row = C >> 3;
+  const int row_lanes = GN_THREADS / (vec_per_row < GN_THREADS ? vec_per_row : GN_THREADS);
+  GnFused fused;
+  fused.tickets = tickets;
+  fused.inv_count = 1.0 / (static_cast<double>(rows_per_sample) * (C / groups));
+  fused.gamma = gamma;
+  fused.beta = beta;
+  fused.eps = eps;
+  fused.scale_shift = scale_shift;
+  launch_pdl(gn_stats_kernel, grid, GN_THREADS, static_cast<size_t>(row_lanes) * 2 * C * sizeof(float), stream,
+             static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1,
+             rows_per_sample, rows_per_chunk, groups, chunks, partial, fused);
+  return lavie_check_launch("gn_stats_kernel(fused)");
 }
 
 extern "C" int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,

@@ -49,6 +49,19 @@ WORKSPACE_BYTES = 128 << 20
 _workspaces = {}
 
 
+_ticket_bufs = {}
+
+
+def _tickets(device, n: int) -> torch.Tensor:
+    """Zero-initialised int32 tickets for "last block finalizes" kernels; the kernels leave them zero."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    t = _ticket_bufs.get(key)
+    if t is None or t.numel() < n:
+        t = torch.zeros(max(n, 256), dtype=torch.int32, device=device)
+        _ticket_bufs[key] = t
+    return t
+
+
 def _workspace(device) -> torch.Tensor:
     """Caller-owned split-K scratch (fp32 partials), one per device, reused by every GEMM on the stream."""
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
@@ -167,8 +180,10 @@ def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride
 
 
 def groupnorm_scale_shift(x: torch.Tensor, samples: int, rows_per_sample: int, gamma: torch.Tensor,
-                          beta: torch.Tensor, eps: float, groups: int = 32, x2: Optional[torch.Tensor] = None):
-    """Statistics + affine folded into per-(sample, channel) (scale, shift): fp32 [samples, C, 2]."""
+                          beta: torch.Tensor, eps: float, groups: int = 32, x2: Optional[torch.Tensor] = None,
+                          fused: bool = True):
+    """Statistics + affine folded into per-(sample, channel) (scale, shift): fp32 [samples, C, 2].
+    fused=False runs the two-launch form (stats, then finalize) -- same arithmetic, kept for the sharded path and tests."""
     lib = _lib.load()
     rows, c0, ld0 = _rows2d(x)
     c1, ld1 = 0, 0
@@ -179,15 +194,23 @@ def groupnorm_scale_shift(x: torch.Tensor, samples: int, rows_per_sample: int, g
     C = c0 + c1
     chunks = lib.lavie_groupnorm_chunks(samples, rows_per_sample)
     partial = torch.empty((samples, chunks, groups, 2), dtype=F32, device=x.device)
-    with _Launch("lavie_groupnorm_stats", 0.0, 2.0 * rows * C, f"gn_stats rows={rows} C={C} samples={samples}"):
-        check(lib.lavie_groupnorm_stats(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample, groups,
-                                        partial.data_ptr(), _stream()), "lavie_groupnorm_stats")
     ss = torch.empty((samples, C, 2), dtype=F32, device=x.device)
     assert gamma.dtype == F32 and beta.dtype == F32 and gamma.numel() == C
-    with _Launch("lavie_groupnorm_finalize"):
-        check(lib.lavie_groupnorm_finalize(partial.data_ptr(), samples, chunks, groups, C,
-                                           rows_per_sample * (C // groups), gamma.data_ptr(), beta.data_ptr(), eps,
-                                           ss.data_ptr(), _stream()), "lavie_groupnorm_finalize")
+    if not fused:
+        with _Launch("lavie_groupnorm_stats", 0.0, 2.0 * rows * C, f"gn_stats rows={rows} C={C} samples={samples}"):
+            check(lib.lavie_groupnorm_stats(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample, groups,
+                                            partial.data_ptr(), _stream()), "lavie_groupnorm_stats")
+        with _Launch("lavie_groupnorm_finalize"):
+            check(lib.lavie_groupnorm_finalize(partial.data_ptr(), samples, chunks, groups, C,
+                                               rows_per_sample * (C // groups), gamma.data_ptr(), beta.data_ptr(), eps,
+                                               ss.data_ptr(), _stream()), "lavie_groupnorm_finalize")
+        return ss
+    # one launch: the last block of each sample folds the partials into (scale, shift)
+    with _Launch("lavie_groupnorm_scale_shift", 0.0, 2.0 * rows * C, f"gn_stats rows={rows} C={C} samples={samples}"):
+        check(lib.lavie_groupnorm_scale_shift(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample,
+                                              groups, gamma.data_ptr(), beta.data_ptr(), eps, partial.data_ptr(),
+                                              _tickets(x.device, samples).data_ptr(), ss.data_ptr(), _stream()),
+              "lavie_groupnorm_scale_shift")
     return ss
 
 

@@ -275,9 +275,24 @@ def test_time_embedding_path():
     assert rel_l2(y2, ref2) < 1e-4
 
 
-def test_conv_in_and_out():
+@pytest.mark.parametrize("rows,C,samples", [(2 * 40 * 64 * 4, 320, 2), (32 * 160, 1280, 32), (2 * 77, 64, 2)])
+def test_groupnorm_fused_finalize_matches_two_launch(rows, C, samples):
+    """The last-block-finalizes kernel must give the same bits as stats + finalize, call after call (tickets reset)."""
     ops = _ops()
-    B, Fr, H, W = 2, 3, 10, 16
+    x = _bf(_rand(rows, C))
+    gamma = _rand(C, seed=2) * 0.1 + 1
+    beta = _rand(C, seed=3) * 0.1
+    ref = ops.groupnorm_scale_shift(x, samples, rows // samples, gamma, beta, 1e-5, fused=False)
+    for _ in range(3):
+        got = ops.groupnorm_scale_shift(x, samples, rows // samples, gamma, beta, 1e-5)
+        assert torch.equal(got, ref)
+
+
+
+@pytest.mark.parametrize("H,W", [(10, 16), (5, 7), (3, 1), (40, 64)])
+def test_conv_in_and_out(H, W):
+    ops = _ops()
+    B, Fr = 2, 3
     x = _rand(B, 4, Fr, H, W)
     w = _rand(320, 4, 3, 3, scale=1 / 6.0)
     b = _rand(320, seed=1)
