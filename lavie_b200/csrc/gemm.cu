@@ -47,7 +47,9 @@ struct GemmParams {
   int M, N, K;
   int num_k_blocks;
   int k_split_blocks;        // plain mode: K blocks [0, k_split) come from A0, the rest from A1
-  int m_tiles, n_tiles;      // m_tiles counts 256-row pair tiles
+  int m_tiles, n_tiles;      // m_tiles counts 256-row pair tiles of THIS launch's window
+  int m_tile0;               // first pair tile of the window (a GEMM may be issued as main window + split-K tail window)
+  int rows_window;           // rows covered by the window (stride of the split-K partial planes)
   int splits, kb_per_split;  // split-K
   // conv3 mode
   int conv;                  // 0 plain, 1 conv3x3 stride 1 pad 1
@@ -178,7 +180,7 @@ __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
   const int split = item % p.splits;
   const int rest = item / p.splits;
   it.n_blk = rest % p.n_tiles;
-  it.m_blk = rest / p.n_tiles;
+  it.m_blk = rest / p.n_tiles + p.m_tile0;
   it.kb_begin = split * p.kb_per_split;
   it.kb_end = min(p.num_k_blocks, it.kb_begin + p.kb_per_split);
   return it;
@@ -442,7 +444,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
 
       if (p.splits > 1) {
         // fp32 partials for the ordered split-K reduction
-        float* dst_row = p.partial + (static_cast<size_t>(split) * p.M + row) * p.N;
+        float* dst_row = p.partial + (static_cast<size_t>(split) * p.rows_window + (row - p.m_tile0 * PAIR_M)) * p.N;
 #pragma unroll 1
         for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT) {
           uint32_t v[32];
@@ -536,7 +538,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* __restrict__ bias,
                      const float* __restrict__ row_bias, int rows_per_batch, int ld_row_bias,
-                     const __nv_bfloat16* __restrict__ residual, int ldr, __nv_bfloat16* __restrict__ out, int ldo) {
+                     const __nv_bfloat16* __restrict__ residual, int ldr, __nv_bfloat16* __restrict__ out, int ldo,
+                     int row0) {
+  // M rows of a window that starts at absolute row row0; partial / residual / out already point at the window
   pdl_prologue();
   const int nvec = N >> 2;
   const long long total = static_cast<long long>(M) * nvec;
@@ -554,7 +558,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
     if (row_bias) {
-      const float4 b = *reinterpret_cast<const float4*>(row_bias + static_cast<size_t>(row / rows_per_batch) * ld_row_bias + col);
+      const float4 b = *reinterpret_cast<const float4*>(row_bias + static_cast<size_t>((row + row0) / rows_per_batch) * ld_row_bias + col);
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
     if (residual) {
@@ -586,12 +590,14 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   int rc = lavie_check_launch("gemm_bf16_tcgen05");
   if (rc) return rc;
   if (p.splits > 1) {
-    const long long total = static_cast<long long>(p.M) * (p.N >> 2);
+    const int row0 = p.m_tile0 * PAIR_M;
+    const long long total = static_cast<long long>(p.rows_window) * (p.N >> 2);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    launch_pdl(splitk_reduce_kernel, static_cast<int>(blocks), 256, 0, stream, p.partial, p.splits, p.M, p.N, p.bias,
-                                                                     p.row_bias, p.rows_per_batch, p.ld_row_bias,
-                                                                     p.residual, p.ldr, p.out, p.ldo);
+    launch_pdl(splitk_reduce_kernel, static_cast<int>(blocks), 256, 0, stream, p.partial, p.splits, p.rows_window, p.N,
+               p.bias, p.row_bias, p.rows_per_batch, p.ld_row_bias,
+               p.residual ? p.residual + static_cast<size_t>(row0) * p.ldr : nullptr, p.ldr,
+               p.out + static_cast<size_t>(row0) * p.ldo, p.ldo, row0);
     rc = lavie_check_launch("splitk_reduce_kernel");
   }
   return rc;
@@ -600,6 +606,7 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
 int g_force_splits = 0;
 int g_debug = 0;
 int g_k_rot = 0;   // measured: no effect on B200 (profiles/r1_notes.md), kept as a tuning hook only
+int g_no_tail = 0; // lavie_debug_set(5, 1): never split a GEMM into main + tail launches (A/B timing)
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -614,42 +621,86 @@ int num_sms() {
 // Tile-shape / split-K choice: minimise  waves x (K blocks per item x per-block time + per-item overhead), where the
 // per-block time is the larger of the MMA time (2*BN cycles per SM) and the L2 feed time of the stage bytes.
 struct Plan {
-  int bn, splits, kb_per_split;
+  int bn;
+  int splits, kb_per_split;            // main window: pair tiles [0, m_tiles - tail_tiles)
+  int tail_tiles;                      // > 0: the last tail_tiles pair-tile rows run as a second, split-K launch
+  int tail_splits, tail_kb_per_split;
 };
+
+// modelled cycles of one launch over `m_tiles` pair-tile rows with `s` K splits (s must divide evenly into k blocks)
+double window_cost(int m_tiles, int n_tiles, int bn, int s, int kbps, double t_kb, double t_epi, int pairs, int N) {
+  const long items = static_cast<long>(m_tiles) * n_tiles * s;
+  const long waves = (items + pairs - 1) / pairs;
+  double cost = static_cast<double>(waves) * (kbps * t_kb + 1500.0 + 6.0 * bn + t_epi);
+  if (s > 1) cost += 4000.0 + 0.0013 * (s + 0.5) * static_cast<double>(m_tiles) * PAIR_M * N;   // reduction pass (HBM)
+  return cost;
+}
+
+// best split-K factor for a window; returns cost, writes s / kbps
+double best_split(int m_tiles, int n_tiles, int bn, int num_k_blocks, int max_splits, double t_kb, double t_epi,
+                  int pairs, int N, size_t ws_bytes, int forced, int* s_out, int* kbps_out) {
+  double best = 1e30;
+  const long tiles = static_cast<long>(m_tiles) * n_tiles;
+  for (int s = 1; s <= max_splits; ++s) {
+    if (s > 1) {
+      if (static_cast<size_t>(s) * m_tiles * PAIR_M * N * 4 > ws_bytes) break;
+      if (num_k_blocks / s < 8) break;
+      if (tiles * (s - 1) >= pairs) break;           // no point splitting once the machine is full
+    }
+    if (forced && s != forced) continue;
+    const int kbps = (num_k_blocks + s - 1) / s;
+    if ((num_k_blocks + kbps - 1) / kbps != s) continue;
+    const double c = window_cost(m_tiles, n_tiles, bn, s, kbps, t_kb, t_epi, pairs, N);
+    if (c < best) {
+      best = c;
+      *s_out = s;
+      *kbps_out = kbps;
+    }
+  }
+  return best;
+}
+
+// Tile shape / split-K / tail choice.  Per K block a CTA pays the larger of the MMA time (2*bn cycles) and the L2
+// feed time of its stage bytes.  A launch whose last wave is mostly empty can instead run as two launches: full waves
+// over the leading tile rows, then the remaining rows split along K so that they fill the machine once more.
 Plan make_plan(int M, int N, int num_k_blocks, int forced_bn, bool geglu, bool conv, size_t ws_bytes) {
   const int pairs = num_sms() / 2;
   const int m_tiles = (M + PAIR_M - 1) / PAIR_M;
   const int cands[6] = {320, 256, 192, 160, 128, 64};
-  Plan best{128, 1, num_k_blocks};
+  Plan best{128, 1, num_k_blocks, 0, 1, num_k_blocks};
   double best_cost = 1e30;
+  const int max_splits = geglu ? 1 : 16;
+  const int forced_s = geglu ? 0 : g_force_splits;
   for (int i = 0; i < 6; ++i) {
     const int bn = cands[i];
     if (forced_bn && bn != forced_bn) continue;
     if (geglu && bn != 256) continue;
     const int n_tiles = (N + bn - 1) / bn;
-    const long tiles = static_cast<long>(m_tiles) * n_tiles;
     // measured L2->SM feed per SM and clock with all SMs pulling (tools/bench_feedtheory.py): ~47 B dense, ~38 B through
     // the im2col-mode TMA; a 64-deep K block needs 16 KiB of A plus 64*bn bytes of B per CTA
     const double t_kb = fmax(2.0 * bn, (16384.0 + 64.0 * bn) / (conv ? 38.0 : 47.0));
     const double t_epi = bn > 256 ? 5000.0 : 0.0;      // single accumulator stage: the epilogue is not overlapped
-    const int max_splits = geglu ? 1 : 16;
-    for (int s = 1; s <= max_splits; ++s) {
-      if (s > 1) {
-        if (static_cast<size_t>(s) * M * N * 4 > ws_bytes) break;
-        if (num_k_blocks / s < 8) break;
-        if (tiles * (s - 1) >= pairs) break;           // no point splitting once the machine is full
-      }
-      if (g_force_splits && s != g_force_splits && !geglu) continue;
-      const int kbps = (num_k_blocks + s - 1) / s;
-      const int eff_s = (num_k_blocks + kbps - 1) / kbps;
-      if (eff_s != s) continue;
-      const long items = tiles * s;
-      const long waves = (items + pairs - 1) / pairs;
-      double cost = static_cast<double>(waves) * (kbps * t_kb + 1500.0 + 6.0 * bn + t_epi);
-      if (s > 1) cost += 4000.0 + 0.0013 * (s + 0.5) * static_cast<double>(M) * N;      // reduction pass (HBM)
-      if (cost < best_cost) {
-        best_cost = cost;
-        best = Plan{bn, s, kbps};
+    int s = 1, kbps = num_k_blocks;
+    const double c1 = best_split(m_tiles, n_tiles, bn, num_k_blocks, max_splits, t_kb, t_epi, pairs, N, ws_bytes,
+                                 forced_s, &s, &kbps);
+    if (c1 < best_cost) {
+      best_cost = c1;
+      best = Plan{bn, s, kbps, 0, 1, num_k_blocks};
+    }
+    // main window (no split) + split-K tail; only when the single launch needs more than one wave
+    const long tiles = static_cast<long>(m_tiles) * n_tiles;
+    if (geglu || forced_s || g_no_tail || tiles <= pairs || num_k_blocks < 16) continue;
+    for (int tail = 1; tail < m_tiles && tail <= 16; ++tail) {
+      const int main_tiles = m_tiles - tail;
+      const long main_items = static_cast<long>(main_tiles) * n_tiles;
+      if (main_items % pairs != 0 && main_items % pairs < pairs * 3 / 4) continue;   // the main window must end on a full wave
+      int ts = 1, tk = num_k_blocks;
+      const double ct = best_split(tail, n_tiles, bn, num_k_blocks, 16, t_kb, t_epi, pairs, N, ws_bytes, 0, &ts, &tk);
+      const double cm = window_cost(main_tiles, n_tiles, bn, 1, num_k_blocks, t_kb, t_epi, pairs, N);
+      const double c2 = cm + ct + 6000.0;              // second launch: prologue + drain
+      if (c2 < 0.93 * best_cost) {
+        best_cost = c2;
+        best = Plan{bn, 1, num_k_blocks, tail, ts, tk};
       }
     }
   }
@@ -672,11 +723,8 @@ int make_epilogue_maps(const GemmParams& p, CUtensorMap* mo, CUtensorMap* mr) {
   return LAVIE_OK;
 }
 
-int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
-             cudaStream_t stream) {
-  CUtensorMap mo, mr;
-  int rc = make_epilogue_maps(p, &mo, &mr);
-  if (rc) return rc;
+int launch_window(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& mo,
+                  const CUtensorMap& mr, const GemmParams& p, cudaStream_t stream) {
   switch (bn) {
     case 64: return launch_gemm<64>(a0, a1, b, mo, mr, p, num_sms(), stream);
     case 128: return launch_gemm<128>(a0, a1, b, mo, mr, p, num_sms(), stream);
@@ -686,6 +734,21 @@ int dispatch(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtenso
     case 320: return launch_gemm<320>(a0, a1, b, mo, mr, p, num_sms(), stream);
     default: lavie_set_error("unsupported BLOCK_N %d", bn); return LAVIE_ERR_SHAPE;
   }
+}
+
+void set_window(GemmParams& p, int m_tile0, int m_tiles, int splits, int kbps);
+
+int dispatch(const Plan& plan, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, GemmParams& p,
+             cudaStream_t stream) {
+  CUtensorMap mo, mr;
+  int rc = make_epilogue_maps(p, &mo, &mr);
+  if (rc) return rc;
+  const int m_tiles = (p.M + PAIR_M - 1) / PAIR_M;
+  set_window(p, 0, m_tiles - plan.tail_tiles, plan.splits, plan.kb_per_split);
+  rc = launch_window(plan.bn, a0, a1, b, mo, mr, p, stream);
+  if (rc || plan.tail_tiles == 0) return rc;
+  set_window(p, m_tiles - plan.tail_tiles, plan.tail_tiles, plan.tail_splits, plan.tail_kb_per_split);
+  return launch_window(plan.bn, a0, a1, b, mo, mr, p, stream);
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -724,13 +787,19 @@ int fill_epilogue(GemmParams& p, const lavie_epilogue* ep, int N, void* out, int
 }
 
 void apply_plan(GemmParams& p, const Plan& plan, void* workspace) {
-  p.m_tiles = (p.M + PAIR_M - 1) / PAIR_M;
   p.n_tiles = (p.N + plan.bn - 1) / plan.bn;
-  p.splits = plan.splits;
-  p.kb_per_split = plan.kb_per_split;
   p.partial = static_cast<float*>(workspace);
   p.debug = g_debug;
   p.k_rot = g_k_rot;
+}
+
+void set_window(GemmParams& p, int m_tile0, int m_tiles, int splits, int kbps) {
+  p.m_tile0 = m_tile0;
+  p.m_tiles = m_tiles;
+  const int rows_left = p.M - m_tile0 * PAIR_M;
+  p.rows_window = rows_left < m_tiles * PAIR_M ? rows_left : m_tiles * PAIR_M;
+  p.splits = splits;
+  p.kb_per_split = kbps;
 }
 
 }  // namespace
@@ -741,6 +810,7 @@ extern "C" int lavie_debug_set(int what, int value) {
   if (what == 0) g_k_rot = value;
   if (what == 3) g_lavie_pdl = value ? 1 : 0;
   if (what == 4) g_lavie_attn_poly = value;
+  if (what == 5) g_no_tail = value;
   return 0;
 }
 
@@ -784,7 +854,7 @@ extern "C" int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1,
   }
   rc = make_weight_map(&mb, w, N, K, plan.bn);
   if (rc) return rc;
-  return dispatch(plan.bn, ma0, ma1, mb, p, stream);
+  return dispatch(plan, ma0, ma1, mb, p, stream);
 }
 
 extern "C" int lavie_conv3x3_supported(int H, int W, int C) {
@@ -842,5 +912,5 @@ extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, in
   if (rc) return rc;
   rc = make_weight_map(&mb, w, N, 9 * C, plan.bn);
   if (rc) return rc;
-  return dispatch(plan.bn, ma, ma, mb, p, stream);
+  return dispatch(plan, ma, ma, mb, p, stream);
 }

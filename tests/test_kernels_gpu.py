@@ -71,6 +71,42 @@ def test_gemm_wide_tile_epilogue(N):
     assert rel_l2(out.float(), ref) < 4e-3
 
 
+def test_gemm_main_plus_splitk_tail_window():
+    """More than one wave of tiles with a nearly empty last wave: the planner issues full waves over the leading tile
+    rows and a split-K launch over the rest.  Same epilogue on both paths; compare with the single-launch result."""
+    ops = _ops()
+    from lavie_b200 import _lib
+    lib = _lib.load()
+    M, N, K, B = 256 * 39 + 100, 640, 2048, 2
+    a = _bf(_rand(M, K))
+    w = _bf(_rand(N, K, scale=K ** -0.5))
+    bias = _rand(N, seed=1)
+    rb = _rand(B, N, seed=2)
+    res = _bf(_rand(M, N, seed=3))
+    rpb = (M + B - 1) // B
+    out = ops.gemm(a, w, bias=bias, row_bias=rb, rows_per_batch=rpb, residual=res)
+    lib.lavie_debug_set(5, 1)
+    try:
+        single = ops.gemm(a, w, bias=bias, row_bias=rb, rows_per_batch=rpb, residual=res)
+    finally:
+        lib.lavie_debug_set(5, 0)
+    ref = a.float() @ w.float().t() + bias + rb.repeat_interleave(rpb, 0)[:M] + res.float()
+    assert rel_l2(out.float(), ref) < 4e-3
+    assert rel_l2(out.float(), single.float()) < 3e-3     # split-K changes the summation order of the tail rows only
+    assert torch.equal(out[: 256 * 30], single[: 256 * 30])
+
+
+def test_conv3x3_main_plus_tail_window():
+    ops = _ops()
+    from lavie_b200.packing import pack_conv3x3
+    NF, H, W, C, N = 32, 10, 16, 128, 1280
+    x = _bf(_rand(NF * H * W, C))
+    w = _bf(_rand(N, C, 3, 3, scale=(9 * C) ** -0.5))
+    res = _bf(_rand(NF * H * W, N, seed=5))
+    out = ops.conv3x3(x, NF, H, W, pack_conv3x3(w), residual=res)
+    assert rel_l2(out.float(), _conv_ref(x, w, NF, H, W) + res.float()) < 4e-3
+
+
 def test_conv3x3_wide_tile():
     ops = _ops()
     from lavie_b200.packing import pack_conv3x3
