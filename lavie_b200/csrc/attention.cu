@@ -482,6 +482,14 @@ __device__ __forceinline__ uint32_t scale_rope_pair(uint32_t w, float scale, boo
   return pack_bf16(f.x, f.y);
 }
 
+// same with the angle's (cos, sin) already in registers ((1, 0) = no rotation)
+__device__ __forceinline__ uint32_t scale_rope_pair_cs(uint32_t w, float scale, float c, float sn) {
+  float2 f = unpack_bf16(w);
+  f.x *= scale;
+  f.y *= scale;
+  return pack_bf16(f.x * c - f.y * sn, f.y * c + f.x * sn);
+}
+
 template <int DP>   // head pitch (d rounded up to 16): 48, 64, 80, 96, 128, 160
 __global__ void __launch_bounds__(128)
 temporal_attn_mma_kernel(const TempParams p) {
@@ -496,8 +504,38 @@ temporal_attn_mma_kernel(const TempParams p) {
   const int F = p.F;
   __nv_bfloat16* sv = s_v[wib];
   const long long warps_total = static_cast<long long>(gridDim.x) * 4;
+  // Per-lane constants hoisted out of the item loop (they were ~50 of the ~65 load instructions per item):
+  //  * the rotary (cos, sin) of the lane's two frames for the 4 channel pairs of the first 32-wide block -- with the
+  //    model's 32 rotated dims that is every rotated pair; pairs >= rot_pairs get (1, 0);
+  //  * the relative-position bias of the lane's 8 score elements (-inf on padded frames, so adding it also masks),
+  //    when the warp keeps the same head for all its items (warps_total % heads == 0; the host sizes the grid so).
+  float cs_lo0[4][2], cs_hi0[4][2];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int pr = t * 4 + w;
+    const bool rot = pr < p.rot_pairs;
+    cs_lo0[w][0] = (rot && g < F) ? __ldg(p.rope + (static_cast<size_t>(g) * p.rot_pairs + pr) * 2) : 1.f;
+    cs_lo0[w][1] = (rot && g < F) ? __ldg(p.rope + (static_cast<size_t>(g) * p.rot_pairs + pr) * 2 + 1) : 0.f;
+    cs_hi0[w][0] = (rot && g + 8 < F) ? __ldg(p.rope + (static_cast<size_t>(g + 8) * p.rot_pairs + pr) * 2) : 1.f;
+    cs_hi0[w][1] = (rot && g + 8 < F) ? __ldg(p.rope + (static_cast<size_t>(g + 8) * p.rot_pairs + pr) * 2 + 1) : 0.f;
+  }
+  float bias_lo[4], bias_hi[4];                   // index nt * 2 + e  <->  key frame nt * 8 + 2 t + e
+  auto load_bias = [&](int h) {
+    const float* bias_h = p.bias + static_cast<size_t>(h) * F * F;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int jn = nt * 8 + 2 * t + e;
+        bias_lo[nt * 2 + e] = (jn < F && g < F) ? __ldg(bias_h + g * F + jn) : -INFINITY;
+        bias_hi[nt * 2 + e] = (jn < F && g + 8 < F) ? __ldg(bias_h + (g + 8) * F + jn) : -INFINITY;
+      }
+  };
+  const bool fixed_head = (warps_total % p.heads) == 0;
+  if (fixed_head) load_bias(static_cast<int>((static_cast<long long>(blockIdx.x) * 4 + wib) % p.heads));
   for (long long item = static_cast<long long>(blockIdx.x) * 4 + wib; item < p.items; item += warps_total) {
     const int h = static_cast<int>(item % p.heads);
+    if (!fixed_head) load_bias(h);
     const long long bp = item / p.heads;
     const int pix = static_cast<int>(bp % p.HW);
     const int b = static_cast<int>(bp / p.HW);
@@ -541,12 +579,19 @@ temporal_attn_mma_kernel(const TempParams p) {
       uint32_t kl[4] = {k_lo.x, k_lo.y, k_lo.z, k_lo.w}, kh[4] = {k_hi.x, k_hi.y, k_hi.z, k_hi.w};
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
-        const int pr = (col >> 1) + w;            // bf16-pair index inside the head
-        const bool rot = pr < p.rot_pairs;
-        ql[w] = scale_rope_pair(ql[w], p.scale, rot && lo_ok, cs_lo + 2 * (rot ? pr : 0));
-        qh[w] = scale_rope_pair(qh[w], p.scale, rot && hi_ok, cs_hi + 2 * (rot ? pr : 0));
-        kl[w] = scale_rope_pair(kl[w], 1.f, rot && lo_ok, cs_lo + 2 * (rot ? pr : 0));
-        kh[w] = scale_rope_pair(kh[w], 1.f, rot && hi_ok, cs_hi + 2 * (rot ? pr : 0));
+        if (blk == 0) {                           // hoisted angles (compile-time branch: the loop is unrolled)
+          ql[w] = scale_rope_pair_cs(ql[w], p.scale, cs_lo0[w][0], cs_lo0[w][1]);
+          qh[w] = scale_rope_pair_cs(qh[w], p.scale, cs_hi0[w][0], cs_hi0[w][1]);
+          kl[w] = scale_rope_pair_cs(kl[w], 1.f, cs_lo0[w][0], cs_lo0[w][1]);
+          kh[w] = scale_rope_pair_cs(kh[w], 1.f, cs_hi0[w][0], cs_hi0[w][1]);
+        } else {
+          const int pr = (col >> 1) + w;          // bf16-pair index inside the head
+          const bool rot = pr < p.rot_pairs;
+          ql[w] = scale_rope_pair(ql[w], p.scale, rot && lo_ok, cs_lo + 2 * (rot ? pr : 0));
+          qh[w] = scale_rope_pair(qh[w], p.scale, rot && hi_ok, cs_hi + 2 * (rot ? pr : 0));
+          kl[w] = scale_rope_pair(kl[w], 1.f, rot && lo_ok, cs_lo + 2 * (rot ? pr : 0));
+          kh[w] = scale_rope_pair(kh[w], 1.f, rot && hi_ok, cs_hi + 2 * (rot ? pr : 0));
+        }
       }
       // words (0,1) form one k-step, words (2,3) the next: a0/a2 = row g, a1/a3 = row g+8; b0/b1 = key frame g (+8)
       const uint32_t a_first[4] = {ql[0], qh[0], ql[1], qh[1]};
@@ -584,16 +629,13 @@ temporal_attn_mma_kernel(const TempParams p) {
     (void)KSTEPS;
 
     // ---- + rel-pos bias, mask padded frames, softmax over the key frames (a row lives in one lane quad) ----
-    const float* bias_h = p.bias + static_cast<size_t>(h) * F * F;
     float mx_lo = -INFINITY, mx_hi = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int jn = nt * 8 + 2 * t + e;
-        const bool jok = jn < F;
-        s[nt][e] = (jok && lo_ok) ? s[nt][e] + __ldg(bias_h + g * F + jn) : -INFINITY;
-        s[nt][2 + e] = (jok && hi_ok) ? s[nt][2 + e] + __ldg(bias_h + (g + 8) * F + jn) : -INFINITY;
+        s[nt][e] += bias_lo[nt * 2 + e];          // -inf on padded frames
+        s[nt][2 + e] += bias_hi[nt * 2 + e];
         mx_lo = fmaxf(mx_lo, s[nt][e]);
         mx_hi = fmaxf(mx_hi, s[nt][2 + e]);
       }
@@ -646,6 +688,10 @@ template <int DP>
 int launch_temporal_mma(const TempParams& p, cudaStream_t stream) {
   long long blocks = (p.items + 3) / 4;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
+  // keep (4 * blocks) % heads == 0 when the grid is capped, so every warp serves a single head (hoisted bias)
+  if (blocks * 4 < p.items) {
+    while (blocks > 1 && (blocks * 4) % p.heads != 0) --blocks;
+  }
   launch_pdl(temporal_attn_mma_kernel<DP>, static_cast<int>(blocks), 128, 0, stream, p);
   return lavie_check_launch("temporal_attn_mma_kernel");
 }
