@@ -39,8 +39,10 @@ struct AttnCfg {
   static constexpr int MIN_BLOCKS = DK <= 64 ? 4 : (DK <= 96 ? 2 : 1);
 };
 
+constexpr int ATT_THREADS = 160;     // warps 0-3: softmax (thread = query row), warp 4: TMA + MMA issue
+
 template <int DK, int POLY, bool ONES>
-__global__ void __launch_bounds__(128, AttnCfg<DK>::MIN_BLOCKS)
+__global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DK>::MIN_BLOCKS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   pdl_launch_dependents();
@@ -53,15 +55,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sV = sK + NC * KV_CHUNK_BYTES;
   uint8_t* sP = sV + NC * KV_CHUNK_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_CHUNKS * CHUNK_BYTES);
-  uint64_t* bar_q = bars + 0;
-  uint64_t* bar_k = bars + 1;
-  uint64_t* bar_v = bars + 2;
-  uint64_t* bar_s = bars + 3;
-  uint64_t* bar_o = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bar_q = bars + 0;        // Q landed (TMA)
+  uint64_t* bar_k = bars + 1;        // K(j) landed, phase j
+  uint64_t* bar_v = bars + 2;        // V(j) landed, phase j
+  uint64_t* bar_s_full = bars + 3;   // S(j) = Q K(j)^T complete in TMEM (tcgen05.commit), phase j
+  uint64_t* bar_s_free = bars + 4;   // all 4 softmax warps hold S(j) in registers, phase j
+  uint64_t* bar_p_full = bars + 5;   // all 4 softmax warps wrote P(j) to smem (and rescaled O if needed), phase j
+  uint64_t* bar_pv = bars + 6;       // O += P(j) V(j) retired (tcgen05.commit), phase j: P / V buffers free, O stable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
+  const int lane = tid & 31;
   const int q_tile = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
   const int kv_batch = batch / p.kv_batch_div;
   const int n_kv = (p.Sk + ATT_N - 1) / ATT_N;
@@ -71,10 +76,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_s_free, 4);
+    mbar_init(bar_p_full, 4);
+    mbar_init(bar_pv, 1);
     mbar_fence_init();
   }
-  if (warp == 0) {
+  if (warp == 4) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -85,235 +96,271 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;             // columns [0, ATT_N)
   const uint32_t tmem_o = tmem_base + ATT_N;     // columns [ATT_N, ATT_N + DK)
+  const bool tl = p.timeline != nullptr && lane == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2 &&
+                  blockIdx.z == gridDim.z / 2;
 
-  if (tid == 0) {
-    mbar_expect_tx(bar_q, NC * CHUNK_BYTES);
-    for (int c = 0; c < NC; ++c) tma_load_3d(sQ + c * CHUNK_BYTES, &tmap_q, bar_q, col0 + c * 64, q_tile * ATT_M, batch);
-    mbar_expect_tx(bar_k, NC * KV_CHUNK_BYTES);
-    for (int c = 0; c < NC; ++c) tma_load_3d(sK + c * KV_CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, 0, kv_batch);
-  }
-
-  constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_M, ATT_N, 0, 0);
-  constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_M, DK, 0, 1);
-  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-
-  // Softmax state per query row (one row per thread).  The output accumulator stays in TMEM across key tiles
-  // (P.V accumulates with use_acc); m_used is the exponent offset currently baked into it.  It is only moved -- and O
-  // rescaled in TMEM -- when the running maximum has grown by more than 2^8 since (lazy rescale): probabilities are
-  // then at most 256, harmless in bf16 / fp32, and the result O / l is unchanged because both use the same offset.
-  float m_used = -INFINITY, l_run = 0.f;
-  // d < DK (d = 40 in a 48-wide head slot): a padded V column is set to 1.0 so that the P.V MMA itself produces the
-  // softmax denominator (sum of the bf16-rounded probabilities) in accumulator column d -- no per-element FADD.
-  constexpr bool ones_col = ONES;              // host: p.d < DK
-
-  // One MMA round trip per key tile: batch j = { O += P(j-1) V(j-1),  S = Q K(j)^T } is committed to ONE barrier.
-  // While it runs, nothing in this CTA can proceed -- the other co-resident CTAs fill the SM.
-  // Operand descriptors are built once; a K-step only adds (byte offset >> 4) to the 14-bit start-address field.
-  const uint64_t desc_q = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-  const uint64_t desc_k = umma_desc_sw128(smem_u32(sK), 16, 1024);
-  const uint64_t desc_p = umma_desc_sw128(smem_u32(sP), 16, 1024);
-  const uint64_t desc_v = umma_desc_sw128(smem_u32(sV), KV_CHUNK_BYTES, 1024);
-  auto issue_qk = [&]() {
+  if (warp == 4) {
+    // =============================== control warp: TMA loads + MMA issue ===============================
+    // The whole warp runs the loop (descriptors stay in uniform registers), one elected lane issues.  None of its
+    // waits is on the softmax warps' critical path: S(j+1) = Q K(j+1)^T is issued as soon as S(j) sits in registers,
+    // so the MMA round trip runs under the exponentials of tile j; P(j) V(j) follows when P(j) is in shared memory.
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_M, ATT_N, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_M, DK, 0, 1);
+    const uint64_t desc_q = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t desc_k = umma_desc_sw128(smem_u32(sK), 16, 1024);
+    const uint64_t desc_p = umma_desc_sw128(smem_u32(sP), 16, 1024);
+    const uint64_t desc_v = umma_desc_sw128(smem_u32(sV), KV_CHUNK_BYTES, 1024);
+    auto issue_qk = [&]() {
 #pragma unroll
-    for (int kk = 0; kk < DK / 16; ++kk) {
-      const uint32_t qoff = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
-      const uint32_t koff = (kk >> 2) * KV_CHUNK_BYTES + (kk & 3) * 32;
-      umma_bf16(tmem_s, desc_q + (qoff >> 4), desc_k + (koff >> 4), idesc_qk, kk != 0);
+      for (int kk = 0; kk < DK / 16; ++kk) {
+        const uint32_t qoff = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
+        const uint32_t koff = (kk >> 2) * KV_CHUNK_BYTES + (kk & 3) * 32;
+        umma_bf16(tmem_s, desc_q + (qoff >> 4), desc_k + (koff >> 4), idesc_qk, kk != 0);
+      }
+    };
+    auto load_k = [&](int j) {
+      mbar_expect_tx(bar_k, NC * KV_CHUNK_BYTES);
+      for (int c = 0; c < NC; ++c) tma_load_3d(sK + c * KV_CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, j * ATT_N, kv_batch);
+    };
+    auto load_v = [&](int j) {
+      mbar_expect_tx(bar_v, NC * KV_CHUNK_BYTES);
+      for (int c = 0; c < NC; ++c) tma_load_3d(sV + c * KV_CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, j * ATT_N, kv_batch);
+    };
+    if (elect_one()) {
+      mbar_expect_tx(bar_q, NC * CHUNK_BYTES);
+      for (int c = 0; c < NC; ++c) tma_load_3d(sQ + c * CHUNK_BYTES, &tmap_q, bar_q, col0 + c * 64, q_tile * ATT_M, batch);
+      load_k(0);
+      load_v(0);
     }
-  };
-  // MMA / TMA issue runs warp-uniformly in warp 0 (descriptors stay in uniform registers; with a divergent
-  // `if (tid == 0)` every tcgen05.mma needed ~5 R2UR moves and cost ~150 cycles to issue) -- one elected lane issues.
-  if (warp == 0) {
+    __syncwarp();
     mbar_wait(bar_q, 0);
     mbar_wait(bar_k, 0);
     tc_fence_after();
     if (elect_one()) {
       issue_qk();
-      umma_commit(bar_s);
+      umma_commit(bar_s_full);
     }
     __syncwarp();
-  }
-  const float sc = p.scale_log2;
-  uint8_t* p_row = sP + tid * 128;
-
-  const bool tl = p.timeline != nullptr && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2 &&
-                  blockIdx.z == gridDim.z / 2;
-  for (int j = 0; j < n_kv; ++j) {
-    const uint32_t ph = j & 1;
-    const int kv_len = min(ATT_N, p.Sk - j * ATT_N);
-    long long* tl_row = p.timeline + j * 8;
-    if (tl) tl_row[0] = clock64();
-    mbar_wait(bar_s, ph);                    // S(j) ready; for j >= 1 also P(j-1) V(j-1) accumulated
-    tc_fence_after();
-    if (tl) tl_row[1] = clock64();
-    if (warp == 0 && elect_one()) {
-      // Both buffers are free (QK(j) and PV(j-1) retired): K(j+1) and V(j) stream in under the softmax and complete
-      // ONE barrier -- every mbarrier wait on the issuing thread's path costs ~130 cycles even when already complete.
-      const bool more = j + 1 < n_kv;
-      mbar_expect_tx(bar_v, (more ? 2 : 1) * NC * KV_CHUNK_BYTES);
-      for (int c = 0; c < NC; ++c)
-        tma_load_3d(sV + c * KV_CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, j * ATT_N, kv_batch);
-      if (more)
-        for (int c = 0; c < NC; ++c)
-          tma_load_3d(sK + c * KV_CHUNK_BYTES, &tmap_k, bar_v, col0 + c * 64, (j + 1) * ATT_N, kv_batch);
+    if (n_kv > 1) {
+      mbar_wait(bar_s_full, 0);                  // Q K(0)^T retired: the K buffer is free
+      if (elect_one()) load_k(1);
+      __syncwarp();
     }
-    __syncwarp();
-
-    // ---- S(j) -> registers, read once ----
-    uint32_t s0[32], s1[32];
-    tmem_ld_32x32(tmem_s + lane_base, s0);
-    tmem_ld_32x32(tmem_s + lane_base + 32, s1);
-    tmem_wait_ld();
-    if (tl) tl_row[2] = clock64();
-    const bool full = (kv_len == ATT_N);           // CTA-uniform
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-    if (full) {
-      float mx2 = -INFINITY, mx3 = -INFINITY;      // four short FMNMX3 chains instead of two long ones
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) {
-        mx0 = fmax3(mx0, __uint_as_float(s0[e]), __uint_as_float(s0[e + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(s1[e]), __uint_as_float(s1[e + 1]));
-        mx2 = fmax3(mx2, __uint_as_float(s0[e + 2]), __uint_as_float(s0[e + 3]));
-        mx3 = fmax3(mx3, __uint_as_float(s1[e + 2]), __uint_as_float(s1[e + 3]));
-      }
-      mx0 = fmaxf(mx0, mx2);
-      mx1 = fmaxf(mx1, mx3);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        if (e < kv_len) mx0 = fmaxf(mx0, __uint_as_float(s0[e]));
-        if (32 + e < kv_len) mx1 = fmaxf(mx1, __uint_as_float(s1[e]));
-      }
-    }
-    const float m_tile = fmaxf(mx0, mx1) * sc;     // sc > 0
-    const bool grow = m_tile > m_used + 8.0f;      // always true for j == 0 (m_used = -inf)
-    if (j > 0 && __any_sync(0xffffffffu, grow)) {
-      const float alpha = grow ? fast_exp2(m_used - m_tile) : 1.0f;
-#pragma unroll
-      for (int c = 0; c < DK / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x16(tmem_o + lane_base + c * 16, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-        tmem_st_32x16(tmem_o + lane_base + c * 16, v);
-      }
-      tmem_wait_st();
-      l_run *= alpha;
-    }
-    if (grow) m_used = m_tile;
-    const float neg_m = -m_used;
-
-    // ---- p = exp2(s*scale - m_used), P -> smem (bf16, 128B swizzle, K-major) ----
-    // Full tiles: every POLY-th exponential runs on the FMA pipe (exp2_poly), the rest on the MUFU.
-    float rs0 = 0.f, rs1 = 0.f;
-    auto soft_half = [&](uint32_t (&sv)[32], int c) {
-      uint32_t pk[16];
-      if (full) {
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float x0 = fmaf(__uint_as_float(sv[e]), sc, neg_m);
-          const float x1 = fmaf(__uint_as_float(sv[e + 1]), sc, neg_m);
-          const float p0 = (POLY > 0 && (e % POLY) == POLY - 1) ? exp2_poly(x0) : fast_exp2(x0);
-          const float p1 = (POLY > 0 && ((e + 1) % POLY) == POLY - 1) ? exp2_poly(x1) : fast_exp2(x1);
-          if (!ones_col) {
-            rs0 += p0;
-            rs1 += p1;
-          }
-          pk[e >> 1] = pack_bf16(p0, p1);
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      const int kv_len = min(ATT_N, p.Sk - j * ATT_N);
+      long long* tl_row = p.timeline + j * 8;
+      if (j + 1 < n_kv) {
+        mbar_wait(bar_s_free, ph);               // S(j) is in registers in all four softmax warps
+        mbar_wait(bar_k, ph ^ 1);                // K(j+1) landed
+        tc_fence_after();
+        if (elect_one()) {
+          issue_qk();
+          umma_commit(bar_s_full);
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = (c * 32 + e < kv_len) ? fast_exp2(fmaf(__uint_as_float(sv[e]), sc, neg_m)) : 0.f;
-          const float p1 = (c * 32 + e + 1 < kv_len) ? fast_exp2(fmaf(__uint_as_float(sv[e + 1]), sc, neg_m)) : 0.f;
-          rs0 += p0;
-          rs1 += p1;
-          pk[e >> 1] = pack_bf16(p0, p1);
-        }
+        __syncwarp();
       }
-      uint8_t* chunk = p_row + (c >> 1) * CHUNK_BYTES;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int c16 = ((c & 1) * 4 + g) ^ (tid & 7);
-        *reinterpret_cast<uint4*>(chunk + c16 * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-      }
-    };
-    soft_half(s0, 0);
-    soft_half(s1, 1);
-    l_run += rs0 + rs1;
-    if (ones_col && tid < ATT_N) {           // V(j)[key = tid][column d] = 1.0 (bf16), 128-byte-swizzled address
-      mbar_wait(bar_v, ph);
-      const int unit = ((p.d >> 3) & 7) ^ (tid & 7);
-      *reinterpret_cast<uint16_t*>(sV + (p.d >> 6) * KV_CHUNK_BYTES + tid * 128 + unit * 16 + (p.d & 7) * 2) = 0x3F80;
-    }
-    if (tl) tl_row[3] = clock64();
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();                         // P(j) complete in smem, S(j) fully read, O rescaled where needed
-    if (tl) tl_row[4] = clock64();
-
-    if (warp == 0) {
-      mbar_wait(bar_v, ph);                  // V(j) and K(j+1) landed
-      tc_fence_after();
       if (tl) tl_row[5] = clock64();
-      const int nk = (kv_len + 15) >> 4;
+      mbar_wait(bar_v, ph);                      // V(j) landed
+      if (ONES) {                                // V(j)[key][column d] = 1.0 (bf16), 128-byte-swizzled address
+#pragma unroll
+        for (int key = lane; key < ATT_N; key += 32) {
+          const int unit = ((p.d >> 3) & 7) ^ (key & 7);
+          *reinterpret_cast<uint16_t*>(sV + (p.d >> 6) * KV_CHUNK_BYTES + key * 128 + unit * 16 + (p.d & 7) * 2) = 0x3F80;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+      }
+      mbar_wait(bar_p_full, ph);                 // P(j) in shared memory, O rescaled where needed
+      tc_fence_after();
       if (elect_one()) {
-        if (full) {
+        if (kv_len == ATT_N) {
 #pragma unroll
           for (int kk = 0; kk < ATT_N / 16; ++kk)
             umma_bf16(tmem_o, desc_p + (((kk >> 2) * CHUNK_BYTES + (kk & 3) * 32) >> 4), desc_v + ((kk * 2048) >> 4),
                       idesc_pv, (j > 0 || kk != 0));
         } else {
+          const int nk = (kv_len + 15) >> 4;
           for (int kk = 0; kk < nk; ++kk)
             umma_bf16(tmem_o, desc_p + (((kk >> 2) * CHUNK_BYTES + (kk & 3) * 32) >> 4), desc_v + ((kk * 2048) >> 4),
                       idesc_pv, (j > 0 || kk != 0));
         }
-        if (tl) tl_row[7] = clock64();
-        if (j + 1 < n_kv) issue_qk();        // S(j+1) in the same batch: one round trip per tile
-        umma_commit(bar_s);
+        umma_commit(bar_pv);
       }
       __syncwarp();
       if (tl) tl_row[6] = clock64();
+      if (j + 2 < n_kv) {
+        mbar_wait(bar_s_full, ph ^ 1);           // Q K(j+1)^T retired: K buffer free -> K(j+2) has a whole tile to land
+        if (elect_one()) load_k(j + 2);
+        __syncwarp();
+      }
+      if (j + 1 < n_kv) {
+        mbar_wait(bar_pv, ph);                   // P(j) V(j) retired: V buffer free
+        if (elect_one()) load_v(j + 1);
+        __syncwarp();
+      }
+      if (tl) tl_row[7] = clock64();
     }
-  }
-  // last batch: O complete
-  mbar_wait(bar_s, n_kv & 1);
-  tc_fence_after();
-  float denom = l_run;
-  if (ones_col) {                            // the ones column of V accumulated the denominator in O[:, d]
-    uint32_t v[16];
-    tmem_ld_32x16(tmem_o + lane_base + (p.d >> 4) * 16, v);
-    tmem_wait_ld();
+  } else {
+    // =============================== softmax warps: one query row per thread ===========================
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    // The output accumulator stays in TMEM across key tiles (P.V accumulates with use_acc); m_used is the exponent
+    // offset currently baked into it.  It is only moved -- and O rescaled in TMEM -- when the running maximum has
+    // grown by more than 2^8 since (lazy rescale): probabilities are then at most 256, harmless in bf16 / fp32, and
+    // the result O / l is unchanged because numerator and denominator use the same offset.
+    float m_used = -INFINITY, l_run = 0.f;
+    // d < DK (d = 40 in a 48-wide head slot): a padded V column is set to 1.0 so that the P.V MMA itself produces the
+    // softmax denominator (sum of the bf16-rounded probabilities) in accumulator column d -- no per-element FADD.
+    constexpr bool ones_col = ONES;              // host: p.d < DK
+    const float sc = p.scale_log2;
+    uint8_t* p_row = sP + tid * 128;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      const int kv_len = min(ATT_N, p.Sk - j * ATT_N);
+      long long* tl_row = p.timeline + j * 8;
+      if (tl && warp == 0) tl_row[0] = clock64();
+      mbar_wait(bar_s_full, ph);
+      tc_fence_after();
+      if (tl && warp == 0) tl_row[1] = clock64();
+      // ---- S(j) -> registers, read once; hand the TMEM buffer back at once ----
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32(tmem_s + lane_base, s0);
+      tmem_ld_32x32(tmem_s + lane_base + 32, s1);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_s_free);
+      if (tl && warp == 0) tl_row[2] = clock64();
+      const bool full = (kv_len == ATT_N);         // CTA-uniform
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (full) {
+        float mx2 = -INFINITY, mx3 = -INFINITY;    // four short FMNMX3 chains instead of two long ones
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
-      if (e == (p.d & 15)) denom = __uint_as_float(v[e]);
-  }
-  const float inv = 1.f / denom;
-  const int qrow = q_tile * ATT_M + tid;
-  __nv_bfloat16* dst = p.o + (static_cast<size_t>(batch) * p.Sq + qrow) * p.ldo + head * p.d;
+        for (int e = 0; e < 32; e += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(s0[e]), __uint_as_float(s0[e + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(s1[e]), __uint_as_float(s1[e + 1]));
+          mx2 = fmax3(mx2, __uint_as_float(s0[e + 2]), __uint_as_float(s0[e + 3]));
+          mx3 = fmax3(mx3, __uint_as_float(s1[e + 2]), __uint_as_float(s1[e + 3]));
+        }
+        mx0 = fmaxf(mx0, mx2);
+        mx1 = fmaxf(mx1, mx3);
+      } else {
 #pragma unroll
-  for (int c = 0; c < DK / 16; ++c) {
-    uint32_t v[16];
-    tmem_ld_32x16(tmem_o + lane_base + c * 16, v);
-    tmem_wait_ld();
-    if (qrow < p.Sq) {
+        for (int e = 0; e < 32; ++e) {
+          if (e < kv_len) mx0 = fmaxf(mx0, __uint_as_float(s0[e]));
+          if (32 + e < kv_len) mx1 = fmaxf(mx1, __uint_as_float(s1[e]));
+        }
+      }
+      const float m_tile = fmaxf(mx0, mx1) * sc;   // sc > 0
+      const bool grow = m_tile > m_used + 8.0f;    // always true for j == 0 (m_used = -inf)
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        mbar_wait(bar_pv, ph ^ 1);                 // P(j-1) V(j-1) retired: O is stable
+        tc_fence_after();
+        const float alpha = grow ? fast_exp2(m_used - m_tile) : 1.0f;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (c * 16 + h * 8 < p.d) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(v[8 * h]) * inv, __uint_as_float(v[8 * h + 1]) * inv);
-          o.y = pack_bf16(__uint_as_float(v[8 * h + 2]) * inv, __uint_as_float(v[8 * h + 3]) * inv);
-          o.z = pack_bf16(__uint_as_float(v[8 * h + 4]) * inv, __uint_as_float(v[8 * h + 5]) * inv);
-          o.w = pack_bf16(__uint_as_float(v[8 * h + 6]) * inv, __uint_as_float(v[8 * h + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + c * 16 + h * 8) = o;
+        for (int c = 0; c < DK / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x16(tmem_o + lane_base + c * 16, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+          tmem_st_32x16(tmem_o + lane_base + c * 16, v);
+        }
+        tmem_wait_st();
+        l_run *= alpha;
+      }
+      if (grow) m_used = m_tile;
+      const float neg_m = -m_used;
+
+      // ---- p = exp2(s*scale - m_used), packed to bf16 in place (s0/s1[0..15] hold the packed pairs) ----
+      // Full tiles: every POLY-th exponential runs on the FMA pipe (exp2_poly), the rest on the MUFU.
+      float rs0 = 0.f, rs1 = 0.f;
+      auto soft_half = [&](uint32_t (&sv)[32], int c) {
+        if (full) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float x0 = fmaf(__uint_as_float(sv[e]), sc, neg_m);
+            const float x1 = fmaf(__uint_as_float(sv[e + 1]), sc, neg_m);
+            const float p0 = (POLY > 0 && (e % POLY) == POLY - 1) ? exp2_poly(x0) : fast_exp2(x0);
+            const float p1 = (POLY > 0 && ((e + 1) % POLY) == POLY - 1) ? exp2_poly(x1) : fast_exp2(x1);
+            if (!ones_col) {
+              rs0 += p0;
+              rs1 += p1;
+            }
+            sv[e >> 1] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = (c * 32 + e < kv_len) ? fast_exp2(fmaf(__uint_as_float(sv[e]), sc, neg_m)) : 0.f;
+            const float p1 = (c * 32 + e + 1 < kv_len) ? fast_exp2(fmaf(__uint_as_float(sv[e + 1]), sc, neg_m)) : 0.f;
+            rs0 += p0;
+            rs1 += p1;
+            sv[e >> 1] = pack_bf16(p0, p1);
+          }
+        }
+      };
+      soft_half(s0, 0);
+      soft_half(s1, 1);
+      l_run += rs0 + rs1;
+      if (tl && warp == 0) tl_row[3] = clock64();
+      if (j > 0) mbar_wait(bar_pv, ph ^ 1);        // P(j-1) V(j-1) retired: the P buffer may be overwritten
+      // P -> smem (bf16, 128B swizzle, K-major)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint8_t* chunk = p_row + (c >> 1) * CHUNK_BYTES;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int c16 = ((c & 1) * 4 + g) ^ (tid & 7);
+          const uint32_t* pk = c == 0 ? s0 : s1;
+          *reinterpret_cast<uint4*>(chunk + c16 * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p_full);
+      if (tl && warp == 0) tl_row[4] = clock64();
+    }
+    // ---- O complete ----
+    mbar_wait(bar_pv, (n_kv - 1) & 1);
+    tc_fence_after();
+    float denom = l_run;
+    if (ones_col) {                            // the ones column of V accumulated the denominator in O[:, d]
+      uint32_t v[16];
+      tmem_ld_32x16(tmem_o + lane_base + (p.d >> 4) * 16, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (e == (p.d & 15)) denom = __uint_as_float(v[e]);
+    }
+    const float inv = 1.f / denom;
+    const int qrow = q_tile * ATT_M + tid;
+    __nv_bfloat16* dst = p.o + (static_cast<size_t>(batch) * p.Sq + qrow) * p.ldo + head * p.d;
+#pragma unroll
+    for (int c = 0; c < DK / 16; ++c) {
+      uint32_t v[16];
+      tmem_ld_32x16(tmem_o + lane_base + c * 16, v);
+      tmem_wait_ld();
+      if (qrow < p.Sq) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (c * 16 + h * 8 < p.d) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(v[8 * h]) * inv, __uint_as_float(v[8 * h + 1]) * inv);
+            o.y = pack_bf16(__uint_as_float(v[8 * h + 2]) * inv, __uint_as_float(v[8 * h + 3]) * inv);
+            o.z = pack_bf16(__uint_as_float(v[8 * h + 4]) * inv, __uint_as_float(v[8 * h + 5]) * inv);
+            o.w = pack_bf16(__uint_as_float(v[8 * h + 6]) * inv, __uint_as_float(v[8 * h + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c * 16 + h * 8) = o;
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
@@ -331,7 +378,7 @@ int launch_attn_inst(const CUtensorMap& mq, const CUtensorMap& mk, const CUtenso
     configured = true;
   }
   dim3 grid((p.Sq + ATT_M - 1) / ATT_M, heads, batch);
-  launch_pdl(attn_fwd_kernel<DK, POLY, ONES>, grid, 128, Cfg::SMEM, stream, mq, mk, mv, p);
+  launch_pdl(attn_fwd_kernel<DK, POLY, ONES>, grid, ATT_THREADS, Cfg::SMEM, stream, mq, mk, mv, p);
   return lavie_check_launch("attn_fwd_kernel");
 }
 

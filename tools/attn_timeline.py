@@ -18,11 +18,11 @@ torch.cuda.synchronize()
 lib.lavie_debug_buffer(None)
 t = buf.cpu().view(-1, 8)
 base = int(t[0, 0])
-print("tile | top  S_ready  S_in_regs  softmax_done  synced  kv_ready  issued | (deltas: wait_S ld softmax sync kv issue | of which PV issue)")
+print("tile | softmax warp 0: top  S_ready  S_in_regs  exps_done  P_written | control warp: QK(j+1)_issued  PV(j)_issued  refills_issued | deltas: wait_S ld exps P")
 n = (Sk + 63) // 64
 for j in list(range(min(n, 6))) + list(range(max(6, n - 4), n)):
-    r = [int(x) - base for x in t[j, :7]]
-    dl = [r[i + 1] - r[i] for i in range(6)] + [int(t[j, 7]) - base - r[5]]
-    print(f"{j:3d} | " + " ".join(f"{x:7d}" for x in r) + " | " + " ".join(f"{x:5d}" for x in dl))
-tot = int(t[n - 1, 6]) - base
+    r = [int(x) - base for x in t[j, :8]]
+    dl = [r[i + 1] - r[i] for i in range(4)]
+    print(f"{j:3d} | " + " ".join(f"{x:7d}" for x in r[:5]) + " | " + " ".join(f"{x:7d}" for x in r[5:8]) + " | " + " ".join(f"{x:5d}" for x in dl))
+tot = int(t[n - 1, 4]) - base
 print(f"per tile: {tot / n:.0f} cycles")
