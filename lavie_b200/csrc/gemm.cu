@@ -804,6 +804,8 @@ void set_window(GemmParams& p, int m_tile0, int m_tiles, int splits, int kbps) {
 
 }  // namespace
 
+extern int g_lavie_gn_target_ctas;
+
 extern "C" int lavie_debug_set(int what, int value) {
   if (what == 1) g_force_splits = value;
   if (what == 2) g_debug = value;
@@ -811,6 +813,7 @@ extern "C" int lavie_debug_set(int what, int value) {
   if (what == 3) g_lavie_pdl = value ? 1 : 0;
   if (what == 4) g_lavie_attn_poly = value;
   if (what == 5) g_no_tail = value;
+  if (what == 6 && value > 0) g_lavie_gn_target_ctas = value;
   return 0;
 }
 

@@ -4,10 +4,14 @@
 //   LayerNorm  : attention.py:444-477 (norm1 / norm2 / norm_temp / norm3).
 #include "common.cuh"
 
+// CTAs per launch (tools/bench_norm.py): the statistics kernel ends in a serial tail (block reduce, ticket, the last
+// block folds every chunk partial), so it wants few, long chunks; the apply kernel is a pure stream and wants many.
+int g_lavie_gn_target_ctas = 148 * 2;      // statistics (lavie_debug_set(6, n) for tuning)
+int g_lavie_gn_apply_ctas = 148 * 8;       // apply
+
 namespace {
 
 constexpr int GN_THREADS = 256;
-constexpr int GN_TARGET_CTAS = 148 * 8;    // enough CTAs in flight to saturate HBM on every level of the UNet
 constexpr int GN_MIN_ROWS_PER_CHUNK = 16;
 
 __device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int ld0, int c0, const __nv_bfloat16* x1, int ld1,
@@ -372,8 +376,8 @@ int check_sources(const void* x0, int ld0, int c0, const void* x1, int ld1, int 
 }  // namespace
 
 namespace {
-int gn_rows_per_chunk(int samples, int rows_per_sample) {
-  int chunks = (GN_TARGET_CTAS + samples - 1) / samples;
+int gn_rows_per_chunk(int samples, int rows_per_sample, int target_ctas) {
+  int chunks = (target_ctas + samples - 1) / samples;
   const int max_chunks = (rows_per_sample + GN_MIN_ROWS_PER_CHUNK - 1) / GN_MIN_ROWS_PER_CHUNK;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -382,7 +386,7 @@ int gn_rows_per_chunk(int samples, int rows_per_sample) {
 }  // namespace
 
 extern "C" int lavie_groupnorm_chunks(int samples, int rows_per_sample) {
-  const int rpc = gn_rows_per_chunk(samples, rows_per_sample);
+  const int rpc = gn_rows_per_chunk(samples, rows_per_sample, g_lavie_gn_target_ctas);
   return (rows_per_sample + rpc - 1) / rpc;
 }
 
@@ -393,7 +397,7 @@ extern "C" int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void
   const int C = c0 + c1;
   LAVIE_REQUIRE(C % groups == 0 && groups <= 64 && C <= 8192, LAVIE_ERR_SHAPE,
                 "groupnorm: C=%d groups=%d unsupported", C, groups);
-  const int rows_per_chunk = gn_rows_per_chunk(samples, rows_per_sample);
+  const int rows_per_chunk = gn_rows_per_chunk(samples, rows_per_sample, g_lavie_gn_target_ctas);
   const int chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
   dim3 grid(chunks, samples);
   const int vec_per_row = C >> 3;
@@ -424,7 +428,7 @@ extern "C" int lavie_groupnorm_scale_shift(const void* x0, int ld0, int c0, cons
                 "groupnorm: C=%d groups=%d unsupported", C, groups);
   LAVIE_REQUIRE(tickets != nullptr && partial != nullptr && scale_shift != nullptr, LAVIE_ERR_SHAPE,
                 "groupnorm_scale_shift: null buffer");
-  const int rows_per_chunk = gn_rows_per_chunk(samples, rows_per_sample);
+  const int rows_per_chunk = gn_rows_per_chunk(samples, rows_per_sample, g_lavie_gn_target_ctas);
   const int chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
   dim3 grid(chunks, samples);
   const int vec_per_row = C >> 3;
@@ -448,7 +452,7 @@ extern "C" int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void
   int rc = check_sources(x0, ld0, c0, x1, ld1, c1);
   if (rc) return rc;
   LAVIE_REQUIRE(al16(y) && ldy % 8 == 0 && al16(scale_shift), LAVIE_ERR_ALIGN, "groupnorm_apply: output alignment");
-  const int rows_per_chunk = gn_rows_per_chunk(samples, rows_per_sample);
+  const int rows_per_chunk = gn_rows_per_chunk(samples, rows_per_sample, g_lavie_gn_apply_ctas);
   const int chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
   dim3 grid(chunks, samples);
   launch_pdl(gn_apply_kernel, grid, 256, 0, stream, static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1, rows_per_sample,

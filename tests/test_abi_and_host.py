@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     # pure host queries (no GPU work)
     assert lib.lavie_conv3x3_supported(40, 64, 320) == 1
     assert lib.lavie_conv3x3_supported(16, 24, 320) == 1 and lib.lavie_conv3x3_supported(16, 24, 4) == 0
-    assert lib.lavie_groupnorm_chunks(2, 16 * 40 * 64) == 586 and lib.lavie_groupnorm_chunks(32, 40) == 3
+    assert lib.lavie_groupnorm_chunks(2, 16 * 40 * 64) == 148 and lib.lavie_groupnorm_chunks(32, 40) == 3
 
 
 def test_epilogue_struct_matches_header():
