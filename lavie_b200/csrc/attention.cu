@@ -538,7 +538,7 @@ __device__ __forceinline__ uint32_t scale_rope_pair_cs(uint32_t w, float scale, 
 }
 
 template <int DP>   // head pitch (d rounded up to 16): 48, 64, 80, 96, 128, 160
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 temporal_attn_mma_kernel(const TempParams p) {
   pdl_prologue();
   constexpr int VP = DP + 8;                      // smem V row pitch (elements): conflict-free ldmatrix rows
@@ -593,13 +593,56 @@ temporal_attn_mma_kernel(const TempParams p) {
     const __nv_bfloat16* r_lo = base + static_cast<size_t>(g) * fstride;
     const __nv_bfloat16* r_hi = base + static_cast<size_t>(g + 8) * fstride;
 
-    // ---- V tile -> shared memory (row-major [frame][DP], 16-byte vectors) ----
-    __syncwarp();
-    for (int i = lane; i < 16 * (DP / 8); i += 32) {
+    // ---- every global load of the item is issued before the first use: V (to registers), then Q / K ----
+    // (a rolled load -> store loop for V followed by per-block Q/K loads cost ~5 dependent DRAM round trips per item)
+    constexpr int VTOT = 16 * (DP / 8);
+    constexpr int VIT = (VTOT + 31) / 32;
+    uint4 vreg[VIT];
+#pragma unroll
+    for (int it = 0; it < VIT; ++it) {
+      const int i = lane + it * 32;
       const int f = i / (DP / 8), vc = i - f * (DP / 8);
-      uint4 val = make_uint4(0, 0, 0, 0);
-      if (f < F) val = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(f) * fstride + p.v_off + vc * 8));
-      *reinterpret_cast<uint4*>(sv + f * VP + vc * 8) = val;
+      vreg[it] = make_uint4(0, 0, 0, 0);
+      if (i < VTOT && f < F)
+        vreg[it] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(f) * fstride + p.v_off + vc * 8));
+    }
+    constexpr bool PRELOAD = DP <= 96;              // registers: 16 per 32-wide block (+ 8 for the 16-wide tail)
+    constexpr int NPRE = PRELOAD ? NB32 : 1;
+    uint4 pq_lo[NPRE], pq_hi[NPRE], pk_lo[NPRE], pk_hi[NPRE];
+    uint2 tq_lo = make_uint2(0, 0), tq_hi = tq_lo, tk_lo = tq_lo, tk_hi = tq_lo;
+    if (PRELOAD) {
+#pragma unroll
+      for (int blk = 0; blk < NB32; ++blk) {
+        const int col = blk * 32 + t * 8;
+        pq_lo[blk] = pq_hi[blk] = pk_lo[blk] = pk_hi[blk] = make_uint4(0, 0, 0, 0);
+        if (lo_ok) {
+          pq_lo[blk] = __ldg(reinterpret_cast<const uint4*>(r_lo + col));
+          pk_lo[blk] = __ldg(reinterpret_cast<const uint4*>(r_lo + p.k_off + col));
+        }
+        if (hi_ok) {
+          pq_hi[blk] = __ldg(reinterpret_cast<const uint4*>(r_hi + col));
+          pk_hi[blk] = __ldg(reinterpret_cast<const uint4*>(r_hi + p.k_off + col));
+        }
+      }
+      if (TAIL16) {
+        const int col = NB32 * 32 + t * 4;
+        if (lo_ok) {
+          tq_lo = __ldg(reinterpret_cast<const uint2*>(r_lo + col));
+          tk_lo = __ldg(reinterpret_cast<const uint2*>(r_lo + p.k_off + col));
+        }
+        if (hi_ok) {
+          tq_hi = __ldg(reinterpret_cast<const uint2*>(r_hi + col));
+          tk_hi = __ldg(reinterpret_cast<const uint2*>(r_hi + p.k_off + col));
+        }
+      }
+    }
+    // ---- V tile -> shared memory (row-major [frame][DP], 16-byte vectors) ----
+    __syncwarp();                                   // the previous item's ldmatrix reads of this buffer are done
+#pragma unroll
+    for (int it = 0; it < VIT; ++it) {
+      const int i = lane + it * 32;
+      const int f = i / (DP / 8), vc = i - f * (DP / 8);
+      if (i < VTOT) *reinterpret_cast<uint4*>(sv + f * VP + vc * 8) = vreg[it];
     }
 
     // ---- S = (scale * rope(Q)) . rope(K)^T ----
@@ -614,13 +657,18 @@ temporal_attn_mma_kernel(const TempParams p) {
     for (int blk = 0; blk < NB32; ++blk) {
       const int col = blk * 32 + t * 8;           // this lane's 8 contiguous channels of the 32-wide block
       uint4 q_lo = make_uint4(0, 0, 0, 0), q_hi = q_lo, k_lo = q_lo, k_hi = q_lo;
-      if (lo_ok) {
-        q_lo = __ldg(reinterpret_cast<const uint4*>(r_lo + col));
-        k_lo = __ldg(reinterpret_cast<const uint4*>(r_lo + p.k_off + col));
-      }
-      if (hi_ok) {
-        q_hi = __ldg(reinterpret_cast<const uint4*>(r_hi + col));
-        k_hi = __ldg(reinterpret_cast<const uint4*>(r_hi + p.k_off + col));
+      if (PRELOAD) {
+        q_lo = pq_lo[PRELOAD ? blk : 0]; q_hi = pq_hi[PRELOAD ? blk : 0];
+        k_lo = pk_lo[PRELOAD ? blk : 0]; k_hi = pk_hi[PRELOAD ? blk : 0];
+      } else {
+        if (lo_ok) {
+          q_lo = __ldg(reinterpret_cast<const uint4*>(r_lo + col));
+          k_lo = __ldg(reinterpret_cast<const uint4*>(r_lo + p.k_off + col));
+        }
+        if (hi_ok) {
+          q_hi = __ldg(reinterpret_cast<const uint4*>(r_hi + col));
+          k_hi = __ldg(reinterpret_cast<const uint4*>(r_hi + p.k_off + col));
+        }
       }
       uint32_t ql[4] = {q_lo.x, q_lo.y, q_lo.z, q_lo.w}, qh[4] = {q_hi.x, q_hi.y, q_hi.z, q_hi.w};
       uint32_t kl[4] = {k_lo.x, k_lo.y, k_lo.z, k_lo.w}, kh[4] = {k_hi.x, k_hi.y, k_hi.z, k_hi.w};
@@ -650,14 +698,16 @@ temporal_attn_mma_kernel(const TempParams p) {
     }
     if (TAIL16) {
       const int col = NB32 * 32 + t * 4;          // 4 contiguous channels of the trailing 16-wide block
-      uint2 q_lo = make_uint2(0, 0), q_hi = q_lo, k_lo = q_lo, k_hi = q_lo;
-      if (lo_ok) {
-        q_lo = __ldg(reinterpret_cast<const uint2*>(r_lo + col));
-        k_lo = __ldg(reinterpret_cast<const uint2*>(r_lo + p.k_off + col));
-      }
-      if (hi_ok) {
-        q_hi = __ldg(reinterpret_cast<const uint2*>(r_hi + col));
-        k_hi = __ldg(reinterpret_cast<const uint2*>(r_hi + p.k_off + col));
+      uint2 q_lo = tq_lo, q_hi = tq_hi, k_lo = tk_lo, k_hi = tk_hi;
+      if (!PRELOAD) {
+        if (lo_ok) {
+          q_lo = __ldg(reinterpret_cast<const uint2*>(r_lo + col));
+          k_lo = __ldg(reinterpret_cast<const uint2*>(r_lo + p.k_off + col));
+        }
+        if (hi_ok) {
+          q_hi = __ldg(reinterpret_cast<const uint2*>(r_hi + col));
+          k_hi = __ldg(reinterpret_cast<const uint2*>(r_hi + p.k_off + col));
+        }
       }
       uint32_t ql[2] = {q_lo.x, q_lo.y}, qh[2] = {q_hi.x, q_hi.y}, kl[2] = {k_lo.x, k_lo.y}, kh[2] = {k_hi.x, k_hi.y};
 #pragma unroll
