@@ -113,7 +113,7 @@ int lavie_make_tmap_im2col(CUtensorMap* map, const void* base, int N, int H, int
 }
 
 int g_lavie_pdl = 1;
-int g_lavie_attn_poly = 0;
+int g_lavie_attn_poly = -1;    // -1: per-shape default, 0: all exponentials on the MUFU, 4: every 4th on the FMA pipe
 void* g_lavie_debug_buf = nullptr;
 
 extern "C" int lavie_debug_buffer(void* device_ptr) {
