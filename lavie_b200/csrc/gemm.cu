@@ -5,29 +5,33 @@
 // Replaces every nn.Linear / 1x1 conv / 3x3 InflatedConv3d call of the reference hot path
 // (base/models/attention.py:95-104,328,356 ; resnet.py:13-21,146,162,171-175 ; diffusers FeedForward).
 //
-// Why CTA pairs: the kernel is fed from L2, and a single-CTA 128 x BN tile needs ~70 FLOP per L2 byte, which capped
-// the first version at ~700 TFLOP/s (profiles/r1_gemm_v1_*).  A pair of SMs computes a 256 x BN tile with ONE
-// tcgen05.mma.cta_group::2 stream: each CTA stages its own 128 rows of A and HALF of the W tile, so L2 traffic per
-// FLOP drops by up to 2x.
+// Why CTA pairs: the kernel is fed from L2, and its throughput follows the L2->SM bytes per flop of the tile shape
+// (tools/bench_feedtheory.py).  A pair of SMs computes a 256 x BN tile with ONE tcgen05.mma.cta_group::2 stream: each
+// CTA stages its own 128 rows of A and HALF of the W tile.  BN = 320 (two 160-wide MMAs per K step sharing the A
+// stage) is the widest tile and the one the N = 320 / 640 layers use.
 //
 // Structure: persistent clusters of 2 CTAs (one pair per two SMs), 320 threads per CTA:
-//   warp 0      : TMA producer   (A 128x64 slab + W (BN/2)x64 slab per stage, 128-byte swizzle, ring of STAGES;
+//   warp 0      : TMA producer   (A 128x64 slab + this CTA's W rows per stage, 128-byte swizzle, ring of STAGES;
 //                                 both CTAs' loads complete on the LEADER CTA's full barrier)
-//   warp 1      : MMA issuer     (leader CTA only: tcgen05.mma.cta_group::2 M=256, N=BN, K=16; commits are multicast
+//   warp 1      : MMA issuer     (leader CTA only: tcgen05.mma.cta_group::2 M=256, N<=256, K=16; commits are multicast
 //                                 to both CTAs' barriers) + TMEM owner (both CTAs)
 //   warps 2..9  : epilogue       (each CTA drains its own 128 accumulator rows: tcgen05.ld -> bias / time-bias /
-//                                 GEGLU / residual -> bf16, or fp32 split-K partials)
-// Two TMEM accumulator stages let the epilogue of item i overlap the main loop of item i+1.
+//                                 GEGLU / TMA-prefetched residual -> bf16 staged in smem -> TMA store, or fp32
+//                                 split-K partials)
+// Two TMEM accumulator stages (one for BN = 320) let the epilogue of item i overlap the main loop of item i+1.
 //
 // Work item = (m_tile, n_tile, k_split).  Split-K (deterministic: fp32 partials + ordered reduction kernel) keeps the
-// 74 pairs busy on the 5x8 / 10x16 levels where M is only 1280..5120 rows but K reaches 23040.
+// 74 pairs busy on the 5x8 / 10x16 levels where M is only 1280..5120 rows but K reaches 23040; a launch whose last
+// wave would be nearly empty is issued as full waves over the leading tile rows plus a split-K "tail window"
+// (make_plan).
 //
 // A-operand modes
 //   plain : A is [M, K] row-major (row stride lda); optionally split along K over two sources
 //           (the folded torch.cat([h, skip], dim=1) in front of a 1x1 shortcut, unet_blocks.py:538,630).
-//   conv3 : A is the channels-last feature map [NF, H, W, C]; K = 9*C ordered (kh, kw, c); every K block is one
-//           (tap, 64-channel) slab fetched with 4-D TMA boxes whose out-of-bounds rows/columns are zero-filled
-//           by the hardware = the conv's zero padding.  128 consecutive output pixels = 128/W whole image rows.
+//   conv  : A is the channels-last feature map [NF, H, W, C]; K = 9*C ordered (kh, kw, c); every K block is one
+//           (tap, 64-channel) slab of 128 consecutive OUTPUT pixels fetched by ONE im2col-mode TMA request (the
+//           hardware walks the pixels, applies the stride and zero-fills the halo = the conv's zero padding).
+//           The first-generation tiled rank-4 path is kept behind a debug bit for A/B timing only.
 #include "common.cuh"
 
 namespace {
