@@ -65,6 +65,12 @@ typedef struct {
  * diffusers FeedForward (mirror vsr/models/diffusers_attention.py:734-822).  block_n = 0 lets the library choose.
  * workspace (optional, caller-owned, fp32) enables deterministic split-K on small-M / large-K problems: the library
  * uses at most workspace_bytes and picks splits <= workspace_bytes / (4*M*N). */
+/* Host-only query: the launch plan the library would choose for a GEMM (conv = 0) or a 3x3 conv (conv = 1, K = 9*Cin)
+ * on the current device (148 SMs assumed when no device is present): tile width, split-K factor of the main window,
+ * number of 256-row tile rows issued as a second split-K "tail window" launch (0 = single launch) and its split-K
+ * factor.  Lets callers and tests see wave quantisation decisions without running anything. */
+int lavie_gemm_plan(int M, int N, int K, int conv, int geglu, size_t workspace_bytes, int* block_n, int* splits,
+                    int* tail_tiles, int* tail_splits);
 int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1, int lda1, int k1, const void* w, void* out,
                     int ldo, int M, int N, const lavie_epilogue* ep, int block_n, void* workspace,
                     size_t workspace_bytes, lavie_stream_t stream);

@@ -37,6 +37,8 @@ SIGNATURES = {
     "lavie_abi_version": (c_int, []),
     "lavie_debug_set": (c_int, [c_int, c_int]),
     "lavie_debug_buffer": (c_int, [c_void_p]),
+    "lavie_gemm_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, c_size_t, POINTER(c_int), POINTER(c_int),
+                                POINTER(c_int), POINTER(c_int)]),
     "lavie_gemm_bf16": (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(Epilogue),
                                 c_int, _P, c_size_t, _P]),
     "lavie_conv3x3_supported": (c_int, [c_int, c_int, c_int]),

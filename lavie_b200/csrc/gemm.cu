@@ -821,6 +821,17 @@ extern "C" int lavie_debug_set(int what, int value) {
   return 0;
 }
 
+extern "C" int lavie_gemm_plan(int M, int N, int K, int conv, int geglu, size_t workspace_bytes, int* block_n,
+                               int* splits, int* tail_tiles, int* tail_splits) {
+  LAVIE_REQUIRE(M > 0 && N > 0 && K > 0, LAVIE_ERR_SHAPE, "gemm_plan: empty problem M=%d N=%d K=%d", M, N, K);
+  const Plan plan = make_plan(M, N, (K + BLOCK_K - 1) / BLOCK_K, 0, geglu != 0, conv != 0, workspace_bytes);
+  if (block_n) *block_n = plan.bn;
+  if (splits) *splits = plan.splits;
+  if (tail_tiles) *tail_tiles = plan.tail_tiles;
+  if (tail_splits) *tail_splits = plan.tail_tiles ? plan.tail_splits : 1;
+  return LAVIE_OK;
+}
+
 extern "C" int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1, int lda1, int k1, const void* w,
                                void* out, int ldo, int M, int N, const lavie_epilogue* ep, int block_n,
                                void* workspace, size_t workspace_bytes, cudaStream_t stream) {

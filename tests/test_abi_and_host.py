@@ -30,6 +30,29 @@ def test_library_exports_every_declared_symbol():
     assert lib.lavie_groupnorm_chunks(2, 16 * 40 * 64) == 148 and lib.lavie_groupnorm_chunks(32, 40) == 3
 
 
+def test_gemm_planner_decisions():
+    """Host-only: tile width / split-K / tail-window choices for the shapes of the full-size step (148 SMs = 74 CTA
+    pairs).  These pin the reasoning of DESIGN.md section 4: wide tiles where L2 feed bounds the conv, split-K where a
+    level has fewer tiles than CTA pairs, a tail window where the last wave would be nearly empty."""
+    import ctypes
+    from lavie_b200 import _lib
+    lib = _lib.load()
+
+    def plan(M, N, K, conv=0, geglu=0, ws=128 << 20):
+        bn, s, tail, ts = (ctypes.c_int() for _ in range(4))
+        assert lib.lavie_gemm_plan(M, N, K, conv, geglu, ws, bn, s, tail, ts) == 0
+        return bn.value, s.value, tail.value, ts.value
+
+    assert plan(81920, 320, 2880, conv=1) == (320, 1, 0, 1)          # 40x64 resnet conv: one 320-wide tile per row tile
+    assert plan(81920, 2560, 320, geglu=1)[0] == 256                  # GEGLU pairs value / gate inside a 256-wide tile
+    bn, s, tail, ts = plan(5120, 1280, 11520, conv=1)                 # 10x16 level: 80 tiles on 74 pairs
+    assert bn == 320 and s == 1 and tail == 2 and ts > 1
+    bn, s, tail, ts = plan(1280, 1280, 11520, conv=1)                 # 5x8 level: 20 tiles -> split-K fills the machine
+    assert s >= 2 and tail == 0
+    assert plan(1280, 1280, 11520, conv=1, ws=0)[1] == 1              # no workspace, no split-K
+    assert lib.lavie_gemm_plan(0, 320, 320, 0, 0, 0, None, None, None, None) != 0
+
+
 def test_epilogue_struct_matches_header():
     import ctypes
     from lavie_b200._lib import Epilogue
