@@ -62,6 +62,23 @@ def test_matches_oracle_on_ragged_geometry(unet, synthetic_sd):
     assert out.shape == ref.shape and err <= BF16_TOL
 
 
+def test_fifty_step_ddim_latent(unet, synthetic_sd):
+    """BASELINE north star: the FINAL latent of the 50-step DDIM + CFG 7.5 loop (pipeline_videogen.py:664-689) against
+    the oracle's loop on the same start noise.  bf16 noise compounds over 50 feed-back steps through a random-init
+    network; stated tolerance 5e-2 (measured 7.4e-3 on B200)."""
+    from lavie_b200.pipeline import CFGDenoiser, DDIMSchedule
+    from lavie_b200.synthetic import synthetic_inputs
+    from oracle import unet3d_oracle as O
+    sample, _, text = synthetic_inputs(2, 2, 8, 8, seed=21)
+    lat0 = sample[:1]
+    ref = O.cfg_ddim_loop(synthetic_sd, lat0, text, 7.5, 50)
+    den = CFGDenoiser(unet, 7.5, DDIMSchedule(50))
+    out = den.loop(lat0.cuda(), text.cuda()).cpu()
+    err = rel_l2(out, ref)
+    print(f"50-step DDIM latent: rel-L2 vs oracle loop = {err:.3e}")
+    assert torch.isfinite(out).all() and err <= 5e-2
+
+
 def test_full_size_properties(unet):
     """BASELINE config 2 geometry [2,4,16,40,64]: too big for the CPU oracle inside a test, so check the
     size-independent properties: finite, deterministic, and the two CFG halves do not interact
