@@ -31,7 +31,6 @@
 //   conv  : A is the channels-last feature map [NF, H, W, C]; K = 9*C ordered (kh, kw, c); every K block is one
 //           (tap, 64-channel) slab of 128 consecutive OUTPUT pixels fetched by ONE im2col-mode TMA request (the
 //           hardware walks the pixels, applies the stride and zero-fills the halo = the conv's zero padding).
-//           The first-generation tiled rank-4 path is kept behind a debug bit for A/B timing only.
 #include "common.cuh"
 
 namespace {
@@ -56,12 +55,8 @@ struct GemmParams {
   int rows_window;           // rows covered by the window (stride of the split-K partial planes)
   int splits, kb_per_split;  // split-K
   // conv3 mode
-  int conv;                  // 0 plain, 1 conv3x3 stride 1 pad 1
+  int conv;                  // 0 plain GEMM, 1 implicit-GEMM 3x3 conv (im2col-mode TMA)
   int c_blocks;              // Cin / 64
-  int img_h, img_w;
-  int box_h;                 // image rows per TMA box
-  int boxes_per_tile;        // 128 / (box_h * W)   (per CTA)
-  int row_groups_per_img;    // H / box_h
   int out_h, out_w, conv_stride;   // im2col-mode conv (conv == 2): output geometry and stride
   // epilogue
   const float* bias;         // [N] or null
@@ -152,14 +147,6 @@ __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, ui
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
       "[%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
-                                             int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
-      "%5, %6}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 // im2col-mode TMA (conv halo handled by the hardware): coordinates = first output pixel of the tile in the bounding box
@@ -275,7 +262,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
             if (rank == 0) mbar_arrive(&full_bar[stage]);
           } else {
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);   // bytes landing in both CTAs
-            if (p.conv == 2) {
+            if (p.conv) {
               // one request: 128 consecutive output pixels x 64 channels of filter tap (r, s)
               const int tap = kb / p.c_blocks;
               const int c0 = (kb - tap * p.c_blocks) * BLOCK_K;
@@ -285,19 +272,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
               const int oy = rem / p.out_w, ox = rem - oy * p.out_w;
               tma2_load_im2col(a_dst, &tmap_a0, full_leader, c0, ox * p.conv_stride - 1, oy * p.conv_stride - 1, img,
                                static_cast<uint16_t>(tap % 3), static_cast<uint16_t>(tap / 3));
-            } else if (p.conv) {
-              const int tap = kb / p.c_blocks;
-              const int c0 = (kb - tap * p.c_blocks) * BLOCK_K;
-              int dy = tap / 3 - 1, dx = tap % 3 - 1;
-              if (p.debug & 4) dx = 0;
-              if (p.debug & 8) dy = 0;
-              const int box_bytes = p.box_h * p.img_w * BLOCK_K * 2;
-              for (int i = 0; i < p.boxes_per_tile; ++i) {
-                const int g = m_cta * p.boxes_per_tile + i;
-                const int img = g / p.row_groups_per_img;
-                const int y0 = (g - img * p.row_groups_per_img) * p.box_h;
-                tma2_load_4d(a_dst + i * box_bytes, &tmap_a0, full_leader, c0, dx, y0 + dy, img);
-              }
             } else if (kb < p.k_split_blocks) {
               tma2_load_2d(a_dst, &tmap_a0, full_leader, kb * BLOCK_K, m_cta * BLOCK_M);
             } else {
@@ -880,10 +854,6 @@ extern "C" int lavie_conv3x3_supported(int H, int W, int C) {
   return C % BLOCK_K == 0 ? 1 : 0;      // im2col-mode TMA handles any image geometry; channels come in 64-wide slabs
 }
 
-namespace {
-bool tiled_geometry_ok(int W) { return W <= BLOCK_M && BLOCK_M % W == 0 && W % 8 == 0; }
-}  // namespace
-
 extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, int stride, const void* w, void* out,
                                   int ldo, int N, const lavie_epilogue* ep, int block_n, void* workspace,
                                   size_t workspace_bytes, cudaStream_t stream) {
@@ -899,34 +869,14 @@ extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, in
   p.num_k_blocks = 9 * (C / BLOCK_K);
   p.k_split_blocks = p.num_k_blocks;
   p.c_blocks = C / BLOCK_K;
-  p.img_h = H; p.img_w = W;
   p.out_h = Ho; p.out_w = Wo; p.conv_stride = stride;
-  const bool tiled = (g_debug & 1024) && stride == 1 && tiled_geometry_ok(W);   // first-generation path, for A/B timing
-  p.conv = tiled ? 1 : 2;
+  p.conv = 1;
   const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, false, true, workspace ? workspace_bytes : 0);
   apply_plan(p, plan, workspace);
   int rc = fill_epilogue(p, ep, N, out, ldo);
   if (rc) return rc;
   CUtensorMap ma, mb;
-  if (tiled) {
-    // largest number of whole image rows per TMA box that divides both H and the 128/W rows of a CTA's M block
-    const int rows_per_tile = BLOCK_M / W;
-    int box_h = 1;
-    for (int h = rows_per_tile; h >= 1; --h) {
-      if (H % h == 0 && rows_per_tile % h == 0) { box_h = h; break; }
-    }
-    p.box_h = box_h;
-    p.boxes_per_tile = rows_per_tile / box_h;
-    p.row_groups_per_img = H / box_h;
-    const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
-                              static_cast<uint64_t>(NF)};
-    const uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(W) * C * 2,
-                                 static_cast<uint64_t>(H) * W * C * 2};
-    const uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(W), static_cast<uint32_t>(box_h), 1};
-    rc = lavie_make_tmap(&ma, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-  } else {
-    rc = lavie_make_tmap_im2col(&ma, x, NF, H, W, C, BLOCK_K, BLOCK_M, stride);
-  }
+  rc = lavie_make_tmap_im2col(&ma, x, NF, H, W, C, BLOCK_K, BLOCK_M, stride);
   if (rc) return rc;
   rc = make_weight_map(&mb, w, N, 9 * C, plan.bn);
   if (rc) return rc;
