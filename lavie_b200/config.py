@@ -37,6 +37,10 @@ class UNetConfig:
     rotary_dim: int = 32                 # RotaryEmbedding(32), unet.py:185
     rel_pos_buckets: int = 32            # RelativePositionBias(num_buckets=32, max_distance=32), attention.py:577
     rel_pos_max_distance: int = 32
+    # "base" = the T2V denoiser (this round's hot path).  "interp" = the frame-interpolation UNet (SURVEY 8f N1,
+    # interpolation/models/unet.py:476-557): 8 input channels, SparseCausal self-attention, plain temporal attention
+    # (no rotary embedding, no relative-position bias keys in the state_dict).  Only the oracle uses "interp" so far.
+    variant: str = "base"
     _diffusers_version: str = "0.16.0"
 
     @property
@@ -52,6 +56,7 @@ class UNetConfig:
 
 
 BASE_CONFIG = UNetConfig()
+INTERP_CONFIG = UNetConfig(in_channels=8, variant="interp")     # copy_no_mask / use_concat: interpolation/models/unet.py:501-507
 
 
 def _resnet(spec, p, cin, cout, temb):
@@ -91,8 +96,9 @@ def _transformer(spec, p, c, cfg: UNetConfig):
     spec[f"{b}.norm2.weight"] = (c,)
     spec[f"{b}.norm2.bias"] = (c,)
     _attn(spec, f"{b}.attn_temp", c, c)
-    spec[f"{b}.attn_temp.time_rel_pos_bias.relative_attention_bias.weight"] = (cfg.rel_pos_buckets, cfg.heads)
-    spec[f"{b}.attn_temp.rotary_emb.freqs"] = (cfg.rotary_dim // 2,)
+    if cfg.variant == "base":
+        spec[f"{b}.attn_temp.time_rel_pos_bias.relative_attention_bias.weight"] = (cfg.rel_pos_buckets, cfg.heads)
+        spec[f"{b}.attn_temp.rotary_emb.freqs"] = (cfg.rotary_dim // 2,)
     spec[f"{b}.norm_temp.weight"] = (c,)
     spec[f"{b}.norm_temp.bias"] = (c,)
     spec[f"{b}.ff.net.0.proj.weight"] = (8 * c, c)

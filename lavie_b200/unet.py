@@ -95,6 +95,9 @@ class UNet3DConditionModel(nn.Module):
 
     def __init__(self, config: UNetConfig = BASE_CONFIG, use_cuda_graph: bool = True):
         super().__init__()
+        if getattr(config, "variant", "base") != "base":
+            raise NotImplementedError(f"UNet variant {config.variant!r}: only the base T2V denoiser has a B200 path so far "
+                                      "(oracle/interp_oracle.py is groundwork for the interpolation model)")
         self.cfg = config
         self.config = _Config(**config.to_dict())
         self.sample_size = config.sample_size

@@ -180,7 +180,7 @@ def transformer_block(sd: SD, p: str, x: torch.Tensor, text: torch.Tensor, frame
     return geglu_ff(sd, f"{p}.ff", ln(x, "norm3")) + x
 
 
-def transformer3d(sd: SD, p: str, x: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
+def transformer3d(sd: SD, p: str, x: torch.Tensor, text: torch.Tensor, block=None) -> torch.Tensor:
     """Transformer3DModel.forward (attention.py:358-407): per-FRAME GroupNorm (4-D input,
     eps 1e-6) -> 1x1 conv -> tokens -> block -> 1x1 conv -> + residual."""
     B, C, Fr, H, W = x.shape
@@ -189,7 +189,7 @@ def transformer3d(sd: SD, p: str, x: torch.Tensor, text: torch.Tensor) -> torch.
     h = F.group_norm(xf, GROUPS, sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], TRANSFORMER_GN_EPS)
     h = F.conv2d(h, sd[f"{p}.proj_in.weight"], sd[f"{p}.proj_in.bias"])
     h = h.permute(0, 2, 3, 1).reshape(B * Fr, H * W, C)
-    h = transformer_block(sd, f"{p}.transformer_blocks.0", h, text_f, Fr)
+    h = (block or transformer_block)(sd, f"{p}.transformer_blocks.0", h, text_f, Fr)
     h = h.reshape(B * Fr, H, W, C).permute(0, 3, 1, 2)
     h = F.conv2d(h, sd[f"{p}.proj_out.weight"], sd[f"{p}.proj_out.bias"]) + xf
     return h.reshape(B, Fr, C, H, W).permute(0, 2, 1, 3, 4)
@@ -206,9 +206,10 @@ def upsample(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------
 @torch.no_grad()
 def unet_forward(sd: SD, sample: torch.Tensor, timestep, text: torch.Tensor,
-                 taps: Optional[dict] = None) -> torch.Tensor:
+                 taps: Optional[dict] = None, block=None) -> torch.Tensor:
     """UNet3DConditionModel.forward (unet.py:366-512).  ``taps`` (optional dict) receives
-    a few intermediate activations for debugging the CUDA path."""
+    a few intermediate activations for debugging the CUDA path.  ``block`` replaces the
+    transformer block (oracle/interp_oracle.py: the interpolation UNet shares everything else)."""
     sample = sample.float()
     text = text.float()
     B = sample.shape[0]
@@ -231,7 +232,7 @@ def unet_forward(sd: SD, sample: torch.Tensor, timestep, text: torch.Tensor,
             if i == 0 and j == 0:
                 tap("down0_res0", x)
             if has_attn:
-                x = transformer3d(sd, f"down_blocks.{i}.attentions.{j}", x, text)
+                x = transformer3d(sd, f"down_blocks.{i}.attentions.{j}", x, text, block)
                 if i == 0 and j == 0:
                     tap("down0_attn0", x)
             skips.append(x)
@@ -241,7 +242,7 @@ def unet_forward(sd: SD, sample: torch.Tensor, timestep, text: torch.Tensor,
             skips.append(x)
     tap("down_out", x)
     x = resnet_block(sd, "mid_block.resnets.0", x, emb)              # unet_blocks.py:226-232
-    x = transformer3d(sd, "mid_block.attentions.0", x, text)
+    x = transformer3d(sd, "mid_block.attentions.0", x, text, block)
     x = resnet_block(sd, "mid_block.resnets.1", x, emb)
     tap("mid", x)
     for i, has_attn in enumerate(UP_HAS_ATTN):                        # unet_blocks.py:524-574, 625-648
@@ -249,7 +250,7 @@ def unet_forward(sd: SD, sample: torch.Tensor, timestep, text: torch.Tensor,
             x = torch.cat([x, skips.pop()], dim=1)
             x = resnet_block(sd, f"up_blocks.{i}.resnets.{j}", x, emb)
             if has_attn:
-                x = transformer3d(sd, f"up_blocks.{i}.attentions.{j}", x, text)
+                x = transformer3d(sd, f"up_blocks.{i}.attentions.{j}", x, text, block)
         if i != len(BLOCK_OUT) - 1:
             x = upsample(sd, f"up_blocks.{i}.upsamplers.0", x)
     tap("up_out", x)

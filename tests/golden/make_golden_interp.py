@@ -1,0 +1,58 @@
+"""Generate the golden vectors that pin ``oracle/interp_oracle.py`` to the reference.
+
+Run ONLY inside the build container (needs /root/reference, read-only):
+
+    python tests/golden/make_golden_interp.py
+
+Imports the UNMODIFIED interpolation model from /root/reference/interpolation/models with the same stand-ins as
+make_golden.py (tests/golden/shims/), builds it with the configuration ``from_pretrained_2d`` would produce for
+``copy_no_mask`` (in_channels 8, use_first_frame True; interpolation/models/unet.py:487-507), loads the deterministic
+synthetic weights with ``load_state_dict(strict=True)`` (which proves the 798-key table of
+``lavie_b200.config.param_spec(INTERP_CONFIG)``), runs the forward on CPU in fp32 and stores inputs and output.
+"""
+import os
+import sys
+import time
+import zlib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, "shims"))
+sys.path.insert(0, "/root/reference/interpolation")
+
+import torch  # noqa: E402
+
+from lavie_b200.config import INTERP_CONFIG, param_spec  # noqa: E402
+from lavie_b200.synthetic import synthetic_state_dict  # noqa: E402
+from models.unet import UNet3DConditionModel  # noqa: E402  (the reference's interpolation UNet)
+
+CASES = {
+    # name: (batch, frames, height, width, timestep, text tokens)
+    "interp_b2_f7_8x8": (2, 7, 8, 8, 500, 77),
+    "interp_b1_f5_16x8": (1, 5, 16, 8, 37, 20),
+}
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    cfg = INTERP_CONFIG.to_dict()
+    cfg["use_first_frame"] = True
+    ref = UNet3DConditionModel.from_config(cfg).eval()
+    sd = synthetic_state_dict(INTERP_CONFIG, seed=0)
+    assert set(ref.state_dict().keys()) == set(param_spec(INTERP_CONFIG).keys())
+    ref.load_state_dict(sd, strict=True)
+    for name, (b, f, h, w, t, ntok) in CASES.items():
+        g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+        sample = torch.randn(b, 8, f, h, w, generator=g)
+        text = torch.randn(b, ntok, 768, generator=g)
+        t0 = time.time()
+        with torch.no_grad():
+            out = ref(sample, t, encoder_hidden_states=text).sample
+        torch.save({"sample": sample, "timestep": t, "text": text, "out": out, "weights_seed": 0,
+                    "shape": (b, f, h, w)}, os.path.join(HERE, f"{name}.pt"))
+        print(f"{name}: out {tuple(out.shape)} std {out.std():.4f} in {time.time() - t0:.1f}s")
+
+
+if __name__ == "__main__":
+    main()
