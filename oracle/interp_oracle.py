@@ -64,3 +64,54 @@ def unet_forward(sd: SD, sample: torch.Tensor, timestep, text: torch.Tensor) -> 
     """UNet3DConditionModel.forward of the interpolation model (interpolation/models/unet.py:320-475):
     sample [B, 8, F, H, W] -> noise prediction [B, 4, F, H, W]."""
     return B.unet_forward(sd, sample, timestep, text, block=transformer_block)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The caller: classifier-free guidance + respaced DDIM with channel-concat conditioning
+# (interpolation/sample.py:138-174 `auto_inpainting_copy_no_mask`, interpolation/diffusion/gaussian_diffusion.py)
+# ----------------------------------------------------------------------------------------------------------------
+def space_timesteps(num_timesteps: int, count: int):
+    """respace.py:9-63 for a single section ("50"): `count` indices from 0 .. num_timesteps-1 with a fractional stride,
+    rounded with Python's round()."""
+    stride = 1 if count <= 1 else (num_timesteps - 1) / (count - 1)
+    return [round(i * stride) for i in range(count)]
+
+
+def ddim_schedule(num_steps: int = 50, num_train: int = 1000):
+    """create_diffusion(str(num_steps)) (diffusion/__init__.py:10-47): linear betas 1e-4 .. 2e-2 in float64
+    (gaussian_diffusion.py:98-113), alphas_cumprod of the retained timesteps (the SpacedDiffusion betas reproduce exactly
+    these products, respace.py:76-89).  Returns (timesteps kept, alpha_bar, alpha_bar_prev) in ascending order."""
+    betas = torch.linspace(1e-4, 2e-2, num_train, dtype=torch.float64)
+    acp = torch.cumprod(1.0 - betas, dim=0)
+    use = space_timesteps(num_train, num_steps)
+    ab = acp[use]
+    ab_prev = torch.cat([torch.ones(1, dtype=torch.float64), ab[:-1]])
+    return use, ab, ab_prev
+
+
+def forward_with_cfg(sd: SD, x: torch.Tensor, t: int, text: torch.Tensor, cfg_scale: float = 4.0) -> torch.Tensor:
+    """UNet3DConditionModel.forward_with_cfg (interpolation/models/unet.py:453-474): the first half of the batch is run
+    with [prompt, negative prompt]; eps = uncond + s (cond - uncond), returned for both halves."""
+    half = x[: len(x) // 2]
+    eps = unet_forward(sd, torch.cat([half, half], dim=0), t, text)
+    cond, uncond = eps.chunk(2, dim=0)
+    g = uncond + cfg_scale * (cond - uncond)
+    return torch.cat([g, g], dim=0)
+
+
+@torch.no_grad()
+def ddim_loop(sd: SD, z: torch.Tensor, x_start: torch.Tensor, text: torch.Tensor, num_steps: int = 50,
+              cfg_scale: float = 4.0, model=None) -> torch.Tensor:
+    """ddim_sample_loop(model.forward_with_cfg, ..., eta=0, clip_denoised=False, use_concat=True, copy_no_mask=True)
+    (gaussian_diffusion.py:282-288, 362-395, 587-642, 723-778): every step feeds cat([x_t, x_start], dim=1) -- the noisy
+    latent next to the copied key-frame latent -- to the UNet.  z, x_start: [2, 4, F, H, W] (both CFG halves);
+    text = [prompt, negative prompt].  ``model(x8, t, text)`` may replace the oracle's guided forward."""
+    use, ab, ab_prev = ddim_schedule(num_steps)
+    fwd = model if model is not None else (lambda x8, t, e: forward_with_cfg(sd, x8, t, e, cfg_scale))
+    x = z.double()
+    for i in reversed(range(len(use))):
+        eps = fwd(torch.cat([x.float(), x_start.float()], dim=1), use[i], text).double()
+        x0 = x / ab[i].sqrt() - (1.0 / ab[i] - 1.0).sqrt() * eps        # _predict_xstart_from_eps
+        x = ab_prev[i].sqrt() * x0 + (1.0 - ab_prev[i]).sqrt() * eps     # eta = 0: no noise term
+        x = x.float().double()                                           # the reference keeps x in fp32 between steps
+    return x.float()

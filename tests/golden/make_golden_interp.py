@@ -52,6 +52,23 @@ def main():
         torch.save({"sample": sample, "timestep": t, "text": text, "out": out, "weights_seed": 0,
                     "shape": (b, f, h, w)}, os.path.join(HERE, f"{name}.pt"))
         print(f"{name}: out {tuple(out.shape)} std {out.std():.4f} in {time.time() - t0:.1f}s")
+    # the caller: respaced DDIM + classifier-free guidance with channel-concat conditioning, exactly as
+    # interpolation/sample.py:138-166 drives it (copy_no_mask, use_concat, eta 0, clip_denoised False, cfg_scale 4.0)
+    from diffusion import create_diffusion  # noqa: E402  (the reference's IDDPM code)
+    steps, f, h, w, ntok = 6, 5, 8, 8, 12
+    g = torch.Generator().manual_seed(zlib.crc32(b"interp_loop"))
+    z = torch.randn(1, 4, f, h, w, generator=g)
+    copied = torch.randn(1, 4, f, h, w, generator=g)
+    text = torch.randn(2, ntok, 768, generator=g)                  # [prompt, negative prompt]
+    z2, x_start = torch.cat([z] * 2), torch.cat([copied] * 2)
+    diffusion = create_diffusion(str(steps))
+    t0 = time.time()
+    samples = diffusion.ddim_sample_loop(ref.forward_with_cfg, z2.shape, z2, clip_denoised=False,
+                                         model_kwargs=dict(encoder_hidden_states=text, class_labels=None), progress=False,
+                                         device="cpu", mask=None, x_start=x_start, use_concat=True, copy_no_mask=True)
+    torch.save({"z": z2, "x_start": x_start, "text": text, "steps": steps, "out": samples, "weights_seed": 0},
+               os.path.join(HERE, "interp_loop_f5_8x8.pt"))
+    print(f"interp_loop_f5_8x8: {steps} DDIM steps, out std {samples.std():.4f} in {time.time() - t0:.1f}s")
 
 
 if __name__ == "__main__":

@@ -48,3 +48,17 @@ def test_sparse_causal_attention_sees_first_and_former_frame():
     x0 = x.clone(); x0[0] += 1.0
     d0 = (O.sparse_causal_attention(sd, p, x0, frames) - y).abs().amax(dim=(1, 2))
     assert bool((d0 > 1e-4).all())
+
+
+def test_interp_ddim_loop_matches_reference_golden():
+    """Respaced DDIM + CFG 4.0 with channel-concat conditioning (interpolation/sample.py:138-166 through the reference's
+    own diffusion/ package and forward_with_cfg) against the oracle's restatement of the loop."""
+    from lavie_b200.config import INTERP_CONFIG
+    from lavie_b200.synthetic import synthetic_state_dict
+    from oracle import interp_oracle as O
+    g = load_golden("interp_loop_f5_8x8")
+    sd = synthetic_state_dict(INTERP_CONFIG, seed=g["weights_seed"])
+    out = O.ddim_loop(sd, g["z"], g["x_start"], g["text"], num_steps=g["steps"], cfg_scale=4.0)
+    assert out.shape == g["out"].shape
+    assert rel_l2(out, g["out"]) < 1e-4
+    assert O.space_timesteps(1000, 50)[:3] == [0, 20, 41] and O.space_timesteps(1000, 50)[-1] == 999
