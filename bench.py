@@ -100,71 +100,92 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU legs
-def oracle_sample_seconds(frames: int, threads: int, sd=None):
-    """One oracle forward at `frames` of the 16 frames (all other dimensions at full size)."""
-    from lavie_b200.synthetic import synthetic_inputs, synthetic_state_dict
+CONFIG = {"workload": WORKLOAD, "weights": "random-init (seeded), 909.1 M params", "timesteps": "DDIM, 50 steps"}
+
+
+def reference_forward():
+    """The reference's own forward on the host CPU: the UNMODIFIED reference model from baseline/_ref (copied there by
+    __graft_entry__.build(), kind "reference"), else the CPU oracle port (kind "port").  Returns (fn, kind)."""
+    from lavie_b200.synthetic import synthetic_state_dict
+    from oracle import reference_loader as R
+    sd = synthetic_state_dict(seed=0)
+    if R.available("base"):
+        ref = R.load_reference_unet("base", sd)
+
+        def fwd(sample, t, text):
+            with torch.no_grad():
+                return ref(sample, t, encoder_hidden_states=text).sample
+        return fwd, "reference"
     from oracle import unet3d_oracle as O
-    torch.set_num_threads(threads)
-    sd = sd if sd is not None else synthetic_state_dict(seed=0)
-    sample, t, text = synthetic_inputs(2, frames, LAT_H, LAT_W, seed=0)
+    return (lambda sample, t, text: O.unet_forward(sd, sample, t, text)), "port"
+
+
+def timed_forward(fwd, frames: int):
+    """One CPU forward on the bench inputs restricted to the first `frames` frames (all other dimensions full size)."""
+    from lavie_b200.synthetic import synthetic_inputs
+    sample, t, text = synthetic_inputs(2, FRAMES, LAT_H, LAT_W, seed=0)
+    sample = sample[:, :, :frames].contiguous()
     t0 = time.time()
-    O.unet_forward(sd, sample, t, text)
-    return time.time() - t0, sd
+    out = fwd(sample, t, text)
+    return time.time() - t0, out
 
 
-def cpu_baseline(budget_s: float = 20.0):
-    """Bounded CPU sample for the N=1 line: per-frame work dominates (conv / spatial attention / FF are per frame), so a
-    forward at f of 16 frames is scaled by 16/f."""
+def cpu_baseline():
+    """N=1 line: ONE full-size forward ([2,4,16,40,64], fp32) of the reference on all host cores.  Its output is kept:
+    it is the parity reference of the product's forward on the same inputs (`parity` key of the line)."""
     threads = os.cpu_count() or 1
-    t1, sd = oracle_sample_seconds(1, threads)
-    frames = 1
-    for f in (2, 4, 8, 16):
-        if t1 * f <= budget_s:
-            frames = f
-    if frames > 1:
-        tf, _ = oracle_sample_seconds(frames, threads, sd)
-    else:
-        tf = t1
-    step_s = tf * FRAMES / frames
-    return {"value": 1.0 / step_s, "unit": "steps/s", "cores": threads, "kind": "port",
-            "sample": f"1 oracle UNet forward (fp32, batch 2, 40x64 latent) at {frames} of {FRAMES} frames = {tf:.2f} s, "
-                      f"scaled x{FRAMES // frames} (per-frame work)", "seconds_per_step": step_s}
+    torch.set_num_threads(threads)
+    fwd, kind = reference_forward()
+    timed_forward(fwd, 1)                                  # warm-up (allocator, oneDNN primitive caches)
+    dt, out = timed_forward(fwd, FRAMES)
+    what = "unmodified reference UNet3DConditionModel (baseline/_ref)" if kind == "reference" else "CPU oracle port"
+    return {"value": 1.0 / dt, "unit": "steps/s", "cores": threads, "kind": kind,
+            "sample": f"1 full forward of the {what}, fp32, [2,4,{FRAMES},{LAT_H},{LAT_W}] = {dt:.2f} s "
+                      f"(guidance combine + DDIM update are negligible on CPU)", "seconds_per_step": dt}, out
 
 
 def run_reference(args):
-    """--impl reference: the reference's algorithm (CPU oracle port; the reference is Python/PyTorch and cannot travel
-    to the GPU box) on all host cores.  Each step is a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation on all host cores.  Every bench step is a BOUNDED SAMPLE
+    of the workload: the reference forward on the first f of the 16 frames (everything else at full size; conv / spatial
+    attention / FF work is per frame), f chosen so that the K + W steps finish in ~2.5 minutes.  `ms_per_step` is the
+    measured wall time of one such bench step; `value` = (f / 16 of a denoise step) / that time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    fwd, kind = reference_forward()
     total = max(1, args.steps + args.warmup)
-    t1, sd = oracle_sample_seconds(1, threads)
+    timed_forward(fwd, 1)
+    t1, _ = timed_forward(fwd, 1)
     frames = 1
     for f in (2, 4, 8, 16):
         if t1 * f * total <= 150.0:
             frames = f
     for _ in range(args.warmup):
-        oracle_sample_seconds(frames, threads, sd)
-    times = []
-    for _ in range(args.steps):
-        dt, _ = oracle_sample_seconds(frames, threads, sd)
-        times.append(dt)
-    step_s = (sum(times) / len(times)) * FRAMES / frames
-    value = 1.0 / step_s
-    sample = (f"oracle UNet forward at {frames} of {FRAMES} frames per step, scaled x{FRAMES // frames}; "
-              f"guidance combine + DDIM update are negligible on CPU")
+        timed_forward(fwd, frames)
+    times = [timed_forward(fwd, frames)[0] for _ in range(args.steps)]
+    step_s = sum(times) / len(times)
+    frac = frames / FRAMES
+    value = frac / step_s
+    sample = (f"per bench step: one forward of the {'unmodified reference (baseline/_ref)' if kind == 'reference' else 'CPU oracle port'}"
+              f" on {frames} of {FRAMES} frames = {frac:g} of a denoise step, measured {step_s:.2f} s")
     line = {"impl": "reference", "metric": "denoise steps/s (320x512x16, CFG)", "value": value, "unit": "steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "device": "host CPU", "threads": threads},
-            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": CONFIG, "setup": {"device": "host CPU", "threads": threads, "sample_fraction": frac},
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- B200 path
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
 def run_b200(args):
     import torch.distributed as dist
     from lavie_b200 import UNet3DConditionModel, ops
@@ -185,10 +206,14 @@ def run_b200(args):
     unet = UNet3DConditionModel()
     unet.load_state_dict(synthetic_state_dict(seed=0), strict=True)
     unet = unet.to(dev).eval()
-    sample, _, text = synthetic_inputs(2, FRAMES, LAT_H, LAT_W, seed=0)
+    sample, t_check, text = synthetic_inputs(2, FRAMES, LAT_H, LAT_W, seed=0)
     latents0 = sample[:1].contiguous()                 # [1,4,16,40,64]
     sched = DDIMSchedule(50)
     timesteps = sched.timesteps
+
+    # ---- parity reference of this run: the un-sharded forward of the bench inputs on THIS GPU (outside any timing) ----
+    full_out = unet(sample.to(dev), t_check, encoder_hidden_states=text.to(dev)).sample
+    torch.cuda.synchronize()
 
     # ---- partitioning: ONE video, strong scaling ----
     # N = 1: both CFG halves on one GPU.  N >= 2: rank = half * P + shard.  The uncond / cond halves never interact
@@ -197,6 +222,7 @@ def run_b200(args):
     # frame-sharded across steps: after the forward the two ranks holding the same frames exchange their noise
     # predictions (all_gather of 2 x 655/P KB) and each applies the fused guidance + DDIM update to its frames.
     jobs, scaling = 1, "strong"
+    parity = None
     if world == 1:
         parallelism = "single"
         pair_group, half, P, shard_idx = None, None, 1, 0
@@ -219,16 +245,30 @@ def run_b200(args):
         unet.set_frame_sharding(frame_group)
         fl = FRAMES // P
         latents0 = latents0[:, :, shard_idx * fl:(shard_idx + 1) * fl].contiguous()
+        # every rank: its shard of the SAME inputs through the sharded path (CUDA graph + peer-memory exchanges, exactly
+        # what is timed below) against the slice of the un-sharded forward computed above
+        shard_in = sample[half:half + 1, :, shard_idx * fl:(shard_idx + 1) * fl].contiguous().to(dev)
+        shard_out = None
+        for _ in range(2):                              # second call = graph replay
+            shard_out = unet(shard_in, t_check, encoder_hidden_states=text[half:half + 1].to(dev)).sample
+        err = rel_l2(shard_out, full_out[half:half + 1, :, shard_idx * fl:(shard_idx + 1) * fl])
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        parity = {"rel_l2": max(errs), "per_rank": [round(e, 6) for e in errs], "tolerance": 2e-2,
+                  "vs": "un-sharded forward of the same inputs on the rank's own GPU",
+                  "shape": [2, 4, FRAMES, LAT_H, LAT_W]}
+        if max(errs) > 2e-2:
+            raise SystemExit(f"sharded forward differs from the un-sharded one: worst rel-L2 {max(errs):.3e} > 2e-2")
 
     lat = latents0.to(dev)
     txt = text.to(dev)
     den = CFGDenoiser(unet, 7.5, sched)
     gather = [torch.empty((1,) + tuple(lat.shape[1:]), dtype=torch.float32, device=dev) for _ in range(2)]
 
-    def one_step(latents, t):
+    def one_step(latents, t, text_in=None):
         if world == 1:
-            return den.step(latents, t, txt)
-        noise = unet(latents, t, encoder_hidden_states=txt[half:half + 1]).sample
+            return den.step(latents, t, txt if text_in is None else text_in)
+        noise = unet(latents, t, encoder_hidden_states=txt[half:half + 1] if text_in is None else text_in).sample
         dist.all_gather(gather, noise.contiguous(), group=pair_group)
         a_t, a_prev = sched.alphas(t)
         return ops.cfg_ddim_step(gather[0], gather[1], 7.5, a_t, a_prev, latents)
@@ -265,24 +305,25 @@ def run_b200(args):
     per_step = graph_launches if graph_launches is not None else 0
     gpu_launches = eager_launches + (per_step * args.steps if unet.use_cuda_graph else 0)
 
-    # ---- e2e: host buffers, H2D + D2H inside the timed region, every step ----
-    lat_host = latents0.clone().pin_memory()
+    # ---- e2e: the same step through the public module API from pinned HOST buffers.  Every step: H2D of the latents
+    # and the text embedding, the step, D2H of the new latents; the next step's input IS that host copy, so the host
+    # waits for the copy's event (not a device-wide synchronize) before it enqueues the next step. ----
+    lat_host = [latents0.clone().pin_memory(), torch.empty_like(latents0).pin_memory()]
     txt_host = (text if world == 1 else text[half:half + 1]).contiguous().pin_memory()
-    out_host = torch.empty_like(lat_host).pin_memory()
+    done = torch.cuda.Event()
+    for i in range(2):                                   # warm the pinned-buffer path
+        new = one_step(lat_host[0].to(dev, non_blocking=True), timesteps[i], txt_host.to(dev, non_blocking=True))
+        lat_host[1].copy_(new, non_blocking=True)
     barrier()
+    lat_host[0].copy_(latents0)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        lat_d = lat_host.to(dev, non_blocking=True)
-        if world == 1:
-            new = den.step(lat_d, timesteps[i % len(timesteps)], txt_host)
-        else:
-            noise = unet(lat_d, timesteps[i % len(timesteps)], encoder_hidden_states=txt_host).sample
-            dist.all_gather(gather, noise.contiguous(), group=pair_group)
-            a_t, a_prev = sched.alphas(timesteps[i % len(timesteps)])
-            new = ops.cfg_ddim_step(gather[0], gather[1], 7.5, a_t, a_prev, lat_d)
-        out_host.copy_(new, non_blocking=True)
-        torch.cuda.synchronize()
-        lat_host.copy_(out_host)
+        src, dst = lat_host[i & 1], lat_host[(i + 1) & 1]
+        new = one_step(src.to(dev, non_blocking=True), timesteps[i % len(timesteps)],
+                       txt_host.to(dev, non_blocking=True))
+        dst.copy_(new, non_blocking=True)
+        done.record()
+        done.synchronize()
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -290,8 +331,8 @@ def run_b200(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax)
     e2e_value = jobs * args.steps / e2e_s
-    h2d = lat_host.numel() * 4 + txt_host.numel() * 4
-    d2h = out_host.numel() * 4
+    h2d = lat_host[0].numel() * 4 + txt_host.numel() * 4
+    d2h = lat_host[0].numel() * 4
 
     # ---- roofline of the dominant kernel: per-launch CUDA events over one eager (un-graphed) step ----
     # (every rank runs the eager pass: with frame sharding its collectives need the whole group; rank 0 reports)
@@ -310,6 +351,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     unet.use_cuda_graph = was
+    weight_bytes = sum(v.numel() * v.element_size() for v in unet.packed_tensors())
     if rank == 0:
         peaks = measured_peaks()
         agg = {}
@@ -321,35 +363,47 @@ def run_b200(args):
             a[3] += nbytes
         total_ms = sum(a[1] for a in agg.values())
         kernels = {k: {"launches": a[0], "ms": round(a[1], 3), "share": round(a[1] / total_ms, 4),
-                       "gflop": round(a[2] / 1e9, 1), "gbytes": round(a[3] / 1e9, 3)}
+                       "gflop": round(a[2] / 1e9, 1), "gbytes": round(a[3] / 1e9, 3),
+                       "tflops": round(a[2] / (a[1] * 1e-3) / 1e12, 1) if a[2] else None,
+                       "gbs": round(a[3] / (a[1] * 1e-3) / 1e9, 1) if a[3] else None}
                    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
         dom = "gemm_bf16_tcgen05"
         d = agg[dom]
         achieved = d[2] / (d[1] * 1e-3) / 1e12
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = "STATIC: " + tj.get("source", "ncu --set full capture committed under profiles/")
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"],
                     "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "launches_per_step": d[0], "avg_launch_ms": d[1] / d[0],
                     "algorithmic_gflop_per_launch": d[2] / d[0] / 1e9, "share_of_step": d[1] / total_ms,
                     "peak_source": peaks["source"]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline()
+        cpu, ref_out = cpu_baseline()
+        err = rel_l2(full_out.cpu(), ref_out)
+        parity = {"rel_l2": err, "tolerance": 2e-2, "shape": [2, 4, FRAMES, LAT_H, LAT_W],
+                  "vs": ("unmodified reference forward, fp32 CPU (baseline/_ref)" if cpu["kind"] == "reference"
+                         else "CPU oracle port, fp32")}
+        if not err <= 2e-2:
+            raise SystemExit(f"parity FAILED at the headline shape: rel-L2 {err:.3e} > 2e-2")
 
     if rank == 0:
         line = {"metric": "denoise steps/s (320x512x16, CFG)", "value": value, "unit": "steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic",
-                "config": {"workload": WORKLOAD, "parallelism": parallelism, "independent_videos": jobs,
-                           "weights": "random-init (seeded), 909.1 M params", "cuda_graph": bool(unet.use_cuda_graph),
-                           "l2": "no flush: one step streams 1.8 GB of weights and several GB of activations, "
-                                 ">> 126 MB L2"},
+                "data": "synthetic", "config": CONFIG,
+                "setup": {"parallelism": parallelism, "independent_videos": jobs, "cuda_graph": bool(unet.use_cuda_graph),
+                          "l2": "no flush: one step streams 1.8 GB of weights and several GB of activations, "
+                                ">> 126 MB L2",
+                          "launches_per_step_per_rank": per_step, "weight_bytes_per_rank": weight_bytes},
+                "parity": parity,
                 "step_tflops": STEP_GFLOP / ms_per_step / 1e3,
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

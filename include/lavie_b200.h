@@ -144,6 +144,12 @@ int lavie_add_gathered_bf16(const void* res, int ldr, const void* z, int ldz, vo
  *  - lavie_add_gathered_p2p: out = res + rows loaded from the peers' y buffers (y_ptrs[r] -> bf16 [F, hw/P, C]);
  *    precede with lavie_rank_barrier (every rank's y complete).
  *  - lavie_rank_barrier: "everything I launched before this is done and visible" handshake among the P ranks. */
+/* Bounded waits: a rank whose peer does not signal within `timeout_seconds` of wall time (default 30; <= 0 keeps the
+ * current value) writes uint32 {0x4C564945, my rank, missing peer, epoch wanted, epoch seen} into `host_mapped_words`
+ * (pinned, device-accessible HOST memory of >= 8 words owned by the caller, or NULL for no report) and traps.  The trap
+ * is a sticky CUDA error on that rank; its peers, never signalled, time out the same way: one rank's failure aborts the
+ * whole frame group. */
+int lavie_p2p_fault_buffer(void* host_mapped_words, int timeout_seconds);
 int lavie_rank_barrier(void* const* flag_ptrs, unsigned int* epoch_counter, int P, int my_rank, lavie_stream_t stream);
 int lavie_gn_exchange_finalize(const float* partial, int samples, int chunks, int groups, int C,
                                long long count_per_group_global, const float* gamma, const float* beta, float eps,

@@ -55,6 +55,7 @@ SIGNATURES = {
     "lavie_layernorm_scatter_bf16": (c_int, [_P, c_int, _P, _P, c_float, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "lavie_add_gathered_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "lavie_groupnorm_reduce": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "lavie_p2p_fault_buffer": (c_int, [_P, c_int]),
     "lavie_rank_barrier": (c_int, [_P, _P, c_int, c_int, _P]),
     "lavie_gn_exchange_finalize": (c_int, [_P, c_int, c_int, c_int, c_int, c_longlong, _P, _P, c_float, _P, _P, _P, _P,
                                            c_int, c_int, _P]),

@@ -353,13 +353,9 @@ template <int DK, int POLY, bool ONES>
 int launch_attn_inst(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p, int batch,
                      int heads, cudaStream_t stream) {
   using Cfg = AttnCfg<DK>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(attn_fwd_kernel<DK, POLY, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    LAVIE_REQUIRE(e == cudaSuccess, LAVIE_ERR_CUDA, "cudaFuncSetAttribute(attn<%d>): %s", DK, cudaGetErrorString(e));
-    configured = true;
-  }
+  static LavieSmemConfig configured;
+  const int rc_cfg = lavie_config_smem(attn_fwd_kernel<DK, POLY, ONES>, Cfg::SMEM, &configured, "attn_fwd_kernel");
+  if (rc_cfg) return rc_cfg;
   dim3 grid((p.Sq + ATT_M - 1) / ATT_M, heads, batch);
   launch_pdl(attn_fwd_kernel<DK, POLY, ONES>, grid, ATT_THREADS, Cfg::SMEM, stream, mq, mk, mv, p);
   return lavie_check_launch("attn_fwd_kernel");
@@ -852,12 +848,9 @@ extern "C" int lavie_temporal_attention_bf16(const void* qkv, int ld, int k_off,
   while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
   const int smem = warps * per_warp;
   LAVIE_REQUIRE(smem <= 227 * 1024, LAVIE_ERR_SHAPE, "temporal attention: F*d too large for shared memory");
-  static int configured_smem = 0;
-  if (smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    LAVIE_REQUIRE(e == cudaSuccess, LAVIE_ERR_CUDA, "cudaFuncSetAttribute(temporal): %s", cudaGetErrorString(e));
-    configured_smem = smem;
-  }
+  static LavieSmemConfig configured_smem;
+  const int rc_cfg = lavie_config_smem(temporal_attn_kernel, smem, &configured_smem, "temporal_attn_kernel");
+  if (rc_cfg) return rc_cfg;
   long long blocks = (p.items + warps - 1) / warps;
   if (blocks > 148LL * 8) blocks = 148LL * 8;
   launch_pdl(temporal_attn_kernel, static_cast<int>(blocks), warps * 32, smem, stream, p);

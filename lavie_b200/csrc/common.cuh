@@ -43,7 +43,23 @@ extern int g_lavie_pdl;       // 1 = on (default); lavie_debug_set(3, 0) turns i
 extern void* g_lavie_debug_buf; // device scratch for the clock64 timelines (lavie_debug_buffer), nullptr = off
 extern int g_lavie_attn_poly; // attention: every n-th exp2 on the FMA pipe (0 = none); lavie_debug_set(4, n)
 
+// Per-DEVICE lazily configured kernel attributes.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the
+// current device only, and one process may drive several GPUs (one host thread per device), so the "already
+// configured" state is an array indexed by cudaGetDevice(); the slow path is serialised by a mutex (host.cu).
+constexpr int LAVIE_MAX_DEVICES = 64;
+struct LavieSmemConfig {
+  int bytes[LAVIE_MAX_DEVICES];     // static storage: zero-initialised
+};
+int lavie_current_device();
+int lavie_num_sms();                // SM count of the current device (cached per device)
+int lavie_config_smem_impl(const void* func, int bytes, LavieSmemConfig* st, const char* what);
+
 #ifdef __CUDACC__
+template <typename K>
+inline int lavie_config_smem(K kernel, int bytes, LavieSmemConfig* st, const char* what) {
+  return lavie_config_smem_impl(reinterpret_cast<const void*>(kernel), bytes, st, what);
+}
+
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg{};

@@ -553,19 +553,14 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
                 const CUtensorMap& mr, const GemmParams& p,
                 int num_sms, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::TOTAL);
-    LAVIE_REQUIRE(e == cudaSuccess, LAVIE_ERR_CUDA, "cudaFuncSetAttribute(gemm<%d>): %s", BLOCK_N,
-                  cudaGetErrorString(e));
-    configured = true;
-  }
+  static LavieSmemConfig configured;
+  int rc = lavie_config_smem(gemm_bf16_tcgen05<BLOCK_N>, L::TOTAL, &configured, "gemm_bf16_tcgen05");
+  if (rc) return rc;
   const int items = p.m_tiles * p.n_tiles * p.splits;
   int pairs = num_sms / 2;
   if (items < pairs) pairs = items;
   launch_pdl(gemm_bf16_tcgen05<BLOCK_N>, 2 * pairs, NUM_THREADS, L::TOTAL, stream, a0, a1, b, mo, mr, p);
-  int rc = lavie_check_launch("gemm_bf16_tcgen05");
+  rc = lavie_check_launch("gemm_bf16_tcgen05");
   if (rc) return rc;
   if (p.splits > 1) {
     const int row0 = p.m_tile0 * PAIR_M;
@@ -585,16 +580,7 @@ int g_force_splits = 0;
 int g_debug = 0;
 int g_k_rot = 0;   // measured: no effect on B200 (profiles/r1_notes.md), kept as a tuning hook only
 int g_no_tail = 0; // lavie_debug_set(5, 1): never split a GEMM into main + tail launches (A/B timing)
-int g_num_sms = 0;
-int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
+int num_sms() { return lavie_num_sms(); }
 
 // Tile-shape / split-K choice: minimise  waves x (K blocks per item x per-block time + per-item overhead), where the
 // per-block time is the larger of the MMA time (2*BN cycles per SM) and the L2 feed time of the stage bytes.

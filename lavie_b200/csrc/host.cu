@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -109,6 +111,45 @@ int lavie_make_tmap_im2col(CUtensorMap* map, const void* base, int N, int H, int
     lavie_set_error("cuTensorMapEncodeIm2col failed: CUresult %d (N=%d H=%d W=%d C=%d)", static_cast<int>(r), N, H, W, C);
     return LAVIE_ERR_DRIVER;
   }
+  return LAVIE_OK;
+}
+
+int lavie_current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    dev = 0;
+  }
+  return (dev >= 0 && dev < LAVIE_MAX_DEVICES) ? dev : 0;
+}
+
+namespace {
+std::mutex g_config_mutex;
+int g_sm_count[LAVIE_MAX_DEVICES];
+}  // namespace
+
+int lavie_num_sms() {
+  const int dev = lavie_current_device();
+  int n = g_sm_count[dev];
+  if (n > 0) return n;
+  std::lock_guard<std::mutex> lock(g_config_mutex);
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = 148;                          // no device (host-only planning queries): a B200
+  }
+  g_sm_count[dev] = n;
+  return n;
+}
+
+int lavie_config_smem_impl(const void* func, int bytes, LavieSmemConfig* st, const char* what) {
+  const int dev = lavie_current_device();
+  if (st->bytes[dev] >= bytes) return LAVIE_OK;
+  std::lock_guard<std::mutex> lock(g_config_mutex);
+  if (st->bytes[dev] >= bytes) return LAVIE_OK;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  LAVIE_REQUIRE(e == cudaSuccess, LAVIE_ERR_CUDA, "cudaFuncSetAttribute(%s, %d bytes) on device %d: %s", what, bytes, dev,
+                cudaGetErrorString(e));
+  st->bytes[dev] = bytes;
   return LAVIE_OK;
 }
 

@@ -319,12 +319,9 @@ extern "C" int lavie_conv_in(const float* x, int B, int Cin, int F, int H, int W
   LAVIE_REQUIRE(Cout % 8 == 0 && ldo % 8 == 0 && al16(out), LAVIE_ERR_SHAPE, "conv_in: Cout/ldo must be multiples of 8");
   const int smem = Cout * Cin * 9 * static_cast<int>(sizeof(float));
   LAVIE_REQUIRE(smem <= 200 * 1024, LAVIE_ERR_SHAPE, "conv_in: weights do not fit shared memory");
-  static int configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    LAVIE_REQUIRE(e == cudaSuccess, LAVIE_ERR_CUDA, "cudaFuncSetAttribute(conv_in): %s", cudaGetErrorString(e));
-    configured = smem;
-  }
+  static LavieSmemConfig configured;
+  const int rc_cfg = lavie_config_smem(conv_in_kernel, smem, &configured, "conv_in_kernel");
+  if (rc_cfg) return rc_cfg;
   LAVIE_REQUIRE(al16(bias), LAVIE_ERR_ALIGN, "conv_in: bias must be 16-byte aligned");
   const long long total = static_cast<long long>(B) * F * H * ((W + CIN_P - 1) / CIN_P) * (Cout / 8);
   long long blocks = (total + 255) / 256;
@@ -340,12 +337,9 @@ extern "C" int lavie_conv_out(const void* x, int ldx, const float* scale_shift, 
   LAVIE_REQUIRE(al16(x) && al16(scale_shift), LAVIE_ERR_ALIGN, "conv_out: alignment");
   const int smem = Cout * 9 * C * static_cast<int>(sizeof(float));
   LAVIE_REQUIRE(smem <= 200 * 1024, LAVIE_ERR_SHAPE, "conv_out: weights do not fit shared memory");
-  static int configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    LAVIE_REQUIRE(e == cudaSuccess, LAVIE_ERR_CUDA, "cudaFuncSetAttribute(conv_out): %s", cudaGetErrorString(e));
-    configured = smem;
-  }
+  static LavieSmemConfig configured;
+  const int rc_cfg = lavie_config_smem(conv_out_kernel<4>, smem, &configured, "conv_out_kernel");
+  if (rc_cfg) return rc_cfg;
   const long long total = static_cast<long long>(B) * F * H * ((W + COUT_P - 1) / COUT_P);
   long long blocks = (total + 7) / 8;
   if (blocks > 148 * 2) blocks = 148 * 2;        // 2 resident blocks per SM (registers): one wave, one weight fill each

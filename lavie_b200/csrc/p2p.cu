@@ -34,29 +34,62 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* addr) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ void wait_flag(const uint32_t* addr, uint32_t epoch) {
+// Fault report: a peer that never arrives must not hang the GPU box, so the wait is bounded by WALL time
+// (%globaltimer, default 30 s: a rank may legitimately be late by seconds -- lazy module load, a host stall, a
+// debugger).  Before trapping, the waiting rank writes {magic, my rank, missing peer, epoch wanted, epoch seen} into a
+// caller-provided HOST-mapped word array (lavie_p2p_fault_buffer), which survives the sticky context error the trap
+// raises on this rank -- and, through the missing flag, on every other rank of the frame group.
+struct FaultCtx {
+  uint32_t* report;            // host-mapped uint32[8] or nullptr
+  unsigned long long timeout_ns;
+};
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void wait_flag(const uint32_t* addr, uint32_t epoch, const FaultCtx& fc, int my_rank,
+                                          int peer) {
   uint32_t spins = 0;
-  while (static_cast<int32_t>(ld_acquire_sys(addr) - epoch) < 0) {
+  unsigned long long t0 = 0;
+  uint32_t seen;
+  while (static_cast<int32_t>((seen = ld_acquire_sys(addr)) - epoch) < 0) {
     __nanosleep(64);
-    if (++spins > (1u << 24)) __trap();
+    if ((++spins & 1023u) == 0) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > fc.timeout_ns) {
+        if (fc.report) {
+          fc.report[1] = static_cast<uint32_t>(my_rank);
+          fc.report[2] = static_cast<uint32_t>(peer);
+          fc.report[3] = epoch;
+          fc.report[4] = seen;
+          __threadfence_system();
+          fc.report[0] = 0x4C564945u;     // "LVIE": report valid
+          __threadfence_system();
+        }
+        __trap();
+      }
+    }
   }
 }
 
 // all threads of ONE block call this; thread r < P signals peer r and waits for peer r
-__device__ __forceinline__ void block_rank_barrier(const PeerPtrs& flags, int P, int my_rank, uint32_t epoch) {
+__device__ __forceinline__ void block_rank_barrier(const PeerPtrs& flags, int P, int my_rank, uint32_t epoch,
+                                                   const FaultCtx& fc) {
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x < P) {
     st_release_sys(static_cast<uint32_t*>(flags.p[threadIdx.x]) + my_rank, epoch);
-    wait_flag(static_cast<const uint32_t*>(flags.p[my_rank]) + threadIdx.x, epoch);
+    wait_flag(static_cast<const uint32_t*>(flags.p[my_rank]) + threadIdx.x, epoch, fc, my_rank, threadIdx.x);
   }
   __syncthreads();
 }
 
-__global__ void rank_barrier_kernel(PeerPtrs flags, uint32_t* epoch_counter, int P, int my_rank) {
+__global__ void rank_barrier_kernel(PeerPtrs flags, uint32_t* epoch_counter, int P, int my_rank, FaultCtx fc) {
   pdl_prologue();
   const uint32_t epoch = *epoch_counter + 1;
-  block_rank_barrier(flags, P, my_rank, epoch);
+  block_rank_barrier(flags, P, my_rank, epoch, fc);
   if (threadIdx.x == 0) *epoch_counter = epoch;
 }
 
@@ -66,7 +99,7 @@ __global__ void __launch_bounds__(256)
 gn_exchange_finalize_kernel(const float* __restrict__ partial, int samples, int chunks, int groups, int C,
                             double inv_count, const float* __restrict__ gamma, const float* __restrict__ beta,
                             float eps, float* __restrict__ scale_shift, PeerPtrs slots, PeerPtrs flags,
-                            uint32_t* epoch_counter, int P, int my_rank) {
+                            uint32_t* epoch_counter, int P, int my_rank, FaultCtx fc) {
   pdl_prologue();
   __shared__ double s_sums[2 * 64 * 2];          // [samples <= 2][groups <= 64][2]
   __shared__ float s_mean[2 * 64], s_rstd[2 * 64];
@@ -109,7 +142,7 @@ gn_exchange_finalize_kernel(const float* __restrict__ partial, int samples, int 
     const int peer = i / n, e = i - peer * n;
     static_cast<double*>(slots.p[peer])[slot_off + e] = s_sums[e];
   }
-  block_rank_barrier(flags, P, my_rank, epoch);
+  block_rank_barrier(flags, P, my_rank, epoch, fc);
   // 3. add the P contributions in rank order (bit-identical on every rank) and finalize
   const double* mine = static_cast<const double*>(slots.p[my_rank]) + static_cast<size_t>(epoch & 1) * P * n;
   for (int sg = threadIdx.x; sg < samples * groups; sg += blockDim.x) {
@@ -246,6 +279,10 @@ add_gathered_p2p_kernel(const __nv_bfloat16* __restrict__ res, int ldr, PeerPtrs
 
 bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+uint32_t* g_fault_report = nullptr;              // host-mapped, set by lavie_p2p_fault_buffer
+unsigned long long g_wait_timeout_ns = 30ull * 1000000000ull;
+FaultCtx fault_ctx() { return FaultCtx{g_fault_report, g_wait_timeout_ns}; }
+
 int fill_peers(PeerPtrs& pp, void* const* ptrs, int P) {
   LAVIE_REQUIRE(P >= 1 && P <= MAX_PEERS, LAVIE_ERR_SHAPE, "p2p: 1 <= peers <= %d", MAX_PEERS);
   for (int i = 0; i < MAX_PEERS; ++i) pp.p[i] = i < P ? ptrs[i] : nullptr;
@@ -260,7 +297,7 @@ extern "C" int lavie_rank_barrier(void* const* flag_ptrs, unsigned int* epoch_co
   PeerPtrs f;
   int rc = fill_peers(f, flag_ptrs, P);
   if (rc) return rc;
-  launch_pdl(rank_barrier_kernel, 1, 32, 0, stream, f, epoch_counter, P, my_rank);
+  launch_pdl(rank_barrier_kernel, 1, 32, 0, stream, f, epoch_counter, P, my_rank, fault_ctx());
   return lavie_check_launch("rank_barrier_kernel");
 }
 
@@ -278,7 +315,7 @@ extern "C" int lavie_gn_exchange_finalize(const float* partial, int samples, int
   if (rc) return rc;
   launch_pdl(gn_exchange_finalize_kernel, 1, 256, 0, stream, partial, samples, chunks, groups, C,
                                                      1.0 / static_cast<double>(count_per_group_global), gamma, beta, eps,
-                                                     scale_shift, s, f, epoch_counter, P, my_rank);
+                                                     scale_shift, s, f, epoch_counter, P, my_rank, fault_ctx());
   return lavie_check_launch("gn_exchange_finalize_kernel");
 }
 
@@ -320,4 +357,10 @@ extern "C" int lavie_add_gathered_p2p(const void* res, int ldr, void* const* y_p
   if (blocks < 1) blocks = 1;
   launch_pdl(add_gathered_p2p_kernel, static_cast<int>(blocks), 256, 0, stream, static_cast<const __nv_bfloat16*>(res), ldr, y, static_cast<__nv_bfloat16*>(out), ldo, rows, C, hw, hwp, my_rank);
   return lavie_check_launch("add_gathered_p2p_kernel");
+}
+
+extern "C" int lavie_p2p_fault_buffer(void* host_mapped_words, int timeout_seconds) {
+  g_fault_report = static_cast<uint32_t*>(host_mapped_words);
+  if (timeout_seconds > 0) g_wait_timeout_ns = static_cast<unsigned long long>(timeout_seconds) * 1000000000ull;
+  return LAVIE_OK;
 }

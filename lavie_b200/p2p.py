@@ -38,8 +38,20 @@ class PeerContext:
         self.peer_base: List[int] = [int(p) for p in self.handle.buffer_ptrs]
         assert len(self.peer_base) == self.P and self.peer_base[self.rank] == self.buf.data_ptr()
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        # pinned host words the kernels fill before trapping on a lost peer (readable after the context died)
+        self.fault = torch.zeros(8, dtype=torch.int32).pin_memory()
+        _lib.load().lavie_p2p_fault_buffer(self.fault.data_ptr(), 0)
         self.token_bytes = tok_b
         dist.barrier(group)                               # everybody has zeroed flags before the first kernel
+
+    def describe_fault(self) -> str:
+        """After a CUDA error on a sharded step: which peer this rank was waiting for (one rank's failure aborts the
+        whole frame group, so the rank that reports a missing peer points at the rank that failed first)."""
+        w = [int(v) & 0xFFFFFFFF for v in self.fault.tolist()]
+        if w[0] != 0x4C564945:
+            return "no peer-wait timeout recorded on this rank"
+        return (f"rank {w[1]} of the frame group timed out waiting for peer {w[2]}: wanted epoch {w[3]}, "
+                f"last seen {w[4]}")
 
     def ptrs(self, what: str):
         off = self.layout[what]

@@ -58,8 +58,11 @@ class _RotaryFreqs(nn.Module):
 
 
 def _leaf_for(key_prefix: str, names: Dict[str, Tuple[int, ...]]) -> nn.Module:
-    """A real torch module (uninitialised storage) for one parameter group, so `.modules()` probing, PEFT's
-    target_modules=["to_q","to_k","to_v","to_out.0"] (fine_tuning.py:296-308) and `.to()` behave as usual."""
+    """A real torch module (uninitialised storage) for one parameter group, so `.modules()` probing, `.to()` and
+    `state_dict()` behave as usual.  The leaves only HOLD parameters: forward() runs from packed copies, which are
+    refreshed whenever a parameter object or its version counter changes (in-place edits, LoRA merges).  Wrapping a leaf
+    (PEFT's target_modules=["to_q","to_k","to_v","to_out.0"], fine_tuning.py:296-308) changes the key set and is rejected
+    in `_pack` -- merge the adapter into the base weights first."""
     w = names.get("weight")
     has_bias = "bias" in names
     last = key_prefix.rsplit(".", 1)[-1]
@@ -112,6 +115,9 @@ class UNet3DConditionModel(nn.Module):
         self._shard = None            # (process group, P, index) when the frames of one CFG half span P GPUs
         self._shard_backend = "p2p"
         self._peer = None
+        self._retired_peers: list = []
+        self._param_versions = None
+        self._param_list = None
         self._graphs: Dict[tuple, dict] = {}
         self._tables: Dict[tuple, tuple] = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
@@ -140,9 +146,37 @@ class UNet3DConditionModel(nn.Module):
         pass
 
     def _invalidate(self):
+        """Drop the packed (kernel-layout) weight copies and every captured step graph.  Called automatically after
+        ``load_state_dict`` / ``.to()`` and when a parameter's version counter moved (in-place edits such as
+        ``param.data.copy_`` or a LoRA merge); replacing or wrapping a leaf module (PEFT) is detected in ``forward``."""
         self._packed = None
+        self._param_versions = None
+        self._param_list = None
         self._graphs.clear()
         self._tables.clear()
+
+    def _weights_fingerprint(self):
+        # version counters of the parameters seen at packing time (~0.1 ms for 830 tensors); module surgery after the
+        # first forward (wrapping a leaf) is NOT seen here -- call _invalidate() after it
+        if self._param_list is None:
+            self._param_list = list(self.parameters())
+        return tuple(p._version for p in self._param_list)
+
+    def packed_tensors(self):
+        """Every device tensor of the packed weights (bench.py reports the per-rank weight bytes)."""
+        out = []
+
+        def walk(v):
+            if torch.is_tensor(v):
+                out.append(v)
+            elif isinstance(v, dict):
+                for x in v.values():
+                    walk(x)
+            elif isinstance(v, (tuple, list)):
+                for x in v:
+                    walk(x)
+        walk(self._packed or {})
+        return out
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)
@@ -172,6 +206,9 @@ class UNet3DConditionModel(nn.Module):
         """Symmetric buffers of the frame group, created at the first sharded forward (collective call)."""
         if self._peer is None or self._peer.token_bytes < token_bytes:
             from .p2p import PeerContext
+            # graphs captured against the previous context have its peer pointers and epoch counter baked in
+            self._graphs.clear()
+            self._retired_peers.append(self._peer)      # keep the old symmetric buffers mapped until the module dies
             self._peer = PeerContext(self._shard[0], token_bytes, self.device)
         return self._peer
 
@@ -204,6 +241,11 @@ class UNet3DConditionModel(nn.Module):
     # ------------------------------------------------------------------ weight packing (post-load)
     def _pack(self):
         sd = {k: v.detach() for k, v in self.state_dict().items()}
+        missing = [k for k in param_spec(self.cfg) if k not in sd]
+        if missing:
+            raise RuntimeError(f"state_dict no longer has the reference layout (first missing key: {missing[0]}); "
+                               "wrapped / replaced leaf modules (e.g. un-merged LoRA adapters) are not executed by the "
+                               "fused path -- merge them into the base weights first")
         dev = self.device
         if dev.type != "cuda":
             raise RuntimeError("lavie_b200.UNet3DConditionModel runs on CUDA (sm_100a) only; move it with .to('cuda')")
@@ -466,8 +508,12 @@ class UNet3DConditionModel(nn.Module):
             raise ValueError(f"sample needs {self.cfg.in_channels} channels and H, W multiples of {1 << n_down}")
         if encoder_hidden_states.shape[0] != B or encoder_hidden_states.shape[-1] != self.cfg.cross_attention_dim:
             raise ValueError(f"encoder_hidden_states must be [B, L, {self.cfg.cross_attention_dim}]")
+        fp = self._weights_fingerprint()
+        if self._packed is not None and fp != self._param_versions:
+            self._invalidate()                  # a parameter was edited in place or replaced since the last packing
         if self._packed is None:
             self._pack()
+            self._param_versions = fp
         dev = self.device
         out_dtype = sample.dtype
         # timestep normalisation of unet.py:413-426

@@ -19,3 +19,9 @@ class BaseOutput(OrderedDict):
 
     def to_tuple(self):
         return tuple(self[k] for k in self.keys())
+
+
+def randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
+    """diffusers.utils.randn_tensor for the single-generator case the vendored scheduler uses."""
+    import torch
+    return torch.randn(shape, generator=generator, device=device, dtype=dtype)

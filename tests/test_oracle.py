@@ -73,3 +73,14 @@ def test_ddim_schedule_and_step():
     prev = O.ddim_step(eps, t, xt, acp, ratio)
     want = acp[t - ratio].sqrt() * x0 + (1 - acp[t - ratio]).sqrt() * eps
     assert torch.allclose(prev, want, atol=1e-5)
+
+
+def test_ddim_step_matches_reference_scheduler():
+    """O.ddim_step / O.ddim_schedule against step() of the DDIMScheduler the reference vendors
+    (vsr/diffusion/scheduling_ddim.py:292-414; fixture made by tests/golden/make_golden_ddim.py)."""
+    g = load_golden("ddim_steps")
+    acp, ts, ratio = O.ddim_schedule(g["num_inference_steps"])
+    assert torch.equal(acp, g["alphas_cumprod"])
+    for c in g["cases"]:
+        got = O.ddim_step(c["model_output"], c["t"], c["sample"], acp, ratio)
+        assert rel_l2(got, c["prev_sample"]) < 1e-6, c["t"]

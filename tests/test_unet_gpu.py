@@ -62,14 +62,18 @@ def test_matches_oracle_on_ragged_geometry(unet, synthetic_sd):
     assert out.shape == ref.shape and err <= BF16_TOL
 
 
-def test_fifty_step_ddim_latent(unet, synthetic_sd):
+@pytest.mark.parametrize("frames,h,w", [(2, 8, 8), (16, 16, 24)])
+def test_fifty_step_ddim_latent(unet, synthetic_sd, frames, h, w):
     """BASELINE north star: the FINAL latent of the 50-step DDIM + CFG 7.5 loop (pipeline_videogen.py:664-689) against
-    the oracle's loop on the same start noise.  bf16 noise compounds over 50 feed-back steps through a random-init
-    network; stated tolerance 5e-2 (measured 7.4e-3 on B200)."""
+    the oracle's loop on the same start noise (the oracle's per-step update is pinned to the reference's own
+    DDIMScheduler.step, tests/test_oracle.py::test_ddim_step_matches_reference_scheduler).  bf16 noise compounds over 50
+    feed-back steps through a random-init network; stated tolerance 5e-2 (measured 7.4e-3 at 2 frames x 8x8 on B200).
+    The second case is a full 16-frame video on a 16x24 latent (all four levels, temporal attention over 16 frames)."""
     from lavie_b200.pipeline import CFGDenoiser, DDIMSchedule
     from lavie_b200.synthetic import synthetic_inputs
     from oracle import unet3d_oracle as O
-    sample, _, text = synthetic_inputs(2, 2, 8, 8, seed=21)
+    torch.set_num_threads(max(1, __import__("os").cpu_count() or 1))
+    sample, _, text = synthetic_inputs(2, frames, h, w, seed=21)
     lat0 = sample[:1]
     ref = O.cfg_ddim_loop(synthetic_sd, lat0, text, 7.5, 50)
     den = CFGDenoiser(unet, 7.5, DDIMSchedule(50))
@@ -77,6 +81,31 @@ def test_fifty_step_ddim_latent(unet, synthetic_sd):
     err = rel_l2(out, ref)
     print(f"50-step DDIM latent: rel-L2 vs oracle loop = {err:.3e}")
     assert torch.isfinite(out).all() and err <= 5e-2
+
+
+def test_full_size_matches_reference(unet, synthetic_sd):
+    """The HEADLINE geometry of BASELINE.json (config 1/2: batch 2 x [4,16,40,64], 77 tokens) against the reference's
+    fp32 CPU forward on the same inputs: the unmodified reference model from baseline/_ref when it travelled with the
+    snapshot, else the pinned CPU oracle.  320-wide tiles over 320 row tiles, tail windows, the 20-tile 2560-key
+    attention and the 148-chunk GroupNorm statistics all run together only here.  ~20 s of CPU on the GPU box."""
+    import os
+    from lavie_b200.synthetic import synthetic_inputs
+    from oracle import reference_loader as R
+    from oracle import unet3d_oracle as O
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    sample, t, text = synthetic_inputs(2, 16, 40, 64, seed=0)
+    if R.available("base"):
+        ref_model = R.load_reference_unet("base", synthetic_sd)
+        with torch.no_grad():
+            ref = ref_model(sample, t, encoder_hidden_states=text).sample
+        who = "unmodified reference (baseline/_ref)"
+    else:
+        ref = O.unet_forward(synthetic_sd, sample, t, text)
+        who = "CPU oracle"
+    out = unet(sample.cuda(), t, encoder_hidden_states=text.cuda()).sample.cpu()
+    err = rel_l2(out, ref)
+    print(f"[2,4,16,40,64]: rel-L2 vs {who} = {err:.3e}")
+    assert out.shape == ref.shape and err <= BF16_TOL
 
 
 def test_full_size_properties(unet):
