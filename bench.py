@@ -416,16 +416,151 @@ def run_b200(args):
         os._exit(0)        # captured NCCL graphs make process-group teardown hang; nothing left to clean up
 
 
+# ----------------------------------------------------------------------------------------------- config 4 (N1)
+INTERP_WORKLOAD = "interpolation UNet 320x512, 16 -> 61 frames (latent 8x61x40x64), CFG batch 2 (scale 4.0), respaced DDIM"
+INTERP_FRAMES = 61
+
+
+def run_interp(args):
+    """BASELINE config 4 on ONE B200 (python bench.py --workload interp): a step = forward_with_cfg of the interpolation
+    UNet on cat([x_t, key-frame latents], 1) = [2,8,61,40,64] + the DDIM update (interpolation/sample.py:138-166).  Parity
+    is checked on a bounded sample (the first 5 frames at full spatial size) against the unmodified reference model: its
+    full-size CPU forward needs a 51 GB score tensor."""
+    from lavie_b200 import UNet3DConditionModel, ops
+    from lavie_b200.config import INTERP_CONFIG
+    from lavie_b200.pipeline import InterpolationSampler
+    from lavie_b200.synthetic import synthetic_state_dict
+    from oracle import reference_loader as R
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    sd = synthetic_state_dict(INTERP_CONFIG, seed=0)
+    unet = UNet3DConditionModel(INTERP_CONFIG)
+    unet.load_state_dict(sd, strict=True)
+    unet = unet.to(dev).eval()
+    g = torch.Generator().manual_seed(4)
+    z = torch.randn(1, 4, INTERP_FRAMES, LAT_H, LAT_W, generator=g)
+    cond = torch.randn(1, 4, INTERP_FRAMES, LAT_H, LAT_W, generator=g)
+    text = torch.randn(2, 77, 768, generator=g)
+    z2, c2 = torch.cat([z, z]), torch.cat([cond, cond])
+    sampler = InterpolationSampler(unet, 4.0, 50)
+    ts = sampler.timesteps[::-1]
+
+    def one_step(x, cnd, txt, i):
+        gd = unet.forward_with_cfg(torch.cat([x, cnd], dim=1), ts[i % 50], encoder_hidden_states=txt, cfg_scale=4.0)
+        a, b = sampler.coefficients(49 - (i % 50))
+        return ops.cfg_linear_step(gd, gd, 0.0, a, b, x)
+
+    x, cnd, txt = z2.to(dev), c2.to(dev), text.to(dev)
+    for i in range(max(args.warmup, 3)):
+        x = one_step(x, cnd, txt, i)
+    torch.cuda.synchronize()
+    per_step = unet.launches_per_step() + 2
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(args.steps):
+            x = one_step(x, cnd, txt, i)
+        ev1.record()
+        torch.cuda.synchronize()
+    ms_per_step = ev0.elapsed_time(ev1) / args.steps
+    # e2e: host buffers in, new latents out, every step
+    xh = [z2.clone().pin_memory(), torch.empty_like(z2).pin_memory()]
+    ch, th = c2.clone().pin_memory(), text.clone().pin_memory()
+    done = torch.cuda.Event()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        new = one_step(xh[i & 1].to(dev, non_blocking=True), ch.to(dev, non_blocking=True),
+                       th.to(dev, non_blocking=True), i)
+        xh[(i + 1) & 1].copy_(new, non_blocking=True)
+        done.record()
+        done.synchronize()
+    e2e_s = time.perf_counter() - t0
+    # per-kernel profile of one eager forward
+    unet.use_cuda_graph = False
+    m_in = torch.cat([torch.cat([z2, c2], dim=1)[:1]] * 2).to(dev)
+    unet(m_in, 500, encoder_hidden_states=txt)
+    ops.PROFILE = []
+    torch.cuda._sleep(300_000_000)
+    unet(m_in, 500, encoder_hidden_states=txt)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    unet.use_cuda_graph = True
+    agg = {}
+    for name, flops, nbytes, e0, e1, _tag in prof:
+        a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
+        a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += flops; a[3] += nbytes
+    total_ms = sum(a[1] for a in agg.values())
+    kernels = {k: {"launches": a[0], "ms": round(a[1], 3), "share": round(a[1] / total_ms, 4),
+                   "gflop": round(a[2] / 1e9, 1), "tflops": round(a[2] / (a[1] * 1e-3) / 1e12, 1) if a[2] else None,
+                   "gbs": round(a[3] / (a[1] * 1e-3) / 1e9, 1) if a[3] else None}
+               for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+    step_gflop = sum(a[2] for a in agg.values()) / 1e9
+    peaks = measured_peaks()
+    d = agg["gemm_bf16_tcgen05"]
+    achieved = d[2] / (d[1] * 1e-3) / 1e12
+    roofline = {"kernel": "gemm_bf16_tcgen05", "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                "launches_per_step": d[0], "share_of_step": d[1] / total_ms, "peak_source": peaks["source"]}
+    # parity + CPU baseline on a bounded sample: 5 frames, full spatial size
+    parity, cpu = None, None
+    if not args.no_cpu_baseline:
+        f = 5
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        m5 = torch.cat([torch.cat([z2, c2], dim=1)[:1, :, :f]] * 2).contiguous()
+        if R.available("interpolation"):
+            ref = R.load_reference_unet("interp", sd)
+            kind = "reference"
+            fwd = lambda: ref(m5, 500, encoder_hidden_states=text).sample
+        else:
+            from oracle import interp_oracle as IO
+            kind = "port"
+            fwd = lambda: IO.unet_forward(sd, m5, 500, text)
+        with torch.no_grad():
+            t0 = time.time()
+            ref_out = fwd()
+            dt = time.time() - t0
+        out5 = unet(m5.to(dev), 500, encoder_hidden_states=txt).sample.cpu()
+        err = rel_l2(out5, ref_out)
+        parity = {"rel_l2": err, "tolerance": 2e-2, "shape": [2, 8, f, LAT_H, LAT_W],
+                  "vs": f"{'unmodified reference interpolation UNet (baseline/_ref)' if kind == 'reference' else 'CPU oracle port'}, fp32"}
+        frac = f / INTERP_FRAMES
+        cpu = {"value": frac / dt, "unit": "steps/s", "cores": threads, "kind": kind,
+               "sample": f"1 forward on {f} of {INTERP_FRAMES} frames ({frac:.3f} of a step; the full-size CPU forward "
+                         f"needs a 51 GB score tensor) = {dt:.2f} s"}
+        if not err <= 2e-2:
+            raise SystemExit(f"interp parity FAILED: {err:.3e}")
+    line = {"metric": "denoise steps/s (interpolation 320x512, 61 frames, CFG)", "value": 1e3 / ms_per_step,
+            "unit": "steps/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": INTERP_WORKLOAD, "weights": "random-init (seeded), 909.1 M params"},
+            "setup": {"parallelism": "single", "cuda_graph": True, "launches_per_step": per_step},
+            "parity": parity, "step_gflop": step_gflop, "step_tflops": step_gflop / ms_per_step,
+            "clocks": clocks.summary(),
+            "e2e": {"value": args.steps / e2e_s, "unit": "steps/s",
+                    "h2d_bytes_per_step": (xh[0].numel() + ch.numel() + th.numel()) * 4,
+                    "d2h_bytes_per_step": xh[0].numel() * 4},
+            "gpu_launches": per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="base", choices=["base", "interp"],
+                    help="base = BASELINE config 1-3 (the headline); interp = config 4 on one GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "interp":
+        run_interp(args)
     else:
         run_b200(args)
 

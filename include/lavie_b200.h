@@ -169,6 +169,20 @@ int lavie_attention_bf16(const void* q, int ldq, const void* k, int ldk, const v
                          int batch, int heads, int Sq, int Sk, int d, int head_pitch, int kv_batch_div, float scale,
                          lavie_stream_t stream);
 
+/* The same kernel with explicit strides (in ELEMENTS) and the interpolation model's attention variants:
+ *  - row of (batch b, token s) = base + b * batch_stride + s * seq_stride, so a sequence need not be contiguous rows:
+ *    the frames of one pixel (seq_stride = H*W*ld, batch_stride = ld) give the PLAIN temporal attention of the
+ *    interpolation UNet (interpolation/models/attention.py:536-545,598-606: CrossAttention over frames, no RoPE, no
+ *    bias) without the two (b f) d c <-> (b d) f c transposes, for any number of frames (61 in LaVie);
+ *  - sparse_causal_frames = F > 0: SparseCausalAttention (interpolation/models/attention.py:611-664): batch = (video,
+ *    frame) and the keys / values of frame f are [the Sk keys of frame 0 | the Sk keys of frame max(f-1, 0)] of the
+ *    same video (2*Sk keys per query, never materialised: the kernel walks two key segments). */
+int lavie_attention_strided_bf16(const void* q, long long q_seq_stride, long long q_batch_stride, const void* k,
+                                 const void* v, long long kv_seq_stride, long long kv_batch_stride, void* o,
+                                 long long o_seq_stride, long long o_batch_stride, int batch, int heads, int Sq, int Sk,
+                                 int d, int head_pitch, int kv_batch_div, int sparse_causal_frames, float scale,
+                                 lavie_stream_t stream);
+
 /* TemporalAttention._attention (attention.py:634-667): per (b, pixel, head) attention over the F frames, with
  * q scaled before RoPE, rotary embedding on the first 2*rot_pairs dims, + rel-pos bias[heads,F,F].
  * qkv rows = (b, f, pixel); q at column 0, k at k_off, v at v_off (+ h*head_pitch).  rope = [F, rot_pairs, 2]
@@ -187,6 +201,11 @@ int lavie_timestep_embedding(const float* t, int B, int dim, float* out, lavie_s
 /* conv_in (unet.py:454): x fp32 [B, Cin, F, H, W] -> bf16 channels-last [B*F*H*W, Cout]; w fp32 [Cout, Cin, 3, 3]. */
 int lavie_conv_in(const float* x, int B, int Cin, int F, int H, int W, const float* w, const float* bias, int Cout,
                   void* out, int ldo, lavie_stream_t stream);
+/* The same with the scheduler's scale_model_input folded in (EulerDiscreteScheduler: x / sqrt(sigma^2 + 1),
+ * pipeline_videogen.py:667): conv_in(s * x) = (s * W) * x + bias, so no separate elementwise pass over the latents.
+ * input_scale is a DEVICE scalar (NULL = 1): a captured CUDA graph of the step serves every sigma of the schedule. */
+int lavie_conv_in_scaled(const float* x, const float* input_scale, int B, int Cin, int F, int H, int W, const float* w,
+                         const float* bias, int Cout, void* out, int ldo, lavie_stream_t stream);
 /* conv_norm_out + SiLU + conv_out (unet.py:504-506): x bf16 [B*F*H*W, C] (raw), scale_shift from
  * lavie_groupnorm_finalize, w fp32 [Cout, 3, 3, C]; writes fp32 [B, Cout, F, H, W]. */
 int lavie_conv_out(const void* x, int ldx, const float* scale_shift, int B, int F, int H, int W, int C,
@@ -200,6 +219,17 @@ int lavie_upsample_nearest2x(const void* x, int NF, int H, int W, int C, void* y
 int lavie_cfg_ddim_step(const float* noise_uncond, const float* noise_text, float guidance, float alpha_t,
                         float alpha_prev, const float* latents, float* latents_out, long long n,
                         lavie_stream_t stream);
+
+/* Guidance + scheduler.step for every epsilon-prediction scheduler the reference wires up (predict.py:74-96: DDIM,
+ * DDPM, EulerDiscrete): eps = u + g (t - u); latents_out = a * latents + b * eps + c_noise * noise (noise may be NULL).
+ * The host computes (a, b, c_noise) per step (lavie_b200/pipeline.py; DDIM mirror vsr/diffusion/scheduling_ddim.py:345-394). */
+int lavie_cfg_linear_step(const float* noise_uncond, const float* noise_text, float guidance, float a, float b,
+                          float c_noise, const float* latents, const float* noise, float* latents_out, long long n,
+                          lavie_stream_t stream);
+/* forward_with_cfg (base/models/unet.py:514-538, interpolation/models/unet.py:453-474): out0 = out1 = uncond +
+ * scale * (cond - uncond); out1 may be NULL. */
+int lavie_cfg_combine(const float* cond, const float* uncond, float scale, float* out0, float* out1, long long n,
+                      lavie_stream_t stream);
 
 #ifdef __cplusplus
 }

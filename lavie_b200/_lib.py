@@ -64,14 +64,20 @@ SIGNATURES = {
     "lavie_groupnorm_finalize_sums": (c_int, [_P, c_int, c_int, c_int, c_longlong, _P, _P, c_float, _P, _P]),
     "lavie_attention_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_float, _P]),
+    "lavie_attention_strided_bf16": (c_int, [_P, c_longlong, c_longlong, _P, _P, c_longlong, c_longlong, _P, c_longlong,
+                                             c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                             c_float, _P]),
     "lavie_temporal_attention_bf16": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                               c_int, c_float, _P, c_int, _P, _P]),
     "lavie_linear_smallm": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, _P]),
     "lavie_timestep_embedding": (c_int, [_P, c_int, c_int, _P, _P]),
     "lavie_conv_in": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
+    "lavie_conv_in_scaled": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
     "lavie_conv_out": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P]),
     "lavie_upsample_nearest2x": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_cfg_ddim_step": (c_int, [_P, _P, c_float, c_float, c_float, _P, _P, c_longlong, _P]),
+    "lavie_cfg_linear_step": (c_int, [_P, _P, c_float, c_float, c_float, c_float, _P, _P, _P, c_longlong, _P]),
+    "lavie_cfg_combine": (c_int, [_P, _P, c_float, _P, _P, c_longlong, _P]),
 }
 
 _lib = None

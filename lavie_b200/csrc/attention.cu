@@ -24,7 +24,12 @@ constexpr int CHUNK_BYTES = 128 * 128;      // one 64-column (128-byte) slab of 
 constexpr int KV_CHUNK_BYTES = ATT_N * 128;  // the same slab of a K / V tile
 
 struct AttnParams {
-  int Sq, Sk, d, head_pitch, kv_batch_div, ldo;
+  int Sq, Sk, d, head_pitch, kv_batch_div;
+  long long o_seq_stride, o_batch_stride;   // elements: output row of (batch, query) = batch*o_batch_stride + query*o_seq_stride
+  // SparseCausalAttention (interpolation/models/attention.py:611-664): batch = (video, frame); the keys of frame f are
+  // [all Sk keys of frame 0 | all Sk keys of frame max(f - 1, 0)] of the same video.  0 = ordinary attention.
+  int sc_frames;
+  int swap_dims;       // tensor maps are (col, batch, seq) instead of (col, seq, batch): batch stride < sequence stride
   float scale_log2;
   __nv_bfloat16* o;
   long long* timeline;   // debug (tools/attn_timeline.py): clock64 stamps of one mid-grid CTA, else nullptr
@@ -67,7 +72,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int lane = tid & 31;
   const int q_tile = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
   const int kv_batch = batch / p.kv_batch_div;
-  const int n_kv = (p.Sk + ATT_N - 1) / ATT_N;
+  // key tiles: one segment of ceil(Sk / 64) tiles, or two of them for SparseCausal attention (first frame | former frame);
+  // a segment's last tile may be partial (rows past Sk are zero-filled by the TMA and masked in the softmax)
+  const int seg_tiles = (p.Sk + ATT_N - 1) / ATT_N;
+  const int n_kv = p.sc_frames > 0 ? 2 * seg_tiles : seg_tiles;
+  const int sc_f = p.sc_frames > 0 ? batch % p.sc_frames : 0;
+  const int kv_batch_seg0 = p.sc_frames > 0 ? batch - sc_f : kv_batch;
+  const int kv_batch_seg1 = p.sc_frames > 0 ? (sc_f > 0 ? batch - 1 : batch) : kv_batch;
   const int col0 = head * p.head_pitch;
 
   if (tid == 0) {
@@ -116,17 +127,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         umma_bf16(tmem_s, desc_q + (qoff >> 4), desc_k + (koff >> 4), idesc_qk, kk != 0);
       }
     };
+    auto load_rows = [&](uint8_t* dst, const CUtensorMap* m, uint64_t* bar, int col, int row, int b) {
+      if (p.swap_dims) tma_load_3d(dst, m, bar, col, b, row);
+      else tma_load_3d(dst, m, bar, col, row, b);
+    };
     auto load_k = [&](int j) {
+      const int seg = j >= seg_tiles, jr = j - seg * seg_tiles;
       mbar_expect_tx(bar_k, NC * KV_CHUNK_BYTES);
-      for (int c = 0; c < NC; ++c) tma_load_3d(sK + c * KV_CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, j * ATT_N, kv_batch);
+      for (int c = 0; c < NC; ++c)
+        load_rows(sK + c * KV_CHUNK_BYTES, &tmap_k, bar_k, col0 + c * 64, jr * ATT_N, seg ? kv_batch_seg1 : kv_batch_seg0);
     };
     auto load_v = [&](int j) {
+      const int seg = j >= seg_tiles, jr = j - seg * seg_tiles;
       mbar_expect_tx(bar_v, NC * KV_CHUNK_BYTES);
-      for (int c = 0; c < NC; ++c) tma_load_3d(sV + c * KV_CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, j * ATT_N, kv_batch);
+      for (int c = 0; c < NC; ++c)
+        load_rows(sV + c * KV_CHUNK_BYTES, &tmap_v, bar_v, col0 + c * 64, jr * ATT_N, seg ? kv_batch_seg1 : kv_batch_seg0);
     };
     if (elect_one()) {
       mbar_expect_tx(bar_q, NC * CHUNK_BYTES);
-      for (int c = 0; c < NC; ++c) tma_load_3d(sQ + c * CHUNK_BYTES, &tmap_q, bar_q, col0 + c * 64, q_tile * ATT_M, batch);
+      for (int c = 0; c < NC; ++c) load_rows(sQ + c * CHUNK_BYTES, &tmap_q, bar_q, col0 + c * 64, q_tile * ATT_M, batch);
       load_k(0);
       load_v(0);
     }
@@ -146,7 +165,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t ph = j & 1;
-      const int kv_len = min(ATT_N, p.Sk - j * ATT_N);
+      const int kv_len = min(ATT_N, p.Sk - (j >= seg_tiles ? j - seg_tiles : j) * ATT_N);
       long long* tl_row = p.timeline + j * 8;
       mbar_wait(bar_v, ph);                      // V(j) landed
       if (ONES) {                                // V(j)[key][column d] = 1.0 (bf16), 128-byte-swizzled address
@@ -207,7 +226,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t ph = j & 1;
-      const int kv_len = min(ATT_N, p.Sk - j * ATT_N);
+      const int kv_len = min(ATT_N, p.Sk - (j >= seg_tiles ? j - seg_tiles : j) * ATT_N);
       long long* tl_row = p.timeline + j * 8;
       if (tl && warp == 0) tl_row[0] = clock64();
       mbar_wait(bar_s_full, ph);
@@ -320,7 +339,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     const float inv = 1.f / denom;
     const int qrow = q_tile * ATT_M + tid;
-    __nv_bfloat16* dst = p.o + (static_cast<size_t>(batch) * p.Sq + qrow) * p.ldo + head * p.d;
+    __nv_bfloat16* dst = p.o + static_cast<size_t>(batch) * p.o_batch_stride + static_cast<size_t>(qrow) * p.o_seq_stride +
+                         head * p.d;
 #pragma unroll
     for (int c = 0; c < DK / 16; ++c) {
       uint32_t v[16];
@@ -374,9 +394,16 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
   return launch_attn_inst<DK, 0, false>(mq, mk, mv, p, batch, heads, stream);
 }
 
-int make_qkv_map(CUtensorMap* map, const void* base, int ld, int cols, int S, int nbatch, int box_rows) {
+int make_qkv_map(CUtensorMap* map, const void* base, long long seq_stride, long long batch_stride, int cols, int S,
+                 int nbatch, int box_rows, bool swap) {
+  if (swap) {      // strides must ascend with the dimension index: (col, batch, seq); the box is still box_rows tokens
+    const uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(nbatch), static_cast<uint64_t>(S)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(batch_stride) * 2, static_cast<uint64_t>(seq_stride) * 2};
+    const uint32_t box[3] = {64, 1, static_cast<uint32_t>(box_rows)};
+    return lavie_make_tmap(map, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
   const uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(S), static_cast<uint64_t>(nbatch)};
-  const uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(S) * ld * 2};
+  const uint64_t strides[2] = {static_cast<uint64_t>(seq_stride) * 2, static_cast<uint64_t>(batch_stride) * 2};
   const uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
   return lavie_make_tmap(map, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
@@ -777,31 +804,45 @@ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
 
-extern "C" int lavie_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o,
-                                    int ldo, int batch, int heads, int Sq, int Sk, int d, int head_pitch,
-                                    int kv_batch_div, float scale, cudaStream_t stream) {
+extern "C" int lavie_attention_strided_bf16(const void* q, long long q_seq_stride, long long q_batch_stride,
+                                            const void* k, const void* v, long long kv_seq_stride,
+                                            long long kv_batch_stride, void* o, long long o_seq_stride,
+                                            long long o_batch_stride, int batch, int heads, int Sq, int Sk, int d,
+                                            int head_pitch, int kv_batch_div, int sparse_causal_frames, float scale,
+                                            cudaStream_t stream) {
   LAVIE_REQUIRE(batch > 0 && heads > 0 && Sq > 0 && Sk > 0 && kv_batch_div > 0 && batch % kv_batch_div == 0,
                 LAVIE_ERR_SHAPE, "attention: bad sizes batch=%d heads=%d Sq=%d Sk=%d div=%d", batch, heads, Sq, Sk,
                 kv_batch_div);
+  LAVIE_REQUIRE(sparse_causal_frames >= 0 && (sparse_causal_frames == 0 ||
+                                              (kv_batch_div == 1 && batch % sparse_causal_frames == 0)),
+                LAVIE_ERR_SHAPE, "attention: sparse-causal mode needs batch %% frames == 0 and kv_batch_div == 1");
   const int dk = (d + 15) & ~15;
   LAVIE_REQUIRE(d % 8 == 0 && head_pitch >= dk && head_pitch % 8 == 0, LAVIE_ERR_SHAPE,
                 "attention: d=%d head_pitch=%d (pitch must be >= d rounded up to 16)", d, head_pitch);
-  LAVIE_REQUIRE(al16(q) && al16(k) && al16(v) && al16(o) && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 &&
-                    ldo % 8 == 0,
+  LAVIE_REQUIRE(al16(q) && al16(k) && al16(v) && al16(o) && q_seq_stride % 8 == 0 && q_batch_stride % 8 == 0 &&
+                    kv_seq_stride % 8 == 0 && kv_batch_stride % 8 == 0 && o_seq_stride % 8 == 0 &&
+                    o_batch_stride % 8 == 0,
                 LAVIE_ERR_ALIGN, "attention: 16-byte alignment required");
-  LAVIE_REQUIRE(heads <= 65535 && batch <= 65535, LAVIE_ERR_SHAPE, "attention: grid too large");
+  LAVIE_REQUIRE(heads <= 65535 && batch <= 65535, LAVIE_ERR_SHAPE, "attention: grid too large (batch=%d heads=%d)",
+                batch, heads);
   AttnParams p;
-  p.Sq = Sq; p.Sk = Sk; p.d = d; p.head_pitch = head_pitch; p.kv_batch_div = kv_batch_div; p.ldo = ldo;
+  p.Sq = Sq; p.Sk = Sk; p.d = d; p.head_pitch = head_pitch; p.kv_batch_div = kv_batch_div;
+  p.o_seq_stride = o_seq_stride; p.o_batch_stride = o_batch_stride;
+  p.sc_frames = sparse_causal_frames;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.o = static_cast<__nv_bfloat16*>(o);
   p.timeline = static_cast<long long*>(g_lavie_debug_buf);
   CUtensorMap mq, mk, mv;
   const int cols = heads * head_pitch;
-  int rc = make_qkv_map(&mq, q, ldq, cols, Sq, batch, ATT_M);
+  const bool swap = q_batch_stride < q_seq_stride;
+  LAVIE_REQUIRE(swap == (kv_batch_stride < kv_seq_stride), LAVIE_ERR_SHAPE,
+                "attention: q and k/v must use the same dimension order (batch stride vs sequence stride)");
+  p.swap_dims = swap ? 1 : 0;
+  int rc = make_qkv_map(&mq, q, q_seq_stride, q_batch_stride, cols, Sq, batch, ATT_M, swap);
   if (rc) return rc;
-  rc = make_qkv_map(&mk, k, ldk, cols, Sk, batch / kv_batch_div, ATT_N);
+  rc = make_qkv_map(&mk, k, kv_seq_stride, kv_batch_stride, cols, Sk, batch / kv_batch_div, ATT_N, swap);
   if (rc) return rc;
-  rc = make_qkv_map(&mv, v, ldv, cols, Sk, batch / kv_batch_div, ATT_N);
+  rc = make_qkv_map(&mv, v, kv_seq_stride, kv_batch_stride, cols, Sk, batch / kv_batch_div, ATT_N, swap);
   if (rc) return rc;
   switch (dk) {
     case 48: return launch_attn<48>(mq, mk, mv, p, batch, heads, stream);
@@ -814,6 +855,15 @@ extern "C" int lavie_attention_bf16(const void* q, int ldq, const void* k, int l
       lavie_set_error("attention: head dim %d (padded %d) not instantiated (48/64/80/96/128/160)", d, dk);
       return LAVIE_ERR_SHAPE;
   }
+}
+
+extern "C" int lavie_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o,
+                                    int ldo, int batch, int heads, int Sq, int Sk, int d, int head_pitch,
+                                    int kv_batch_div, float scale, cudaStream_t stream) {
+  LAVIE_REQUIRE(ldk == ldv, LAVIE_ERR_SHAPE, "attention: k and v must share their row stride (ldk=%d ldv=%d)", ldk, ldv);
+  return lavie_attention_strided_bf16(q, ldq, static_cast<long long>(Sq) * ldq, k, v, ldk,
+                                      static_cast<long long>(Sk) * ldk, o, ldo, static_cast<long long>(Sq) * ldo, batch,
+                                      heads, Sq, Sk, d, head_pitch, kv_batch_div, 0, scale, stream);
 }
 
 extern "C" int lavie_temporal_attention_bf16(const void* qkv, int ld, int k_off, int v_off, void* o, int ldo, int B,

@@ -79,13 +79,15 @@ linear_smallm_kernel(const float* __restrict__ x, int M, int K, const __nv_bfloa
 constexpr int CIN_P = 4;
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x, int B, int Cin, int F, int H, int W, const float* __restrict__ w,
-               const float* __restrict__ bias, int Cout, __nv_bfloat16* __restrict__ out, int ldo) {
+               const float* __restrict__ bias, int Cout, __nv_bfloat16* __restrict__ out, int ldo,
+               const float* __restrict__ input_scale_ptr) {
   pdl_prologue();
+  const float input_scale = input_scale_ptr ? __ldg(input_scale_ptr) : 1.0f;
   extern __shared__ float s_w[];     // transposed to [Cin*9][Cout]: a warp reads 1 KiB contiguous per tap
   const int kk = Cin * 9;
   for (int i = threadIdx.x; i < Cout * kk; i += blockDim.x) {
     const int o = i / kk, r = i - o * kk;
-    s_w[r * Cout + o] = w[i];
+    s_w[r * Cout + o] = w[i] * input_scale;      // conv(s * x) = (s * W) * x: the scheduler's scale_model_input, folded
   }
   __syncthreads();
   const int groups = Cout >> 3;
@@ -287,6 +289,34 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ nu, const float* __res
   }
 }
 
+// eps = u + g (c - u); out = a * latents + b * eps (+ c_noise * noise): every epsilon-prediction scheduler update of
+// the reference pipelines is this linear form (DDIM eta 0, DDPM ancestral, EulerDiscrete), coefficients from the host.
+__global__ void cfg_linear_step_kernel(const float* __restrict__ nu, const float* __restrict__ nt, float g, float a,
+                                       float b, float c_noise, const float* __restrict__ lat,
+                                       const float* __restrict__ noise, float* __restrict__ out, long long n) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float eps = nu[i] + g * (nt[i] - nu[i]);
+    float v = fmaf(a, lat[i], b * eps);
+    if (noise) v = fmaf(c_noise, noise[i], v);
+    out[i] = v;
+  }
+}
+
+// forward_with_cfg (base/models/unet.py:514-538): half_eps = uncond + s (cond - uncond), returned for both halves
+__global__ void cfg_combine_kernel(const float* __restrict__ cond, const float* __restrict__ uncond, float s,
+                                   float* __restrict__ out0, float* __restrict__ out1, long long n) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float u = uncond[i];
+    const float v = u + s * (cond[i] - u);
+    out0[i] = v;
+    if (out1) out1[i] = v;
+  }
+}
+
 int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   if (b > 148LL * 32) b = 148LL * 32;
@@ -314,8 +344,9 @@ extern "C" int lavie_linear_smallm(const float* x, int M, int K, const void* w, 
   return lavie_check_launch("linear_smallm_kernel");
 }
 
-extern "C" int lavie_conv_in(const float* x, int B, int Cin, int F, int H, int W, const float* w, const float* bias,
-                             int Cout, void* out, int ldo, cudaStream_t stream) {
+namespace {
+int conv_in_impl(const float* x, int B, int Cin, int F, int H, int W, const float* w, const float* bias, int Cout,
+                 void* out, int ldo, const float* input_scale, cudaStream_t stream) {
   LAVIE_REQUIRE(Cout % 8 == 0 && ldo % 8 == 0 && al16(out), LAVIE_ERR_SHAPE, "conv_in: Cout/ldo must be multiples of 8");
   const int smem = Cout * Cin * 9 * static_cast<int>(sizeof(float));
   LAVIE_REQUIRE(smem <= 200 * 1024, LAVIE_ERR_SHAPE, "conv_in: weights do not fit shared memory");
@@ -327,8 +358,20 @@ extern "C" int lavie_conv_in(const float* x, int B, int Cin, int F, int H, int W
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   launch_pdl(conv_in_kernel, static_cast<int>(blocks), 256, smem, stream, x, B, Cin, F, H, W, w, bias, Cout,
-                                                                  static_cast<__nv_bfloat16*>(out), ldo);
+             static_cast<__nv_bfloat16*>(out), ldo, input_scale);
   return lavie_check_launch("conv_in_kernel");
+}
+}  // namespace
+
+extern "C" int lavie_conv_in(const float* x, int B, int Cin, int F, int H, int W, const float* w, const float* bias,
+                             int Cout, void* out, int ldo, cudaStream_t stream) {
+  return conv_in_impl(x, B, Cin, F, H, W, w, bias, Cout, out, ldo, nullptr, stream);
+}
+
+extern "C" int lavie_conv_in_scaled(const float* x, const float* input_scale, int B, int Cin, int F, int H, int W,
+                                    const float* w, const float* bias, int Cout, void* out, int ldo,
+                                    cudaStream_t stream) {
+  return conv_in_impl(x, B, Cin, F, H, W, w, bias, Cout, out, ldo, input_scale, stream);
 }
 
 extern "C" int lavie_conv_out(const void* x, int ldx, const float* scale_shift, int B, int F, int H, int W, int C,
@@ -377,4 +420,22 @@ extern "C" int lavie_cfg_ddim_step(const float* noise_uncond, const float* noise
                                                         sqrtf(1.f - alpha_t), sqrtf(alpha_prev),
                                                         sqrtf(1.f - alpha_prev), latents, latents_out, n);
   return lavie_check_launch("cfg_ddim_kernel");
+}
+
+
+extern "C" int lavie_cfg_linear_step(const float* noise_uncond, const float* noise_text, float guidance, float a,
+                                     float b, float c_noise, const float* latents, const float* noise,
+                                     float* latents_out, long long n, cudaStream_t stream) {
+  LAVIE_REQUIRE(n > 0 && noise_uncond && noise_text && latents && latents_out, LAVIE_ERR_SHAPE,
+                "cfg_linear_step: bad arguments");
+  launch_pdl(cfg_linear_step_kernel, grid_for(n, 256), 256, 0, stream, noise_uncond, noise_text, guidance, a, b, c_noise,
+             latents, noise, latents_out, n);
+  return lavie_check_launch("cfg_linear_step_kernel");
+}
+
+extern "C" int lavie_cfg_combine(const float* cond, const float* uncond, float scale, float* out0, float* out1,
+                                 long long n, cudaStream_t stream) {
+  LAVIE_REQUIRE(n > 0 && cond && uncond && out0, LAVIE_ERR_SHAPE, "cfg_combine: bad arguments");
+  launch_pdl(cfg_combine_kernel, grid_for(n, 256), 256, 0, stream, cond, uncond, scale, out0, out1, n);
+  return lavie_check_launch("cfg_combine_kernel");
 }

@@ -311,23 +311,51 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, heads: int, Sq: int, Sk: int, d: int,
               head_pitch: int, kv_batch_div: int = 1, scale: Optional[float] = None,
-              out: Optional[torch.Tensor] = None):
-    """q: [batch*Sq, >=heads*pitch] view, k/v: [(batch/kv_batch_div)*Sk, ...] views; returns [batch*Sq, heads*d]."""
+              out: Optional[torch.Tensor] = None, sparse_causal_frames: int = 0):
+    """q: [batch*Sq, >=heads*pitch] view, k/v: [(batch/kv_batch_div)*Sk, ...] views; returns [batch*Sq, heads*d].
+    sparse_causal_frames = F: batch = (video, frame), keys of frame f = [frame 0 | frame max(f-1, 0)] (2*Sk keys)."""
     lib = _lib.load()
     rq, _, ldq = _rows2d(q)
     rk, _, ldk = _rows2d(k)
     rv, _, ldv = _rows2d(v)
-    assert rq == batch * Sq and rk == (batch // kv_batch_div) * Sk and rv == rk
+    assert rq == batch * Sq and rk == (batch // kv_batch_div) * Sk and rv == rk and ldk == ldv
     if out is None:
         out = torch.empty((rq, heads * d), dtype=BF16, device=q.device)
     _, _, ldo = _rows2d(out)
     if scale is None:
         scale = d ** -0.5
-    with _Launch("lavie_attention_bf16", 4.0 * batch * heads * Sq * Sk * d, 2.0 * (rq + 2 * rk) * heads * head_pitch + 2.0 * rq * heads * d,
-                 f"attn B={batch} Sq={Sq} Sk={Sk} d={d}"):
-        check(lib.lavie_attention_bf16(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), ldo, batch,
-                                       heads, Sq, Sk, d, head_pitch, kv_batch_div, scale, _stream()),
-              "lavie_attention_bf16")
+    keys = Sk * (2 if sparse_causal_frames else 1)
+    with _Launch("lavie_attention_bf16", 4.0 * batch * heads * Sq * keys * d,
+                 2.0 * (rq + 2 * rk) * heads * head_pitch + 2.0 * rq * heads * d,
+                 f"attn B={batch} Sq={Sq} Sk={keys} d={d}"):
+        check(lib.lavie_attention_strided_bf16(q.data_ptr(), ldq, Sq * ldq, k.data_ptr(), v.data_ptr(), ldk, Sk * ldk,
+                                               out.data_ptr(), ldo, Sq * ldo, batch, heads, Sq, Sk, d, head_pitch,
+                                               kv_batch_div, sparse_causal_frames, scale, _stream()),
+              "lavie_attention_strided_bf16")
+    return out
+
+
+def frame_attention(qkv: torch.Tensor, B: int, F: int, HW: int, heads: int, d: int, head_pitch: int,
+                    out: Optional[torch.Tensor] = None):
+    """Plain attention over the F frames of every pixel (the interpolation UNet's attn_temp,
+    interpolation/models/attention.py:598-606), read in place: qkv rows = (b, f, pixel), columns q | k | v; sequence
+    stride = HW rows, batch (pixel) stride = one row.  Any F (one launch per video: the pixels are the batch)."""
+    lib = _lib.load()
+    rows, cols, ld = _rows2d(qkv)
+    hp = heads * head_pitch
+    assert rows == B * F * HW and cols == 3 * hp
+    if out is None:
+        out = torch.empty((rows, heads * d), dtype=BF16, device=qkv.device)
+    _, _, ldo = _rows2d(out)
+    for b in range(B):
+        base = qkv[b * F * HW:]
+        o_b = out[b * F * HW:]
+        with _Launch("lavie_attention_bf16", 4.0 * HW * heads * F * F * d, 2.0 * F * HW * (cols + heads * d),
+                     f"frame_attn F={F} HW={HW} d={d}"):
+            check(lib.lavie_attention_strided_bf16(base.data_ptr(), HW * ld, ld, base[:, hp:].data_ptr(),
+                                                   base[:, 2 * hp:].data_ptr(), HW * ld, ld, o_b.data_ptr(), HW * ldo,
+                                                   ldo, HW, heads, F, F, d, head_pitch, 1, 0, d ** -0.5, _stream()),
+                  "lavie_attention_strided_bf16")
     return out
 
 
@@ -374,8 +402,9 @@ def timestep_embedding(t: torch.Tensor, dim: int):
     return out
 
 
-def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor):
-    """x fp32 [B,Cin,F,H,W] -> bf16 [B*F*H*W, Cout]; w fp32 [Cout,Cin,3,3]."""
+def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, input_scale: Optional[torch.Tensor] = None):
+    """x fp32 [B,Cin,F,H,W] -> bf16 [B*F*H*W, Cout]; w fp32 [Cout,Cin,3,3]; computes conv(input_scale * x) with
+    input_scale a device fp32 scalar tensor (None = 1)."""
     lib = _lib.load()
     assert x.dtype == F32 and x.is_contiguous() and x.dim() == 5
     B, Cin, Fr, H, W = x.shape
@@ -383,8 +412,9 @@ def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor):
     assert w.dtype == F32 and w.is_contiguous() and bias.dtype == F32
     out = torch.empty((B * Fr * H * W, Cout), dtype=BF16, device=x.device)
     with _Launch("lavie_conv_in"):
-        check(lib.lavie_conv_in(x.data_ptr(), B, Cin, Fr, H, W, w.data_ptr(), bias.data_ptr(), Cout, out.data_ptr(), Cout,
-                                _stream()), "lavie_conv_in")
+        assert input_scale is None or (input_scale.dtype == F32 and input_scale.is_cuda and input_scale.numel() == 1)
+        check(lib.lavie_conv_in_scaled(x.data_ptr(), _ptr(input_scale), B, Cin, Fr, H, W, w.data_ptr(), bias.data_ptr(),
+                                       Cout, out.data_ptr(), Cout, _stream()), "lavie_conv_in_scaled")
     return out
 
 
@@ -424,4 +454,33 @@ def cfg_ddim_step(noise_uncond, noise_text, guidance: float, alpha_t: float, alp
         check(lib.lavie_cfg_ddim_step(noise_uncond.data_ptr(), noise_text.data_ptr(), guidance, alpha_t, alpha_prev,
                                       latents.data_ptr(), out.data_ptr(), latents.numel(), _stream()),
               "lavie_cfg_ddim_step")
+    return out
+
+
+def cfg_linear_step(noise_uncond, noise_text, guidance: float, a: float, b: float, latents, noise=None,
+                    c_noise: float = 0.0, out: Optional[torch.Tensor] = None):
+    """eps = u + g (t - u); out = a * latents + b * eps (+ c_noise * noise)."""
+    lib = _lib.load()
+    for t in (noise_uncond, noise_text, latents) + ((noise,) if noise is not None else ()):
+        assert t.dtype == F32 and t.is_contiguous() and t.numel() == latents.numel()
+    if out is None:
+        out = torch.empty_like(latents)
+    with _Launch("lavie_cfg_linear_step"):
+        check(lib.lavie_cfg_linear_step(noise_uncond.data_ptr(), noise_text.data_ptr(), guidance, a, b, c_noise,
+                                        latents.data_ptr(), _ptr(noise), out.data_ptr(), latents.numel(), _stream()),
+              "lavie_cfg_linear_step")
+    return out
+
+
+def cfg_combine(cond, uncond, scale: float, duplicate: bool = True):
+    """uncond + scale * (cond - uncond), returned as cat([g, g]) when `duplicate` (forward_with_cfg's contract)."""
+    lib = _lib.load()
+    assert cond.dtype == F32 and uncond.dtype == F32 and cond.is_contiguous() and uncond.is_contiguous()
+    assert cond.shape == uncond.shape
+    n = cond.numel()
+    out = torch.empty(((2 if duplicate else 1) * cond.shape[0],) + tuple(cond.shape[1:]), dtype=F32, device=cond.device)
+    second = out[cond.shape[0]:] if duplicate else None
+    with _Launch("lavie_cfg_combine"):
+        check(lib.lavie_cfg_combine(cond.data_ptr(), uncond.data_ptr(), float(scale), out.data_ptr(), _ptr(second), n,
+                                    _stream()), "lavie_cfg_combine")
     return out

@@ -98,9 +98,9 @@ class UNet3DConditionModel(nn.Module):
 
     def __init__(self, config: UNetConfig = BASE_CONFIG, use_cuda_graph: bool = True):
         super().__init__()
-        if getattr(config, "variant", "base") != "base":
-            raise NotImplementedError(f"UNet variant {config.variant!r}: only the base T2V denoiser has a B200 path so far "
-                                      "(oracle/interp_oracle.py is groundwork for the interpolation model)")
+        if getattr(config, "variant", "base") not in ("base", "interp"):
+            raise NotImplementedError(f"UNet variant {config.variant!r}: the base T2V denoiser and the frame-interpolation "
+                                      "denoiser have a B200 path")
         self.cfg = config
         self.config = _Config(**config.to_dict())
         self.sample_size = config.sample_size
@@ -118,6 +118,7 @@ class UNet3DConditionModel(nn.Module):
         self._retired_peers: list = []
         self._param_versions = None
         self._param_list = None
+        self._scale_one = None
         self._graphs: Dict[tuple, dict] = {}
         self._tables: Dict[tuple, tuple] = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
@@ -306,8 +307,9 @@ class UNet3DConditionModel(nn.Module):
             wi, bi = interleave_geglu(sd[f"{b}.ff.net.0.proj.weight"], sd[f"{b}.ff.net.0.proj.bias"])
             t["ff1_w"], t["ff1_b"] = b16(wi), bi.to(device=dev, dtype=F32).contiguous()
             t["ff2_w"], t["ff2_b"] = b16(sd[f"{b}.ff.net.2.weight"]), f32(f"{b}.ff.net.2.bias")
-            t["rel_emb"] = f32(f"{b}.attn_temp.time_rel_pos_bias.relative_attention_bias.weight")
-            t["freqs"] = f32(f"{b}.attn_temp.rotary_emb.freqs")
+            if self.cfg.variant == "base":      # the interpolation model's temporal attention has neither
+                t["rel_emb"] = f32(f"{b}.attn_temp.time_rel_pos_bias.relative_attention_bias.weight")
+                t["freqs"] = f32(f"{b}.attn_temp.rotary_emb.freqs")
             P[p] = t
 
         for key in self._resnet_prefixes():
@@ -372,12 +374,15 @@ class UNet3DConditionModel(nn.Module):
         t = self._packed[p]
         heads, d, pitch, hp = self.cfg.heads, t["d"], t["pitch"], t["hp"]
         NF, HW = B * Fr, H * W
+        interp = self.cfg.variant == "interp"
         h = ops.groupnorm(x, NF, HW, t["gn_g"], t["gn_b"], 1e-6, silu=False)          # per-frame GN (4-D input)
         tok = ops.gemm(h, t["w_in"], bias=t["b_in"])
-        # spatial self-attention
+        # spatial self-attention; interpolation model: SparseCausalAttention, the keys of frame f are those of frame 0
+        # and of frame f-1 (interpolation/models/attention.py:611-664) -- two key segments, never concatenated
         n = ops.layernorm(tok, t["norm1_g"], t["norm1_b"])
         qkv = ops.gemm(n, t["attn1_qkv"])
-        a = ops.attention(qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:], NF, heads, HW, HW, d, pitch)
+        a = ops.attention(qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:], NF, heads, HW, HW, d, pitch,
+                          sparse_causal_frames=Fr if interp else 0)
         tok = ops.gemm(a, t["attn1_wo"], bias=t["attn1_bo"], residual=tok)
         # text cross-attention: keys/values projected once per batch item, shared by its frames
         n = ops.layernorm(tok, t["norm2_g"], t["norm2_b"])
@@ -386,6 +391,20 @@ class UNet3DConditionModel(nn.Module):
         a = ops.attention(q, kv_all[:, ko:ko + hp], kv_all[:, ko + hp:ko + 2 * hp], NF, heads, HW, text_len, d, pitch,
                           kv_batch_div=Fr)
         tok = ops.gemm(a, t["attn2_wo"], bias=t["attn2_bo"], residual=tok)
+        if interp:
+            # interpolation block order (interpolation/models/attention.py:566-608): feed-forward BEFORE the temporal
+            # attention, which is a plain attention over the frames of a pixel (no rotary embedding, no bias)
+            if self._shard is not None:
+                raise NotImplementedError("frame sharding of the interpolation model (frame-0 broadcast + 1-frame halo, "
+                                          "SURVEY 8e) is not built yet")
+            n = ops.layernorm(tok, t["norm3_g"], t["norm3_b"])
+            g = ops.gemm(n, t["ff1_w"], bias=t["ff1_b"], geglu=True)
+            tok = ops.gemm(g, t["ff2_w"], bias=t["ff2_b"], residual=tok)
+            n = ops.layernorm(tok, t["norm_temp_g"], t["norm_temp_b"])
+            qkv = ops.gemm(n, t["attn_temp_qkv"])
+            a = ops.frame_attention(qkv, B, Fr, HW, heads, d, pitch)
+            tok = ops.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"], residual=tok)
+            return ops.gemm(tok, t["w_out"], bias=t["b_out"], residual=x)
         # temporal attention: frames read in place with a row stride of HW (no (b f) d c <-> (b d) f c copies)
         if self._shard is None:
             n = ops.layernorm(tok, t["norm_temp_g"], t["norm_temp_b"])
@@ -427,7 +446,8 @@ class UNet3DConditionModel(nn.Module):
         tok = ops.gemm(g, t["ff2_w"], bias=t["ff2_b"], residual=tok)
         return ops.gemm(tok, t["w_out"], bias=t["b_out"], residual=x)
 
-    def _step(self, sample: torch.Tensor, t: torch.Tensor, text: torch.Tensor, taps: Optional[dict] = None):
+    def _step(self, sample: torch.Tensor, t: torch.Tensor, text: torch.Tensor, taps: Optional[dict] = None,
+              input_scale: Optional[torch.Tensor] = None):
         """One denoiser evaluation.  sample fp32 [B,C,F,H,W], t fp32 [B], text bf16 [B*L, ctx] -> fp32 [B,Co,F,H,W]."""
         P = self._packed
         cfg = self.cfg
@@ -451,7 +471,7 @@ class UNet3DConditionModel(nn.Module):
         # all 16 cross-attention K/V projections of the text in one GEMM
         kv_all = ops.gemm(text, P["kv_w"])
 
-        x = ops.conv_in(sample, P["conv_in"][0], P["conv_in"][1])
+        x = ops.conv_in(sample, P["conv_in"][0], P["conv_in"][1], input_scale)
         tap("conv_in", x, boc[0], H, W)
         skips = [(x, boc[0])]
         h, w = H, W
@@ -492,10 +512,14 @@ class UNet3DConditionModel(nn.Module):
     @torch.no_grad()
     def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
                 encoder_hidden_states: torch.Tensor = None, class_labels=None, attention_mask=None,
-                use_image_num: int = 0, return_dict: bool = True, taps: Optional[dict] = None):
-        """Same contract as base/models/unet.py:366-512.  ``attention_mask`` is accepted and ignored exactly like the
-        reference (it never reaches the blocks, unet_blocks.py:352); ``class_labels``/``use_image_num`` must be unset
-        (no class embedding in the base config; joint image-video training is out of scope)."""
+                use_image_num: int = 0, return_dict: bool = True, taps: Optional[dict] = None,
+                input_scale: float = 1.0):
+        """Same contract as base/models/unet.py:366-512 (interpolation/models/unet.py:313-451 for the "interp" variant).
+        ``attention_mask`` is accepted and ignored exactly like the reference (it never reaches the blocks,
+        unet_blocks.py:352); ``class_labels``/``use_image_num`` must be unset (no class embedding in these configs; joint
+        image-video training is out of scope).  Extension: ``input_scale`` multiplies ``sample`` inside conv_in, i.e.
+        ``unet(x, t, e, input_scale=s) == unet(scheduler.scale_model_input(x, t), t, e)`` for EulerDiscrete's
+        s = 1 / sqrt(sigma^2 + 1) without a pass over the latents."""
         if class_labels is not None or use_image_num:
             raise NotImplementedError("class_labels / use_image_num are not part of the base T2V inference path")
         if encoder_hidden_states is None:
@@ -527,10 +551,16 @@ class UNet3DConditionModel(nn.Module):
         txt = encoder_hidden_states.to(device=dev, dtype=BF16, non_blocking=True).reshape(
             -1, self.cfg.cross_attention_dim).contiguous()
 
-        if self.use_cuda_graph and taps is None:
-            out = self._graph_step(x, t, txt)
+        if float(input_scale) == 1.0:
+            if self._scale_one is None or self._scale_one.device != dev:
+                self._scale_one = torch.ones(1, dtype=F32, device=dev)
+            scale = self._scale_one
         else:
-            out = self._step(x, t, txt, taps)
+            scale = torch.full((1,), float(input_scale), dtype=F32, device=dev)
+        if self.use_cuda_graph and taps is None:
+            out = self._graph_step(x, t, txt, scale)
+        else:
+            out = self._step(x, t, txt, taps, scale)
         out = out.to(out_dtype) if out_dtype != F32 else out.clone()   # never hand out the graph's static buffer
         if not return_dict:
             return (out,)
@@ -540,22 +570,38 @@ class UNet3DConditionModel(nn.Module):
         """Kernel launches of this library inside the most recently replayed step graph."""
         return getattr(self, "_last_graph_launches", 0)
 
-    def _graph_step(self, x, t, txt):
+    @torch.no_grad()
+    def forward_with_cfg(self, x: torch.Tensor, t, encoder_hidden_states: torch.Tensor = None, class_labels=None,
+                         cfg_scale: float = 4.0, use_fp16: bool = False) -> torch.Tensor:
+        """base/models/unet.py:514-538 and interpolation/models/unet.py:453-474: the FIRST half of the batch is run twice,
+        against encoder_hidden_states = [cond prompt(s), uncond prompt(s)]; returns uncond + s (cond - uncond) for both
+        halves (a plain Tensor, like the reference).  ``use_fp16`` only chose the reference's input dtype; compute here
+        is bf16/fp32-accumulate either way."""
+        n = len(x) // 2
+        half = x[:n]
+        combined = torch.cat([half, half], dim=0)
+        out = self.forward(combined, t, encoder_hidden_states, class_labels).sample
+        co = self.cfg.out_channels
+        eps = out[:, :co].float().contiguous()
+        g = ops.cfg_combine(eps[:n], eps[n:], cfg_scale).to(out.dtype)
+        return g if out.shape[1] == co else torch.cat([g, out[:, co:]], dim=1)
+
+    def _graph_step(self, x, t, txt, scale):
         key = (tuple(x.shape), tuple(txt.shape))
         g = self._graphs.get(key)
         if g is None:
-            g = {"x": x.clone(), "t": t.clone(), "txt": txt.clone()}
+            g = {"x": x.clone(), "t": t.clone(), "txt": txt.clone(), "scale": scale.clone()}
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):          # warm-up run: sets kernel attributes, fills table caches
-                self._step(g["x"], g["t"], g["txt"])
+                self._step(g["x"], g["t"], g["txt"], None, g["scale"])
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             before = ops.LAUNCHES
             # with frame sharding the NCCL collectives of the step are captured too (same sequence on every rank)
             with torch.cuda.graph(graph):
-                g["out"] = self._step(g["x"], g["t"], g["txt"])
+                g["out"] = self._step(g["x"], g["t"], g["txt"], None, g["scale"])
             g["launches"] = ops.LAUNCHES - before      # kernel nodes of ours in the captured step
             g["graph"] = graph
             self._graphs[key] = g
@@ -563,5 +609,6 @@ class UNet3DConditionModel(nn.Module):
         g["x"].copy_(x, non_blocking=True)
         g["t"].copy_(t, non_blocking=True)
         g["txt"].copy_(txt, non_blocking=True)
+        g["scale"].copy_(scale, non_blocking=True)
         g["graph"].replay()
         return g["out"]

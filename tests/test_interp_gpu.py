@@ -1,0 +1,122 @@
+"""SURVEY 8f row N1 on the B200: the frame-INTERPOLATION denoiser (interpolation/models/*) through the same module
+and kernels -- SparseCausal self-attention (two key segments), feed-forward before a plain temporal attention over the
+frames (strided tensor maps, any F), 8-channel conv_in, forward_with_cfg with [cond, uncond] text order -- against the
+goldens the UNMODIFIED reference produced (tests/golden/make_golden_interp.py) and against the pinned CPU oracle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 2e-2
+DEV = "cuda"
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+@pytest.fixture(scope="module")
+def interp_sd():
+    from lavie_b200.config import INTERP_CONFIG
+    from lavie_b200.synthetic import synthetic_state_dict
+    return synthetic_state_dict(INTERP_CONFIG, seed=0)
+
+
+@pytest.fixture(scope="module")
+def unet(interp_sd):
+    from lavie_b200 import UNet3DConditionModel
+    from lavie_b200.config import INTERP_CONFIG
+    m = UNet3DConditionModel(INTERP_CONFIG)
+    m.load_state_dict(interp_sd, strict=True)
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("frames,S,d", [(5, 160, 160), (3, 640, 80), (4, 2560, 40), (7, 40, 160), (2, 100, 40)])
+def test_sparse_causal_attention_kernel(frames, S, d):
+    """keys of frame f = [frame 0 | frame max(f-1, 0)] (interpolation/models/attention.py:629-638), two videos."""
+    from lavie_b200 import ops
+    from lavie_b200.packing import head_pitch
+    heads, vids = 8, 2
+    pitch = head_pitch(d)
+    g = torch.Generator().manual_seed(frames * 1000 + S)
+    qkv = torch.zeros(vids * frames * S, 3 * heads * pitch)
+    for part in range(3):
+        for h in range(heads):
+            c0 = part * heads * pitch + h * pitch
+            qkv[:, c0:c0 + d] = torch.randn(vids * frames * S, d, generator=g)
+    qkv = _bf(qkv.to(DEV))
+    hp = heads * pitch
+    out = ops.attention(qkv[:, :hp], qkv[:, hp:2 * hp], qkv[:, 2 * hp:], vids * frames, heads, S, S, d, pitch,
+                        sparse_causal_frames=frames)
+    x = qkv.float().reshape(vids, frames, S, 3, heads, pitch)[..., :d]
+    q, k, v = x[:, :, :, 0], x[:, :, :, 1], x[:, :, :, 2]                      # [vids, frames, S, heads, d]
+    former = (torch.arange(frames) - 1).clamp_min(0)
+    kk = torch.cat([k[:, [0] * frames], k[:, former]], dim=2)                    # [vids, frames, 2S, heads, d]
+    vv = torch.cat([v[:, [0] * frames], v[:, former]], dim=2)
+    ref = F.scaled_dot_product_attention(q.permute(0, 1, 3, 2, 4), kk.permute(0, 1, 3, 2, 4), vv.permute(0, 1, 3, 2, 4))
+    ref = ref.permute(0, 1, 3, 2, 4).reshape(vids * frames * S, heads * d)
+    assert rel_l2(out.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("frames,HW,d", [(61, 40, 160), (61, 160, 40), (16, 64, 80), (7, 24, 40), (64, 8, 160)])
+def test_frame_attention_kernel(frames, HW, d):
+    """plain attention over the frames of each pixel, read in place with strided tensor maps (any F <= 64 here; the
+    kernel has no frame limit)."""
+    from lavie_b200 import ops
+    from lavie_b200.packing import head_pitch
+    heads, B = 8, 2
+    pitch = head_pitch(d)
+    g = torch.Generator().manual_seed(frames * 100 + HW)
+    qkv = torch.zeros(B * frames * HW, 3 * heads * pitch)
+    for part in range(3):
+        for h in range(heads):
+            c0 = part * heads * pitch + h * pitch
+            qkv[:, c0:c0 + d] = torch.randn(B * frames * HW, d, generator=g)
+    qkv = _bf(qkv.to(DEV))
+    out = ops.frame_attention(qkv, B, frames, HW, heads, d, pitch)
+    x = qkv.float().reshape(B, frames, HW, 3, heads, pitch)[..., :d]
+    q, k, v = (x[:, :, :, i].permute(0, 2, 3, 1, 4) for i in range(3))           # [B, HW, heads, frames, d]
+    ref = F.scaled_dot_product_attention(q, k, v).permute(0, 3, 1, 2, 4).reshape(B * frames * HW, heads * d)
+    assert rel_l2(out.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("name", ["interp_b2_f7_8x8", "interp_b1_f5_16x8"])
+def test_interp_matches_reference_golden(unet, name):
+    g = load_golden(name)
+    out = unet(g["sample"].to(DEV), g["timestep"], encoder_hidden_states=g["text"].to(DEV)).sample
+    assert out.shape == g["out"].shape and out.dtype == torch.float32
+    err = rel_l2(out.cpu(), g["out"])
+    print(f"{name}: rel-L2 vs reference fp32 = {err:.3e}")
+    assert err <= BF16_TOL
+
+
+def test_interp_matches_oracle_on_long_video(unet, interp_sd):
+    """61 frames (the model's real length: 16 key frames -> 61), 8x16 latent: temporal attention over 61 tokens,
+    SparseCausal attention at 128 / 32 / 8 / 2 tokens per frame (partial key tiles in both segments)."""
+    from oracle import interp_oracle as O
+    g = torch.Generator().manual_seed(61)
+    sample = torch.randn(1, 8, 61, 8, 16, generator=g)
+    text = torch.randn(1, 77, 768, generator=g)
+    ref = O.unet_forward(interp_sd, sample, 321, text)
+    out = unet(sample.to(DEV), 321, encoder_hidden_states=text.to(DEV)).sample
+    err = rel_l2(out.cpu(), ref)
+    print(f"61 frames x 8x16: rel-L2 vs oracle = {err:.3e}")
+    assert err <= BF16_TOL
+
+
+def test_interp_forward_with_cfg_and_ddim_loop(unet, interp_sd):
+    """forward_with_cfg ([cond, uncond] text order, one UNet evaluation per step) and the respaced-DDIM caller
+    against the golden of the reference's own ddim_sample_loop driving the reference UNet."""
+    from lavie_b200.pipeline import InterpolationSampler
+    from oracle import interp_oracle as O
+    g = load_golden("interp_loop_f5_8x8")
+    x8 = torch.cat([g["z"], g["x_start"]], dim=1)
+    want = O.forward_with_cfg(interp_sd, x8, 500, g["text"], 4.0)
+    got = unet.forward_with_cfg(x8.to(DEV), 500, encoder_hidden_states=g["text"].to(DEV), cfg_scale=4.0)
+    assert got.shape == want.shape and rel_l2(got.cpu(), want) <= BF16_TOL
+    out = InterpolationSampler(unet, 4.0, g["steps"]).loop(g["z"], g["x_start"], g["text"]).cpu()
+    err = rel_l2(out, g["out"])
+    print(f"{g['steps']}-step interpolation DDIM loop: rel-L2 vs reference loop = {err:.3e}")
+    assert out.shape == g["out"].shape and err <= 5e-2
