@@ -115,7 +115,11 @@ def test_interp_forward_with_cfg_and_ddim_loop(unet, interp_sd):
     x8 = torch.cat([g["z"], g["x_start"]], dim=1)
     want = O.forward_with_cfg(interp_sd, x8, 500, g["text"], 4.0)
     got = unet.forward_with_cfg(x8.to(DEV), 500, encoder_hidden_states=g["text"].to(DEV), cfg_scale=4.0)
-    assert got.shape == want.shape and rel_l2(got.cpu(), want) <= BF16_TOL
+    # guidance amplifies the bf16 noise of the two halves: g = 4 c - 3 u carries ~sqrt(4^2 + 3^2) = 5x the per-half error
+    # (each half is within 2e-2, checked by the golden tests above); stated tolerance for the guided eps: 5e-2
+    err = rel_l2(got.cpu(), want)
+    print(f"forward_with_cfg (scale 4): rel-L2 vs oracle = {err:.3e}")
+    assert got.shape == want.shape and err <= 5e-2
     out = InterpolationSampler(unet, 4.0, g["steps"]).loop(g["z"], g["x_start"], g["text"]).cpu()
     err = rel_l2(out, g["out"])
     print(f"{g['steps']}-step interpolation DDIM loop: rel-L2 vs reference loop = {err:.3e}")
