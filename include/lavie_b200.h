@@ -231,6 +231,45 @@ int lavie_cfg_linear_step(const float* noise_uncond, const float* noise_text, fl
 int lavie_cfg_combine(const float* cond, const float* uncond, float scale, float* out0, float* out1, long long n,
                       lavie_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * fp32-accumulate CHECK MODE (BASELINE north star: noise-prediction rel-L2 <= 1e-3 against the reference fp32 forward).
+ * Activations are "split-bf16 triples": a row of C channels is stored as [hi | lo | hi] (3C bf16, hi = bf16(x),
+ * lo = bf16(x - hi), ~16 mantissa bits).  With weights repacked by the caller as W' = [Wh | Wh | Wl] along K the
+ * product's own tcgen05 mainloop computes Ah Wh + Al Wh + Ah Wl in fp32; lavie_check_gemm / lavie_check_conv3x3 are
+ * lavie_gemm_bf16 / lavie_conv3x3_bf16 with k0 / k1 / C counting the TRIPLED widths, the accumulators leaving as fp32
+ * through the workspace (>= 4 * M rounded up to 256 * N bytes) and the epilogue (bias, row_bias, residual triple of width
+ * N, GEGLU with the exact erf GELU) evaluated in fp32; out is the triple [M, 3 * n_out].  The remaining entry points are
+ * the fp32 twins of the normalisation / attention / small kernels reading hi + lo.  Same reference calls as their bf16
+ * counterparts above. */
+int lavie_check_split3(const float* x, long long rows, int C, void* y_triple, lavie_stream_t stream);
+int lavie_check_gemm(const void* a0, int lda0, int k0, const void* a1, int lda1, int k1, const void* w, void* out,
+                     int ldo, int M, int N, const lavie_epilogue* ep, void* workspace, size_t workspace_bytes,
+                     lavie_stream_t stream);
+int lavie_check_conv3x3(const void* x, int NF, int H, int W, int C3, int stride, const void* w, void* out, int ldo,
+                        int N, const lavie_epilogue* ep, void* workspace, size_t workspace_bytes, lavie_stream_t stream);
+int lavie_check_groupnorm_stats(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
+                                int rows_per_sample, int groups, float* partial, lavie_stream_t stream);
+int lavie_check_groupnorm_apply(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
+                                int rows_per_sample, const float* scale_shift, int silu, void* y, int ldy,
+                                lavie_stream_t stream);
+int lavie_check_layernorm(const void* x, int ldx, const float* gamma, const float* beta, float eps, void* y, int ldy,
+                          int rows, int C, lavie_stream_t stream);
+/* One fp32 attention core for every attention of both models: strides as lavie_attention_strided_bf16, *_lo_offset =
+ * column distance from a hi block to its lo block (o_lo_offset = heads * d), optional q pre-scale + rotary table
+ * [S, rot_pairs, 2] + bias [heads, Sq, Sk] (the base model's temporal attention), optional sparse-causal key segments. */
+int lavie_check_attention(const void* q, long long q_seq_stride, long long q_batch_stride, int q_lo_offset,
+                          const void* k, const void* v, long long kv_seq_stride, long long kv_batch_stride,
+                          int kv_lo_offset, void* o, long long o_seq_stride, long long o_batch_stride, int o_lo_offset,
+                          int batch, int heads, int Sq, int Sk, int d, int head_pitch, int kv_batch_div,
+                          int sparse_causal_frames, float scale, const float* rope, int rot_pairs, const float* bias,
+                          lavie_stream_t stream);
+int lavie_check_linear_smallm(const float* x, int M, int K, const float* w_fp32, const float* bias, float* out, int N,
+                              int silu_in, int silu_out, lavie_stream_t stream);
+int lavie_check_conv_in(const float* x, const float* input_scale, int B, int Cin, int F, int H, int W, const float* w,
+                        const float* bias, int Cout, void* out_triple, int ldo, lavie_stream_t stream);
+int lavie_check_conv_out(const void* x_triple, int ldx, const float* scale_shift, int B, int F, int H, int W, int C,
+                         const float* w, const float* bias, int Cout, float* out, lavie_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,21 @@ SIGNATURES = {
     "lavie_cfg_ddim_step": (c_int, [_P, _P, c_float, c_float, c_float, _P, _P, c_longlong, _P]),
     "lavie_cfg_linear_step": (c_int, [_P, _P, c_float, c_float, c_float, c_float, _P, _P, _P, c_longlong, _P]),
     "lavie_cfg_combine": (c_int, [_P, _P, c_float, _P, _P, c_longlong, _P]),
+    # fp32-accumulate check mode (split-bf16 triples)
+    "lavie_check_split3": (c_int, [_P, c_longlong, c_int, _P, _P]),
+    "lavie_check_gemm": (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(Epilogue), _P,
+                                 c_size_t, _P]),
+    "lavie_check_conv3x3": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, POINTER(Epilogue), _P,
+                                    c_size_t, _P]),
+    "lavie_check_groupnorm_stats": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "lavie_check_groupnorm_apply": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),
+    "lavie_check_layernorm": (c_int, [_P, c_int, _P, _P, c_float, _P, c_int, c_int, c_int, _P]),
+    "lavie_check_attention": (c_int, [_P, c_longlong, c_longlong, c_int, _P, _P, c_longlong, c_longlong, c_int, _P,
+                                      c_longlong, c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_float, _P, c_int, _P, _P]),
+    "lavie_check_linear_smallm": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "lavie_check_conv_in": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
+    "lavie_check_conv_out": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P]),
 }
 
 _lib = None

@@ -69,6 +69,8 @@ struct GemmParams {
   __nv_bfloat16* out;
   int ldo;
   float* partial;            // split-K workspace [splits, M, N] fp32 (splits > 1)
+  int check;                 // fp32-accumulate check mode: accumulators ALWAYS leave as fp32 partials (even with
+                             // splits == 1); bias / residual / GEGLU run in fp32 on split-bf16 triples (check reduce)
   int k_rot;                 // K-sweep rotation stride per M tile (0 = off)
   int debug;                 // tuning only: 1 = skip TMA (pure MMA issue rate), 2 = skip MMA (pure TMA feed rate)
 };
@@ -359,7 +361,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       const int row = wrow0 + lane;
       const bool row_ok = row < p.M;
       const int n0 = it.n_blk * BLOCK_N;
-      const bool staged = p.splits == 1;
+      const bool staged = p.splits == 1 && !p.check;
       const bool has_res = staged && p.residual != nullptr;
       const bool tl = (p.debug & 512) && blockIdx.x == 0 && ew == 0 && lane == 0;
       long long* tl_row = reinterpret_cast<long long*>(p.partial) + ((item - pair) / num_pairs) * 8;
@@ -420,7 +422,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         }
       };
 
-      if (p.splits > 1) {
+      if (p.splits > 1 || p.check) {
         // fp32 partials for the ordered split-K reduction
         float* dst_row = p.partial + (static_cast<size_t>(split) * p.rows_window + (row - p.m_tile0 * PAIR_M)) * p.N;
 #pragma unroll 1
@@ -548,6 +550,48 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N
   }
 }
 
+// Check-mode epilogue: ordered sum of the fp32 partials, then bias / time bias / residual / GEGLU in fp32 (exact erf
+// GELU) on split-bf16 triples: residual row = [hi | lo | hi] of width N each, output row = [hi | lo | hi] of width n_out.
+__global__ void __launch_bounds__(256)
+splitk_reduce_check_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* __restrict__ bias,
+                           const float* __restrict__ row_bias, int rows_per_batch, int ld_row_bias,
+                           const __nv_bfloat16* __restrict__ residual, int ldr, int geglu,
+                           __nv_bfloat16* __restrict__ out, int ldo, int row0) {
+  pdl_prologue();
+  const int n_out = geglu ? N / 2 : N;
+  const long long total = static_cast<long long>(M) * n_out;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / n_out);
+    const int col = static_cast<int>(i - static_cast<long long>(row) * n_out);
+    auto acc_at = [&](int c) {
+      float a = partial[static_cast<size_t>(row) * N + c];
+      for (int s = 1; s < splits; ++s) a += partial[(static_cast<size_t>(s) * M + row) * N + c];
+      if (bias) a += bias[c];
+      return a;
+    };
+    float v;
+    if (geglu) {                                   // 256-column tiles: 128 value columns, then their 128 gate columns
+      const int t = col >> 7, j = col & 127;
+      const float val = acc_at(t * 256 + j), gate = acc_at(t * 256 + 128 + j);
+      v = val * (0.5f * gate * (1.0f + erff(gate * 0.70710678118654752440f)));
+    } else {
+      v = acc_at(col);
+      if (row_bias) v += row_bias[static_cast<size_t>((row + row0) / rows_per_batch) * ld_row_bias + col];
+      if (residual) {
+        const __nv_bfloat16* r = residual + static_cast<size_t>(row) * ldr + col;
+        v += __bfloat162float(r[0]) + __bfloat162float(r[N]);
+      }
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* o = out + static_cast<size_t>(row) * ldo + col;
+    o[0] = hi;
+    o[n_out] = lo;
+    o[2 * n_out] = hi;
+  }
+}
+
 template <int BLOCK_N>
 int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& mo,
                 const CUtensorMap& mr, const GemmParams& p,
@@ -562,7 +606,17 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   launch_pdl(gemm_bf16_tcgen05<BLOCK_N>, 2 * pairs, NUM_THREADS, L::TOTAL, stream, a0, a1, b, mo, mr, p);
   rc = lavie_check_launch("gemm_bf16_tcgen05");
   if (rc) return rc;
-  if (p.splits > 1) {
+  if (p.check) {
+    const int row0 = p.m_tile0 * PAIR_M;
+    const long long total = static_cast<long long>(p.rows_window) * (p.geglu ? p.N / 2 : p.N);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    launch_pdl(splitk_reduce_check_kernel, static_cast<int>(blocks), 256, 0, stream, p.partial, p.splits, p.rows_window,
+               p.N, p.bias, p.row_bias, p.rows_per_batch, p.ld_row_bias,
+               p.residual ? p.residual + static_cast<size_t>(row0) * p.ldr : nullptr, p.ldr, p.geglu,
+               p.out + static_cast<size_t>(row0) * p.ldo, p.ldo, row0);
+    rc = lavie_check_launch("splitk_reduce_check_kernel");
+  } else if (p.splits > 1) {
     const int row0 = p.m_tile0 * PAIR_M;
     const long long total = static_cast<long long>(p.rows_window) * (p.N >> 2);
     long long blocks = (total + 255) / 256;
@@ -792,9 +846,19 @@ extern "C" int lavie_gemm_plan(int M, int N, int K, int conv, int geglu, size_t 
   return LAVIE_OK;
 }
 
-extern "C" int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1, int lda1, int k1, const void* w,
-                               void* out, int ldo, int M, int N, const lavie_epilogue* ep, int block_n,
-                               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+namespace {
+// check-mode launches need room for one fp32 plane of the (256-row padded) output in the workspace
+int check_workspace(int check, int M, int N, const void* workspace, size_t workspace_bytes) {
+  if (!check) return LAVIE_OK;
+  const size_t need = static_cast<size_t>((M + PAIR_M - 1) / PAIR_M) * PAIR_M * N * sizeof(float);
+  LAVIE_REQUIRE(workspace != nullptr && workspace_bytes >= need, LAVIE_ERR_WORKSPACE,
+                "check mode: workspace of %zu bytes needed (fp32 accumulator plane), got %zu", need, workspace_bytes);
+  return LAVIE_OK;
+}
+
+int gemm_impl(const void* a0, int lda0, int k0, const void* a1, int lda1, int k1, const void* w, void* out, int ldo,
+              int M, int N, const lavie_epilogue* ep, int block_n, void* workspace, size_t workspace_bytes, int check,
+              cudaStream_t stream) {
   const int K = k0 + k1;
   LAVIE_REQUIRE(M > 0 && N > 0 && K > 0, LAVIE_ERR_SHAPE, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   LAVIE_REQUIRE(N % 8 == 0 && k0 % 8 == 0 && k1 % 8 == 0, LAVIE_ERR_SHAPE, "gemm: N, K must be multiples of 8");
@@ -809,9 +873,12 @@ extern "C" int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1,
   p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   p.k_split_blocks = k1 ? k0 / BLOCK_K : p.num_k_blocks;
   p.conv = 0;
+  p.check = check;
+  int rc = check_workspace(check, M, N, workspace, workspace_bytes);
+  if (rc) return rc;
   const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, geglu, false, workspace ? workspace_bytes : 0);
   apply_plan(p, plan, workspace);
-  int rc = fill_epilogue(p, ep, N, out, ldo);
+  rc = fill_epilogue(p, ep, N, out, ldo);
   if (rc) return rc;
   CUtensorMap ma0, ma1, mb;
   {
@@ -834,15 +901,29 @@ extern "C" int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1,
   if (rc) return rc;
   return dispatch(plan, ma0, ma1, mb, p, stream);
 }
+}  // namespace
+
+extern "C" int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1, int lda1, int k1, const void* w,
+                               void* out, int ldo, int M, int N, const lavie_epilogue* ep, int block_n,
+                               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return gemm_impl(a0, lda0, k0, a1, lda1, k1, w, out, ldo, M, N, ep, block_n, workspace, workspace_bytes, 0, stream);
+}
+
+extern "C" int lavie_check_gemm(const void* a0, int lda0, int k0, const void* a1, int lda1, int k1, const void* w,
+                                void* out, int ldo, int M, int N, const lavie_epilogue* ep, void* workspace,
+                                size_t workspace_bytes, cudaStream_t stream) {
+  return gemm_impl(a0, lda0, k0, a1, lda1, k1, w, out, ldo, M, N, ep, 0, workspace, workspace_bytes, 1, stream);
+}
 
 extern "C" int lavie_conv3x3_supported(int H, int W, int C) {
   (void)H; (void)W;
   return C % BLOCK_K == 0 ? 1 : 0;      // im2col-mode TMA handles any image geometry; channels come in 64-wide slabs
 }
 
-extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, int stride, const void* w, void* out,
-                                  int ldo, int N, const lavie_epilogue* ep, int block_n, void* workspace,
-                                  size_t workspace_bytes, cudaStream_t stream) {
+namespace {
+int conv3x3_impl(const void* x, int NF, int H, int W, int C, int stride, const void* w, void* out, int ldo, int N,
+                 const lavie_epilogue* ep, int block_n, void* workspace, size_t workspace_bytes, int check,
+                 cudaStream_t stream) {
   LAVIE_REQUIRE(lavie_conv3x3_supported(H, W, C), LAVIE_ERR_SHAPE, "conv3x3: C=%d must be a multiple of 64", C);
   LAVIE_REQUIRE(stride == 1 || stride == 2, LAVIE_ERR_SHAPE, "conv3x3: stride must be 1 or 2");
   LAVIE_REQUIRE(N % 8 == 0 && aligned16(x) && aligned16(w), LAVIE_ERR_ALIGN, "conv3x3: alignment");
@@ -857,9 +938,12 @@ extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, in
   p.c_blocks = C / BLOCK_K;
   p.out_h = Ho; p.out_w = Wo; p.conv_stride = stride;
   p.conv = 1;
+  p.check = check;
+  int rc = check_workspace(check, M, N, workspace, workspace_bytes);
+  if (rc) return rc;
   const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, false, true, workspace ? workspace_bytes : 0);
   apply_plan(p, plan, workspace);
-  int rc = fill_epilogue(p, ep, N, out, ldo);
+  rc = fill_epilogue(p, ep, N, out, ldo);
   if (rc) return rc;
   CUtensorMap ma, mb;
   rc = lavie_make_tmap_im2col(&ma, x, NF, H, W, C, BLOCK_K, BLOCK_M, stride);
@@ -867,4 +951,17 @@ extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, in
   rc = make_weight_map(&mb, w, N, 9 * C, plan.bn);
   if (rc) return rc;
   return dispatch(plan, ma, ma, mb, p, stream);
+}
+}  // namespace
+
+extern "C" int lavie_conv3x3_bf16(const void* x, int NF, int H, int W, int C, int stride, const void* w, void* out,
+                                  int ldo, int N, const lavie_epilogue* ep, int block_n, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream) {
+  return conv3x3_impl(x, NF, H, W, C, stride, w, out, ldo, N, ep, block_n, workspace, workspace_bytes, 0, stream);
+}
+
+extern "C" int lavie_check_conv3x3(const void* x, int NF, int H, int W, int C3, int stride, const void* w, void* out,
+                                   int ldo, int N, const lavie_epilogue* ep, void* workspace, size_t workspace_bytes,
+                                   cudaStream_t stream) {
+  return conv3x3_impl(x, NF, H, W, C3, stride, w, out, ldo, N, ep, 0, workspace, workspace_bytes, 1, stream);
 }

@@ -80,7 +80,7 @@ constexpr int CIN_P = 4;
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x, int B, int Cin, int F, int H, int W, const float* __restrict__ w,
                const float* __restrict__ bias, int Cout, __nv_bfloat16* __restrict__ out, int ldo,
-               const float* __restrict__ input_scale_ptr) {
+               const float* __restrict__ input_scale_ptr, int triple) {
   pdl_prologue();
   const float input_scale = input_scale_ptr ? __ldg(input_scale_ptr) : 1.0f;
   extern __shared__ float s_w[];     // transposed to [Cin*9][Cout]: a warp reads 1 KiB contiguous per tap
@@ -146,6 +146,16 @@ conv_in_kernel(const float* __restrict__ x, int B, int Cin, int F, int H, int W,
         o.z = pack_bf16(acc[pp][4], acc[pp][5]);
         o.w = pack_bf16(acc[pp][6], acc[pp][7]);
         *reinterpret_cast<uint4*>(out + (pix0 + pp) * ldo + g * 8) = o;
+        if (triple) {      // check mode: [hi | lo | hi]
+          const float2 h0 = unpack_bf16(o.x), h1 = unpack_bf16(o.y), h2 = unpack_bf16(o.z), h3 = unpack_bf16(o.w);
+          uint4 l;
+          l.x = pack_bf16(acc[pp][0] - h0.x, acc[pp][1] - h0.y);
+          l.y = pack_bf16(acc[pp][2] - h1.x, acc[pp][3] - h1.y);
+          l.z = pack_bf16(acc[pp][4] - h2.x, acc[pp][5] - h2.y);
+          l.w = pack_bf16(acc[pp][6] - h3.x, acc[pp][7] - h3.y);
+          *reinterpret_cast<uint4*>(out + (pix0 + pp) * ldo + Cout + g * 8) = l;
+          *reinterpret_cast<uint4*>(out + (pix0 + pp) * ldo + 2 * Cout + g * 8) = o;
+        }
       }
     }
   }
@@ -162,7 +172,7 @@ template <int COUT>
 __global__ void __launch_bounds__(256)
 conv_out_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ scale_shift, int B, int F,
                 int H, int W, int C, const float* __restrict__ w, const float* __restrict__ bias,
-                float* __restrict__ out) {
+                float* __restrict__ out, int lo_off) {
   pdl_prologue();
   extern __shared__ float s_w[];     // [9][COUT][C]   (source layout [COUT][9][C])
   for (int i = threadIdx.x; i < COUT * 9 * C; i += blockDim.x) {
@@ -202,7 +212,12 @@ conv_out_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __res
         for (int i = 0; i < COUT_P + 2; ++i) {
           const int xx = xs - 1 + i;
           if (row_ok && xx >= 0 && xx < W) {
-            const float2 t2 = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(xp + i * ldx)));
+            float2 t2 = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(xp + i * ldx)));
+            if (lo_off) {            // check mode: x = hi + lo of the split-bf16 triple
+              const float2 tl = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(xp + i * ldx + lo_off)));
+              t2.x += tl.x;
+              t2.y += tl.y;
+            }
             a0[i] = silu_f(t2.x * ss.x + ss.y);
             a1[i] = silu_f(t2.y * ss.z + ss.w);
           } else {
@@ -346,7 +361,7 @@ extern "C" int lavie_linear_smallm(const float* x, int M, int K, const void* w, 
 
 namespace {
 int conv_in_impl(const float* x, int B, int Cin, int F, int H, int W, const float* w, const float* bias, int Cout,
-                 void* out, int ldo, const float* input_scale, cudaStream_t stream) {
+                 void* out, int ldo, const float* input_scale, int triple, cudaStream_t stream) {
   LAVIE_REQUIRE(Cout % 8 == 0 && ldo % 8 == 0 && al16(out), LAVIE_ERR_SHAPE, "conv_in: Cout/ldo must be multiples of 8");
   const int smem = Cout * Cin * 9 * static_cast<int>(sizeof(float));
   LAVIE_REQUIRE(smem <= 200 * 1024, LAVIE_ERR_SHAPE, "conv_in: weights do not fit shared memory");
@@ -358,24 +373,33 @@ int conv_in_impl(const float* x, int B, int Cin, int F, int H, int W, const floa
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   launch_pdl(conv_in_kernel, static_cast<int>(blocks), 256, smem, stream, x, B, Cin, F, H, W, w, bias, Cout,
-             static_cast<__nv_bfloat16*>(out), ldo, input_scale);
+             static_cast<__nv_bfloat16*>(out), ldo, input_scale, triple);
   return lavie_check_launch("conv_in_kernel");
 }
 }  // namespace
 
 extern "C" int lavie_conv_in(const float* x, int B, int Cin, int F, int H, int W, const float* w, const float* bias,
                              int Cout, void* out, int ldo, cudaStream_t stream) {
-  return conv_in_impl(x, B, Cin, F, H, W, w, bias, Cout, out, ldo, nullptr, stream);
+  return conv_in_impl(x, B, Cin, F, H, W, w, bias, Cout, out, ldo, nullptr, 0, stream);
 }
 
 extern "C" int lavie_conv_in_scaled(const float* x, const float* input_scale, int B, int Cin, int F, int H, int W,
                                     const float* w, const float* bias, int Cout, void* out, int ldo,
                                     cudaStream_t stream) {
-  return conv_in_impl(x, B, Cin, F, H, W, w, bias, Cout, out, ldo, input_scale, stream);
+  return conv_in_impl(x, B, Cin, F, H, W, w, bias, Cout, out, ldo, input_scale, 0, stream);
 }
 
-extern "C" int lavie_conv_out(const void* x, int ldx, const float* scale_shift, int B, int F, int H, int W, int C,
-                              const float* w, const float* bias, int Cout, float* out, cudaStream_t stream) {
+/* check mode: fp32 conv_in (already fp32 arithmetic) writing the split-bf16 triple [rows, 3*Cout] (ldo >= 3*Cout) */
+extern "C" int lavie_check_conv_in(const float* x, const float* input_scale, int B, int Cin, int F, int H, int W,
+                                   const float* w, const float* bias, int Cout, void* out, int ldo,
+                                   cudaStream_t stream) {
+  LAVIE_REQUIRE(ldo >= 3 * Cout, LAVIE_ERR_SHAPE, "check_conv_in: ldo must cover the triple");
+  return conv_in_impl(x, B, Cin, F, H, W, w, bias, Cout, out, ldo, input_scale, 1, stream);
+}
+
+namespace {
+int conv_out_impl(const void* x, int ldx, const float* scale_shift, int B, int F, int H, int W, int C, const float* w,
+                  const float* bias, int Cout, float* out, int lo_off, cudaStream_t stream) {
   LAVIE_REQUIRE(Cout == 4 && C % 8 == 0 && ldx % 8 == 0, LAVIE_ERR_SHAPE, "conv_out: Cout must be 4, C %% 8 == 0");
   LAVIE_REQUIRE(al16(x) && al16(scale_shift), LAVIE_ERR_ALIGN, "conv_out: alignment");
   const int smem = Cout * 9 * C * static_cast<int>(sizeof(float));
@@ -387,8 +411,21 @@ extern "C" int lavie_conv_out(const void* x, int ldx, const float* scale_shift, 
   long long blocks = (total + 7) / 8;
   if (blocks > 148 * 2) blocks = 148 * 2;        // 2 resident blocks per SM (registers): one wave, one weight fill each
   launch_pdl(conv_out_kernel<4>, static_cast<int>(blocks), 256, smem, stream, static_cast<const __nv_bfloat16*>(x), ldx,
-                                                                      scale_shift, B, F, H, W, C, w, bias, out);
+             scale_shift, B, F, H, W, C, w, bias, out, lo_off);
   return lavie_check_launch("conv_out_kernel");
+}
+}  // namespace
+
+extern "C" int lavie_conv_out(const void* x, int ldx, const float* scale_shift, int B, int F, int H, int W, int C,
+                              const float* w, const float* bias, int Cout, float* out, cudaStream_t stream) {
+  return conv_out_impl(x, ldx, scale_shift, B, F, H, W, C, w, bias, Cout, out, 0, stream);
+}
+
+/* check mode: x is the split-bf16 triple [rows, 3C] (ldx >= 2C) */
+extern "C" int lavie_check_conv_out(const void* x, int ldx, const float* scale_shift, int B, int F, int H, int W, int C,
+                                    const float* w, const float* bias, int Cout, float* out, cudaStream_t stream) {
+  LAVIE_REQUIRE(ldx >= 2 * C, LAVIE_ERR_SHAPE, "check_conv_out: ldx must cover hi and lo");
+  return conv_out_impl(x, ldx, scale_shift, B, F, H, W, C, w, bias, Cout, out, C, stream);
 }
 
 extern "C" int lavie_im2col3x3_bf16(const void* x, int NF, int H, int W, int C, int stride, void* col,

@@ -20,6 +20,13 @@ __device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int ld0, int c
   return __ldg(reinterpret_cast<const uint4*>(src));
 }
 
+// check mode (split-bf16 triples, check.cu): the lo half of the same 8 channels sits c0 (c1) columns further
+__device__ __forceinline__ uint4 ld_vec8_lo(const __nv_bfloat16* x0, int ld0, int c0, const __nv_bfloat16* x1, int ld1,
+                                            int c1, size_t row, int col) {
+  const __nv_bfloat16* src = (col < c0) ? x0 + row * ld0 + c0 + col : x1 + row * ld1 + c1 + (col - c0);
+  return __ldg(reinterpret_cast<const uint4*>(src));
+}
+
 // combine the chunk partials of one sample in fp64 (fixed order) and emit per-channel (scale, shift); whole block
 __device__ __forceinline__ void gn_finalize_sample(const float* __restrict__ partial, int sample, int chunks, int groups,
                                                    int C, double inv_count, const float* __restrict__ gamma,
@@ -89,6 +96,7 @@ struct GnFused {
 };
 
 // partial[sample][chunk][group][2]
+template <bool TRIPLE>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __nv_bfloat16* __restrict__ x1, int ld1,
                 int c1, int rows_per_sample, int rows_per_chunk, int groups, int chunks, float* __restrict__ partial,
@@ -114,20 +122,27 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __n
       for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
       constexpr int U = 8;                     // independent 16-byte loads in flight per thread
       for (int r = r_begin + my_rl; r < r_end; r += row_lanes * U) {
-        uint4 v[U];
+        uint4 v[U], vl[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int rr = r + u * row_lanes;
           const size_t row = static_cast<size_t>(sample) * rows_per_sample + (rr < r_end ? rr : r);
           v[u] = ld_vec8(x0, ld0, c0, x1, ld1, row, my_vec * 8);
+          if (TRIPLE) vl[u] = ld_vec8_lo(x0, ld0, c0, x1, ld1, c1, row, my_vec * 8);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (r + u * row_lanes < r_end) {
             const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            const uint32_t wl[4] = {vl[u].x, vl[u].y, vl[u].z, vl[u].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16(w[e]);
+              float2 f = unpack_bf16(w[e]);
+              if (TRIPLE) {
+                const float2 fl = unpack_bf16(wl[e]);
+                f.x += fl.x;
+                f.y += fl.y;
+              }
               s[2 * e] += f.x; q[2 * e] += f.x * f.x;
               s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
             }
@@ -169,6 +184,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __n
 // y = act(x * scale + shift).  A thread owns one 8-channel column vector and walks down the rows of ONE sample, so the
 // 16 (scale, shift) floats stay in registers (they are 4x the bytes of the data they apply to); 4 independent 16-byte
 // loads are in flight per thread.  grid = (row chunks, samples).
+template <bool TRIPLE>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __nv_bfloat16* __restrict__ x1, int ld1,
                 int c1, int rows_per_sample, int rows_per_chunk, const float* __restrict__ scale_shift, int silu,
@@ -194,12 +210,13 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __n
       sc[2 * e] = p.x; sh[2 * e] = p.y; sc[2 * e + 1] = p.z; sh[2 * e + 1] = p.w;
     }
     for (int r = r_begin + my_rl; r < r_end; r += row_lanes * U) {
-      uint4 v[U];
+      uint4 v[U], vl[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int rr = r + u * row_lanes;
         const size_t row = static_cast<size_t>(sample) * rows_per_sample + (rr < r_end ? rr : r);
         v[u] = ld_vec8(x0, ld0, c0, x1, ld1, row, col);
+        if (TRIPLE) vl[u] = ld_vec8_lo(x0, ld0, c0, x1, ld1, c1, row, col);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -207,16 +224,33 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __n
         if (rr >= r_end) break;
         const size_t row = static_cast<size_t>(sample) * rows_per_sample + rr;
         const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-        uint32_t o[4];
+        const uint32_t wl[4] = {vl[u].x, vl[u].y, vl[u].z, vl[u].w};
+        uint32_t o[4], ol[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack_bf16(w[e]);
+          float2 f = unpack_bf16(w[e]);
+          if (TRIPLE) {
+            const float2 fl = unpack_bf16(wl[e]);
+            f.x += fl.x;
+            f.y += fl.y;
+          }
           float a = f.x * sc[2 * e] + sh[2 * e];
           float b = f.y * sc[2 * e + 1] + sh[2 * e + 1];
-          if (silu) { a = silu_f(a); b = silu_f(b); }
+          if (silu) {
+            if (TRIPLE) { a = a / (1.0f + expf(-a)); b = b / (1.0f + expf(-b)); }
+            else { a = silu_f(a); b = silu_f(b); }
+          }
           o[e] = pack_bf16(a, b);
+          if (TRIPLE) {
+            const float2 hi = unpack_bf16(o[e]);
+            ol[e] = pack_bf16(a - hi.x, b - hi.y);
+          }
         }
         *reinterpret_cast<uint4*>(y + row * ldy + col) = make_uint4(o[0], o[1], o[2], o[3]);
+        if (TRIPLE) {      // [hi | lo | hi]
+          *reinterpret_cast<uint4*>(y + row * ldy + C + col) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+          *reinterpret_cast<uint4*>(y + row * ldy + 2 * C + col) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
       }
     }
   }
@@ -390,8 +424,9 @@ extern "C" int lavie_groupnorm_chunks(int samples, int rows_per_sample) {
   return (rows_per_sample + rpc - 1) / rpc;
 }
 
-extern "C" int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
-                                     int rows_per_sample, int groups, float* partial, cudaStream_t stream) {
+namespace {
+int gn_stats_impl(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples, int rows_per_sample,
+                  int groups, float* partial, bool triple, cudaStream_t stream) {
   int rc = check_sources(x0, ld0, c0, x1, ld1, c1);
   if (rc) return rc;
   const int C = c0 + c1;
@@ -402,9 +437,29 @@ extern "C" int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void
   dim3 grid(chunks, samples);
   const int vec_per_row = C >> 3;
   const int row_lanes = GN_THREADS / (vec_per_row < GN_THREADS ? vec_per_row : GN_THREADS);
-  launch_pdl(gn_stats_kernel, grid, GN_THREADS, static_cast<size_t>(row_lanes) * 2 * C * sizeof(float), stream, static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1,
-      rows_per_sample, rows_per_chunk, groups, chunks, partial, GnFused{});
+  if (triple)
+    launch_pdl(gn_stats_kernel<true>, grid, GN_THREADS, static_cast<size_t>(row_lanes) * 2 * C * sizeof(float), stream,
+               static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1,
+               rows_per_sample, rows_per_chunk, groups, chunks, partial, GnFused{});
+  else
+    launch_pdl(gn_stats_kernel<false>, grid, GN_THREADS, static_cast<size_t>(row_lanes) * 2 * C * sizeof(float), stream,
+               static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1,
+               rows_per_sample, rows_per_chunk, groups, chunks, partial, GnFused{});
   return lavie_check_launch("gn_stats_kernel");
+}
+}  // namespace
+
+extern "C" int lavie_groupnorm_stats(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
+                                     int rows_per_sample, int groups, float* partial, cudaStream_t stream) {
+  return gn_stats_impl(x0, ld0, c0, x1, ld1, c1, samples, rows_per_sample, groups, partial, false, stream);
+}
+
+/* check mode: the sources are split-bf16 triples (row = [hi | lo | hi], c0 / c1 = width of ONE block) */
+extern "C" int lavie_check_groupnorm_stats(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1,
+                                           int samples, int rows_per_sample, int groups, float* partial,
+                                           cudaStream_t stream) {
+  LAVIE_REQUIRE(ld0 >= 2 * c0 && (c1 == 0 || ld1 >= 2 * c1), LAVIE_ERR_SHAPE, "check_groupnorm_stats: triple strides");
+  return gn_stats_impl(x0, ld0, c0, x1, ld1, c1, samples, rows_per_sample, groups, partial, true, stream);
 }
 
 extern "C" int lavie_groupnorm_finalize(const float* partial, int samples, int chunks, int groups, int C,
@@ -440,24 +495,46 @@ extern "C" int lavie_groupnorm_scale_shift(const void* x0, int ld0, int c0, cons
   fused.beta = beta;
   fused.eps = eps;
   fused.scale_shift = scale_shift;
-  launch_pdl(gn_stats_kernel, grid, GN_THREADS, static_cast<size_t>(row_lanes) * 2 * C * sizeof(float), stream,
+  launch_pdl(gn_stats_kernel<false>, grid, GN_THREADS, static_cast<size_t>(row_lanes) * 2 * C * sizeof(float), stream,
              static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1,
              rows_per_sample, rows_per_chunk, groups, chunks, partial, fused);
   return lavie_check_launch("gn_stats_kernel(fused)");
 }
 
-extern "C" int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
-                                     int rows_per_sample, const float* scale_shift, int silu, void* y, int ldy,
-                                     cudaStream_t stream) {
+namespace {
+int gn_apply_impl(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples, int rows_per_sample,
+                  const float* scale_shift, int silu, void* y, int ldy, bool triple, cudaStream_t stream) {
   int rc = check_sources(x0, ld0, c0, x1, ld1, c1);
   if (rc) return rc;
   LAVIE_REQUIRE(al16(y) && ldy % 8 == 0 && al16(scale_shift), LAVIE_ERR_ALIGN, "groupnorm_apply: output alignment");
   const int rows_per_chunk = gn_rows_per_chunk(samples, rows_per_sample, g_lavie_gn_apply_ctas);
   const int chunks = (rows_per_sample + rows_per_chunk - 1) / rows_per_chunk;
   dim3 grid(chunks, samples);
-  launch_pdl(gn_apply_kernel, grid, 256, 0, stream, static_cast<const __nv_bfloat16*>(x0), ld0, c0, static_cast<const __nv_bfloat16*>(x1), ld1, c1, rows_per_sample,
-      rows_per_chunk, scale_shift, silu, static_cast<__nv_bfloat16*>(y), ldy);
+  if (triple)
+    launch_pdl(gn_apply_kernel<true>, grid, 256, 0, stream, static_cast<const __nv_bfloat16*>(x0), ld0, c0,
+               static_cast<const __nv_bfloat16*>(x1), ld1, c1, rows_per_sample, rows_per_chunk, scale_shift, silu,
+               static_cast<__nv_bfloat16*>(y), ldy);
+  else
+    launch_pdl(gn_apply_kernel<false>, grid, 256, 0, stream, static_cast<const __nv_bfloat16*>(x0), ld0, c0,
+               static_cast<const __nv_bfloat16*>(x1), ld1, c1, rows_per_sample, rows_per_chunk, scale_shift, silu,
+               static_cast<__nv_bfloat16*>(y), ldy);
   return lavie_check_launch("gn_apply_kernel");
+}
+}  // namespace
+
+extern "C" int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1, int samples,
+                                     int rows_per_sample, const float* scale_shift, int silu, void* y, int ldy,
+                                     cudaStream_t stream) {
+  return gn_apply_impl(x0, ld0, c0, x1, ld1, c1, samples, rows_per_sample, scale_shift, silu, y, ldy, false, stream);
+}
+
+/* check mode: triple sources in, triple [rows, 3C] out (ldy >= 3C) */
+extern "C" int lavie_check_groupnorm_apply(const void* x0, int ld0, int c0, const void* x1, int ld1, int c1,
+                                           int samples, int rows_per_sample, const float* scale_shift, int silu,
+                                           void* y, int ldy, cudaStream_t stream) {
+  LAVIE_REQUIRE(ld0 >= 2 * c0 && (c1 == 0 || ld1 >= 2 * c1) && ldy >= 3 * (c0 + c1), LAVIE_ERR_SHAPE,
+                "check_groupnorm_apply: triple strides");
+  return gn_apply_impl(x0, ld0, c0, x1, ld1, c1, samples, rows_per_sample, scale_shift, silu, y, ldy, true, stream);
 }
 
 namespace {

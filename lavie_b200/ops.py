@@ -106,6 +106,27 @@ def _epilogue(bias=None, row_bias=None, rows_per_batch=1, residual=None, geglu=F
     return ep
 
 
+# ---- layout helpers shared with the check-mode provider (lavie_b200/check.py implements the same names on triples) ----
+def cols(x: torch.Tensor, a: int, b: int) -> torch.Tensor:
+    return x[:, a:b]
+
+
+def weight(w: torch.Tensor, device) -> torch.Tensor:
+    """kernel-side copy of a weight matrix: bf16, contiguous."""
+    return w.to(device=device, dtype=BF16).contiguous()
+
+
+weight_small = weight          # the time-embedding linears read bf16 weights too
+
+
+def to_float(x: torch.Tensor) -> torch.Tensor:
+    return x.float()
+
+
+def text_input(text: torch.Tensor, ctx: int) -> torch.Tensor:
+    return text                # already bf16 [B*L, ctx] (cast by the caller outside the captured graph)
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None, bias=None, row_bias=None,
          rows_per_batch=1, residual=None, geglu=False, out: Optional[torch.Tensor] = None, block_n: int = 0):
     """out[M,N] = [a | a2] @ w^T (+ fused epilogue).  w: bf16 [N, K] contiguous."""

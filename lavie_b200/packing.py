@@ -9,15 +9,18 @@ BF16 = torch.bfloat16
 GEGLU_HALF = 128          # the GEGLU GEMM epilogue pairs column j with column j + 128 inside a 256-wide tile
 
 
-def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
-    """[Cout, Cin, 3, 3] -> bf16 [Cout, 9*Cin] with K ordered (kh, kw, cin) = the implicit-GEMM K order."""
+def pack_conv3x3(w: torch.Tensor, dtype=BF16) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> [Cout, 9*Cin] with K ordered (kh, kw, cin) = the implicit-GEMM K order (bf16 by default;
+    dtype=None keeps the source precision for the check-mode (hi, lo) split)."""
     co, ci, kh, kw = w.shape
     assert kh == 3 and kw == 3
-    return w.permute(0, 2, 3, 1).reshape(co, 9 * ci).to(BF16).contiguous()
+    out = w.permute(0, 2, 3, 1).reshape(co, 9 * ci)
+    return (out if dtype is None else out.to(dtype)).contiguous()
 
 
-def pack_conv1x1(w: torch.Tensor) -> torch.Tensor:
-    return w.reshape(w.shape[0], w.shape[1]).to(BF16).contiguous()
+def pack_conv1x1(w: torch.Tensor, dtype=BF16) -> torch.Tensor:
+    out = w.reshape(w.shape[0], w.shape[1])
+    return (out if dtype is None else out.to(dtype)).contiguous()
 
 
 def head_pitch(d: int) -> int:
