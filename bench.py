@@ -385,6 +385,7 @@ def run_b200(args):
                     "peak_source": peaks["source"]}
 
     cpu = None
+    used_graph = bool(unet.use_cuda_graph)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, ref_out = cpu_baseline()
         err = rel_l2(full_out.cpu(), ref_out)
@@ -393,13 +394,26 @@ def run_b200(args):
                          else "CPU oracle port, fp32")}
         if not err <= 2e-2:
             raise SystemExit(f"parity FAILED at the headline shape: rel-L2 {err:.3e} > 2e-2")
+        # the fp32-accumulate check mode (north star: <= 1e-3) on the same inputs, same launch sequence
+        del unet
+        torch.cuda.empty_cache()
+        chk = UNet3DConditionModel(check_mode=True)
+        chk.load_state_dict(synthetic_state_dict(seed=0), strict=True)
+        chk = chk.to(dev).eval()
+        out_chk = chk(sample.to(dev), t_check, encoder_hidden_states=text.to(dev)).sample.cpu()
+        err_chk = rel_l2(out_chk, ref_out)
+        parity["check_mode"] = {"rel_l2": err_chk, "tolerance": 1e-3,
+                                "what": "split-bf16 operands through the same tcgen05 GEMM/conv mainloops, fp32 "
+                                        "epilogues / norms / attention (UNet3DConditionModel(check_mode=True))"}
+        if not err_chk <= 1e-3:
+            raise SystemExit(f"check-mode parity FAILED at the headline shape: rel-L2 {err_chk:.3e} > 1e-3")
 
     if rank == 0:
         line = {"metric": "denoise steps/s (320x512x16, CFG)", "value": value, "unit": "steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": CONFIG,
-                "setup": {"parallelism": parallelism, "independent_videos": jobs, "cuda_graph": bool(unet.use_cuda_graph),
+                "setup": {"parallelism": parallelism, "independent_videos": jobs, "cuda_graph": used_graph,
                           "l2": "no flush: one step streams 1.8 GB of weights and several GB of activations, "
                                 ">> 126 MB L2",
                           "launches_per_step_per_rank": per_step, "weight_bytes_per_rank": weight_bytes},
