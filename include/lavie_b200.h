@@ -57,6 +57,10 @@ typedef struct {
   const void* residual;  /* bf16 [M, ld_residual] or NULL */
   int ld_residual;
   int geglu;
+  float* col_stats;      /* NULL or fp32 [ceil(M / 32), N, 2]: per 32-row slab and output column, (sum, sum of squares) of the
+                            bf16-rounded outputs.  This is the statistics pass of the GroupNorm that consumes the output
+                            (resnet.py:180,191; attention.py:369), emitted by the producer's epilogue instead of a second
+                            read of the tensor; fold with lavie_groupnorm_finalize_colsums.  Not in check mode. */
 } lavie_epilogue;
 
 /* nn.Linear / 1x1 InflatedConv3d: out[M,N] = [a0 | a1][M, k0+k1] * w[N, k0+k1]^T (+ epilogue).
@@ -110,6 +114,16 @@ int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void* x1, int l
                           int rows_per_sample, const float* scale_shift, int silu, void* y, int ldy,
                           lavie_stream_t stream);
 
+/* GroupNorm statistics from the PRODUCERS' column sums (lavie_epilogue.col_stats) instead of lavie_groupnorm_stats:
+ * cs0 / cs1 = [rows / 32, c0 | c1, 2] of the one or two concatenated sources; rows_per_sample must be a multiple of 32
+ * (a slab never straddles two samples).  Same (scale, shift) output and fp64 combination as lavie_groupnorm_finalize.
+ * lavie_groupnorm_reduce_colsums stops at sums[samples, groups, 2] (fp64), the quantity frame shards exchange. */
+int lavie_groupnorm_finalize_colsums(const float* cs0, int c0, const float* cs1, int c1, int samples,
+                                     int rows_per_sample, int groups, const float* gamma, const float* beta, float eps,
+                                     float* scale_shift, lavie_stream_t stream);
+int lavie_groupnorm_reduce_colsums(const float* cs0, int c0, const float* cs1, int c1, int samples, int rows_per_sample,
+                                   int groups, double* sums, lavie_stream_t stream);
+
 /* nn.LayerNorm over the channel dimension of every row (attention.py:444-477 norm1/norm2/norm_temp/norm3). */
 int lavie_layernorm_bf16(const void* x, int ldx, const float* gamma, const float* beta, float eps, void* y, int ldy,
                          int rows, int C, lavie_stream_t stream);
@@ -155,6 +169,11 @@ int lavie_gn_exchange_finalize(const float* partial, int samples, int chunks, in
                                long long count_per_group_global, const float* gamma, const float* beta, float eps,
                                float* scale_shift, void* const* slot_ptrs, void* const* flag_ptrs,
                                unsigned int* epoch_counter, int P, int my_rank, lavie_stream_t stream);
+/* the same exchange starting from this rank's fp64 sums[samples, groups, 2] (lavie_groupnorm_reduce_colsums) */
+int lavie_gn_exchange_finalize_sums(const double* local_sums, int samples, int groups, int C,
+                                    long long count_per_group_global, const float* gamma, const float* beta, float eps,
+                                    float* scale_shift, void* const* slot_ptrs, void* const* flag_ptrs,
+                                    unsigned int* epoch_counter, int P, int my_rank, lavie_stream_t stream);
 int lavie_layernorm_scatter_p2p(const void* x, int ldx, const float* gamma, const float* beta, float eps,
                                 void* const* recv_ptrs, int rows, int C, int hw, int hwp, int P, int my_rank,
                                 lavie_stream_t stream);

@@ -27,6 +27,7 @@ class Epilogue(Structure):
         ("residual", c_void_p),
         ("ld_residual", c_int),
         ("geglu", c_int),
+        ("col_stats", c_void_p),
     ]
 
 
@@ -50,6 +51,8 @@ SIGNATURES = {
     "lavie_groupnorm_finalize": (c_int, [_P, c_int, c_int, c_int, c_int, c_longlong, _P, _P, c_float, _P, _P]),
     "lavie_groupnorm_scale_shift": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float,
                                             _P, _P, _P, _P]),
+    "lavie_groupnorm_finalize_colsums": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, _P]),
+    "lavie_groupnorm_reduce_colsums": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_groupnorm_apply": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),
     "lavie_layernorm_bf16": (c_int, [_P, c_int, _P, _P, c_float, _P, c_int, c_int, c_int, _P]),
     "lavie_layernorm_scatter_bf16": (c_int, [_P, c_int, _P, _P, c_float, _P, c_int, c_int, c_int, c_int, c_int, _P]),
@@ -59,6 +62,8 @@ SIGNATURES = {
     "lavie_rank_barrier": (c_int, [_P, _P, c_int, c_int, _P]),
     "lavie_gn_exchange_finalize": (c_int, [_P, c_int, c_int, c_int, c_int, c_longlong, _P, _P, c_float, _P, _P, _P, _P,
                                            c_int, c_int, _P]),
+    "lavie_gn_exchange_finalize_sums": (c_int, [_P, c_int, c_int, c_int, c_longlong, _P, _P, c_float, _P, _P, _P, _P, c_int,
+                                                c_int, _P]),
     "lavie_layernorm_scatter_p2p": (c_int, [_P, c_int, _P, _P, c_float, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "lavie_add_gathered_p2p": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "lavie_groupnorm_finalize_sums": (c_int, [_P, c_int, c_int, c_int, c_longlong, _P, _P, c_float, _P, _P]),

@@ -135,8 +135,9 @@ def text_input(text: torch.Tensor, ctx: int) -> Triple:
 
 # ------------------------------------------------------------------------------------------------ GEMM / conv
 def gemm(a: Triple, w: WPair, *, a2: Optional[Triple] = None, bias=None, row_bias=None, rows_per_batch=1,
-         residual: Optional[Triple] = None, geglu=False, out: Optional[Triple] = None, block_n: int = 0) -> Triple:
-    lib = _lib.load()
+         residual: Optional[Triple] = None, geglu=False, out: Optional[Triple] = None, block_n: int = 0,
+         stats: bool = False) -> Triple:
+    lib = _lib.load()          # (stats: the bf16 path's fused GroupNorm statistics; check mode runs the fp32 pass)
     assert a.full() and (a2 is None or a2.full()), "GEMM inputs must be whole triples"
     M, k0 = a.rows, a.C
     k1 = a2.C if a2 is not None else 0
@@ -166,7 +167,8 @@ def gemm(a: Triple, w: WPair, *, a2: Optional[Triple] = None, bias=None, row_bia
 
 
 def conv3x3(x: Triple, NF: int, H: int, W: int, w: WPair, *, stride: int = 1, bias=None, row_bias=None,
-            rows_per_batch=1, residual: Optional[Triple] = None, out: Optional[Triple] = None, block_n: int = 0) -> Triple:
+            rows_per_batch=1, residual: Optional[Triple] = None, out: Optional[Triple] = None, block_n: int = 0,
+            stats: bool = False) -> Triple:
     lib = _lib.load()
     assert x.full() and x.ld == 3 * x.C and x.rows == NF * H * W, "conv3x3 needs a contiguous whole triple"
     C = x.C

@@ -69,6 +69,8 @@ struct GemmParams {
   __nv_bfloat16* out;
   int ldo;
   float* partial;            // split-K workspace [splits, M, N] fp32 (splits > 1)
+  float* colstats;           // [M / 32, N, 2] or null: per 32-row slab and output column, (sum, sum of squares) of the
+                             // bf16-rounded outputs -- the GroupNorm statistics of the NEXT layer, emitted by the producer
   int check;                 // fp32-accumulate check mode: accumulators ALWAYS leave as fp32 partials (even with
                              // splits == 1); bias / residual / GEGLU run in fp32 on split-bf16 triples (check reduce)
   int k_rot;                 // K-sweep rotation stride per M tile (0 = off)
@@ -413,6 +415,32 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         }
         fence_proxy_async_smem();
         __syncwarp();
+        if (p.colstats != nullptr && col_out0 < p.N && wrow0 < p.M) {
+          // GroupNorm statistics of the consumer, from the staged bf16 chunk (exactly the values that reach memory):
+          // lane = (row parity, column pair); 16 conflict-free LDS.32 walk the 32 rows, one shuffle folds the parities,
+          // lanes 0-15 store 16 coalesced float4 {sum, sumsq} x 2 columns.  Rows past M do not count.
+          const int par = lane >> 4, c2 = lane & 15;
+          const uint8_t* chunk = my_stage + k * EPI_CHUNK_BYTES;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = 2 * i + par;
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(chunk + r * 64 + (((c2 >> 2) ^ ((r >> 1) & 3)) << 4) +
+                                                                   (c2 & 3) * 4);
+            float2 v2 = unpack_bf16(w);
+            if (wrow0 + r >= p.M) v2 = make_float2(0.f, 0.f);
+            s0 += v2.x; q0 = fmaf(v2.x, v2.x, q0);
+            s1 += v2.y; q1 = fmaf(v2.y, v2.y, q1);
+          }
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+          q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+          const int col = col_out0 + 2 * c2;
+          if (par == 0 && col < p.N)
+            *reinterpret_cast<float4*>(p.colstats + (static_cast<size_t>(wrow0 >> 5) * p.N + col) * 2) =
+                make_float4(s0, q0, s1, q1);
+        }
         if (lane == 0 && !(p.debug & 16)) {
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                            reinterpret_cast<uint64_t>(&tmap_out)),
@@ -550,6 +578,51 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N
   }
 }
 
+// Split-K reduction that also emits the consumer's GroupNorm column statistics (same layout as the epilogue's):
+// block = one 32-row slab x 1024 columns, thread = 4 columns walking down the 32 rows.
+__global__ void __launch_bounds__(256)
+splitk_reduce_stats_kernel(const float* __restrict__ partial, int splits, int M, int N, int M_total,
+                           const float* __restrict__ bias, const float* __restrict__ row_bias, int rows_per_batch,
+                           int ld_row_bias, const __nv_bfloat16* __restrict__ residual, int ldr,
+                           __nv_bfloat16* __restrict__ out, int ldo, int row0, float* __restrict__ colstats) {
+  pdl_prologue();
+  const int col = (blockIdx.y * 256 + threadIdx.x) * 4;
+  if (col >= N) return;
+  const int r_begin = blockIdx.x * 32;                 // window-relative; row0 is a multiple of 256
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) b4 = *reinterpret_cast<const float4*>(bias + col);
+  for (int row = r_begin; row < r_begin + 32 && row < M; ++row) {
+    float4 a = *reinterpret_cast<const float4*>(partial + static_cast<size_t>(row) * N + col);
+    for (int sp = 1; sp < splits; ++sp) {
+      const float4 b = *reinterpret_cast<const float4*>(partial + (static_cast<size_t>(sp) * M + row) * N + col);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+    if (row_bias) {
+      const float4 b = *reinterpret_cast<const float4*>(row_bias + static_cast<size_t>((row + row0) / rows_per_batch) * ld_row_bias + col);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (residual) {
+      const uint2 r = *reinterpret_cast<const uint2*>(residual + static_cast<size_t>(row) * ldr + col);
+      const float2 r0 = unpack_bf16(r.x), r1 = unpack_bf16(r.y);
+      a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
+    }
+    const uint2 o = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+    *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * ldo + col) = o;
+    if (row + row0 < M_total) {
+      const float2 v0 = unpack_bf16(o.x), v1 = unpack_bf16(o.y);
+      s[0] += v0.x; q[0] = fmaf(v0.x, v0.x, q[0]);
+      s[1] += v0.y; q[1] = fmaf(v0.y, v0.y, q[1]);
+      s[2] += v1.x; q[2] = fmaf(v1.x, v1.x, q[2]);
+      s[3] += v1.y; q[3] = fmaf(v1.y, v1.y, q[3]);
+    }
+  }
+  float* dst = colstats + (static_cast<size_t>((r_begin + row0) >> 5) * N + col) * 2;
+  *reinterpret_cast<float4*>(dst) = make_float4(s[0], q[0], s[1], q[1]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(s[2], q[2], s[3], q[3]);
+}
+
 // Check-mode epilogue: ordered sum of the fp32 partials, then bias / time bias / residual / GEGLU in fp32 (exact erf
 // GELU) on split-bf16 triples: residual row = [hi | lo | hi] of width N each, output row = [hi | lo | hi] of width n_out.
 __global__ void __launch_bounds__(256)
@@ -616,6 +689,14 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
                p.residual ? p.residual + static_cast<size_t>(row0) * p.ldr : nullptr, p.ldr, p.geglu,
                p.out + static_cast<size_t>(row0) * p.ldo, p.ldo, row0);
     rc = lavie_check_launch("splitk_reduce_check_kernel");
+  } else if (p.splits > 1 && p.colstats != nullptr) {
+    const int row0 = p.m_tile0 * PAIR_M;
+    dim3 grid((p.rows_window + 31) / 32, (p.N / 4 + 255) / 256);
+    launch_pdl(splitk_reduce_stats_kernel, grid, 256, 0, stream, p.partial, p.splits, p.rows_window, p.N, p.M, p.bias,
+               p.row_bias, p.rows_per_batch, p.ld_row_bias,
+               p.residual ? p.residual + static_cast<size_t>(row0) * p.ldr : nullptr, p.ldr,
+               p.out + static_cast<size_t>(row0) * p.ldo, p.ldo, row0, p.colstats);
+    rc = lavie_check_launch("splitk_reduce_stats_kernel");
   } else if (p.splits > 1) {
     const int row0 = p.m_tile0 * PAIR_M;
     const long long total = static_cast<long long>(p.rows_window) * (p.N >> 2);
@@ -782,7 +863,11 @@ int make_weight_map(CUtensorMap* map, const void* w, int N, int K, int bn) {
 int fill_epilogue(GemmParams& p, const lavie_epilogue* ep, int N, void* out, int ldo) {
   p.bias = nullptr; p.row_bias = nullptr; p.rows_per_batch = 1; p.ld_row_bias = N; p.residual = nullptr; p.ldr = 0;
   p.geglu = 0;
+  p.colstats = nullptr;
   if (ep) {
+    p.colstats = ep->col_stats;
+    LAVIE_REQUIRE(!p.colstats || (aligned16(p.colstats) && !ep->geglu && N % 4 == 0), LAVIE_ERR_SHAPE,
+                  "gemm: col_stats needs a 16-byte aligned buffer, N %% 4 == 0 and no GEGLU");
     p.bias = ep->bias;
     p.row_bias = ep->row_bias;
     p.rows_per_batch = ep->rows_per_batch > 0 ? ep->rows_per_batch : 1;

@@ -651,6 +651,95 @@ __global__ void gn_finalize_sums_kernel(const double* __restrict__ sums, int gro
 }
 }  // namespace
 
+namespace {
+// GroupNorm statistics from the producers' per-slab column sums (gemm.cu epilogue): one block per (group, sample)
+// folds slabs_per_sample x (C / groups) x {sum, sumsq} in a FIXED order (thread-strided fp32 partials over at most a few
+// dozen terms each, then an fp64 tree), so the result is deterministic.  The group's channels may straddle the seam of
+// a two-source concat.  sums != nullptr: stop at the fp64 (sum, sumsq) per (sample, group) (frame-sharded exchange).
+__global__ void __launch_bounds__(256)
+gn_colsums_kernel(const float* __restrict__ cs0, int c0, const float* __restrict__ cs1, int c1, int slabs_per_sample,
+                  int groups, double inv_count, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                  float* __restrict__ scale_shift, double* __restrict__ sums) {
+  pdl_prologue();
+  const int g = blockIdx.x, sample = blockIdx.y;
+  const int C = c0 + c1, cpg = C / groups;
+  const int ch0 = g * cpg;
+  const long long total = static_cast<long long>(slabs_per_sample) * cpg;
+  double a = 0.0, b = 0.0;
+  // chunks of 32 terms accumulated in fp32, chunk results in fp64
+  for (long long base = static_cast<long long>(threadIdx.x) * 32; base < total; base += 256LL * 32) {
+    float fa = 0.f, fb = 0.f;
+    const long long end = base + 32 < total ? base + 32 : total;
+    for (long long i = base; i < end; ++i) {
+      const long long slab = static_cast<long long>(sample) * slabs_per_sample + i / cpg;
+      const int ch = ch0 + static_cast<int>(i % cpg);
+      const float2 v = ch < c0 ? __ldg(reinterpret_cast<const float2*>(cs0 + (slab * c0 + ch) * 2))
+                               : __ldg(reinterpret_cast<const float2*>(cs1 + (slab * c1 + (ch - c0)) * 2));
+      fa += v.x;
+      fb += v.y;
+    }
+    a += fa;
+    b += fb;
+  }
+  __shared__ double sa[256], sb[256];
+  sa[threadIdx.x] = a;
+  sb[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sa[threadIdx.x] += sa[threadIdx.x + o];
+      sb[threadIdx.x] += sb[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (sums != nullptr) {
+    if (threadIdx.x == 0) {
+      sums[(static_cast<size_t>(sample) * groups + g) * 2] = sa[0];
+      sums[(static_cast<size_t>(sample) * groups + g) * 2 + 1] = sb[0];
+    }
+    return;
+  }
+  const double mean = sa[0] * inv_count;
+  double var = sb[0] * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  for (int c = threadIdx.x; c < cpg; c += blockDim.x) {
+    const float sc = rstd * gamma[ch0 + c];
+    float* dst = scale_shift + (static_cast<size_t>(sample) * C + ch0 + c) * 2;
+    dst[0] = sc;
+    dst[1] = beta[ch0 + c] - static_cast<float>(mean) * sc;
+  }
+}
+
+int colsums_impl(const float* cs0, int c0, const float* cs1, int c1, int samples, int rows_per_sample, int groups,
+                 const float* gamma, const float* beta, float eps, float* scale_shift, double* sums,
+                 cudaStream_t stream) {
+  const int C = c0 + c1;
+  LAVIE_REQUIRE(samples > 0 && rows_per_sample > 0 && rows_per_sample % 32 == 0 && groups > 0 && C % groups == 0 &&
+                    c0 > 0 && c0 % 2 == 0 && c1 % 2 == 0,
+                LAVIE_ERR_SHAPE, "groupnorm colsums: rows_per_sample=%d must be a multiple of 32, C=%d groups=%d",
+                rows_per_sample, C, groups);
+  LAVIE_REQUIRE(cs0 != nullptr && (c1 == 0 || cs1 != nullptr), LAVIE_ERR_SHAPE, "groupnorm colsums: null statistics");
+  dim3 grid(groups, samples);
+  launch_pdl(gn_colsums_kernel, grid, 256, 0, stream, cs0, c0, cs1, c1, rows_per_sample / 32, groups,
+             1.0 / (static_cast<double>(rows_per_sample) * (C / groups)), gamma, beta, eps, scale_shift, sums);
+  return lavie_check_launch("gn_colsums_kernel");
+}
+}  // namespace
+
+extern "C" int lavie_groupnorm_finalize_colsums(const float* cs0, int c0, const float* cs1, int c1, int samples,
+                                                int rows_per_sample, int groups, const float* gamma, const float* beta,
+                                                float eps, float* scale_shift, cudaStream_t stream) {
+  LAVIE_REQUIRE(scale_shift != nullptr && gamma != nullptr && beta != nullptr, LAVIE_ERR_SHAPE, "groupnorm colsums: null");
+  return colsums_impl(cs0, c0, cs1, c1, samples, rows_per_sample, groups, gamma, beta, eps, scale_shift, nullptr, stream);
+}
+
+extern "C" int lavie_groupnorm_reduce_colsums(const float* cs0, int c0, const float* cs1, int c1, int samples,
+                                              int rows_per_sample, int groups, double* sums, cudaStream_t stream) {
+  LAVIE_REQUIRE(sums != nullptr, LAVIE_ERR_SHAPE, "groupnorm colsums: null sums");
+  return colsums_impl(cs0, c0, cs1, c1, samples, rows_per_sample, groups, nullptr, nullptr, 0.f, nullptr, sums, stream);
+}
+
 extern "C" int lavie_layernorm_bf16(const void* x, int ldx, const float* gamma, const float* beta, float eps, void* y,
                                     int ldy, int rows, int C, cudaStream_t stream) {
   return layernorm_impl(x, ldx, gamma, beta, eps, y, ldy, rows, C, 0, 0, stream);

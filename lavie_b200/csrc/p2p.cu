@@ -96,7 +96,8 @@ __global__ void rank_barrier_kernel(PeerPtrs flags, uint32_t* epoch_counter, int
 // partial[samples][chunks][groups][2] -> exchange -> scale_shift[samples][C][2]
 // slots: per peer a buffer double[2 (epoch parity)][P][samples*groups*2]
 __global__ void __launch_bounds__(256)
-gn_exchange_finalize_kernel(const float* __restrict__ partial, int samples, int chunks, int groups, int C,
+gn_exchange_finalize_kernel(const float* __restrict__ partial, const double* __restrict__ local_sums, int samples,
+                            int chunks, int groups, int C,
                             double inv_count, const float* __restrict__ gamma, const float* __restrict__ beta,
                             float eps, float* __restrict__ scale_shift, PeerPtrs slots, PeerPtrs flags,
                             uint32_t* epoch_counter, int P, int my_rank, FaultCtx fc) {
@@ -105,8 +106,12 @@ gn_exchange_finalize_kernel(const float* __restrict__ partial, int samples, int 
   __shared__ float s_mean[2 * 64], s_rstd[2 * 64];
   const uint32_t epoch = *epoch_counter + 1;
   const int n = samples * groups * 2;
-  // 1. ordered local reduction of the chunk partials (8 lanes per (sample, group))
+  // 1. ordered local reduction of the chunk partials (8 lanes per (sample, group)) -- or the local sums as they come
+  //    from the producers' column statistics (lavie_groupnorm_reduce_colsums)
   const int sub = threadIdx.x & 7;
+  if (local_sums != nullptr) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_sums[i] = local_sums[i];
+  } else
   for (int sg = threadIdx.x >> 3; sg < samples * groups; sg += blockDim.x >> 3) {
     const int sample = sg / groups, g = sg - sample * groups;
     double a = 0.0, b = 0.0;
@@ -301,10 +306,11 @@ extern "C" int lavie_rank_barrier(void* const* flag_ptrs, unsigned int* epoch_co
   return lavie_check_launch("rank_barrier_kernel");
 }
 
-extern "C" int lavie_gn_exchange_finalize(const float* partial, int samples, int chunks, int groups, int C,
-                                          long long count_per_group_global, const float* gamma, const float* beta,
-                                          float eps, float* scale_shift, void* const* slot_ptrs, void* const* flag_ptrs,
-                                          unsigned int* epoch_counter, int P, int my_rank, cudaStream_t stream) {
+namespace {
+int gn_exchange_impl(const float* partial, const double* local_sums, int samples, int chunks, int groups, int C,
+                     long long count_per_group_global, const float* gamma, const float* beta, float eps,
+                     float* scale_shift, void* const* slot_ptrs, void* const* flag_ptrs, unsigned int* epoch_counter,
+                     int P, int my_rank, cudaStream_t stream) {
   LAVIE_REQUIRE(samples >= 1 && samples <= 2 && groups <= 64 && groups % 4 == 0 && C % groups == 0 &&
                     count_per_group_global > 0,
                 LAVIE_ERR_SHAPE, "gn_exchange_finalize: samples <= 2, groups <= 64 (multiple of 4)");
@@ -313,10 +319,29 @@ extern "C" int lavie_gn_exchange_finalize(const float* partial, int samples, int
   if (rc) return rc;
   rc = fill_peers(f, flag_ptrs, P);
   if (rc) return rc;
-  launch_pdl(gn_exchange_finalize_kernel, 1, 256, 0, stream, partial, samples, chunks, groups, C,
+  launch_pdl(gn_exchange_finalize_kernel, 1, 256, 0, stream, partial, local_sums, samples, chunks, groups, C,
                                                      1.0 / static_cast<double>(count_per_group_global), gamma, beta, eps,
                                                      scale_shift, s, f, epoch_counter, P, my_rank, fault_ctx());
   return lavie_check_launch("gn_exchange_finalize_kernel");
+}
+}  // namespace
+
+extern "C" int lavie_gn_exchange_finalize(const float* partial, int samples, int chunks, int groups, int C,
+                                          long long count_per_group_global, const float* gamma, const float* beta,
+                                          float eps, float* scale_shift, void* const* slot_ptrs, void* const* flag_ptrs,
+                                          unsigned int* epoch_counter, int P, int my_rank, cudaStream_t stream) {
+  return gn_exchange_impl(partial, nullptr, samples, chunks, groups, C, count_per_group_global, gamma, beta, eps,
+                          scale_shift, slot_ptrs, flag_ptrs, epoch_counter, P, my_rank, stream);
+}
+
+extern "C" int lavie_gn_exchange_finalize_sums(const double* local_sums, int samples, int groups, int C,
+                                               long long count_per_group_global, const float* gamma, const float* beta,
+                                               float eps, float* scale_shift, void* const* slot_ptrs,
+                                               void* const* flag_ptrs, unsigned int* epoch_counter, int P, int my_rank,
+                                               cudaStream_t stream) {
+  LAVIE_REQUIRE(local_sums != nullptr, LAVIE_ERR_SHAPE, "gn_exchange_finalize_sums: null sums");
+  return gn_exchange_impl(nullptr, local_sums, samples, 1, groups, C, count_per_group_global, gamma, beta, eps, scale_shift,
+                          slot_ptrs, flag_ptrs, epoch_counter, P, my_rank, stream);
 }
 
 extern "C" int lavie_layernorm_scatter_p2p(const void* x, int ldx, const float* gamma, const float* beta, float eps,

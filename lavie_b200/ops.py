@@ -86,10 +86,11 @@ def _rows2d(t: torch.Tensor) -> Tuple[int, int, int]:
     return t.shape[0], t.shape[1], t.stride(0)
 
 
-def _epilogue(bias=None, row_bias=None, rows_per_batch=1, residual=None, geglu=False):
-    if bias is None and row_bias is None and residual is None and not geglu:
+def _epilogue(bias=None, row_bias=None, rows_per_batch=1, residual=None, geglu=False, col_stats=None):
+    if bias is None and row_bias is None and residual is None and not geglu and col_stats is None:
         return None
     ep = Epilogue()
+    ep.col_stats = _ptr(col_stats)
     ep.bias = _ptr(bias)
     ep.row_bias = _ptr(row_bias)
     ep.rows_per_batch = int(rows_per_batch)
@@ -128,8 +129,10 @@ def text_input(text: torch.Tensor, ctx: int) -> torch.Tensor:
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None, bias=None, row_bias=None,
-         rows_per_batch=1, residual=None, geglu=False, out: Optional[torch.Tensor] = None, block_n: int = 0):
-    """out[M,N] = [a | a2] @ w^T (+ fused epilogue).  w: bf16 [N, K] contiguous."""
+         rows_per_batch=1, residual=None, geglu=False, out: Optional[torch.Tensor] = None, block_n: int = 0,
+         stats: bool = False):
+    """out[M,N] = [a | a2] @ w^T (+ fused epilogue).  w: bf16 [N, K] contiguous.  stats=True: the epilogue also emits the
+    per-slab column sums the consuming GroupNorm needs (attached to the result, see `colsums`)."""
     lib = _lib.load()
     M, k0, lda = _rows2d(a)
     k1, lda2 = 0, 0
@@ -143,7 +146,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None,
         out = torch.empty((M, n_out), dtype=BF16, device=a.device)
     Mo, No, ldo = _rows2d(out)
     assert Mo == M and No == n_out
-    ep = _epilogue(bias, row_bias, rows_per_batch, residual, geglu)
+    cs = _new_colsums(M, n_out, a.device) if stats and not geglu else None
+    ep = _epilogue(bias, row_bias, rows_per_batch, residual, geglu, cs)
     ws = _workspace(a.device)
     with _Launch("gemm_bf16_tcgen05", 2.0 * M * N * (k0 + k1), 2.0 * (M * (k0 + k1) + N * (k0 + k1) + M * n_out),
                  f"gemm M={M} N={N} K={k0 + k1}{' geglu' if geglu else ''}"):
@@ -151,6 +155,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None,
                                  ctypes.byref(ep) if ep is not None else None, block_n, ws.data_ptr(), ws.numel(),
                                  _stream())
     check(rc, "lavie_gemm_bf16")
+    if cs is not None:
+        out._gn_colsums = cs
     return out
 
 
@@ -172,7 +178,7 @@ def im2col3x3(x: torch.Tensor, NF: int, H: int, W: int, stride: int = 1) -> torc
 
 def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride: int = 1, bias=None, row_bias=None,
             rows_per_batch=1, residual=None, out: Optional[torch.Tensor] = None, block_n: int = 0,
-            force_im2col: bool = False):
+            force_im2col: bool = False, stats: bool = False):
     """3x3 pad-1 InflatedConv3d on a contiguous channels-last map; w: bf16 [N, 9*C] in (kh, kw, c) order."""
     lib = _lib.load()
     rows, C, ld = _rows2d(x)
@@ -182,14 +188,15 @@ def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride
     if force_im2col or not conv3x3_supported(H, W, C):
         col = im2col3x3(x, NF, H, W, stride)
         return gemm(col, w, bias=bias, row_bias=row_bias, rows_per_batch=rows_per_batch, residual=residual, out=out,
-                    block_n=block_n)
+                    block_n=block_n, stats=stats)
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     m_out = NF * Ho * Wo
     if out is None:
         out = torch.empty((m_out, N), dtype=BF16, device=x.device)
     Mo, No, ldo = _rows2d(out)
     assert Mo == m_out and No == N
-    ep = _epilogue(bias, row_bias, rows_per_batch, residual, False)
+    cs = _new_colsums(m_out, N, x.device) if stats else None
+    ep = _epilogue(bias, row_bias, rows_per_batch, residual, False, cs)
     ws = _workspace(x.device)
     with _Launch("gemm_bf16_tcgen05", 2.0 * m_out * N * 9 * C, 2.0 * (rows * C + N * 9 * C + m_out * N),
                  f"conv3x3 M={m_out} N={N} K={9 * C} W={W} s={stride}"):
@@ -197,7 +204,25 @@ def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride
                                     ctypes.byref(ep) if ep is not None else None, block_n, ws.data_ptr(),
                                     ws.numel(), _stream())
     check(rc, "lavie_conv3x3_bf16")
+    if cs is not None:
+        out._gn_colsums = cs
     return out
+
+
+def _new_colsums(M: int, N: int, device) -> torch.Tensor:
+    return torch.empty(((M + 31) // 32, N, 2), dtype=F32, device=device)
+
+
+def colsums(x: torch.Tensor, rows_per_sample: int, x2: Optional[torch.Tensor] = None):
+    """The producers' column statistics of (x, x2) when every source carries them and slabs do not straddle samples;
+    else None (the caller runs the stand-alone statistics pass)."""
+    if rows_per_sample % 32:
+        return None
+    cs0 = getattr(x, "_gn_colsums", None)
+    cs1 = getattr(x2, "_gn_colsums", None) if x2 is not None else None
+    if cs0 is None or (x2 is not None and cs1 is None):
+        return None
+    return cs0, cs1
 
 
 def groupnorm_scale_shift(x: torch.Tensor, samples: int, rows_per_sample: int, gamma: torch.Tensor,
@@ -213,10 +238,19 @@ def groupnorm_scale_shift(x: torch.Tensor, samples: int, rows_per_sample: int, g
         assert rows2 == rows
     assert rows == samples * rows_per_sample
     C = c0 + c1
-    chunks = lib.lavie_groupnorm_chunks(samples, rows_per_sample)
-    partial = torch.empty((samples, chunks, groups, 2), dtype=F32, device=x.device)
     ss = torch.empty((samples, C, 2), dtype=F32, device=x.device)
     assert gamma.dtype == F32 and beta.dtype == F32 and gamma.numel() == C
+    cs = colsums(x, rows_per_sample, x2) if fused else None
+    if cs is not None:
+        # the statistics pass already happened in the producers' epilogues: fold their column sums (one small launch)
+        with _Launch("lavie_groupnorm_finalize_colsums", 0.0, 8.0 * (rows // 32) * C,
+                     f"gn_colsums rows={rows} C={C} samples={samples}"):
+            check(lib.lavie_groupnorm_finalize_colsums(cs[0].data_ptr(), c0, _ptr(cs[1]), c1, samples, rows_per_sample,
+                                                       groups, gamma.data_ptr(), beta.data_ptr(), eps, ss.data_ptr(),
+                                                       _stream()), "lavie_groupnorm_finalize_colsums")
+        return ss
+    chunks = lib.lavie_groupnorm_chunks(samples, rows_per_sample)
+    partial = torch.empty((samples, chunks, groups, 2), dtype=F32, device=x.device)
     if not fused:
         with _Launch("lavie_groupnorm_stats", 0.0, 2.0 * rows * C, f"gn_stats rows={rows} C={C} samples={samples}"):
             check(lib.lavie_groupnorm_stats(x.data_ptr(), ld0, c0, _ptr(x2), ld1, c1, samples, rows_per_sample, groups,
@@ -244,6 +278,13 @@ def groupnorm_sums(x: torch.Tensor, samples: int, rows_per_sample: int, groups: 
     if x2 is not None:
         _, c1, ld1 = _rows2d(x2)
     assert rows == samples * rows_per_sample
+    cs = colsums(x, rows_per_sample, x2)
+    if cs is not None:
+        sums = torch.empty((samples, groups, 2), dtype=torch.float64, device=x.device)
+        with _Launch("lavie_groupnorm_reduce_colsums"):
+            check(lib.lavie_groupnorm_reduce_colsums(cs[0].data_ptr(), c0, _ptr(cs[1]), c1, samples, rows_per_sample,
+                                                     groups, sums.data_ptr(), _stream()), "lavie_groupnorm_reduce_colsums")
+        return sums
     chunks = lib.lavie_groupnorm_chunks(samples, rows_per_sample)
     partial = torch.empty((samples, chunks, groups, 2), dtype=F32, device=x.device)
     with _Launch("lavie_groupnorm_stats", 0.0, 2.0 * rows * (c0 + c1), f"gn_stats rows={rows} C={c0 + c1} samples={samples}"):

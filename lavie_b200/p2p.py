@@ -78,6 +78,18 @@ class PeerContext:
         if x2 is not None:
             _, c1, ld1 = _rows2d(x2)
         C = c0 + c1
+        from . import ops
+        if ops.colsums(x, rows_local, x2) is not None:
+            # local sums from the producers' column statistics, then the same peer exchange + finalize
+            sums = ops.groupnorm_sums(x, samples, rows_local, groups, x2)
+            ss = torch.empty((samples, C, 2), dtype=F32, device=x.device)
+            with _Launch("lavie_gn_exchange_finalize"):
+                check(lib.lavie_gn_exchange_finalize_sums(sums.data_ptr(), samples, groups, C,
+                                                          rows_local * self.P * (C // groups), gamma.data_ptr(),
+                                                          beta.data_ptr(), eps, ss.data_ptr(), self.ptrs("slots"),
+                                                          self.ptrs("flags"), self.epoch.data_ptr(), self.P, self.rank,
+                                                          _stream()), "lavie_gn_exchange_finalize_sums")
+            return ss
         chunks = lib.lavie_groupnorm_chunks(samples, rows_local)
         partial = torch.empty((samples, chunks, groups, 2), dtype=F32, device=x.device)
         with _Launch("lavie_groupnorm_stats", 0.0, 2.0 * rows * C, f"gn_stats rows={rows} C={C} samples={samples}"):

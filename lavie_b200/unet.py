@@ -239,7 +239,7 @@ class UNet3DConditionModel(nn.Module):
         import torch.distributed as dist
         group, P, _ = self._shard
         C = x.shape[1] + (x2.shape[1] if x2 is not None else 0)
-        sums = ops.groupnorm_sums(x, B, rows_local, x2=x2)                  # fp64 [B, 32, 2]
+        sums = ops.groupnorm_sums(x, B, rows_local, x2=x2)                  # fp64 [B, 32, 2] (producers' column sums if any)
         dist.all_reduce(sums, group=group)                                   # 512 B per call
         return ops.groupnorm_finalize_sums(sums, C, rows_local * P * (C // 32), gamma, beta, eps)
 
@@ -380,14 +380,16 @@ class UNet3DConditionModel(nn.Module):
         eps = self.cfg.norm_eps
         h = self._gn5(x, x2, B, rps, r["g1"], r["b1"], eps, True)
         off, cout = self._packed["temb_slices"][p]
-        h = K.conv3x3(h, NF, H, W, r["w1"], bias=r["cb1"], row_bias=temb_all[:, off:off + cout], rows_per_batch=rps)
+        # stats=True: the conv's epilogue also emits the column sums the NEXT GroupNorm needs (no second read of h)
+        h = K.conv3x3(h, NF, H, W, r["w1"], bias=r["cb1"], row_bias=temb_all[:, off:off + cout], rows_per_batch=rps,
+                      stats=True)
         h = self._gn5(h, None, B, rps, r["g2"], r["b2"], eps, True)
         if "wsc" in r:
             sc = K.gemm(x, r["wsc"], a2=x2, bias=r["bsc"])
         else:
             assert x2 is None
             sc = x
-        return K.conv3x3(h, NF, H, W, r["w2"], bias=r["cb2"], residual=sc)
+        return K.conv3x3(h, NF, H, W, r["w2"], bias=r["cb2"], residual=sc, stats=True)
 
     def _transformer(self, p, x, kv_all, B, Fr, H, W, text_len):
         """Transformer3DModel.forward + BasicTransformerBlock.forward (attention.py:358-407, 511-560)."""
@@ -425,7 +427,7 @@ class UNet3DConditionModel(nn.Module):
             qkv = K.gemm(n, t["attn_temp_qkv"])
             a = K.frame_attention(qkv, B, Fr, HW, heads, d, pitch)
             tok = K.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"], residual=tok)
-            return K.gemm(tok, t["w_out"], bias=t["b_out"], residual=x)
+            return K.gemm(tok, t["w_out"], bias=t["b_out"], residual=x, stats=True)
         # temporal attention: frames read in place with a row stride of HW (no (b f) d c <-> (b d) f c copies)
         if self._shard is None:
             n = K.layernorm(tok, t["norm_temp_g"], t["norm_temp_b"])
@@ -466,7 +468,7 @@ class UNet3DConditionModel(nn.Module):
         n = K.layernorm(tok, t["norm3_g"], t["norm3_b"])
         g = K.gemm(n, t["ff1_w"], bias=t["ff1_b"], geglu=True)
         tok = K.gemm(g, t["ff2_w"], bias=t["ff2_b"], residual=tok)
-        return K.gemm(tok, t["w_out"], bias=t["b_out"], residual=x)
+        return K.gemm(tok, t["w_out"], bias=t["b_out"], residual=x, stats=True)
 
     def _step(self, sample: torch.Tensor, t: torch.Tensor, text: torch.Tensor, taps: Optional[dict] = None,
               input_scale: Optional[torch.Tensor] = None):
@@ -512,7 +514,7 @@ class UNet3DConditionModel(nn.Module):
                 skips.append((x, boc[i]))
             if i != len(boc) - 1:
                 wd, bd = P[f"down_blocks.{i}.downsamplers.0.conv"]
-                x = K.conv3x3(x, B * Fr, h, w, wd, stride=2, bias=bd)
+                x = K.conv3x3(x, B * Fr, h, w, wd, stride=2, bias=bd, stats=True)
                 h, w = h // 2, w // 2
                 skips.append((x, boc[i]))
         x = self._resnet("mid_block.resnets.0", x, None, temb_all, B, Fr, h, w)
@@ -529,7 +531,7 @@ class UNet3DConditionModel(nn.Module):
                 wu, bu = P[f"up_blocks.{i}.upsamplers.0.conv"]
                 x = K.upsample_nearest2x(x, B * Fr, h, w)
                 h, w = 2 * h, 2 * w
-                x = K.conv3x3(x, B * Fr, h, w, wu, bias=bu)
+                x = K.conv3x3(x, B * Fr, h, w, wu, bias=bu, stats=True)
         tap("up_out", x, boc[0], h, w)
         ss = self._gn5_scale_shift(x, None, B, Fr * h * w, P["norm_out"][0], P["norm_out"][1], cfg.norm_eps)
         return K.conv_out(x, ss, B, Fr, h, w, P["conv_out"][0], P["conv_out"][1])

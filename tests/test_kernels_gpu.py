@@ -399,3 +399,73 @@ def test_conv3x3_small_m_large_k():
     out = ops.conv3x3(x, NF, H, W, pack_conv3x3(w), row_bias=temb, rows_per_batch=16 * H * W)
     ref = _conv_ref(x, w, NF, H, W) + temb.repeat_interleave(16 * H * W, 0)
     assert rel_l2(out.float(), ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm statistics from the producer's epilogue
+def _colsums_ref(out, M, N):
+    """[ceil(M/32), N, 2] (sum, sumsq) of the bf16 output, per 32-row slab."""
+    slabs = (M + 31) // 32
+    pad = torch.zeros(slabs * 32, N, device=out.device)
+    pad[:M] = out.float()
+    v = pad.reshape(slabs, 32, N)
+    return torch.stack([v.sum(1), (v * v).sum(1)], dim=-1)
+
+
+@pytest.mark.parametrize("M,N,K,block_n", [(2560, 320, 320, 0), (1000, 640, 1280, 0), (256 * 150 + 96, 320, 192, 320),
+                                           (640, 1280, 2560, 0), (4096, 1152, 320, 128)])
+def test_gemm_emits_groupnorm_column_sums(M, N, K, block_n):
+    """lavie_epilogue.col_stats: the producer's epilogue (or the split-K reduction) writes the consumer's GroupNorm
+    statistics; they must equal the sums of the bf16 values actually stored (incl. bias + residual, M tails)."""
+    ops = _ops()
+    a = _bf(_rand(M, K))
+    w = _bf(_rand(N, K, scale=K ** -0.5))
+    bias = _rand(N, seed=1)
+    res = _bf(_rand(M, N, seed=3))
+    out = ops.gemm(a, w, bias=bias, residual=res, stats=True, block_n=block_n)
+    plain = ops.gemm(a, w, bias=bias, residual=res, block_n=block_n)
+    assert torch.equal(out, plain)                                   # the statistics do not change the output
+    cs = out._gn_colsums
+    ref = _colsums_ref(out, M, N)
+    assert cs.shape == ref.shape
+    assert rel_l2(cs, ref) < 1e-5
+
+
+def test_splitk_gemm_emits_groupnorm_column_sums():
+    ops = _ops()
+    from lavie_b200 import _lib
+    lib = _lib.load()
+    M, N, K = 1280, 1280, 11520
+    a = _bf(_rand(M, K))
+    w = _bf(_rand(N, K, scale=K ** -0.5))
+    lib.lavie_debug_set(1, 4)                                        # force split-K
+    try:
+        out = ops.gemm(a, w, bias=_rand(N, seed=1), stats=True)
+    finally:
+        lib.lavie_debug_set(1, 0)
+    assert rel_l2(out._gn_colsums, _colsums_ref(out, M, N)) < 1e-5
+
+
+@pytest.mark.parametrize("NF,H,W,C,N,stride", [(4, 16, 32, 320, 640, 1), (2, 40, 64, 320, 320, 1), (3, 20, 32, 640, 640, 2)])
+def test_conv_column_sums_feed_groupnorm(NF, H, W, C, N, stride):
+    """conv (stats=True) -> GroupNorm through the column sums == conv -> stand-alone statistics pass, for 5-D statistics
+    (sample = all frames) and for the per-frame norm, incl. a two-source concat whose groups straddle the seam."""
+    ops = _ops()
+    from lavie_b200.packing import pack_conv3x3
+    x = _bf(_rand(NF * H * W, C))
+    w = pack_conv3x3(_rand(N, C, 3, 3, scale=(9 * C) ** -0.5)).to(DEV)
+    y = ops.conv3x3(x, NF, H, W, w, stride=stride, bias=_rand(N, seed=2), stats=True)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    rows = NF * Ho * Wo
+    assert rel_l2(y._gn_colsums, _colsums_ref(y, rows, N)) < 1e-5
+    gamma, beta = _rand(N, seed=4) * 0.1 + 1, _rand(N, seed=5) * 0.1
+    plain = y.clone()                                                # a copy carries no statistics -> stand-alone pass
+    for samples in (1, NF):
+        ss = ops.groupnorm_scale_shift(y, samples, rows // samples, gamma, beta, 1e-5)
+        ss_ref = ops.groupnorm_scale_shift(plain, samples, rows // samples, gamma, beta, 1e-5)
+        assert rel_l2(ss, ss_ref) < 1e-5
+    # concat [y | y2] with 32 groups over N + N2 channels
+    y2 = ops.gemm(_bf(_rand(rows, 64, seed=9)), _bf(_rand(320, 64, seed=10, scale=0.1)), stats=True)
+    g2, b2 = _rand(N + 320, seed=6) * 0.1 + 1, _rand(N + 320, seed=7) * 0.1
+    ss = ops.groupnorm_scale_shift(y, 1, rows, g2, b2, 1e-5, x2=y2)
+    ss_ref = ops.groupnorm_scale_shift(plain, 1, rows, g2, b2, 1e-5, x2=y2.clone())
+    assert rel_l2(ss, ss_ref) < 1e-5
