@@ -57,10 +57,13 @@ typedef struct {
   const void* residual;  /* bf16 [M, ld_residual] or NULL */
   int ld_residual;
   int geglu;
-  float* col_stats;      /* NULL or fp32 [ceil(M / 32), N, 2]: per 32-row slab and output column, (sum, sum of squares) of the
-                            bf16-rounded outputs.  This is the statistics pass of the GroupNorm that consumes the output
-                            (resnet.py:180,191; attention.py:369), emitted by the producer's epilogue instead of a second
-                            read of the tensor; fold with lavie_groupnorm_finalize_colsums.  Not in check mode. */
+  float* col_stats;      /* NULL or fp32 [ceil(M / 32), N / 32, 4, 2] (N % 32 == 0): per 32-row slab and 10-channel micro-group,
+                            (sum, sum of squares) of the bf16-rounded outputs; entry [slab][chunk][piece] covers the part of
+                            decade (chunk * 32) / 10 + piece that lies inside columns [chunk * 32, chunk * 32 + 32).  This is
+                            the statistics pass of the GroupNorm that consumes the output (resnet.py:180,191;
+                            attention.py:369; every group of the model is a whole number of decades), emitted by the
+                            producer's epilogue instead of a second read of the tensor; fold with
+                            lavie_groupnorm_finalize_colsums.  Not in check mode. */
 } lavie_epilogue;
 
 /* nn.Linear / 1x1 InflatedConv3d: out[M,N] = [a0 | a1][M, k0+k1] * w[N, k0+k1]^T (+ epilogue).
@@ -114,9 +117,10 @@ int lavie_groupnorm_apply(const void* x0, int ld0, int c0, const void* x1, int l
                           int rows_per_sample, const float* scale_shift, int silu, void* y, int ldy,
                           lavie_stream_t stream);
 
-/* GroupNorm statistics from the PRODUCERS' column sums (lavie_epilogue.col_stats) instead of lavie_groupnorm_stats:
- * cs0 / cs1 = [rows / 32, c0 | c1, 2] of the one or two concatenated sources; rows_per_sample must be a multiple of 32
- * (a slab never straddles two samples).  Same (scale, shift) output and fp64 combination as lavie_groupnorm_finalize.
+/* GroupNorm statistics from the PRODUCERS' micro-group sums (lavie_epilogue.col_stats) instead of lavie_groupnorm_stats:
+ * cs0 / cs1 = [rows / 32, c / 32, 4, 2] of the one or two concatenated sources (c0, c1 multiples of 32; C / groups a
+ * multiple of 10); rows_per_sample must be a multiple of 32 (a slab never straddles two samples).  Same (scale, shift)
+ * output and fp64 combination as lavie_groupnorm_finalize.
  * lavie_groupnorm_reduce_colsums stops at sums[samples, groups, 2] (fp64), the quantity frame shards exchange. */
 int lavie_groupnorm_finalize_colsums(const float* cs0, int c0, const float* cs1, int c1, int samples,
                                      int rows_per_sample, int groups, const float* gamma, const float* beta, float eps,

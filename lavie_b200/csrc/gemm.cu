@@ -69,8 +69,9 @@ struct GemmParams {
   __nv_bfloat16* out;
   int ldo;
   float* partial;            // split-K workspace [splits, M, N] fp32 (splits > 1)
-  float* colstats;           // [M / 32, N, 2] or null: per 32-row slab and output column, (sum, sum of squares) of the
-                             // bf16-rounded outputs -- the GroupNorm statistics of the NEXT layer, emitted by the producer
+  float* colstats;           // [M / 32, N / 32, 4, 2] or null: per 32-row slab and 10-channel micro-group (stored per
+                             // 32-column chunk and decade piece), (sum, sum of squares) of the bf16-rounded outputs: the
+                             // GroupNorm statistics of the NEXT layer, emitted by the producer
   int check;                 // fp32-accumulate check mode: accumulators ALWAYS leave as fp32 partials (even with
                              // splits == 1); bias / residual / GEGLU run in fp32 on split-bf16 triples (check reduce)
   int k_rot;                 // K-sweep rotation stride per M tile (0 = off)
@@ -416,12 +417,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         fence_proxy_async_smem();
         __syncwarp();
         if (p.colstats != nullptr && col_out0 < p.N && wrow0 < p.M) {
-          // GroupNorm statistics of the consumer, from the staged bf16 chunk (exactly the values that reach memory):
-          // lane = (row parity, column pair); 16 conflict-free LDS.32 walk the 32 rows, one shuffle folds the parities,
-          // lanes 0-15 store 16 coalesced float4 {sum, sumsq} x 2 columns.  Rows past M do not count.
+          // GroupNorm statistics of the consumer, from the staged bf16 chunk (exactly the values that reach memory).
+          // lane = (row parity, column pair): 16 conflict-free LDS.32 walk the 32 rows and one shuffle folds the parities;
+          // a segmented scan over the 16 column pairs then folds them into 10-channel MICRO-GROUPS (every GroupNorm of
+          // the model has C / 32 = a multiple of 10 channels per group, so any consumer -- also a later concat with
+          // another group size -- can assemble its groups from them).  A 32-column chunk overlaps at most 4 decades:
+          // colstats[slab][chunk][piece 0..3] = (sum, sumsq), piece = decade - first decade of the chunk.  Rows >= M skip.
           const int par = lane >> 4, c2 = lane & 15;
           const uint8_t* chunk = my_stage + k * EPI_CHUNK_BYTES;
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          float s0 = 0.f, q0 = 0.f;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int r = 2 * i + par;
@@ -429,17 +433,30 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
                                                                    (c2 & 3) * 4);
             float2 v2 = unpack_bf16(w);
             if (wrow0 + r >= p.M) v2 = make_float2(0.f, 0.f);
-            s0 += v2.x; q0 = fmaf(v2.x, v2.x, q0);
-            s1 += v2.y; q1 = fmaf(v2.y, v2.y, q1);
+            s0 += v2.x + v2.y;
+            q0 = fmaf(v2.x, v2.x, fmaf(v2.y, v2.y, q0));
           }
           s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
           q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
-          q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
-          const int col = col_out0 + 2 * c2;
-          if (par == 0 && col < p.N)
-            *reinterpret_cast<float4*>(p.colstats + (static_cast<size_t>(wrow0 >> 5) * p.N + col) * 2) =
-                make_float4(s0, q0, s1, q1);
+          const int col = col_out0 + 2 * c2;                         // even; a pair never straddles a decade
+          const int dec = (col * 6554) >> 16;                        // col / 10 for col < 16384
+          const int dec0 = (col_out0 * 6554) >> 16;
+          // segmented inclusive scan over lanes 0..15 of each half (segments = equal decade, contiguous lanes)
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1) {
+            const float ts = __shfl_up_sync(0xffffffffu, s0, o);
+            const float tq = __shfl_up_sync(0xffffffffu, q0, o);
+            const int td = __shfl_up_sync(0xffffffffu, dec, o);
+            if (c2 >= o && td == dec) {
+              s0 += ts;
+              q0 += tq;
+            }
+          }
+          const int dec_next = __shfl_down_sync(0xffffffffu, dec, 1);
+          const bool last_of_piece = (c2 == 15) || (dec_next != dec) || (col + 2 >= p.N);
+          if (par == 0 && last_of_piece && col < p.N)
+            *reinterpret_cast<float2*>(p.colstats + ((static_cast<size_t>(wrow0 >> 5) * (p.N >> 5) + (col_out0 >> 5)) * 4 +
+                                                     (dec - dec0)) * 2) = make_float2(s0, q0);
         }
         if (lane == 0 && !(p.debug & 16)) {
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -578,49 +595,90 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N
   }
 }
 
-// Split-K reduction that also emits the consumer's GroupNorm column statistics (same layout as the epilogue's):
-// block = one 32-row slab x 1024 columns, thread = 4 columns walking down the 32 rows.
+// Split-K reduction that also emits the consumer's GroupNorm micro-group statistics (same layout as the epilogue's):
+// block = one 32-row slab x 256 columns; thread = (4 columns, 8 rows), the 8 row loads are independent.
 __global__ void __launch_bounds__(256)
 splitk_reduce_stats_kernel(const float* __restrict__ partial, int splits, int M, int N, int M_total,
                            const float* __restrict__ bias, const float* __restrict__ row_bias, int rows_per_batch,
                            int ld_row_bias, const __nv_bfloat16* __restrict__ residual, int ldr,
                            __nv_bfloat16* __restrict__ out, int ldo, int row0, float* __restrict__ colstats) {
   pdl_prologue();
-  const int col = (blockIdx.y * 256 + threadIdx.x) * 4;
-  if (col >= N) return;
-  const int r_begin = blockIdx.x * 32;                 // window-relative; row0 is a multiple of 256
+  __shared__ float s_cs[4][256][2];                    // [row group][column][sum, sumsq]
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int col = blockIdx.y * 256 + tx * 4;
+  const int r_begin = blockIdx.x * 32 + ty * 8;        // window-relative; row0 is a multiple of 256
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (bias) b4 = *reinterpret_cast<const float4*>(bias + col);
-  for (int row = r_begin; row < r_begin + 32 && row < M; ++row) {
-    float4 a = *reinterpret_cast<const float4*>(partial + static_cast<size_t>(row) * N + col);
+  if (col < N) {
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) b4 = *reinterpret_cast<const float4*>(bias + col);
+    float4 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = r_begin + i;
+      acc[i] = row < M ? *reinterpret_cast<const float4*>(partial + static_cast<size_t>(row) * N + col) : b4;
+    }
     for (int sp = 1; sp < splits; ++sp) {
-      const float4 b = *reinterpret_cast<const float4*>(partial + (static_cast<size_t>(sp) * M + row) * N + col);
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = r_begin + i;
+        if (row < M) {
+          const float4 b = *reinterpret_cast<const float4*>(partial + (static_cast<size_t>(sp) * M + row) * N + col);
+          acc[i].x += b.x; acc[i].y += b.y; acc[i].z += b.z; acc[i].w += b.w;
+        }
+      }
     }
-    a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-    if (row_bias) {
-      const float4 b = *reinterpret_cast<const float4*>(row_bias + static_cast<size_t>((row + row0) / rows_per_batch) * ld_row_bias + col);
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-    }
-    if (residual) {
-      const uint2 r = *reinterpret_cast<const uint2*>(residual + static_cast<size_t>(row) * ldr + col);
-      const float2 r0 = unpack_bf16(r.x), r1 = unpack_bf16(r.y);
-      a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
-    }
-    const uint2 o = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
-    *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * ldo + col) = o;
-    if (row + row0 < M_total) {
-      const float2 v0 = unpack_bf16(o.x), v1 = unpack_bf16(o.y);
-      s[0] += v0.x; q[0] = fmaf(v0.x, v0.x, q[0]);
-      s[1] += v0.y; q[1] = fmaf(v0.y, v0.y, q[1]);
-      s[2] += v1.x; q[2] = fmaf(v1.x, v1.x, q[2]);
-      s[3] += v1.y; q[3] = fmaf(v1.y, v1.y, q[3]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = r_begin + i;
+      if (row >= M) continue;
+      float4 a = acc[i];
+      a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+      if (row_bias) {
+        const float4 b = *reinterpret_cast<const float4*>(row_bias + static_cast<size_t>((row + row0) / rows_per_batch) * ld_row_bias + col);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      if (residual) {
+        const uint2 r = *reinterpret_cast<const uint2*>(residual + static_cast<size_t>(row) * ldr + col);
+        const float2 r0 = unpack_bf16(r.x), r1 = unpack_bf16(r.y);
+        a.x += r0.x; a.y += r0.y; a.z += r1.x; a.w += r1.y;
+      }
+      const uint2 o = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+      *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * ldo + col) = o;
+      if (row + row0 < M_total) {
+        const float2 v0 = unpack_bf16(o.x), v1 = unpack_bf16(o.y);
+        s[0] += v0.x; q[0] = fmaf(v0.x, v0.x, q[0]);
+        s[1] += v0.y; q[1] = fmaf(v0.y, v0.y, q[1]);
+        s[2] += v1.x; q[2] = fmaf(v1.x, v1.x, q[2]);
+        s[3] += v1.y; q[3] = fmaf(v1.y, v1.y, q[3]);
+      }
     }
   }
-  float* dst = colstats + (static_cast<size_t>((r_begin + row0) >> 5) * N + col) * 2;
-  *reinterpret_cast<float4*>(dst) = make_float4(s[0], q[0], s[1], q[1]);
-  *reinterpret_cast<float4*>(dst + 4) = make_float4(s[2], q[2], s[3], q[3]);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    s_cs[ty][tx * 4 + e][0] = s[e];
+    s_cs[ty][tx * 4 + e][1] = q[e];
+  }
+  __syncthreads();
+  // 8 chunks x 4 pieces: thread t < 32 folds the columns of one (chunk, decade) piece, row groups in a fixed order
+  if (threadIdx.x < 32) {
+    const int cl = threadIdx.x >> 2, piece = threadIdx.x & 3;
+    const int c0 = blockIdx.y * 256 + cl * 32;
+    if (c0 < N) {
+      const int dec = ((c0 * 6554) >> 16) + piece;
+      const int lo = max(c0, dec * 10), hi = min(min(c0 + 32, dec * 10 + 10), N);
+      if (lo < hi) {
+        float a = 0.f, b = 0.f;
+        for (int c = lo; c < hi; ++c)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            a += s_cs[g][c - blockIdx.y * 256][0];
+            b += s_cs[g][c - blockIdx.y * 256][1];
+          }
+        const size_t slab = static_cast<size_t>((blockIdx.x * 32 + row0) >> 5);
+        *reinterpret_cast<float2*>(colstats + ((slab * (N >> 5) + (c0 >> 5)) * 4 + piece) * 2) = make_float2(a, b);
+      }
+    }
+  }
 }
 
 // Check-mode epilogue: ordered sum of the fp32 partials, then bias / time bias / residual / GEGLU in fp32 (exact erf
@@ -691,7 +749,7 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     rc = lavie_check_launch("splitk_reduce_check_kernel");
   } else if (p.splits > 1 && p.colstats != nullptr) {
     const int row0 = p.m_tile0 * PAIR_M;
-    dim3 grid((p.rows_window + 31) / 32, (p.N / 4 + 255) / 256);
+    dim3 grid((p.rows_window + 31) / 32, (p.N + 255) / 256);
     launch_pdl(splitk_reduce_stats_kernel, grid, 256, 0, stream, p.partial, p.splits, p.rows_window, p.N, p.M, p.bias,
                p.row_bias, p.rows_per_batch, p.ld_row_bias,
                p.residual ? p.residual + static_cast<size_t>(row0) * p.ldr : nullptr, p.ldr,
@@ -866,8 +924,8 @@ int fill_epilogue(GemmParams& p, const lavie_epilogue* ep, int N, void* out, int
   p.colstats = nullptr;
   if (ep) {
     p.colstats = ep->col_stats;
-    LAVIE_REQUIRE(!p.colstats || (aligned16(p.colstats) && !ep->geglu && N % 4 == 0), LAVIE_ERR_SHAPE,
-                  "gemm: col_stats needs a 16-byte aligned buffer, N %% 4 == 0 and no GEGLU");
+    LAVIE_REQUIRE(!p.colstats || (aligned16(p.colstats) && !ep->geglu && N % 32 == 0 && N <= 8192), LAVIE_ERR_SHAPE,
+                  "gemm: col_stats needs a 16-byte aligned buffer, N %% 32 == 0 (<= 8192) and no GEGLU");
     p.bias = ep->bias;
     p.row_bias = ep->row_bias;
     p.rows_per_batch = ep->rows_per_batch > 0 ? ep->rows_per_batch : 1;

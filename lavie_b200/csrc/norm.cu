@@ -652,10 +652,11 @@ __global__ void gn_finalize_sums_kernel(const double* __restrict__ sums, int gro
 }  // namespace
 
 namespace {
-// GroupNorm statistics from the producers' per-slab column sums (gemm.cu epilogue): one block per (group, sample)
-// folds slabs_per_sample x (C / groups) x {sum, sumsq} in a FIXED order (thread-strided fp32 partials over at most a few
-// dozen terms each, then an fp64 tree), so the result is deterministic.  The group's channels may straddle the seam of
-// a two-source concat.  sums != nullptr: stop at the fp64 (sum, sumsq) per (sample, group) (frame-sharded exchange).
+// GroupNorm statistics from the producers' per-slab micro-group sums (gemm.cu epilogue): one block per (group, sample).
+// A group is a run of whole decades (10 channels) of the concatenated sources; a decade lies in one or two 32-column
+// chunks of its source, so every (slab, decade) costs one or two 8-byte loads.  Fixed summation order: thread-strided
+// fp32 partials over a few terms each, then an fp64 tree -> deterministic.  sums != nullptr: stop at the fp64
+// (sum, sumsq) per (sample, group) (frame-sharded exchange).
 __global__ void __launch_bounds__(256)
 gn_colsums_kernel(const float* __restrict__ cs0, int c0, const float* __restrict__ cs1, int c1, int slabs_per_sample,
                   int groups, double inv_count, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -664,22 +665,30 @@ gn_colsums_kernel(const float* __restrict__ cs0, int c0, const float* __restrict
   const int g = blockIdx.x, sample = blockIdx.y;
   const int C = c0 + c1, cpg = C / groups;
   const int ch0 = g * cpg;
-  const long long total = static_cast<long long>(slabs_per_sample) * cpg;
+  const int decs = cpg / 10;
+  const long long total = static_cast<long long>(slabs_per_sample) * decs;
   double a = 0.0, b = 0.0;
-  // chunks of 32 terms accumulated in fp32, chunk results in fp64
-  for (long long base = static_cast<long long>(threadIdx.x) * 32; base < total; base += 256LL * 32) {
-    float fa = 0.f, fb = 0.f;
-    const long long end = base + 32 < total ? base + 32 : total;
-    for (long long i = base; i < end; ++i) {
-      const long long slab = static_cast<long long>(sample) * slabs_per_sample + i / cpg;
-      const int ch = ch0 + static_cast<int>(i % cpg);
-      const float2 v = ch < c0 ? __ldg(reinterpret_cast<const float2*>(cs0 + (slab * c0 + ch) * 2))
-                               : __ldg(reinterpret_cast<const float2*>(cs1 + (slab * c1 + (ch - c0)) * 2));
-      fa += v.x;
-      fb += v.y;
+  for (long long i = threadIdx.x; i < total; i += 256) {
+    const long long slab = static_cast<long long>(sample) * slabs_per_sample + i / decs;
+    int ch = ch0 + static_cast<int>(i % decs) * 10;            // first channel of the decade in the concat
+    const float* cs = cs0;
+    int cn = c0;
+    if (ch >= c0) {
+      ch -= c0;
+      cs = cs1;
+      cn = c1;
     }
-    a += fa;
-    b += fb;
+    const int dec = ch / 10;
+    const int k_lo = ch >> 5, k_hi = (ch + 9) >> 5;            // the chunk(s) the decade touches
+    const float* row = cs + slab * (cn >> 5) * 8;
+    float2 v = __ldg(reinterpret_cast<const float2*>(row + (k_lo * 4 + (dec - (k_lo * 32) / 10)) * 2));
+    if (k_hi != k_lo) {
+      const float2 w = __ldg(reinterpret_cast<const float2*>(row + (k_hi * 4 + (dec - (k_hi * 32) / 10)) * 2));
+      v.x += w.x;
+      v.y += w.y;
+    }
+    a += v.x;
+    b += v.y;
   }
   __shared__ double sa[256], sb[256];
   sa[threadIdx.x] = a;
@@ -716,9 +725,10 @@ int colsums_impl(const float* cs0, int c0, const float* cs1, int c1, int samples
                  cudaStream_t stream) {
   const int C = c0 + c1;
   LAVIE_REQUIRE(samples > 0 && rows_per_sample > 0 && rows_per_sample % 32 == 0 && groups > 0 && C % groups == 0 &&
-                    c0 > 0 && c0 % 2 == 0 && c1 % 2 == 0,
-                LAVIE_ERR_SHAPE, "groupnorm colsums: rows_per_sample=%d must be a multiple of 32, C=%d groups=%d",
-                rows_per_sample, C, groups);
+                    (C / groups) % 10 == 0 && c0 > 0 && c0 % 32 == 0 && c1 % 32 == 0 && c0 % 10 == 0,
+                LAVIE_ERR_SHAPE,
+                "groupnorm colsums: rows_per_sample=%d must be a multiple of 32, C=%d / groups=%d a multiple of 10, "
+                "sources multiples of 32 channels", rows_per_sample, C, groups);
   LAVIE_REQUIRE(cs0 != nullptr && (c1 == 0 || cs1 != nullptr), LAVIE_ERR_SHAPE, "groupnorm colsums: null statistics");
   dim3 grid(groups, samples);
   launch_pdl(gn_colsums_kernel, grid, 256, 0, stream, cs0, c0, cs1, c1, rows_per_sample / 32, groups,

@@ -45,6 +45,11 @@ class _Launch:
         return False
 
 
+# GroupNorm statistics emitted by the producing GEMM / conv epilogue (lavie_epilogue.col_stats).  LAVIE_FUSE_GN_STATS=0
+# switches back to the stand-alone statistics pass (A/B timing).
+import os as _os
+FUSE_GN_STATS = _os.environ.get("LAVIE_FUSE_GN_STATS", "1") != "0"
+
 WORKSPACE_BYTES = 128 << 20
 _workspaces = {}
 
@@ -146,7 +151,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None,
         out = torch.empty((M, n_out), dtype=BF16, device=a.device)
     Mo, No, ldo = _rows2d(out)
     assert Mo == M and No == n_out
-    cs = _new_colsums(M, n_out, a.device) if stats and not geglu else None
+    cs = _new_colsums(M, n_out, a.device) if stats and not geglu and FUSE_GN_STATS else None
     ep = _epilogue(bias, row_bias, rows_per_batch, residual, geglu, cs)
     ws = _workspace(a.device)
     with _Launch("gemm_bf16_tcgen05", 2.0 * M * N * (k0 + k1), 2.0 * (M * (k0 + k1) + N * (k0 + k1) + M * n_out),
@@ -195,7 +200,7 @@ def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride
         out = torch.empty((m_out, N), dtype=BF16, device=x.device)
     Mo, No, ldo = _rows2d(out)
     assert Mo == m_out and No == N
-    cs = _new_colsums(m_out, N, x.device) if stats else None
+    cs = _new_colsums(m_out, N, x.device) if stats and FUSE_GN_STATS else None
     ep = _epilogue(bias, row_bias, rows_per_batch, residual, False, cs)
     ws = _workspace(x.device)
     with _Launch("gemm_bf16_tcgen05", 2.0 * m_out * N * 9 * C, 2.0 * (rows * C + N * 9 * C + m_out * N),
@@ -209,8 +214,11 @@ def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride
     return out
 
 
-def _new_colsums(M: int, N: int, device) -> torch.Tensor:
-    return torch.empty(((M + 31) // 32, N, 2), dtype=F32, device=device)
+def _new_colsums(M: int, N: int, device) -> Optional[torch.Tensor]:
+    """[slabs of 32 rows, 32-column chunks, 4 decade pieces, (sum, sumsq)] -- see lavie_epilogue.col_stats."""
+    if N % 32 or N % 10:
+        return None
+    return torch.empty(((M + 31) // 32, N // 32, 4, 2), dtype=F32, device=device)
 
 
 def colsums(x: torch.Tensor, rows_per_sample: int, x2: Optional[torch.Tensor] = None):
@@ -221,6 +229,9 @@ def colsums(x: torch.Tensor, rows_per_sample: int, x2: Optional[torch.Tensor] = 
     cs0 = getattr(x, "_gn_colsums", None)
     cs1 = getattr(x2, "_gn_colsums", None) if x2 is not None else None
     if cs0 is None or (x2 is not None and cs1 is None):
+        return None
+    C = x.shape[1] + (x2.shape[1] if x2 is not None else 0)
+    if (C // 32) % 10:
         return None
     return cs0, cs1
 
@@ -243,7 +254,7 @@ def groupnorm_scale_shift(x: torch.Tensor, samples: int, rows_per_sample: int, g
     cs = colsums(x, rows_per_sample, x2) if fused else None
     if cs is not None:
         # the statistics pass already happened in the producers' epilogues: fold their column sums (one small launch)
-        with _Launch("lavie_groupnorm_finalize_colsums", 0.0, 8.0 * (rows // 32) * C,
+        with _Launch("lavie_groupnorm_finalize_colsums", 0.0, 1.0 * (rows // 32) * C,
                      f"gn_colsums rows={rows} C={C} samples={samples}"):
             check(lib.lavie_groupnorm_finalize_colsums(cs[0].data_ptr(), c0, _ptr(cs[1]), c1, samples, rows_per_sample,
                                                        groups, gamma.data_ptr(), beta.data_ptr(), eps, ss.data_ptr(),

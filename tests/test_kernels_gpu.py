@@ -403,16 +403,30 @@ def test_conv3x3_small_m_large_k():
 
 # ------------------------------------------------------------------------------------------------ GroupNorm statistics from the producer's epilogue
 def _colsums_ref(out, M, N):
-    """[ceil(M/32), N, 2] (sum, sumsq) of the bf16 output, per 32-row slab."""
+    """[ceil(M/32), N/10, 2] (sum, sumsq) of the bf16 output per 32-row slab and 10-channel micro-group."""
     slabs = (M + 31) // 32
     pad = torch.zeros(slabs * 32, N, device=out.device)
     pad[:M] = out.float()
-    v = pad.reshape(slabs, 32, N)
-    return torch.stack([v.sum(1), (v * v).sum(1)], dim=-1)
+    v = pad.reshape(slabs, 32, N // 10, 10)
+    return torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], dim=-1)
+
+
+def _micro(cs, N):
+    """kernel layout [slabs, N/32, 4, 2] (chunk, decade piece) -> [slabs, N/10, 2]; unwritten pieces are ignored."""
+    slabs = cs.shape[0]
+    out = torch.zeros(slabs, N // 10, 2, device=cs.device)
+    for k in range(N // 32):
+        d0 = (k * 32) // 10
+        for piece in range(4):
+            dec = d0 + piece
+            lo, hi = max(k * 32, dec * 10), min(k * 32 + 32, dec * 10 + 10, N)
+            if lo < hi:
+                out[:, dec] += cs[:, k, piece]
+    return out
 
 
 @pytest.mark.parametrize("M,N,K,block_n", [(2560, 320, 320, 0), (1000, 640, 1280, 0), (256 * 150 + 96, 320, 192, 320),
-                                           (640, 1280, 2560, 0), (4096, 1152, 320, 128)])
+                                           (640, 1280, 2560, 0), (4096, 960, 320, 128)])
 def test_gemm_emits_groupnorm_column_sums(M, N, K, block_n):
     """lavie_epilogue.col_stats: the producer's epilogue (or the split-K reduction) writes the consumer's GroupNorm
     statistics; they must equal the sums of the bf16 values actually stored (incl. bias + residual, M tails)."""
@@ -424,7 +438,7 @@ def test_gemm_emits_groupnorm_column_sums(M, N, K, block_n):
     out = ops.gemm(a, w, bias=bias, residual=res, stats=True, block_n=block_n)
     plain = ops.gemm(a, w, bias=bias, residual=res, block_n=block_n)
     assert torch.equal(out, plain)                                   # the statistics do not change the output
-    cs = out._gn_colsums
+    cs = _micro(out._gn_colsums, N)
     ref = _colsums_ref(out, M, N)
     assert cs.shape == ref.shape
     assert rel_l2(cs, ref) < 1e-5
@@ -442,7 +456,7 @@ def test_splitk_gemm_emits_groupnorm_column_sums():
         out = ops.gemm(a, w, bias=_rand(N, seed=1), stats=True)
     finally:
         lib.lavie_debug_set(1, 0)
-    assert rel_l2(out._gn_colsums, _colsums_ref(out, M, N)) < 1e-5
+    assert rel_l2(_micro(out._gn_colsums, N), _colsums_ref(out, M, N)) < 1e-5
 
 
 @pytest.mark.parametrize("NF,H,W,C,N,stride", [(4, 16, 32, 320, 640, 1), (2, 40, 64, 320, 320, 1), (3, 20, 32, 640, 640, 2)])
@@ -456,7 +470,7 @@ def test_conv_column_sums_feed_groupnorm(NF, H, W, C, N, stride):
     y = ops.conv3x3(x, NF, H, W, w, stride=stride, bias=_rand(N, seed=2), stats=True)
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     rows = NF * Ho * Wo
-    assert rel_l2(y._gn_colsums, _colsums_ref(y, rows, N)) < 1e-5
+    assert rel_l2(_micro(y._gn_colsums, N), _colsums_ref(y, rows, N)) < 1e-5
     gamma, beta = _rand(N, seed=4) * 0.1 + 1, _rand(N, seed=5) * 0.1
     plain = y.clone()                                                # a copy carries no statistics -> stand-alone pass
     for samples in (1, NF):
