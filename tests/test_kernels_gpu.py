@@ -483,3 +483,61 @@ def test_conv_column_sums_feed_groupnorm(NF, H, W, C, N, stride):
     ss = ops.groupnorm_scale_shift(y, 1, rows, g2, b2, 1e-5, x2=y2)
     ss_ref = ops.groupnorm_scale_shift(plain, 1, rows, g2, b2, 1e-5, x2=y2.clone())
     assert rel_l2(ss, ss_ref) < 1e-5
+
+
+def test_out_of_bounds_canaries():
+    """compute-sanitizer is closed on this GPU pool (profiles/r2_compute_sanitizer_closed.txt), so the memory-safety
+    evidence is canaries: every output lives inside a larger poisoned allocation and the bytes around it must survive
+    kernels that run with ragged sizes (M, N and key tails, partial slabs)."""
+    ops = _ops()
+    from lavie_b200 import _lib
+    from lavie_b200._lib import Epilogue, check
+    import ctypes
+    lib = _lib.load()
+    POISON = -7.0
+
+    def guarded(rows, cols, dtype):
+        big = torch.full((rows + 16, cols), POISON, dtype=dtype, device=DEV)
+        return big, big[8:8 + rows]
+
+    # GEMM with an M tail (not a multiple of 32 / 128 / 256) + column statistics with a partial last slab
+    M, N, K = 1000, 320, 320
+    a, w = _bf(_rand(M, K)), _bf(_rand(N, K, scale=K ** -0.5))
+    big_out, out = guarded(M, N, torch.bfloat16)
+    slabs = (M + 31) // 32
+    big_cs = torch.full((slabs + 2, N // 32, 4, 2), POISON, device=DEV)
+    cs = big_cs[1:1 + slabs]
+    ep = Epilogue()
+    ep.rows_per_batch = 1
+    ep.col_stats = cs.data_ptr()
+    ws = ops._workspace(a.device)
+    check(lib.lavie_gemm_bf16(a.data_ptr(), K, K, None, 0, 0, w.data_ptr(), out.data_ptr(), N, M, N, ctypes.byref(ep), 0,
+                              ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "gemm")
+    torch.cuda.synchronize()
+    assert (big_out[:8].float() == POISON).all() and (big_out[8 + M:].float() == POISON).all()
+    assert (big_cs[0] == POISON).all() and (big_cs[-1] == POISON).all()
+    assert rel_l2(out.float(), a.float() @ w.float().t()) < 4e-3
+    # attention with ragged query / key counts writing into a guarded, strided output
+    batch, heads, Sq, Sk, d, pitch = 3, 8, 200, 77, 40, 48
+    q = torch.zeros(batch * Sq, heads, pitch, device=DEV)
+    q[..., :d] = torch.randn(batch * Sq, heads, d, device=DEV)
+    kv = torch.zeros(batch * Sk, 2, heads, pitch, device=DEV)
+    kv[..., :d] = torch.randn(batch * Sk, 2, heads, d, device=DEV)
+    q, kv = _bf(q.reshape(batch * Sq, -1)), _bf(kv.reshape(batch * Sk, -1))
+    big_o, o = guarded(batch * Sq, heads * d + 64, torch.bfloat16)
+    ops.attention(q, kv[:, :heads * pitch], kv[:, heads * pitch:], batch, heads, Sq, Sk, d, pitch, out=o[:, :heads * d])
+    torch.cuda.synchronize()
+    assert (big_o[:8].float() == POISON).all() and (big_o[8 + batch * Sq:].float() == POISON).all()
+    assert (o[:, heads * d:].float() == POISON).all()
+    # norms on a ragged row count
+    rows, C = 2 * 77, 320
+    x = _bf(_rand(rows, C))
+    g, b = _rand(C, seed=1) * 0.1 + 1, _rand(C, seed=2) * 0.1
+    big_y, y = guarded(rows, C, torch.bfloat16)
+    ops.layernorm(x, g, b, out=y)
+    ss = ops.groupnorm_scale_shift(x, 2, 77, g, b, 1e-5)
+    big_z, z = guarded(rows, C, torch.bfloat16)
+    ops.groupnorm_apply(x, ss, 2, 77, True, out=z)
+    torch.cuda.synchronize()
+    for bigt, n in ((big_y, rows), (big_z, rows)):
+        assert (bigt[:8].float() == POISON).all() and (bigt[8 + n:].float() == POISON).all()
