@@ -178,11 +178,19 @@ int lavie_gn_exchange_finalize_sums(const double* local_sums, int samples, int g
                                     long long count_per_group_global, const float* gamma, const float* beta, float eps,
                                     float* scale_shift, void* const* slot_ptrs, void* const* flag_ptrs,
                                     unsigned int* epoch_counter, int P, int my_rank, lavie_stream_t stream);
+/* frame_off = global index of this rank's first frame (shards may be uneven: 61 interpolation frames = 16/15/15/15);
+ * negative = my_rank * rows / hw (equal shards). */
 int lavie_layernorm_scatter_p2p(const void* x, int ldx, const float* gamma, const float* beta, float eps,
                                 void* const* recv_ptrs, int rows, int C, int hw, int hwp, int P, int my_rank,
-                                lavie_stream_t stream);
+                                int frame_off, lavie_stream_t stream);
 int lavie_add_gathered_p2p(const void* res, int ldr, void* const* y_ptrs, void* out, int ldo, int rows, int C, int hw,
-                           int hwp, int P, int my_rank, lavie_stream_t stream);
+                           int hwp, int P, int my_rank, int frame_off, lavie_stream_t stream);
+/* Halo exchange of SparseCausalAttention under frame sharding (interpolation/models/attention.py:629-638): ext_ptrs[r] ->
+ * rank r's buffer [2 halo frames | its local frames] of frame_bytes each.  Rank 0 stores first_frame (frame 0 of the
+ * video) into block 0 of EVERY rank, every rank but the last stores last_frame (its last local frame) into block 1 of its
+ * right neighbour.  Follow with lavie_rank_barrier, then lavie_attention_strided_bf16(sc_halo = 1, or 2 on rank 0). */
+int lavie_halo_push_p2p(const void* first_frame, const void* last_frame, long long frame_bytes, void* const* ext_ptrs,
+                        int P, int my_rank, lavie_stream_t stream);
 
 /* softmax(q k^T * scale) v per (batch, head)  (CrossAttention._attention, attention.py:209-239).
  * q rows = batch*Sq, k/v rows = (batch / kv_batch_div)*Sk (kv_batch_div = F shares the text keys across frames,
@@ -199,12 +207,14 @@ int lavie_attention_bf16(const void* q, int ldq, const void* k, int ldk, const v
  *    bias) without the two (b f) d c <-> (b d) f c transposes, for any number of frames (61 in LaVie);
  *  - sparse_causal_frames = F > 0: SparseCausalAttention (interpolation/models/attention.py:611-664): batch = (video,
  *    frame) and the keys / values of frame f are [the Sk keys of frame 0 | the Sk keys of frame max(f-1, 0)] of the
- *    same video (2*Sk keys per query, never materialised: the kernel walks two key segments). */
+ *    same video (2*Sk keys per query, never materialised: the kernel walks two key segments).  sc_halo != 0 (frame
+ *    sharding, one video): k / v start with two halo frames [frame 0 of the video | the frame before this rank's first]
+ *    followed by the `batch` local frames (lavie_halo_push_p2p); sc_halo = 2 on the rank that owns frame 0. */
 int lavie_attention_strided_bf16(const void* q, long long q_seq_stride, long long q_batch_stride, const void* k,
                                  const void* v, long long kv_seq_stride, long long kv_batch_stride, void* o,
                                  long long o_seq_stride, long long o_batch_stride, int batch, int heads, int Sq, int Sk,
-                                 int d, int head_pitch, int kv_batch_div, int sparse_causal_frames, float scale,
-                                 lavie_stream_t stream);
+                                 int d, int head_pitch, int kv_batch_div, int sparse_causal_frames, int sc_halo,
+                                 float scale, lavie_stream_t stream);
 
 /* TemporalAttention._attention (attention.py:634-667): per (b, pixel, head) attention over the F frames, with
  * q scaled before RoPE, rotary embedding on the first 2*rot_pairs dims, + rel-pos bias[heads,F,F].

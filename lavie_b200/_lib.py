@@ -64,13 +64,15 @@ SIGNATURES = {
                                            c_int, c_int, _P]),
     "lavie_gn_exchange_finalize_sums": (c_int, [_P, c_int, c_int, c_int, c_longlong, _P, _P, c_float, _P, _P, _P, _P, c_int,
                                                 c_int, _P]),
-    "lavie_layernorm_scatter_p2p": (c_int, [_P, c_int, _P, _P, c_float, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
-    "lavie_add_gathered_p2p": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "lavie_layernorm_scatter_p2p": (c_int, [_P, c_int, _P, _P, c_float, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                            _P]),
+    "lavie_add_gathered_p2p": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "lavie_halo_push_p2p": (c_int, [_P, _P, c_longlong, _P, c_int, c_int, _P]),
     "lavie_groupnorm_finalize_sums": (c_int, [_P, c_int, c_int, c_int, c_longlong, _P, _P, c_float, _P, _P]),
     "lavie_attention_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_float, _P]),
     "lavie_attention_strided_bf16": (c_int, [_P, c_longlong, c_longlong, _P, _P, c_longlong, c_longlong, _P, c_longlong,
-                                             c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                             c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                              c_float, _P]),
     "lavie_temporal_attention_bf16": (c_int, [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                               c_int, c_float, _P, c_int, _P, _P]),

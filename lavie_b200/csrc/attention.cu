@@ -29,6 +29,7 @@ struct AttnParams {
   // SparseCausalAttention (interpolation/models/attention.py:611-664): batch = (video, frame); the keys of frame f are
   // [all Sk keys of frame 0 | all Sk keys of frame max(f - 1, 0)] of the same video.  0 = ordinary attention.
   int sc_frames;
+  int sc_halo;         // frame-sharded SparseCausal: k / v = [frame 0 | previous rank's last frame | local frames]; 2 = first rank
   int swap_dims;       // tensor maps are (col, batch, seq) instead of (col, seq, batch): batch stride < sequence stride
   float scale_log2;
   __nv_bfloat16* o;
@@ -77,8 +78,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int seg_tiles = (p.Sk + ATT_N - 1) / ATT_N;
   const int n_kv = p.sc_frames > 0 ? 2 * seg_tiles : seg_tiles;
   const int sc_f = p.sc_frames > 0 ? batch % p.sc_frames : 0;
-  const int kv_batch_seg0 = p.sc_frames > 0 ? batch - sc_f : kv_batch;
-  const int kv_batch_seg1 = p.sc_frames > 0 ? (sc_f > 0 ? batch - 1 : batch) : kv_batch;
+  // sc_halo: one video per launch, local frame b lives at k/v index b + 2, halo frame 0 at index 0, the frame in front
+  // of local frame 0 at index 1 (on the first rank frame 0 is its own former frame: index 2)
+  const int kv_batch_seg0 = p.sc_halo ? 0 : (p.sc_frames > 0 ? batch - sc_f : kv_batch);
+  const int kv_batch_seg1 = p.sc_halo ? (batch > 0 ? batch + 1 : (p.sc_halo == 2 ? 2 : 1))
+                                      : (p.sc_frames > 0 ? (sc_f > 0 ? batch - 1 : batch) : kv_batch);
   const int col0 = head * p.head_pitch;
 
   if (tid == 0) {
@@ -808,8 +812,8 @@ extern "C" int lavie_attention_strided_bf16(const void* q, long long q_seq_strid
                                             const void* k, const void* v, long long kv_seq_stride,
                                             long long kv_batch_stride, void* o, long long o_seq_stride,
                                             long long o_batch_stride, int batch, int heads, int Sq, int Sk, int d,
-                                            int head_pitch, int kv_batch_div, int sparse_causal_frames, float scale,
-                                            cudaStream_t stream) {
+                                            int head_pitch, int kv_batch_div, int sparse_causal_frames, int sc_halo,
+                                            float scale, cudaStream_t stream) {
   LAVIE_REQUIRE(batch > 0 && heads > 0 && Sq > 0 && Sk > 0 && kv_batch_div > 0 && batch % kv_batch_div == 0,
                 LAVIE_ERR_SHAPE, "attention: bad sizes batch=%d heads=%d Sq=%d Sk=%d div=%d", batch, heads, Sq, Sk,
                 kv_batch_div);
@@ -829,6 +833,9 @@ extern "C" int lavie_attention_strided_bf16(const void* q, long long q_seq_strid
   p.Sq = Sq; p.Sk = Sk; p.d = d; p.head_pitch = head_pitch; p.kv_batch_div = kv_batch_div;
   p.o_seq_stride = o_seq_stride; p.o_batch_stride = o_batch_stride;
   p.sc_frames = sparse_causal_frames;
+  p.sc_halo = sc_halo;
+  LAVIE_REQUIRE(sc_halo == 0 || (sc_halo >= 1 && sc_halo <= 2 && sparse_causal_frames == batch), LAVIE_ERR_SHAPE,
+                "attention: sc_halo needs sparse-causal mode with one video per launch (frames == batch)");
   p.scale_log2 = scale * 1.4426950408889634f;
   p.o = static_cast<__nv_bfloat16*>(o);
   p.timeline = static_cast<long long*>(g_lavie_debug_buf);
@@ -840,9 +847,10 @@ extern "C" int lavie_attention_strided_bf16(const void* q, long long q_seq_strid
   p.swap_dims = swap ? 1 : 0;
   int rc = make_qkv_map(&mq, q, q_seq_stride, q_batch_stride, cols, Sq, batch, ATT_M, swap);
   if (rc) return rc;
-  rc = make_qkv_map(&mk, k, kv_seq_stride, kv_batch_stride, cols, Sk, batch / kv_batch_div, ATT_N, swap);
+  const int kv_batches = batch / kv_batch_div + (sc_halo ? 2 : 0);
+  rc = make_qkv_map(&mk, k, kv_seq_stride, kv_batch_stride, cols, Sk, kv_batches, ATT_N, swap);
   if (rc) return rc;
-  rc = make_qkv_map(&mv, v, kv_seq_stride, kv_batch_stride, cols, Sk, batch / kv_batch_div, ATT_N, swap);
+  rc = make_qkv_map(&mv, v, kv_seq_stride, kv_batch_stride, cols, Sk, kv_batches, ATT_N, swap);
   if (rc) return rc;
   switch (dk) {
     case 48: return launch_attn<48>(mq, mk, mv, p, batch, heads, stream);
@@ -863,7 +871,7 @@ extern "C" int lavie_attention_bf16(const void* q, int ldq, const void* k, int l
   LAVIE_REQUIRE(ldk == ldv, LAVIE_ERR_SHAPE, "attention: k and v must share their row stride (ldk=%d ldv=%d)", ldk, ldv);
   return lavie_attention_strided_bf16(q, ldq, static_cast<long long>(Sq) * ldq, k, v, ldk,
                                       static_cast<long long>(Sk) * ldk, o, ldo, static_cast<long long>(Sq) * ldo, batch,
-                                      heads, Sq, Sk, d, head_pitch, kv_batch_div, 0, scale, stream);
+                                      heads, Sq, Sk, d, head_pitch, kv_batch_div, 0, 0, scale, stream);
 }
 
 extern "C" int lavie_temporal_attention_bf16(const void* qkv, int ld, int k_off, int v_off, void* o, int ldo, int B,

@@ -174,12 +174,13 @@ gn_exchange_finalize_kernel(const float* __restrict__ partial, const double* __r
   if (threadIdx.x == 0) *epoch_counter = epoch;
 }
 
-// LayerNorm (C = 40*L) with peer-scattered output: row (f, pixel) -> peer (pixel / hwp), row (my_rank*F_loc + f, pixel % hwp)
+// LayerNorm (C = 40*L) with peer-scattered output: row (f, pixel) -> peer (pixel / hwp), row (frame_off + f, pixel % hwp)
+// (frame_off = global index of this rank's first frame; shards may hold different numbers of frames)
 template <int L>
 __global__ void __launch_bounds__(256)
 layernorm_scatter_p2p_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gamma,
                              const float* __restrict__ beta, float eps, PeerPtrs recv, int rows, int hw, int hwp,
-                             int my_rank) {
+                             int frame_off) {
   pdl_prologue();
   constexpr int VPL = 5;
   constexpr int C = 40 * L;
@@ -221,10 +222,9 @@ layernorm_scatter_p2p_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const
   for (int o = L / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / static_cast<float>(C) + eps);
   if (!ok) return;
-  const int f_loc = rows / hw;
   const int fr = static_cast<int>(row / hw), pix = static_cast<int>(row - static_cast<long long>(fr) * hw);
   const int blk = pix / hwp;
-  const size_t drow = (static_cast<size_t>(my_rank) * f_loc + fr) * hwp + (pix - blk * hwp);
+  const size_t drow = (static_cast<size_t>(frame_off) + fr) * hwp + (pix - blk * hwp);     // global frame index
   __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(recv.p[blk]) + drow * C;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
@@ -242,13 +242,12 @@ layernorm_scatter_p2p_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const
   }
 }
 
-// out[(f, blk*hwp + j)] = res[(f, blk*hwp + j)] + y_of_peer_blk[(my_rank*F_loc + f)*hwp + j]   (peer loads over NVLink)
+// out[(f, blk*hwp + j)] = res[(f, blk*hwp + j)] + y_of_peer_blk[(frame_off + f)*hwp + j]   (peer loads over NVLink)
 __global__ void __launch_bounds__(256)
 add_gathered_p2p_kernel(const __nv_bfloat16* __restrict__ res, int ldr, PeerPtrs ybuf, __nv_bfloat16* __restrict__ out,
-                        int ldo, int rows, int C, int hw, int hwp, int my_rank) {
+                        int ldo, int rows, int C, int hw, int hwp, int frame_off) {
   pdl_prologue();
   const int nvec = C >> 3;
-  const int f_loc = rows / hw;
   const long long total = static_cast<long long>(rows) * nvec;
   constexpr int U = 4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -262,7 +261,7 @@ add_gathered_p2p_kernel(const __nv_bfloat16* __restrict__ res, int ldr, PeerPtrs
       const int row = static_cast<int>(idx[u] / nvec), v = static_cast<int>(idx[u] % nvec);
       const int f = row / hw, pix = row - f * hw;
       const int blk = pix / hwp;
-      const size_t yrow = (static_cast<size_t>(my_rank) * f_loc + f) * hwp + (pix - blk * hwp);
+      const size_t yrow = (static_cast<size_t>(frame_off) + f) * hwp + (pix - blk * hwp);
       a[u] = __ldg(reinterpret_cast<const uint4*>(res + static_cast<size_t>(row) * ldr + v * 8));
       b[u] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(ybuf.p[blk]) + yrow * C + v * 8);
     }
@@ -279,6 +278,23 @@ add_gathered_p2p_kernel(const __nv_bfloat16* __restrict__ res, int ldr, PeerPtrs
       }
       *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ldo + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
+  }
+}
+
+// SparseCausalAttention under frame sharding: every rank needs the projected q|k|v rows of
+// frame 0 of the video (from the first rank) and of the frame in front of its first frame (from its left neighbour).
+// The receiving buffer on every rank is [halo block 0 = frame 0 | halo block 1 = previous frame | local frames].
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const uint4* __restrict__ first_frame, const uint4* __restrict__ last_frame, long long n16,
+                 PeerPtrs dst, int P, int my_rank) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n16;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (my_rank == 0) {
+      const uint4 v = __ldg(first_frame + i);
+      for (int r = 0; r < P; ++r) static_cast<uint4*>(dst.p[r])[i] = v;
+    }
+    if (my_rank + 1 < P) static_cast<uint4*>(dst.p[my_rank + 1])[n16 + i] = __ldg(last_frame + i);
   }
 }
 
@@ -346,7 +362,8 @@ extern "C" int lavie_gn_exchange_finalize_sums(const double* local_sums, int sam
 
 extern "C" int lavie_layernorm_scatter_p2p(const void* x, int ldx, const float* gamma, const float* beta, float eps,
                                            void* const* recv_ptrs, int rows, int C, int hw, int hwp, int P, int my_rank,
-                                           cudaStream_t stream) {
+                                           int frame_off, cudaStream_t stream) {
+  if (frame_off < 0) frame_off = my_rank * (hw > 0 ? rows / hw : 0);        // equal shards
   LAVIE_REQUIRE(C == 320 || C == 640 || C == 1280, LAVIE_ERR_SHAPE, "layernorm_scatter_p2p: C must be 320/640/1280");
   LAVIE_REQUIRE(hw > 0 && hwp > 0 && hw == hwp * P && rows % hw == 0 && ldx % 8 == 0, LAVIE_ERR_SHAPE,
                 "layernorm_scatter_p2p: rows=%d hw=%d hwp=%d P=%d", rows, hw, hwp, P);
@@ -360,16 +377,17 @@ extern "C" int lavie_layernorm_scatter_p2p(const void* x, int ldx, const float* 
   const int blocks = static_cast<int>((warps + 7) / 8);
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   if (lanes == 8)
-    launch_pdl(layernorm_scatter_p2p_kernel<8>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, my_rank);
+    launch_pdl(layernorm_scatter_p2p_kernel<8>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, frame_off);
   else if (lanes == 16)
-    launch_pdl(layernorm_scatter_p2p_kernel<16>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, my_rank);
+    launch_pdl(layernorm_scatter_p2p_kernel<16>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, frame_off);
   else
-    launch_pdl(layernorm_scatter_p2p_kernel<32>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, my_rank);
+    launch_pdl(layernorm_scatter_p2p_kernel<32>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, frame_off);
   return lavie_check_launch("layernorm_scatter_p2p_kernel");
 }
 
 extern "C" int lavie_add_gathered_p2p(const void* res, int ldr, void* const* y_ptrs, void* out, int ldo, int rows, int C,
-                                      int hw, int hwp, int P, int my_rank, cudaStream_t stream) {
+                                      int hw, int hwp, int P, int my_rank, int frame_off, cudaStream_t stream) {
+  if (frame_off < 0) frame_off = my_rank * (hw > 0 ? rows / hw : 0);        // equal shards
   LAVIE_REQUIRE(C % 8 == 0 && ldr % 8 == 0 && ldo % 8 == 0 && hw > 0 && hwp > 0 && hw == hwp * P && rows % hw == 0,
                 LAVIE_ERR_SHAPE, "add_gathered_p2p: rows=%d C=%d hw=%d hwp=%d P=%d", rows, C, hw, hwp, P);
   LAVIE_REQUIRE(al16(res) && al16(out), LAVIE_ERR_ALIGN, "add_gathered_p2p: alignment");
@@ -380,7 +398,7 @@ extern "C" int lavie_add_gathered_p2p(const void* res, int ldr, void* const* y_p
   long long blocks = (total + 1023) / 1024;
   if (blocks > 148LL * 8) blocks = 148LL * 8;
   if (blocks < 1) blocks = 1;
-  launch_pdl(add_gathered_p2p_kernel, static_cast<int>(blocks), 256, 0, stream, static_cast<const __nv_bfloat16*>(res), ldr, y, static_cast<__nv_bfloat16*>(out), ldo, rows, C, hw, hwp, my_rank);
+  launch_pdl(add_gathered_p2p_kernel, static_cast<int>(blocks), 256, 0, stream, static_cast<const __nv_bfloat16*>(res), ldr, y, static_cast<__nv_bfloat16*>(out), ldo, rows, C, hw, hwp, frame_off);
   return lavie_check_launch("add_gathered_p2p_kernel");
 }
 
@@ -388,4 +406,19 @@ extern "C" int lavie_p2p_fault_buffer(void* host_mapped_words, int timeout_secon
   g_fault_report = static_cast<uint32_t*>(host_mapped_words);
   if (timeout_seconds > 0) g_wait_timeout_ns = static_cast<unsigned long long>(timeout_seconds) * 1000000000ull;
   return LAVIE_OK;
+}
+
+extern "C" int lavie_halo_push_p2p(const void* first_frame, const void* last_frame, long long frame_bytes,
+                                   void* const* ext_ptrs, int P, int my_rank, cudaStream_t stream) {
+  LAVIE_REQUIRE(frame_bytes > 0 && frame_bytes % 16 == 0 && al16(first_frame) && al16(last_frame), LAVIE_ERR_ALIGN,
+                "halo_push: frame size and pointers must be 16-byte multiples");
+  PeerPtrs d;
+  int rc = fill_peers(d, ext_ptrs, P);
+  if (rc) return rc;
+  const long long n16 = frame_bytes / 16;
+  long long blocks = (n16 + 255) / 256;
+  if (blocks > 148LL * 4) blocks = 148LL * 4;
+  launch_pdl(halo_push_kernel, static_cast<int>(blocks), 256, 0, stream, static_cast<const uint4*>(first_frame),
+             static_cast<const uint4*>(last_frame), n16, d, P, my_rank);
+  return lavie_check_launch("halo_push_kernel");
 }

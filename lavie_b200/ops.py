@@ -384,14 +384,15 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, heads: int, Sq: int, Sk: int, d: int,
               head_pitch: int, kv_batch_div: int = 1, scale: Optional[float] = None,
-              out: Optional[torch.Tensor] = None, sparse_causal_frames: int = 0):
+              out: Optional[torch.Tensor] = None, sparse_causal_frames: int = 0, sc_halo: int = 0):
     """q: [batch*Sq, >=heads*pitch] view, k/v: [(batch/kv_batch_div)*Sk, ...] views; returns [batch*Sq, heads*d].
-    sparse_causal_frames = F: batch = (video, frame), keys of frame f = [frame 0 | frame max(f-1, 0)] (2*Sk keys)."""
+    sparse_causal_frames = F: batch = (video, frame), keys of frame f = [frame 0 | frame max(f-1, 0)] (2*Sk keys).
+    sc_halo (frame sharding): k/v carry two extra leading frames [frame 0 | previous rank's last frame]; 2 on rank 0."""
     lib = _lib.load()
     rq, _, ldq = _rows2d(q)
     rk, _, ldk = _rows2d(k)
     rv, _, ldv = _rows2d(v)
-    assert rq == batch * Sq and rk == (batch // kv_batch_div) * Sk and rv == rk and ldk == ldv
+    assert rq == batch * Sq and rk == (batch // kv_batch_div + (2 if sc_halo else 0)) * Sk and rv == rk and ldk == ldv
     if out is None:
         out = torch.empty((rq, heads * d), dtype=BF16, device=q.device)
     _, _, ldo = _rows2d(out)
@@ -403,7 +404,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, hea
                  f"attn B={batch} Sq={Sq} Sk={keys} d={d}"):
         check(lib.lavie_attention_strided_bf16(q.data_ptr(), ldq, Sq * ldq, k.data_ptr(), v.data_ptr(), ldk, Sk * ldk,
                                                out.data_ptr(), ldo, Sq * ldo, batch, heads, Sq, Sk, d, head_pitch,
-                                               kv_batch_div, sparse_causal_frames, scale, _stream()),
+                                               kv_batch_div, sparse_causal_frames, sc_halo, scale, _stream()),
               "lavie_attention_strided_bf16")
     return out
 
@@ -427,7 +428,7 @@ def frame_attention(qkv: torch.Tensor, B: int, F: int, HW: int, heads: int, d: i
                      f"frame_attn F={F} HW={HW} d={d}"):
             check(lib.lavie_attention_strided_bf16(base.data_ptr(), HW * ld, ld, base[:, hp:].data_ptr(),
                                                    base[:, 2 * hp:].data_ptr(), HW * ld, ld, o_b.data_ptr(), HW * ldo,
-                                                   ldo, HW, heads, F, F, d, head_pitch, 1, 0, d ** -0.5, _stream()),
+                                                   ldo, HW, heads, F, F, d, head_pitch, 1, 0, 0, d ** -0.5, _stream()),
                   "lavie_attention_strided_bf16")
     return out
 

@@ -20,17 +20,24 @@ from .ops import _Launch, _rows2d, _stream, BF16, F32
 class PeerContext:
     """Symmetric buffers of one frame group: flags, GroupNorm slots, and the two token exchange buffers."""
 
-    def __init__(self, group, token_bytes: int, device: torch.device):
+    def __init__(self, group, token_bytes: int, device: torch.device, frame_off: int = -1, halo_bytes: int = 0):
+        """token_bytes: size of one all-to-all buffer (all frames x this rank's pixel slice x C at level 0);
+        frame_off: global index of this rank's first frame (-1 = equal shards); halo_bytes: size of the
+        [2 halo frames | local frames] q|k|v buffer of the interpolation model's SparseCausal attention (0 = none)."""
         import torch.distributed._symmetric_memory as symm
         self.group = group
         self.P = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.device = device
+        self.frame_off = frame_off
         flags_b = 256                                     # uint32[P], padded
         slots_b = 2 * self.P * (2 * 64 * 2) * 8           # double[2][P][samples<=2 * groups<=64 * 2]
         tok_b = (token_bytes + 255) // 256 * 256
-        self.layout = {"flags": 0, "slots": flags_b, "recv": flags_b + slots_b, "y": flags_b + slots_b + tok_b}
-        total = flags_b + slots_b + 2 * tok_b
+        halo_b = (halo_bytes + 255) // 256 * 256
+        self.layout = {"flags": 0, "slots": flags_b, "recv": flags_b + slots_b, "y": flags_b + slots_b + tok_b,
+                       "kvx": flags_b + slots_b + 2 * tok_b}
+        self.halo_bytes = halo_b
+        total = flags_b + slots_b + 2 * tok_b + halo_b
         self.buf = symm.empty(total, dtype=torch.uint8, device=device)
         self.buf.zero_()
         torch.cuda.synchronize(device)
@@ -58,11 +65,25 @@ class PeerContext:
         return (ctypes.c_void_p * self.P)(*[b + off for b in self.peer_base])
 
     def local(self, what: str, rows: int, cols: int) -> torch.Tensor:
-        """bf16 [rows, cols] view of this rank's `recv` / `y` buffer."""
+        """bf16 [rows, cols] view of this rank's `recv` / `y` / `kvx` buffer."""
         off = self.layout[what]
         n = rows * cols * 2
-        assert n <= self.token_bytes, (n, self.token_bytes)
+        assert n <= (self.halo_bytes if what == "kvx" else self.token_bytes), (what, n)
         return self.buf[off:off + n].view(BF16).view(rows, cols)
+
+    def push_halo(self, ext: torch.Tensor, n_local: int, hw: int):
+        """ext = this rank's `kvx` view [(2 + n_local) * hw, cols] whose local frames (rows 2*hw ..) were just written:
+        store frame 0 into every rank's halo block 0 (first rank) and my last frame into my right neighbour's block 1,
+        then the flag barrier; afterwards ext's halo rows are valid on every rank."""
+        lib = _lib.load()
+        cols = ext.shape[1]
+        frame_bytes = hw * cols * 2
+        first = ext[2 * hw:3 * hw]
+        last = ext[(1 + n_local) * hw:(2 + n_local) * hw]
+        with _Launch("lavie_halo_push_p2p", 0.0, 2.0 * frame_bytes):
+            check(lib.lavie_halo_push_p2p(first.data_ptr(), last.data_ptr(), frame_bytes, self.ptrs("kvx"), self.P,
+                                          self.rank, _stream()), "lavie_halo_push_p2p")
+        self.barrier()
 
     # ---- fused kernels ----
     def barrier(self):
@@ -71,8 +92,10 @@ class PeerContext:
             check(lib.lavie_rank_barrier(self.ptrs("flags"), self.epoch.data_ptr(), self.P, self.rank, _stream()),
                   "lavie_rank_barrier")
 
-    def gn_scale_shift(self, x, x2, samples, rows_local, gamma, beta, eps, groups=32):
+    def gn_scale_shift(self, x, x2, samples, rows_local, gamma, beta, eps, groups=32, rows_global=None):
+        """rows_global: rows of one sample over ALL ranks (default rows_local * P: equal shards)."""
         lib = _lib.load()
+        rows_global = rows_local * self.P if rows_global is None else rows_global
         rows, c0, ld0 = _rows2d(x)
         c1, ld1 = 0, 0
         if x2 is not None:
@@ -85,7 +108,7 @@ class PeerContext:
             ss = torch.empty((samples, C, 2), dtype=F32, device=x.device)
             with _Launch("lavie_gn_exchange_finalize"):
                 check(lib.lavie_gn_exchange_finalize_sums(sums.data_ptr(), samples, groups, C,
-                                                          rows_local * self.P * (C // groups), gamma.data_ptr(),
+                                                          rows_global * (C // groups), gamma.data_ptr(),
                                                           beta.data_ptr(), eps, ss.data_ptr(), self.ptrs("slots"),
                                                           self.ptrs("flags"), self.epoch.data_ptr(), self.P, self.rank,
                                                           _stream()), "lavie_gn_exchange_finalize_sums")
@@ -99,23 +122,24 @@ class PeerContext:
         ss = torch.empty((samples, C, 2), dtype=F32, device=x.device)
         with _Launch("lavie_gn_exchange_finalize"):
             check(lib.lavie_gn_exchange_finalize(partial.data_ptr(), samples, chunks, groups, C,
-                                                 rows_local * self.P * (C // groups), gamma.data_ptr(), beta.data_ptr(),
+                                                 rows_global * (C // groups), gamma.data_ptr(), beta.data_ptr(),
                                                  eps, ss.data_ptr(), self.ptrs("slots"), self.ptrs("flags"),
                                                  self.epoch.data_ptr(), self.P, self.rank, _stream()),
                   "lavie_gn_exchange_finalize")
         return ss
 
-    def layernorm_scatter(self, x, gamma, beta, hw, eps=1e-5):
+    def layernorm_scatter(self, x, gamma, beta, hw, eps=1e-5, frames_total=None):
         """LayerNorm + all-to-all (store side).  Returns this rank's receive buffer [F, hw/P, C] (valid after barrier)."""
         lib = _lib.load()
         rows, C, ldx = _rows2d(x)
         hwp = hw // self.P
         with _Launch("lavie_layernorm_scatter_p2p", 0.0, 4.0 * rows * C, f"ln_scatter_p2p rows={rows} C={C}"):
             check(lib.lavie_layernorm_scatter_p2p(x.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), eps,
-                                                  self.ptrs("recv"), rows, C, hw, hwp, self.P, self.rank, _stream()),
-                  "lavie_layernorm_scatter_p2p")
+                                                  self.ptrs("recv"), rows, C, hw, hwp, self.P, self.rank, self.frame_off,
+                                                  _stream()), "lavie_layernorm_scatter_p2p")
         self.barrier()
-        return self.local("recv", rows, C)
+        frames_total = rows // hw * self.P if frames_total is None else frames_total
+        return self.local("recv", frames_total * hwp, C)
 
     def add_gathered(self, res, hw):
         """res + all-to-all back (load side) of the peers' `y` buffers."""
@@ -126,5 +150,5 @@ class PeerContext:
         out = torch.empty((rows, C), dtype=BF16, device=res.device)
         with _Launch("lavie_add_gathered_p2p", 0.0, 6.0 * rows * C):
             check(lib.lavie_add_gathered_p2p(res.data_ptr(), ldr, self.ptrs("y"), out.data_ptr(), C, rows, C, hw, hwp,
-                                             self.P, self.rank, _stream()), "lavie_add_gathered_p2p")
+                                             self.P, self.rank, self.frame_off, _stream()), "lavie_add_gathered_p2p")
         return out

@@ -124,6 +124,7 @@ class UNet3DConditionModel(nn.Module):
         self._shard = None            # (process group, P, index) when the frames of one CFG half span P GPUs
         self._shard_backend = "p2p"
         self._peer = None
+        self._frame_counts = None
         self._retired_peers: list = []
         self._param_versions = None
         self._param_list = None
@@ -193,13 +194,16 @@ class UNet3DConditionModel(nn.Module):
         self._invalidate()
         return out
 
-    def set_frame_sharding(self, group=None, backend: str = "p2p"):
+    def set_frame_sharding(self, group=None, backend: str = "p2p", frame_counts=None):
         """Frame sharding: this rank holds F/P consecutive frames of the video; `group` is the
         torch.distributed process group of the P ranks that share one CFG half (rank order = frame order).
         Per-frame work (convs, per-frame GroupNorm, LayerNorm, spatial / cross attention, FF) runs shard-local;
         5-D GroupNorm statistics are all-reduced and the tokens are exchanged all-to-all around every temporal
         attention.  backend "p2p" (default) runs those exchanges inside this library's kernels over NVLink peer memory
-        (csrc/p2p.cu); "nccl" keeps the exchanges in torch.distributed collectives.  `None` switches sharding off."""
+        (csrc/p2p.cu); "nccl" keeps the exchanges in torch.distributed collectives.  `None` switches sharding off.
+        `frame_counts` (p2p only): frames held by each rank of the group when the shards are uneven, e.g. [16,15,15,15]
+        for the 61-frame interpolation model (default: every rank holds as many frames as this one).  The interpolation
+        variant additionally exchanges the SparseCausal halo (frame 0 of the video + the left neighbour's last frame)."""
         if backend not in ("p2p", "nccl"):
             raise ValueError("backend must be 'p2p' or 'nccl'")
         if group is not None and self.check_mode:
@@ -210,18 +214,31 @@ class UNet3DConditionModel(nn.Module):
             import torch.distributed as dist
             P = dist.get_world_size(group)
             self._shard = None if P == 1 else (group, P, dist.get_rank(group))
+            if frame_counts is not None:
+                if backend != "p2p" or len(frame_counts) != P:
+                    raise ValueError("frame_counts needs the p2p backend and one entry per rank of the group")
+        self._frame_counts = list(frame_counts) if (frame_counts is not None and self._shard is not None) else None
         self._shard_backend = backend
         self._peer = None
         self._graphs.clear()
 
-    def _peer_ctx(self, token_bytes: int):
+    def _frames(self, f_local: int):
+        """(global frame count, global index of this rank's first frame) of the sharded video."""
+        _, P, idx = self._shard
+        if self._frame_counts is None:
+            return f_local * P, idx * f_local
+        assert self._frame_counts[idx] == f_local, (self._frame_counts, idx, f_local)
+        return sum(self._frame_counts), sum(self._frame_counts[:idx])
+
+    def _peer_ctx(self, token_bytes: int, halo_bytes: int = 0, frame_off: int = -1):
         """Symmetric buffers of the frame group, created at the first sharded forward (collective call)."""
-        if self._peer is None or self._peer.token_bytes < token_bytes:
+        if (self._peer is None or self._peer.token_bytes < token_bytes or self._peer.halo_bytes < halo_bytes
+                or self._peer.frame_off != frame_off):
             from .p2p import PeerContext
             # graphs captured against the previous context have its peer pointers and epoch counter baked in
             self._graphs.clear()
             self._retired_peers.append(self._peer)      # keep the old symmetric buffers mapped until the module dies
-            self._peer = PeerContext(self._shard[0], token_bytes, self.device)
+            self._peer = PeerContext(self._shard[0], token_bytes, self.device, frame_off, halo_bytes)
         return self._peer
 
     def _gn5(self, x, x2, B, rows_local, gamma, beta, eps, silu):
@@ -235,7 +252,9 @@ class UNet3DConditionModel(nn.Module):
         if self._shard is None:
             return self._k.groupnorm_scale_shift(x, B, rows_local, gamma, beta, eps, x2=x2)
         if self._shard_backend == "p2p":
-            return self._peer.gn_scale_shift(x, x2, B, rows_local, gamma, beta, eps)
+            f_loc, f_total = self._shard_frames        # rows of one sample over ALL frame shards (shards may be uneven)
+            return self._peer.gn_scale_shift(x, x2, B, rows_local, gamma, beta, eps,
+                                             rows_global=rows_local // f_loc * f_total)
         import torch.distributed as dist
         group, P, _ = self._shard
         C = x.shape[1] + (x2.shape[1] if x2 is not None else 0)
@@ -403,9 +422,20 @@ class UNet3DConditionModel(nn.Module):
         # spatial self-attention; interpolation model: SparseCausalAttention, the keys of frame f are those of frame 0
         # and of frame f-1 (interpolation/models/attention.py:611-664) -- two key segments, never concatenated
         n = K.layernorm(tok, t["norm1_g"], t["norm1_b"])
-        qkv = K.gemm(n, t["attn1_qkv"])
-        a = K.attention(K.cols(qkv, 0, hp), K.cols(qkv, hp, 2 * hp), K.cols(qkv, 2 * hp, 3 * hp), NF, heads, HW, HW, d,
-                        pitch, sparse_causal_frames=Fr if interp else 0)
+        if interp and self._shard is not None:
+            # frame-sharded SparseCausal attention: q|k|v of the local frames land behind two halo frames that the first
+            # rank (frame 0 of the video) and the left neighbour (its last frame) fill over NVLink
+            assert B == 1, "frame sharding runs one CFG half per rank"
+            ctx = self._peer
+            ext = ctx.local("kvx", (2 + Fr) * HW, 3 * hp)
+            qkv = ops.gemm(n, t["attn1_qkv"], out=ext[2 * HW:])
+            ctx.push_halo(ext, Fr, HW)
+            a = ops.attention(qkv[:, :hp], ext[:, hp:2 * hp], ext[:, 2 * hp:], Fr, heads, HW, HW, d, pitch,
+                              sparse_causal_frames=Fr, sc_halo=2 if self._frames(Fr)[1] == 0 else 1)
+        else:
+            qkv = K.gemm(n, t["attn1_qkv"])
+            a = K.attention(K.cols(qkv, 0, hp), K.cols(qkv, hp, 2 * hp), K.cols(qkv, 2 * hp, 3 * hp), NF, heads, HW, HW,
+                            d, pitch, sparse_causal_frames=Fr if interp else 0)
         tok = K.gemm(a, t["attn1_wo"], bias=t["attn1_bo"], residual=tok)
         # text cross-attention: keys/values projected once per batch item, shared by its frames
         n = K.layernorm(tok, t["norm2_g"], t["norm2_b"])
@@ -417,16 +447,28 @@ class UNet3DConditionModel(nn.Module):
         if interp:
             # interpolation block order (interpolation/models/attention.py:566-608): feed-forward BEFORE the temporal
             # attention, which is a plain attention over the frames of a pixel (no rotary embedding, no bias)
-            if self._shard is not None:
-                raise NotImplementedError("frame sharding of the interpolation model (frame-0 broadcast + 1-frame halo, "
-                                          "SURVEY 8e) is not built yet")
             n = K.layernorm(tok, t["norm3_g"], t["norm3_b"])
             g = K.gemm(n, t["ff1_w"], bias=t["ff1_b"], geglu=True)
             tok = K.gemm(g, t["ff2_w"], bias=t["ff2_b"], residual=tok)
-            n = K.layernorm(tok, t["norm_temp_g"], t["norm_temp_b"])
-            qkv = K.gemm(n, t["attn_temp_qkv"])
-            a = K.frame_attention(qkv, B, Fr, HW, heads, d, pitch)
-            tok = K.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"], residual=tok)
+            if self._shard is None:
+                n = K.layernorm(tok, t["norm_temp_g"], t["norm_temp_b"])
+                qkv = K.gemm(n, t["attn_temp_qkv"])
+                a = K.frame_attention(qkv, B, Fr, HW, heads, d, pitch)
+                tok = K.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"], residual=tok)
+            else:
+                # all-to-all to pixel sharding around the plain temporal attention (peer-memory back end only)
+                if self._shard_backend != "p2p":
+                    raise NotImplementedError("the interpolation model shards frames over the p2p back end only")
+                _, P, _ = self._shard
+                assert HW % P == 0, "frame sharding needs H*W divisible by the number of frame shards"
+                hwp = HW // P
+                f_total = self._frames(Fr)[0]
+                ctx = self._peer
+                recv = ctx.layernorm_scatter(tok, t["norm_temp_g"], t["norm_temp_b"], HW, frames_total=f_total)
+                qkv = ops.gemm(recv, t["attn_temp_qkv"])
+                a = ops.frame_attention(qkv, 1, f_total, hwp, heads, d, pitch)
+                ops.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"], out=ctx.local("y", f_total * hwp, t["C"]))
+                tok = ctx.add_gathered(tok, HW)
             return K.gemm(tok, t["w_out"], bias=t["b_out"], residual=x, stats=True)
         # temporal attention: frames read in place with a row stride of HW (no (b f) d c <-> (b d) f c copies)
         if self._shard is None:
@@ -441,14 +483,15 @@ class UNet3DConditionModel(nn.Module):
             group, P, _ = self._shard
             assert B == 1 and HW % P == 0, "frame sharding runs one CFG half per rank and needs H*W divisible by P"
             hwp = HW // P
-            rope, bias = self._frame_tables(p, Fr * P)
+            f_total = self._frames(Fr)[0]
+            rope, bias = self._frame_tables(p, f_total)
             if self._shard_backend == "p2p":
                 # the all-to-alls are the store side of the LayerNorm and the load side of the residual add
                 ctx = self._peer
-                recv = ctx.layernorm_scatter(tok, t["norm_temp_g"], t["norm_temp_b"], HW)     # [F, hwp, C]
+                recv = ctx.layernorm_scatter(tok, t["norm_temp_g"], t["norm_temp_b"], HW, frames_total=f_total)
                 qkv = ops.gemm(recv, t["attn_temp_qkv"])
-                a = ops.temporal_attention(qkv, 1, Fr * P, hwp, heads, d, pitch, rope, bias)
-                ops.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"], out=ctx.local("y", Fr * P * hwp, t["C"]))
+                a = ops.temporal_attention(qkv, 1, f_total, hwp, heads, d, pitch, rope, bias)
+                ops.gemm(a, t["attn_temp_wo"], bias=t["attn_temp_bo"], out=ctx.local("y", f_total * hwp, t["C"]))
                 tok = ctx.add_gathered(tok, HW)
                 return self._ff_and_out(t, tok, x)
             send = ops.layernorm_scatter(tok, t["norm_temp_g"], t["norm_temp_b"], HW, hwp)   # [P, F_loc, hwp, C]
@@ -482,7 +525,14 @@ class UNet3DConditionModel(nn.Module):
         text = K.text_input(text, cfg.cross_attention_dim)
         boc = cfg.block_out_channels
         if self._shard is not None and self._shard_backend == "p2p":
-            self._peer_ctx(B * Fr * H * W * boc[0] * 2)        # largest token tensor = level 0
+            f_total, f_off = self._frames(Fr)
+            P_ = self._shard[1]
+            self._shard_frames = (Fr, f_total)
+            halo = 0
+            if cfg.variant == "interp":                # [2 halo frames | local frames] x q|k|v of level 0
+                halo = (2 + max(self._frame_counts or [Fr])) * H * W * 3 * cfg.heads * head_pitch(boc[0] // cfg.heads) * 2
+            # largest all-to-all buffer = level 0: all frames x this rank's pixel slice
+            self._peer_ctx(B * f_total * (H * W // P_) * boc[0] * 2, halo, f_off if self._frame_counts else -1)
 
         def tap(name, x, C, h, w):
             if taps is not None:

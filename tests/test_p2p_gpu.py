@@ -29,8 +29,10 @@ def solo_ctx():
             flags_b = 256
             slots_b = 2 * self.P * (2 * 64 * 2) * 8
             tok_b = (token_bytes + 255) // 256 * 256
-            self.layout = {"flags": 0, "slots": flags_b, "recv": flags_b + slots_b, "y": flags_b + slots_b + tok_b}
-            self.buf = torch.zeros(flags_b + slots_b + 2 * tok_b, dtype=torch.uint8, device=device)
+            self.layout = {"flags": 0, "slots": flags_b, "recv": flags_b + slots_b, "y": flags_b + slots_b + tok_b,
+                           "kvx": flags_b + slots_b + 2 * tok_b}
+            self.frame_off, self.halo_bytes = -1, tok_b
+            self.buf = torch.zeros(flags_b + slots_b + 3 * tok_b, dtype=torch.uint8, device=device)
             self.peer_base = [self.buf.data_ptr()]
             self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
             self.fault = torch.zeros(8, dtype=torch.int32).pin_memory()
@@ -60,8 +62,26 @@ def test_p2p_kernels_with_a_single_peer(solo_ctx):
     for _ in range(3):
         ss = ctx.gn_scale_shift(x, None, 1, f_loc * hw, gamma, beta, 1e-5)
         assert rel_l2(ss, ops.groupnorm_scale_shift(x, 1, f_loc * hw, gamma, beta, 1e-5)) < 1e-6
+    # SparseCausal halo exchange with a single rank: frame 0 lands in halo block 0, block 1 stays untouched (no right
+    # neighbour), and the attention over [halo | local] equals the un-sharded sparse-causal attention
+    from lavie_b200.packing import head_pitch
+    heads, d, frames, S = 8, 40, 3, 64
+    hp = heads * head_pitch(d)
+    ext = ctx.local("kvx", (2 + frames) * S, 3 * hp)
+    ext.zero_()
+    qkv = torch.zeros(frames * S, 3, heads, head_pitch(d))
+    qkv[..., :d] = torch.randn(frames * S, 3, heads, d, generator=g)
+    ext[2 * S:].copy_(qkv.reshape(frames * S, 3 * hp).to(torch.bfloat16))
+    ctx.push_halo(ext, frames, S)
+    assert torch.equal(ext[:S], ext[2 * S:3 * S]) and float(ext[S:2 * S].abs().max()) == 0.0
+    loc = ext[2 * S:]
+    got = ops.attention(loc[:, :hp], ext[:, hp:2 * hp], ext[:, 2 * hp:], frames, heads, S, S, d, head_pitch(d),
+                        sparse_causal_frames=frames, sc_halo=2)
+    want = ops.attention(loc[:, :hp], loc[:, hp:2 * hp], loc[:, 2 * hp:], frames, heads, S, S, d, head_pitch(d),
+                         sparse_causal_frames=frames)
+    assert torch.equal(got, want)
     torch.cuda.synchronize()
-    assert int(ctx.epoch) == e0 + 2 + 3           # every exchange advanced the epoch exactly once
+    assert int(ctx.epoch) == e0 + 2 + 3 + 1       # every exchange advanced the epoch exactly once
     assert ctx.describe_fault().startswith("no peer-wait timeout")
 
 
@@ -106,6 +126,29 @@ def _two_gpu_worker(rank, world, port, q):
                            encoder_hidden_states=e2.to(dev)).sample  # regrow
                 errs["p2p/regrow"] = rel_l2(big, r2[:, :, rank * fl:(rank + 1) * fl])
                 errs["p2p/after-regrow"] = rel_l2(unet(shard, t, encoder_hidden_states=text).sample, want)
+        # the interpolation model with UNEVEN shards (7 frames = 4 + 3), SparseCausal halo + plain temporal attention
+        from lavie_b200.config import INTERP_CONFIG
+        del unet
+        torch.cuda.empty_cache()
+        iu = UNet3DConditionModel(INTERP_CONFIG)
+        iu.load_state_dict(synthetic_state_dict(INTERP_CONFIG, seed=0), strict=True)
+        iu = iu.to(dev).eval()
+        g = torch.Generator().manual_seed(17)
+        xs = torch.randn(1, 8, 7, 16, 32, generator=g).to(dev)
+        te = torch.randn(1, 77, 768, generator=g).to(dev)
+        iref = iu(xs, 400, encoder_hidden_states=te).sample
+        counts = [4, 3]
+        off = sum(counts[:rank])
+        iu.set_frame_sharding(dist.group.WORLD, backend="p2p", frame_counts=counts)
+        ish = xs[:, :, off:off + counts[rank]].contiguous()
+        iwant = iref[:, :, off:off + counts[rank]]
+        iu.use_cuda_graph = False
+        errs["interp/eager"] = rel_l2(iu(ish, 400, encoder_hidden_states=te).sample, iwant)
+        iu.use_cuda_graph = True
+        worst = 0.0
+        for _ in range(3):
+            worst = max(worst, rel_l2(iu(ish, 400, encoder_hidden_states=te).sample, iwant))
+        errs["interp/graph"] = worst
         q.put((rank, errs))
         torch.cuda.synchronize()
         dist.barrier()
