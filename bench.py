@@ -436,17 +436,26 @@ INTERP_FRAMES = 61
 
 
 def run_interp(args):
-    """BASELINE config 4 on ONE B200 (python bench.py --workload interp): a step = forward_with_cfg of the interpolation
-    UNet on cat([x_t, key-frame latents], 1) = [2,8,61,40,64] + the DDIM update (interpolation/sample.py:138-166).  Parity
-    is checked on a bounded sample (the first 5 frames at full spatial size) against the unmodified reference model: its
-    full-size CPU forward needs a 51 GB score tensor."""
+    """BASELINE config 4 (python bench.py --workload interp [--gpus N under torchrun]): a step = forward_with_cfg of the
+    interpolation UNet on cat([x_t, key-frame latents], 1) = [2,8,61,40,64] + the DDIM update
+    (interpolation/sample.py:138-166).  N >= 2: the cond / uncond halves go to the two halves of the ranks and each half
+    shards its 61 frames over P = N/2 GPUs (16/15/15/15 at N = 8): SparseCausal halo exchange, all-to-all around the
+    temporal attention and GroupNorm sum exchange over NVLink peer memory; the sharded forward of every rank is checked
+    against the un-sharded one on its own GPU.  N = 1 parity: a bounded sample (the first 5 frames at full spatial size)
+    against the unmodified reference model, whose full-size CPU forward needs a 51 GB score tensor."""
+    import torch.distributed as dist
     from lavie_b200 import UNet3DConditionModel, ops
     from lavie_b200.config import INTERP_CONFIG
     from lavie_b200.pipeline import InterpolationSampler
     from lavie_b200.synthetic import synthetic_state_dict
     from oracle import reference_loader as R
-    dev = torch.device("cuda", 0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     sd = synthetic_state_dict(INTERP_CONFIG, seed=0)
     unet = UNet3DConditionModel(INTERP_CONFIG)
     unet.load_state_dict(sd, strict=True)
@@ -454,35 +463,93 @@ def run_interp(args):
     g = torch.Generator().manual_seed(4)
     z = torch.randn(1, 4, INTERP_FRAMES, LAT_H, LAT_W, generator=g)
     cond = torch.randn(1, 4, INTERP_FRAMES, LAT_H, LAT_W, generator=g)
-    text = torch.randn(2, 77, 768, generator=g)
-    z2, c2 = torch.cat([z, z]), torch.cat([cond, cond])
+    text = torch.randn(2, 77, 768, generator=g)                    # [prompt, negative prompt]
     sampler = InterpolationSampler(unet, 4.0, 50)
     ts = sampler.timesteps[::-1]
+    parity = None
 
-    def one_step(x, cnd, txt, i):
-        gd = unet.forward_with_cfg(torch.cat([x, cnd], dim=1), ts[i % 50], encoder_hidden_states=txt, cfg_scale=4.0)
-        a, b = sampler.coefficients(49 - (i % 50))
-        return ops.cfg_linear_step(gd, gd, 0.0, a, b, x)
+    if world == 1:
+        parallelism = "single"
+        z2, c2 = torch.cat([z, z]), torch.cat([cond, cond])
+        x, cnd, txt = z2.to(dev), c2.to(dev), text.to(dev)
 
-    x, cnd, txt = z2.to(dev), c2.to(dev), text.to(dev)
+        def one_step(x, cnd, txt, i):
+            gd = unet.forward_with_cfg(torch.cat([x, cnd], dim=1), ts[i % 50], encoder_hidden_states=txt, cfg_scale=4.0)
+            a, b = sampler.coefficients(49 - (i % 50))
+            return ops.cfg_linear_step(gd, gd, 0.0, a, b, x)
+        host_in = [z2, c2, text]
+    else:
+        if world % 2 or (LAT_H * LAT_W) % (world // 2):
+            raise SystemExit("--gpus must be 1, 2, 4 or 8")
+        P = world // 2
+        half, shard_idx = rank // P, rank % P
+        counts = [INTERP_FRAMES // P + (1 if r < INTERP_FRAMES % P else 0) for r in range(P)]
+        off = sum(counts[:shard_idx])
+        parallelism = "cfg2" if P == 1 else f"cfg2 x frames{P} ({'/'.join(map(str, counts))})"
+        frame_group = pair_group = None
+        for hh in range(2):
+            gg = dist.new_group(list(range(hh * P, hh * P + P)))
+            if hh == half:
+                frame_group = gg
+        for ss in range(P):
+            gg = dist.new_group([ss, P + ss])
+            if ss == shard_idx:
+                pair_group = gg
+        my_text = text[half:half + 1].to(dev)                       # half 0 = cond prompt, half 1 = negative prompt
+        full_in = torch.cat([z, cond], dim=1).to(dev)
+        full_out = unet(full_in, 500, encoder_hidden_states=my_text).sample
+        unet.set_frame_sharding(frame_group, frame_counts=counts if P > 1 else None)
+        sl = slice(off, off + counts[shard_idx])
+        shard_out = None
+        for _ in range(2):
+            shard_out = unet(full_in[:, :, sl].contiguous(), 500, encoder_hidden_states=my_text).sample
+        err = rel_l2(shard_out, full_out[:, :, sl])
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        parity = {"rel_l2": max(errs), "per_rank": [round(e, 6) for e in errs], "tolerance": 2e-2,
+                  "vs": "un-sharded forward of the same inputs on the rank's own GPU",
+                  "shape": [1, 8, INTERP_FRAMES, LAT_H, LAT_W]}
+        if max(errs) > 2e-2:
+            raise SystemExit(f"sharded interpolation forward differs from the un-sharded one: {max(errs):.3e}")
+        del full_out, full_in
+        x, cnd, txt = z[:, :, sl].contiguous().to(dev), cond[:, :, sl].contiguous().to(dev), my_text
+        gather = [torch.empty_like(x) for _ in range(2)]
+
+        def one_step(x, cnd, txt, i):
+            eps = unet(torch.cat([x, cnd], dim=1), ts[i % 50], encoder_hidden_states=txt).sample
+            dist.all_gather(gather, eps.contiguous(), group=pair_group)      # [cond eps, uncond eps] of my frames
+            a, b = sampler.coefficients(49 - (i % 50))
+            return ops.cfg_linear_step(gather[1], gather[0], 4.0, a, b, x)
+        host_in = [z[:, :, sl].contiguous(), cond[:, :, sl].contiguous(), text[half:half + 1].contiguous()]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for i in range(max(args.warmup, 3)):
         x = one_step(x, cnd, txt, i)
-    torch.cuda.synchronize()
+    barrier()
     per_step = unet.launches_per_step() + 2
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(0) as clocks:
-        torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clocks:
+        barrier()
         ev0.record()
         for i in range(args.steps):
             x = one_step(x, cnd, txt, i)
         ev1.record()
-        torch.cuda.synchronize()
-    ms_per_step = ev0.elapsed_time(ev1) / args.steps
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax)
+    ms_per_step = ms / args.steps
     # e2e: host buffers in, new latents out, every step
-    xh = [z2.clone().pin_memory(), torch.empty_like(z2).pin_memory()]
-    ch, th = c2.clone().pin_memory(), text.clone().pin_memory()
+    xh = [host_in[0].clone().pin_memory(), torch.empty_like(host_in[0]).pin_memory()]
+    ch, th = host_in[1].clone().pin_memory(), host_in[2].clone().pin_memory()
     done = torch.cuda.Event()
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         new = one_step(xh[i & 1].to(dev, non_blocking=True), ch.to(dev, non_blocking=True),
@@ -490,13 +557,20 @@ def run_interp(args):
         xh[(i + 1) & 1].copy_(new, non_blocking=True)
         done.record()
         done.synchronize()
+    barrier()
     e2e_s = time.perf_counter() - t0
-    # per-kernel profile of one eager forward
+    if world > 1:
+        tmax = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax)
+    # per-kernel profile of one eager forward (every rank runs it: the sharded exchanges need the whole group)
     unet.use_cuda_graph = False
-    m_in = torch.cat([torch.cat([z2, c2], dim=1)[:1]] * 2).to(dev)
+    m_in = (torch.cat([torch.cat([z, z]), torch.cat([cond, cond])], dim=1) if world == 1 else
+            torch.cat([host_in[0], host_in[1]], dim=1)).to(dev)
     unet(m_in, 500, encoder_hidden_states=txt)
     ops.PROFILE = []
-    torch.cuda._sleep(300_000_000)
+    if world == 1:
+        torch.cuda._sleep(300_000_000)
     unet(m_in, 500, encoder_hidden_states=txt)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
@@ -510,20 +584,20 @@ def run_interp(args):
                    "gflop": round(a[2] / 1e9, 1), "tflops": round(a[2] / (a[1] * 1e-3) / 1e12, 1) if a[2] else None,
                    "gbs": round(a[3] / (a[1] * 1e-3) / 1e9, 1) if a[3] else None}
                for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
-    step_gflop = sum(a[2] for a in agg.values()) / 1e9
+    step_gflop = sum(a[2] for a in agg.values()) / 1e9 * world      # every rank does 1/world of the step
     peaks = measured_peaks()
     d = agg["gemm_bf16_tcgen05"]
     achieved = d[2] / (d[1] * 1e-3) / 1e12
     roofline = {"kernel": "gemm_bf16_tcgen05", "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None,
                 "launches_per_step": d[0], "share_of_step": d[1] / total_ms, "peak_source": peaks["source"]}
-    # parity + CPU baseline on a bounded sample: 5 frames, full spatial size
-    parity, cpu = None, None
-    if not args.no_cpu_baseline:
+    # N = 1: parity + CPU baseline on a bounded sample: 5 frames, full spatial size
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
         f = 5
         threads = os.cpu_count() or 1
         torch.set_num_threads(threads)
-        m5 = torch.cat([torch.cat([z2, c2], dim=1)[:1, :, :f]] * 2).contiguous()
+        m5 = torch.cat([torch.cat([z, cond], dim=1)[:1, :, :f]] * 2).contiguous()
         if R.available("interpolation"):
             ref = R.load_reference_unet("interp", sd)
             kind = "reference"
@@ -546,19 +620,25 @@ def run_interp(args):
                          f"needs a 51 GB score tensor) = {dt:.2f} s"}
         if not err <= 2e-2:
             raise SystemExit(f"interp parity FAILED: {err:.3e}")
-    line = {"metric": "denoise steps/s (interpolation 320x512, 61 frames, CFG)", "value": 1e3 / ms_per_step,
-            "unit": "steps/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": INTERP_WORKLOAD, "weights": "random-init (seeded), 909.1 M params"},
-            "setup": {"parallelism": "single", "cuda_graph": True, "launches_per_step": per_step},
-            "parity": parity, "step_gflop": step_gflop, "step_tflops": step_gflop / ms_per_step,
-            "clocks": clocks.summary(),
-            "e2e": {"value": args.steps / e2e_s, "unit": "steps/s",
-                    "h2d_bytes_per_step": (xh[0].numel() + ch.numel() + th.numel()) * 4,
-                    "d2h_bytes_per_step": xh[0].numel() * 4},
-            "gpu_launches": per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        line = {"metric": "denoise steps/s (interpolation 320x512, 61 frames, CFG)", "value": 1e3 / ms_per_step,
+                "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": INTERP_WORKLOAD, "weights": "random-init (seeded), 909.1 M params"},
+                "setup": {"parallelism": parallelism, "cuda_graph": True, "launches_per_step_per_rank": per_step},
+                "parity": parity, "step_gflop": step_gflop, "step_tflops": step_gflop / ms_per_step,
+                "clocks": clocks.summary(),
+                "e2e": {"value": args.steps / e2e_s, "unit": "steps/s",
+                        "h2d_bytes_per_step": (xh[0].numel() + ch.numel() + th.numel()) * 4,
+                        "d2h_bytes_per_step": xh[0].numel() * 4},
+                "gpu_launches": per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
