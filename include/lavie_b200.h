@@ -179,18 +179,34 @@ int lavie_gn_exchange_finalize_sums(const double* local_sums, int samples, int g
                                     float* scale_shift, void* const* slot_ptrs, void* const* flag_ptrs,
                                     unsigned int* epoch_counter, int P, int my_rank, lavie_stream_t stream);
 /* frame_off = global index of this rank's first frame (shards may be uneven: 61 interpolation frames = 16/15/15/15);
- * negative = my_rank * rows / hw (equal shards). */
+ * negative = my_rank * rows / hw (equal shards).
+ * Fused barriers (flag_ptrs != NULL, with the rank's epoch counter and a zero-initialised device int `ticket` that the
+ * kernel leaves zero): the flag barrier runs INSIDE the kernel instead of a separate lavie_rank_barrier launch --
+ * scatter / halo push: the last block to finish signals the peers and waits for theirs (kernel completion == every
+ * rank's rows have landed); add_gathered: block 0 signals "my y buffer is complete", every block waits for all peers
+ * before its first peer load. */
 int lavie_layernorm_scatter_p2p(const void* x, int ldx, const float* gamma, const float* beta, float eps,
                                 void* const* recv_ptrs, int rows, int C, int hw, int hwp, int P, int my_rank,
-                                int frame_off, lavie_stream_t stream);
+                                int frame_off, void* const* flag_ptrs, unsigned int* epoch_counter, int* ticket,
+                                lavie_stream_t stream);
 int lavie_add_gathered_p2p(const void* res, int ldr, void* const* y_ptrs, void* out, int ldo, int rows, int C, int hw,
-                           int hwp, int P, int my_rank, int frame_off, lavie_stream_t stream);
+                           int hwp, int P, int my_rank, int frame_off, void* const* flag_ptrs,
+                           unsigned int* epoch_counter, int* ticket, lavie_stream_t stream);
+/* lavie_gn_exchange_finalize starting from the producers' micro-group statistics of this rank (lavie_epilogue.col_stats):
+ * local reduction, peer exchange and finalize in ONE single-block launch. */
+int lavie_gn_exchange_finalize_colsums(const float* cs0, int c0, const float* cs1, int c1, int samples, int rows_local,
+                                       int groups, long long count_per_group_global, const float* gamma,
+                                       const float* beta, float eps, float* scale_shift, void* const* slot_ptrs,
+                                       void* const* flag_ptrs, unsigned int* epoch_counter, int P, int my_rank,
+                                       lavie_stream_t stream);
 /* Halo exchange of SparseCausalAttention under frame sharding (interpolation/models/attention.py:629-638): ext_ptrs[r] ->
  * rank r's buffer [2 halo frames | its local frames] of frame_bytes each.  Rank 0 stores first_frame (frame 0 of the
  * video) into block 0 of EVERY rank, every rank but the last stores last_frame (its last local frame) into block 1 of its
- * right neighbour.  Follow with lavie_rank_barrier, then lavie_attention_strided_bf16(sc_halo = 1, or 2 on rank 0). */
+ * right neighbour.  Follow with lavie_rank_barrier (or pass flag_ptrs for the fused barrier), then
+ * lavie_attention_strided_bf16(sc_halo = 1, or 2 on rank 0). */
 int lavie_halo_push_p2p(const void* first_frame, const void* last_frame, long long frame_bytes, void* const* ext_ptrs,
-                        int P, int my_rank, lavie_stream_t stream);
+                        int P, int my_rank, void* const* flag_ptrs, unsigned int* epoch_counter, int* ticket,
+                        lavie_stream_t stream);
 
 /* softmax(q k^T * scale) v per (batch, head)  (CrossAttention._attention, attention.py:209-239).
  * q rows = batch*Sq, k/v rows = (batch / kv_batch_div)*Sk (kv_batch_div = F shares the text keys across frames,

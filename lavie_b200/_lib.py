@@ -65,9 +65,12 @@ SIGNATURES = {
     "lavie_gn_exchange_finalize_sums": (c_int, [_P, c_int, c_int, c_int, c_longlong, _P, _P, c_float, _P, _P, _P, _P, c_int,
                                                 c_int, _P]),
     "lavie_layernorm_scatter_p2p": (c_int, [_P, c_int, _P, _P, c_float, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                            _P]),
-    "lavie_add_gathered_p2p": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
-    "lavie_halo_push_p2p": (c_int, [_P, _P, c_longlong, _P, c_int, c_int, _P]),
+                                            _P, _P, _P, _P]),
+    "lavie_add_gathered_p2p": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P,
+                                       _P, _P]),
+    "lavie_halo_push_p2p": (c_int, [_P, _P, c_longlong, _P, c_int, c_int, _P, _P, _P, _P]),
+    "lavie_gn_exchange_finalize_colsums": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_longlong, _P, _P, c_float,
+                                                   _P, _P, _P, _P, c_int, c_int, _P]),
     "lavie_groupnorm_finalize_sums": (c_int, [_P, c_int, c_int, c_int, c_longlong, _P, _P, c_float, _P, _P]),
     "lavie_attention_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_float, _P]),

@@ -93,11 +93,107 @@ __global__ void rank_barrier_kernel(PeerPtrs flags, uint32_t* epoch_counter, int
   if (threadIdx.x == 0) *epoch_counter = epoch;
 }
 
+// Barrier folded into the END of a multi-block kernel: every block publishes its peer stores (system fence) and takes a
+// ticket; the LAST block to finish signals the peers, waits for theirs and bumps the epoch, so kernel completion implies
+// "all ranks passed the barrier" and no separate barrier launch is needed.  Every thread of every block must call it.
+struct SyncCtx {
+  PeerPtrs flags;
+  uint32_t* epoch_counter;
+  int* ticket;               // device int, zero on entry, left zero
+  int P, my_rank;
+  FaultCtx fc;
+};
+__device__ __forceinline__ void grid_end_barrier(const SyncCtx& sc) {
+  __shared__ int s_last_blk;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last_blk = (atomicAdd(sc.ticket, 1) == static_cast<int>(gridDim.x) - 1);
+  __syncthreads();
+  if (!s_last_blk) return;
+  __threadfence();
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(sc.epoch_counter) + 1;
+  block_rank_barrier(sc.flags, sc.P, sc.my_rank, epoch, sc.fc);
+  if (threadIdx.x == 0) {
+    *sc.epoch_counter = epoch;
+    *sc.ticket = 0;
+  }
+}
+// Barrier folded into the START of a multi-block kernel whose blocks all read peer memory: block 0 signals, every block
+// waits for all peers; the last block to FINISH bumps the epoch (every block has read it by then).
+__device__ __forceinline__ uint32_t grid_start_barrier(const SyncCtx& sc) {
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(sc.epoch_counter) + 1;
+  if (blockIdx.x == 0 && threadIdx.x < sc.P) {
+    __threadfence_system();
+    st_release_sys(static_cast<uint32_t*>(sc.flags.p[threadIdx.x]) + sc.my_rank, epoch);
+  }
+  if (threadIdx.x < sc.P)
+    wait_flag(static_cast<const uint32_t*>(sc.flags.p[sc.my_rank]) + threadIdx.x, epoch, sc.fc, sc.my_rank, threadIdx.x);
+  __syncthreads();
+  return epoch;
+}
+__device__ __forceinline__ void grid_start_barrier_finish(const SyncCtx& sc, uint32_t epoch) {
+  __shared__ int s_last_blk2;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last_blk2 = (atomicAdd(sc.ticket, 1) == static_cast<int>(gridDim.x) - 1);
+  __syncthreads();
+  if (s_last_blk2 && threadIdx.x == 0) {
+    *sc.epoch_counter = epoch;
+    *sc.ticket = 0;
+  }
+}
+
+// this rank's GroupNorm sums straight from the producers' micro-group statistics (gemm.cu epilogue; layout and address
+// arithmetic of norm.cu's gn_colsums_kernel): warp per (sample, group), fp64 lanes, fixed shuffle tree
+struct ColSrc {
+  const float* cs0;
+  const float* cs1;
+  int c0, c1, slabs_per_sample;
+};
+__device__ __forceinline__ void block_colsums(const ColSrc& src, int samples, int groups, double* s_sums) {
+  const int C = src.c0 + src.c1, cpg = C / groups, decs = cpg / 10;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int sg = warp; sg < samples * groups; sg += nwarps) {
+    const int sample = sg / groups, g = sg - sample * groups;
+    const long long total = static_cast<long long>(src.slabs_per_sample) * decs;
+    double a = 0.0, b = 0.0;
+    for (long long i = lane; i < total; i += 32) {
+      const long long slab = static_cast<long long>(sample) * src.slabs_per_sample + i / decs;
+      int ch = g * cpg + static_cast<int>(i % decs) * 10;
+      const float* cs = src.cs0;
+      int cn = src.c0;
+      if (ch >= src.c0) {
+        ch -= src.c0;
+        cs = src.cs1;
+        cn = src.c1;
+      }
+      const int dec = ch / 10, k_lo = ch >> 5, k_hi = (ch + 9) >> 5;
+      const float* row = cs + slab * (cn >> 5) * 8;
+      float2 v = *reinterpret_cast<const float2*>(row + (k_lo * 4 + (dec - (k_lo * 32) / 10)) * 2);
+      if (k_hi != k_lo) {
+        const float2 w = *reinterpret_cast<const float2*>(row + (k_hi * 4 + (dec - (k_hi * 32) / 10)) * 2);
+        v.x += w.x;
+        v.y += w.y;
+      }
+      a += v.x;
+      b += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      s_sums[sg * 2] = a;
+      s_sums[sg * 2 + 1] = b;
+    }
+  }
+}
+
 // partial[samples][chunks][groups][2] -> exchange -> scale_shift[samples][C][2]
 // slots: per peer a buffer double[2 (epoch parity)][P][samples*groups*2]
 __global__ void __launch_bounds__(256)
-gn_exchange_finalize_kernel(const float* __restrict__ partial, const double* __restrict__ local_sums, int samples,
-                            int chunks, int groups, int C,
+gn_exchange_finalize_kernel(const float* __restrict__ partial, const double* __restrict__ local_sums, ColSrc colsrc,
+                            int samples, int chunks, int groups, int C,
                             double inv_count, const float* __restrict__ gamma, const float* __restrict__ beta,
                             float eps, float* __restrict__ scale_shift, PeerPtrs slots, PeerPtrs flags,
                             uint32_t* epoch_counter, int P, int my_rank, FaultCtx fc) {
@@ -109,7 +205,9 @@ gn_exchange_finalize_kernel(const float* __restrict__ partial, const double* __r
   // 1. ordered local reduction of the chunk partials (8 lanes per (sample, group)) -- or the local sums as they come
   //    from the producers' column statistics (lavie_groupnorm_reduce_colsums)
   const int sub = threadIdx.x & 7;
-  if (local_sums != nullptr) {
+  if (colsrc.cs0 != nullptr) {
+    block_colsums(colsrc, samples, groups, s_sums);
+  } else if (local_sums != nullptr) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) s_sums[i] = local_sums[i];
   } else
   for (int sg = threadIdx.x >> 3; sg < samples * groups; sg += blockDim.x >> 3) {
@@ -180,7 +278,7 @@ template <int L>
 __global__ void __launch_bounds__(256)
 layernorm_scatter_p2p_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gamma,
                              const float* __restrict__ beta, float eps, PeerPtrs recv, int rows, int hw, int hwp,
-                             int frame_off) {
+                             int frame_off, SyncCtx sync) {
   pdl_prologue();
   constexpr int VPL = 5;
   constexpr int C = 40 * L;
@@ -221,7 +319,7 @@ layernorm_scatter_p2p_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const
 #pragma unroll
   for (int o = L / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / static_cast<float>(C) + eps);
-  if (!ok) return;
+  if (ok) {
   const int fr = static_cast<int>(row / hw), pix = static_cast<int>(row - static_cast<long long>(fr) * hw);
   const int blk = pix / hwp;
   const size_t drow = (static_cast<size_t>(frame_off) + fr) * hwp + (pix - blk * hwp);     // global frame index
@@ -240,13 +338,17 @@ layernorm_scatter_p2p_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const
     o.w = pack_bf16((f[i][6] - mean) * rstd * g1.z + b1.z, (f[i][7] - mean) * rstd * g1.w + b1.w);
     *reinterpret_cast<uint4*>(dst + v * 8) = o;
   }
+  }
+  if (sync.ticket != nullptr) grid_end_barrier(sync);    // kernel completion == every rank's rows have landed
 }
 
 // out[(f, blk*hwp + j)] = res[(f, blk*hwp + j)] + y_of_peer_blk[(frame_off + f)*hwp + j]   (peer loads over NVLink)
 __global__ void __launch_bounds__(256)
 add_gathered_p2p_kernel(const __nv_bfloat16* __restrict__ res, int ldr, PeerPtrs ybuf, __nv_bfloat16* __restrict__ out,
-                        int ldo, int rows, int C, int hw, int hwp, int frame_off) {
+                        int ldo, int rows, int C, int hw, int hwp, int frame_off, SyncCtx sync) {
   pdl_prologue();
+  uint32_t epoch = 0;
+  if (sync.ticket != nullptr) epoch = grid_start_barrier(sync);      // every rank's y buffer is complete
   const int nvec = C >> 3;
   const long long total = static_cast<long long>(rows) * nvec;
   constexpr int U = 4;
@@ -279,6 +381,7 @@ add_gathered_p2p_kernel(const __nv_bfloat16* __restrict__ res, int ldr, PeerPtrs
       *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ldo + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
+  if (sync.ticket != nullptr) grid_start_barrier_finish(sync, epoch);
 }
 
 // SparseCausalAttention under frame sharding: every rank needs the projected q|k|v rows of
@@ -286,7 +389,7 @@ add_gathered_p2p_kernel(const __nv_bfloat16* __restrict__ res, int ldr, PeerPtrs
 // The receiving buffer on every rank is [halo block 0 = frame 0 | halo block 1 = previous frame | local frames].
 __global__ void __launch_bounds__(256)
 halo_push_kernel(const uint4* __restrict__ first_frame, const uint4* __restrict__ last_frame, long long n16,
-                 PeerPtrs dst, int P, int my_rank) {
+                 PeerPtrs dst, int P, int my_rank, SyncCtx sync) {
   pdl_prologue();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n16;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -296,6 +399,7 @@ halo_push_kernel(const uint4* __restrict__ first_frame, const uint4* __restrict_
     }
     if (my_rank + 1 < P) static_cast<uint4*>(dst.p[my_rank + 1])[n16 + i] = __ldg(last_frame + i);
   }
+  if (sync.ticket != nullptr) grid_end_barrier(sync);
 }
 
 bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -303,6 +407,24 @@ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 uint32_t* g_fault_report = nullptr;              // host-mapped, set by lavie_p2p_fault_buffer
 unsigned long long g_wait_timeout_ns = 30ull * 1000000000ull;
 FaultCtx fault_ctx() { return FaultCtx{g_fault_report, g_wait_timeout_ns}; }
+
+int fill_peers(PeerPtrs& pp, void* const* ptrs, int P);
+// optional fused barrier: flag_ptrs == nullptr -> no barrier inside the kernel (caller issues lavie_rank_barrier)
+int fill_sync(SyncCtx& sc, void* const* flag_ptrs, unsigned int* epoch_counter, int* ticket, int P, int my_rank) {
+  sc.epoch_counter = epoch_counter;
+  sc.ticket = nullptr;
+  sc.P = P;
+  sc.my_rank = my_rank;
+  sc.fc = fault_ctx();
+  for (int i = 0; i < MAX_PEERS; ++i) sc.flags.p[i] = nullptr;
+  if (flag_ptrs == nullptr) return LAVIE_OK;
+  LAVIE_REQUIRE(epoch_counter != nullptr && ticket != nullptr, LAVIE_ERR_SHAPE,
+                "p2p: a fused barrier needs the epoch counter and a ticket word");
+  int rc = fill_peers(sc.flags, flag_ptrs, P);
+  if (rc) return rc;
+  sc.ticket = ticket;
+  return LAVIE_OK;
+}
 
 int fill_peers(PeerPtrs& pp, void* const* ptrs, int P) {
   LAVIE_REQUIRE(P >= 1 && P <= MAX_PEERS, LAVIE_ERR_SHAPE, "p2p: 1 <= peers <= %d", MAX_PEERS);
@@ -323,7 +445,8 @@ extern "C" int lavie_rank_barrier(void* const* flag_ptrs, unsigned int* epoch_co
 }
 
 namespace {
-int gn_exchange_impl(const float* partial, const double* local_sums, int samples, int chunks, int groups, int C,
+int gn_exchange_impl(const float* partial, const double* local_sums, ColSrc colsrc, int samples, int chunks, int groups,
+                     int C,
                      long long count_per_group_global, const float* gamma, const float* beta, float eps,
                      float* scale_shift, void* const* slot_ptrs, void* const* flag_ptrs, unsigned int* epoch_counter,
                      int P, int my_rank, cudaStream_t stream) {
@@ -335,7 +458,7 @@ int gn_exchange_impl(const float* partial, const double* local_sums, int samples
   if (rc) return rc;
   rc = fill_peers(f, flag_ptrs, P);
   if (rc) return rc;
-  launch_pdl(gn_exchange_finalize_kernel, 1, 256, 0, stream, partial, local_sums, samples, chunks, groups, C,
+  launch_pdl(gn_exchange_finalize_kernel, 1, 256, 0, stream, partial, local_sums, colsrc, samples, chunks, groups, C,
                                                      1.0 / static_cast<double>(count_per_group_global), gamma, beta, eps,
                                                      scale_shift, s, f, epoch_counter, P, my_rank, fault_ctx());
   return lavie_check_launch("gn_exchange_finalize_kernel");
@@ -346,8 +469,9 @@ extern "C" int lavie_gn_exchange_finalize(const float* partial, int samples, int
                                           long long count_per_group_global, const float* gamma, const float* beta,
                                           float eps, float* scale_shift, void* const* slot_ptrs, void* const* flag_ptrs,
                                           unsigned int* epoch_counter, int P, int my_rank, cudaStream_t stream) {
-  return gn_exchange_impl(partial, nullptr, samples, chunks, groups, C, count_per_group_global, gamma, beta, eps,
-                          scale_shift, slot_ptrs, flag_ptrs, epoch_counter, P, my_rank, stream);
+  return gn_exchange_impl(partial, nullptr, ColSrc{nullptr, nullptr, 0, 0, 0}, samples, chunks, groups, C,
+                          count_per_group_global, gamma, beta, eps, scale_shift, slot_ptrs, flag_ptrs, epoch_counter, P,
+                          my_rank, stream);
 }
 
 extern "C" int lavie_gn_exchange_finalize_sums(const double* local_sums, int samples, int groups, int C,
@@ -356,14 +480,33 @@ extern "C" int lavie_gn_exchange_finalize_sums(const double* local_sums, int sam
                                                void* const* flag_ptrs, unsigned int* epoch_counter, int P, int my_rank,
                                                cudaStream_t stream) {
   LAVIE_REQUIRE(local_sums != nullptr, LAVIE_ERR_SHAPE, "gn_exchange_finalize_sums: null sums");
-  return gn_exchange_impl(nullptr, local_sums, samples, 1, groups, C, count_per_group_global, gamma, beta, eps, scale_shift,
-                          slot_ptrs, flag_ptrs, epoch_counter, P, my_rank, stream);
+  return gn_exchange_impl(nullptr, local_sums, ColSrc{nullptr, nullptr, 0, 0, 0}, samples, 1, groups, C,
+                          count_per_group_global, gamma, beta, eps, scale_shift, slot_ptrs, flag_ptrs, epoch_counter, P,
+                          my_rank, stream);
+}
+
+extern "C" int lavie_gn_exchange_finalize_colsums(const float* cs0, int c0, const float* cs1, int c1, int samples,
+                                                  int rows_local, int groups, long long count_per_group_global,
+                                                  const float* gamma, const float* beta, float eps, float* scale_shift,
+                                                  void* const* slot_ptrs, void* const* flag_ptrs,
+                                                  unsigned int* epoch_counter, int P, int my_rank, cudaStream_t stream) {
+  const int C = c0 + c1;
+  LAVIE_REQUIRE(cs0 != nullptr && (c1 == 0 || cs1 != nullptr) && rows_local > 0 && rows_local % 32 == 0 && groups > 0 &&
+                    C % groups == 0 && (C / groups) % 10 == 0 && c0 % 32 == 0 && c1 % 32 == 0 && c0 % 10 == 0,
+                LAVIE_ERR_SHAPE, "gn_exchange_finalize_colsums: rows_local=%d C=%d groups=%d", rows_local, C, groups);
+  return gn_exchange_impl(nullptr, nullptr, ColSrc{cs0, cs1, c0, c1, rows_local / 32}, samples, 1, groups, C,
+                          count_per_group_global, gamma, beta, eps, scale_shift, slot_ptrs, flag_ptrs, epoch_counter, P,
+                          my_rank, stream);
 }
 
 extern "C" int lavie_layernorm_scatter_p2p(const void* x, int ldx, const float* gamma, const float* beta, float eps,
                                            void* const* recv_ptrs, int rows, int C, int hw, int hwp, int P, int my_rank,
-                                           int frame_off, cudaStream_t stream) {
+                                           int frame_off, void* const* flag_ptrs, unsigned int* epoch_counter,
+                                           int* ticket, cudaStream_t stream) {
   if (frame_off < 0) frame_off = my_rank * (hw > 0 ? rows / hw : 0);        // equal shards
+  SyncCtx sync;
+  int rcs = fill_sync(sync, flag_ptrs, epoch_counter, ticket, P, my_rank);
+  if (rcs) return rcs;
   LAVIE_REQUIRE(C == 320 || C == 640 || C == 1280, LAVIE_ERR_SHAPE, "layernorm_scatter_p2p: C must be 320/640/1280");
   LAVIE_REQUIRE(hw > 0 && hwp > 0 && hw == hwp * P && rows % hw == 0 && ldx % 8 == 0, LAVIE_ERR_SHAPE,
                 "layernorm_scatter_p2p: rows=%d hw=%d hwp=%d P=%d", rows, hw, hwp, P);
@@ -377,17 +520,21 @@ extern "C" int lavie_layernorm_scatter_p2p(const void* x, int ldx, const float* 
   const int blocks = static_cast<int>((warps + 7) / 8);
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   if (lanes == 8)
-    launch_pdl(layernorm_scatter_p2p_kernel<8>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, frame_off);
+    launch_pdl(layernorm_scatter_p2p_kernel<8>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, frame_off, sync);
   else if (lanes == 16)
-    launch_pdl(layernorm_scatter_p2p_kernel<16>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, frame_off);
+    launch_pdl(layernorm_scatter_p2p_kernel<16>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, frame_off, sync);
   else
-    launch_pdl(layernorm_scatter_p2p_kernel<32>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, frame_off);
+    launch_pdl(layernorm_scatter_p2p_kernel<32>, blocks, 256, 0, stream, xp, ldx, gamma, beta, eps, r, rows, hw, hwp, frame_off, sync);
   return lavie_check_launch("layernorm_scatter_p2p_kernel");
 }
 
 extern "C" int lavie_add_gathered_p2p(const void* res, int ldr, void* const* y_ptrs, void* out, int ldo, int rows, int C,
-                                      int hw, int hwp, int P, int my_rank, int frame_off, cudaStream_t stream) {
+                                      int hw, int hwp, int P, int my_rank, int frame_off, void* const* flag_ptrs,
+                                      unsigned int* epoch_counter, int* ticket, cudaStream_t stream) {
   if (frame_off < 0) frame_off = my_rank * (hw > 0 ? rows / hw : 0);        // equal shards
+  SyncCtx sync;
+  int rcs = fill_sync(sync, flag_ptrs, epoch_counter, ticket, P, my_rank);
+  if (rcs) return rcs;
   LAVIE_REQUIRE(C % 8 == 0 && ldr % 8 == 0 && ldo % 8 == 0 && hw > 0 && hwp > 0 && hw == hwp * P && rows % hw == 0,
                 LAVIE_ERR_SHAPE, "add_gathered_p2p: rows=%d C=%d hw=%d hwp=%d P=%d", rows, C, hw, hwp, P);
   LAVIE_REQUIRE(al16(res) && al16(out), LAVIE_ERR_ALIGN, "add_gathered_p2p: alignment");
@@ -398,7 +545,7 @@ extern "C" int lavie_add_gathered_p2p(const void* res, int ldr, void* const* y_p
   long long blocks = (total + 1023) / 1024;
   if (blocks > 148LL * 8) blocks = 148LL * 8;
   if (blocks < 1) blocks = 1;
-  launch_pdl(add_gathered_p2p_kernel, static_cast<int>(blocks), 256, 0, stream, static_cast<const __nv_bfloat16*>(res), ldr, y, static_cast<__nv_bfloat16*>(out), ldo, rows, C, hw, hwp, frame_off);
+  launch_pdl(add_gathered_p2p_kernel, static_cast<int>(blocks), 256, 0, stream, static_cast<const __nv_bfloat16*>(res), ldr, y, static_cast<__nv_bfloat16*>(out), ldo, rows, C, hw, hwp, frame_off, sync);
   return lavie_check_launch("add_gathered_p2p_kernel");
 }
 
@@ -409,7 +556,11 @@ extern "C" int lavie_p2p_fault_buffer(void* host_mapped_words, int timeout_secon
 }
 
 extern "C" int lavie_halo_push_p2p(const void* first_frame, const void* last_frame, long long frame_bytes,
-                                   void* const* ext_ptrs, int P, int my_rank, cudaStream_t stream) {
+                                   void* const* ext_ptrs, int P, int my_rank, void* const* flag_ptrs,
+                                   unsigned int* epoch_counter, int* ticket, cudaStream_t stream) {
+  SyncCtx sync;
+  int rcs = fill_sync(sync, flag_ptrs, epoch_counter, ticket, P, my_rank);
+  if (rcs) return rcs;
   LAVIE_REQUIRE(frame_bytes > 0 && frame_bytes % 16 == 0 && al16(first_frame) && al16(last_frame), LAVIE_ERR_ALIGN,
                 "halo_push: frame size and pointers must be 16-byte multiples");
   PeerPtrs d;
@@ -419,6 +570,6 @@ extern "C" int lavie_halo_push_p2p(const void* first_frame, const void* last_fra
   long long blocks = (n16 + 255) / 256;
   if (blocks > 148LL * 4) blocks = 148LL * 4;
   launch_pdl(halo_push_kernel, static_cast<int>(blocks), 256, 0, stream, static_cast<const uint4*>(first_frame),
-             static_cast<const uint4*>(last_frame), n16, d, P, my_rank);
+             static_cast<const uint4*>(last_frame), n16, d, P, my_rank, sync);
   return lavie_check_launch("halo_push_kernel");
 }

@@ -45,6 +45,7 @@ class PeerContext:
         self.peer_base: List[int] = [int(p) for p in self.handle.buffer_ptrs]
         assert len(self.peer_base) == self.P and self.peer_base[self.rank] == self.buf.data_ptr()
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)     # "last block" counter of the fused barriers
         # pinned host words the kernels fill before trapping on a lost peer (readable after the context died)
         self.fault = torch.zeros(8, dtype=torch.int32).pin_memory()
         _lib.load().lavie_p2p_fault_buffer(self.fault.data_ptr(), 0)
@@ -80,10 +81,10 @@ class PeerContext:
         frame_bytes = hw * cols * 2
         first = ext[2 * hw:3 * hw]
         last = ext[(1 + n_local) * hw:(2 + n_local) * hw]
-        with _Launch("lavie_halo_push_p2p", 0.0, 2.0 * frame_bytes):
+        with _Launch("lavie_halo_push_p2p", 0.0, 2.0 * frame_bytes):      # flag barrier fused into the kernel's last block
             check(lib.lavie_halo_push_p2p(first.data_ptr(), last.data_ptr(), frame_bytes, self.ptrs("kvx"), self.P,
-                                          self.rank, _stream()), "lavie_halo_push_p2p")
-        self.barrier()
+                                          self.rank, self.ptrs("flags"), self.epoch.data_ptr(), self.ticket.data_ptr(),
+                                          _stream()), "lavie_halo_push_p2p")
 
     # ---- fused kernels ----
     def barrier(self):
@@ -102,16 +103,18 @@ class PeerContext:
             _, c1, ld1 = _rows2d(x2)
         C = c0 + c1
         from . import ops
-        if ops.colsums(x, rows_local, x2) is not None:
-            # local sums from the producers' column statistics, then the same peer exchange + finalize
-            sums = ops.groupnorm_sums(x, samples, rows_local, groups, x2)
+        cs = ops.colsums(x, rows_local, x2)
+        if cs is not None:
+            # the statistics pass already happened in the producers' epilogues: local reduction of their micro-group
+            # sums, peer exchange and finalize in ONE single-block launch
             ss = torch.empty((samples, C, 2), dtype=F32, device=x.device)
             with _Launch("lavie_gn_exchange_finalize"):
-                check(lib.lavie_gn_exchange_finalize_sums(sums.data_ptr(), samples, groups, C,
-                                                          rows_global * (C // groups), gamma.data_ptr(),
-                                                          beta.data_ptr(), eps, ss.data_ptr(), self.ptrs("slots"),
-                                                          self.ptrs("flags"), self.epoch.data_ptr(), self.P, self.rank,
-                                                          _stream()), "lavie_gn_exchange_finalize_sums")
+                check(lib.lavie_gn_exchange_finalize_colsums(cs[0].data_ptr(), c0, cs[1].data_ptr() if cs[1] is not None
+                                                             else None, c1, samples, rows_local, groups,
+                                                             rows_global * (C // groups), gamma.data_ptr(),
+                                                             beta.data_ptr(), eps, ss.data_ptr(), self.ptrs("slots"),
+                                                             self.ptrs("flags"), self.epoch.data_ptr(), self.P, self.rank,
+                                                             _stream()), "lavie_gn_exchange_finalize_colsums")
             return ss
         chunks = lib.lavie_groupnorm_chunks(samples, rows_local)
         partial = torch.empty((samples, chunks, groups, 2), dtype=F32, device=x.device)
@@ -129,15 +132,16 @@ class PeerContext:
         return ss
 
     def layernorm_scatter(self, x, gamma, beta, hw, eps=1e-5, frames_total=None):
-        """LayerNorm + all-to-all (store side).  Returns this rank's receive buffer [F, hw/P, C] (valid after barrier)."""
+        """LayerNorm + all-to-all (store side) + flag barrier (fused: the kernel's last block).  Returns this rank's
+        receive buffer [F, hw/P, C], valid once the kernel has completed."""
         lib = _lib.load()
         rows, C, ldx = _rows2d(x)
         hwp = hw // self.P
         with _Launch("lavie_layernorm_scatter_p2p", 0.0, 4.0 * rows * C, f"ln_scatter_p2p rows={rows} C={C}"):
             check(lib.lavie_layernorm_scatter_p2p(x.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), eps,
                                                   self.ptrs("recv"), rows, C, hw, hwp, self.P, self.rank, self.frame_off,
+                                                  self.ptrs("flags"), self.epoch.data_ptr(), self.ticket.data_ptr(),
                                                   _stream()), "lavie_layernorm_scatter_p2p")
-        self.barrier()
         frames_total = rows // hw * self.P if frames_total is None else frames_total
         return self.local("recv", frames_total * hwp, C)
 
@@ -146,9 +150,9 @@ class PeerContext:
         lib = _lib.load()
         rows, C, ldr = _rows2d(res)
         hwp = hw // self.P
-        self.barrier()                                    # every rank's y is complete
-        out = torch.empty((rows, C), dtype=BF16, device=res.device)
+        out = torch.empty((rows, C), dtype=BF16, device=res.device)    # (barrier "every rank's y is complete": fused)
         with _Launch("lavie_add_gathered_p2p", 0.0, 6.0 * rows * C):
             check(lib.lavie_add_gathered_p2p(res.data_ptr(), ldr, self.ptrs("y"), out.data_ptr(), C, rows, C, hw, hwp,
-                                             self.P, self.rank, self.frame_off, _stream()), "lavie_add_gathered_p2p")
+                                             self.P, self.rank, self.frame_off, self.ptrs("flags"), self.epoch.data_ptr(),
+                                             self.ticket.data_ptr(), _stream()), "lavie_add_gathered_p2p")
         return out

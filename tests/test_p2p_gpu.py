@@ -35,6 +35,7 @@ def solo_ctx():
             self.buf = torch.zeros(flags_b + slots_b + 3 * tok_b, dtype=torch.uint8, device=device)
             self.peer_base = [self.buf.data_ptr()]
             self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+            self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
             self.fault = torch.zeros(8, dtype=torch.int32).pin_memory()
             self.token_bytes = tok_b
 
