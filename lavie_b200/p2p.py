@@ -17,6 +17,18 @@ from ._lib import check
 from .ops import _Launch, _rows2d, _stream, BF16, F32
 
 
+import os as _os
+# Launch-count switches, both OFF by default because they measured SLOWER on 4 x B200 (profiles/r2_ab_p2p.txt, same box,
+# ms per step: neither 9.12 | fused barriers 9.29 | one-launch GroupNorm exchange 10.01 | both 10.17):
+#  * FUSED_BARRIERS: the flag barrier runs inside the scatter / halo-push (last block) and gather-add (every block polls in
+#    its prologue) kernels instead of a separate one-warp lavie_rank_barrier launch (-32 launches per step);
+#  * GN_ONE_LAUNCH: the single-block GroupNorm exchange kernel folds the producers' micro-group statistics itself
+#    instead of a 64-block reduction launch in front of it (-45 launches, but one block reading up to 160 KB).
+# The sharded step is bound by the latency of its ~500 dependent small kernels, not by their count.
+FUSED_BARRIERS = _os.environ.get("LAVIE_P2P_FUSED_BARRIERS", "0") != "0"
+GN_ONE_LAUNCH = _os.environ.get("LAVIE_P2P_GN_ONE_LAUNCH", "0") != "0"
+
+
 class PeerContext:
     """Symmetric buffers of one frame group: flags, GroupNorm slots, and the two token exchange buffers."""
 
@@ -61,6 +73,12 @@ class PeerContext:
         return (f"rank {w[1]} of the frame group timed out waiting for peer {w[2]}: wanted epoch {w[3]}, "
                 f"last seen {w[4]}")
 
+    def _sync_args(self):
+        """(flag_ptrs, epoch, ticket) of a fused barrier, or NULLs when the barrier is a separate launch."""
+        if FUSED_BARRIERS:
+            return self.ptrs("flags"), self.epoch.data_ptr(), self.ticket.data_ptr()
+        return None, None, None
+
     def ptrs(self, what: str):
         off = self.layout[what]
         return (ctypes.c_void_p * self.P)(*[b + off for b in self.peer_base])
@@ -83,8 +101,9 @@ class PeerContext:
         last = ext[(1 + n_local) * hw:(2 + n_local) * hw]
         with _Launch("lavie_halo_push_p2p", 0.0, 2.0 * frame_bytes):      # flag barrier fused into the kernel's last block
             check(lib.lavie_halo_push_p2p(first.data_ptr(), last.data_ptr(), frame_bytes, self.ptrs("kvx"), self.P,
-                                          self.rank, self.ptrs("flags"), self.epoch.data_ptr(), self.ticket.data_ptr(),
-                                          _stream()), "lavie_halo_push_p2p")
+                                          self.rank, *self._sync_args(), _stream()), "lavie_halo_push_p2p")
+        if not FUSED_BARRIERS:
+            self.barrier()
 
     # ---- fused kernels ----
     def barrier(self):
@@ -104,6 +123,16 @@ class PeerContext:
         C = c0 + c1
         from . import ops
         cs = ops.colsums(x, rows_local, x2)
+        if cs is not None and not GN_ONE_LAUNCH:
+            sums = ops.groupnorm_sums(x, samples, rows_local, groups, x2)      # multi-block reduction of the statistics
+            ss = torch.empty((samples, C, 2), dtype=F32, device=x.device)
+            with _Launch("lavie_gn_exchange_finalize"):
+                check(lib.lavie_gn_exchange_finalize_sums(sums.data_ptr(), samples, groups, C,
+                                                          rows_global * (C // groups), gamma.data_ptr(),
+                                                          beta.data_ptr(), eps, ss.data_ptr(), self.ptrs("slots"),
+                                                          self.ptrs("flags"), self.epoch.data_ptr(), self.P, self.rank,
+                                                          _stream()), "lavie_gn_exchange_finalize_sums")
+            return ss
         if cs is not None:
             # the statistics pass already happened in the producers' epilogues: local reduction of their micro-group
             # sums, peer exchange and finalize in ONE single-block launch
@@ -140,8 +169,9 @@ class PeerContext:
         with _Launch("lavie_layernorm_scatter_p2p", 0.0, 4.0 * rows * C, f"ln_scatter_p2p rows={rows} C={C}"):
             check(lib.lavie_layernorm_scatter_p2p(x.data_ptr(), ldx, gamma.data_ptr(), beta.data_ptr(), eps,
                                                   self.ptrs("recv"), rows, C, hw, hwp, self.P, self.rank, self.frame_off,
-                                                  self.ptrs("flags"), self.epoch.data_ptr(), self.ticket.data_ptr(),
-                                                  _stream()), "lavie_layernorm_scatter_p2p")
+                                                  *self._sync_args(), _stream()), "lavie_layernorm_scatter_p2p")
+        if not FUSED_BARRIERS:
+            self.barrier()
         frames_total = rows // hw * self.P if frames_total is None else frames_total
         return self.local("recv", frames_total * hwp, C)
 
@@ -150,9 +180,11 @@ class PeerContext:
         lib = _lib.load()
         rows, C, ldr = _rows2d(res)
         hwp = hw // self.P
-        out = torch.empty((rows, C), dtype=BF16, device=res.device)    # (barrier "every rank's y is complete": fused)
+        if not FUSED_BARRIERS:
+            self.barrier()                                # every rank's y is complete
+        out = torch.empty((rows, C), dtype=BF16, device=res.device)
         with _Launch("lavie_add_gathered_p2p", 0.0, 6.0 * rows * C):
             check(lib.lavie_add_gathered_p2p(res.data_ptr(), ldr, self.ptrs("y"), out.data_ptr(), C, rows, C, hw, hwp,
-                                             self.P, self.rank, self.frame_off, self.ptrs("flags"), self.epoch.data_ptr(),
-                                             self.ticket.data_ptr(), _stream()), "lavie_add_gathered_p2p")
+                                             self.P, self.rank, self.frame_off, *self._sync_args(), _stream()),
+                  "lavie_add_gathered_p2p")
         return out
