@@ -60,7 +60,7 @@ def test_epilogue_struct_matches_header():
     body = text[text.index("typedef struct {"):text.index("} lavie_epilogue;")]
     fields = re.findall(r"\b(\w+);", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
     assert [f for f, _ in Epilogue._fields_] == fields
-    assert ctypes.sizeof(Epilogue) == 40      # 3 pointers + 4 ints, natural alignment
+    assert ctypes.sizeof(Epilogue) == 48      # 4 pointers + 4 ints, natural alignment
 
 
 def test_param_table_is_the_reference_contract():
