@@ -596,30 +596,32 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N
 }
 
 // Split-K reduction that also emits the consumer's GroupNorm micro-group statistics (same layout as the epilogue's):
-// block = one 32-row slab x 256 columns; thread = (4 columns, 8 rows), the 8 row loads are independent.
+// block = one 32-row slab x 128 columns; thread = (4 columns, 4 rows) with all its loads independent.
 __global__ void __launch_bounds__(256)
 splitk_reduce_stats_kernel(const float* __restrict__ partial, int splits, int M, int N, int M_total,
                            const float* __restrict__ bias, const float* __restrict__ row_bias, int rows_per_batch,
                            int ld_row_bias, const __nv_bfloat16* __restrict__ residual, int ldr,
                            __nv_bfloat16* __restrict__ out, int ldo, int row0, float* __restrict__ colstats) {
   pdl_prologue();
-  __shared__ float s_cs[4][256][2];                    // [row group][column][sum, sumsq]
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  const int col = blockIdx.y * 256 + tx * 4;
-  const int r_begin = blockIdx.x * 32 + ty * 8;        // window-relative; row0 is a multiple of 256
+  constexpr int R = 4;                                 // rows per thread
+  __shared__ float s_cs[8][128][2];                    // [row group][column][sum, sumsq]
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int cbase = blockIdx.y * 128;
+  const int col = cbase + tx * 4;
+  const int r_begin = blockIdx.x * 32 + ty * R;        // window-relative; row0 is a multiple of 256
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   if (col < N) {
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias) b4 = *reinterpret_cast<const float4*>(bias + col);
-    float4 acc[8];
+    float4 acc[R];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < R; ++i) {
       const int row = r_begin + i;
       acc[i] = row < M ? *reinterpret_cast<const float4*>(partial + static_cast<size_t>(row) * N + col) : b4;
     }
     for (int sp = 1; sp < splits; ++sp) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < R; ++i) {
         const int row = r_begin + i;
         if (row < M) {
           const float4 b = *reinterpret_cast<const float4*>(partial + (static_cast<size_t>(sp) * M + row) * N + col);
@@ -628,7 +630,7 @@ splitk_reduce_stats_kernel(const float* __restrict__ partial, int splits, int M,
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < R; ++i) {
       const int row = r_begin + i;
       if (row >= M) continue;
       float4 a = acc[i];
@@ -659,10 +661,10 @@ splitk_reduce_stats_kernel(const float* __restrict__ partial, int splits, int M,
     s_cs[ty][tx * 4 + e][1] = q[e];
   }
   __syncthreads();
-  // 8 chunks x 4 pieces: thread t < 32 folds the columns of one (chunk, decade) piece, row groups in a fixed order
-  if (threadIdx.x < 32) {
+  // 4 chunks x 4 pieces: thread t < 16 folds the columns of one (chunk, decade) piece, row groups in a fixed order
+  if (threadIdx.x < 16) {
     const int cl = threadIdx.x >> 2, piece = threadIdx.x & 3;
-    const int c0 = blockIdx.y * 256 + cl * 32;
+    const int c0 = cbase + cl * 32;
     if (c0 < N) {
       const int dec = ((c0 * 6554) >> 16) + piece;
       const int lo = max(c0, dec * 10), hi = min(min(c0 + 32, dec * 10 + 10), N);
@@ -670,9 +672,9 @@ splitk_reduce_stats_kernel(const float* __restrict__ partial, int splits, int M,
         float a = 0.f, b = 0.f;
         for (int c = lo; c < hi; ++c)
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            a += s_cs[g][c - blockIdx.y * 256][0];
-            b += s_cs[g][c - blockIdx.y * 256][1];
+          for (int g = 0; g < 8; ++g) {
+            a += s_cs[g][c - cbase][0];
+            b += s_cs[g][c - cbase][1];
           }
         const size_t slab = static_cast<size_t>((blockIdx.x * 32 + row0) >> 5);
         *reinterpret_cast<float2*>(colstats + ((slab * (N >> 5) + (c0 >> 5)) * 4 + piece) * 2) = make_float2(a, b);
@@ -749,7 +751,7 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     rc = lavie_check_launch("splitk_reduce_check_kernel");
   } else if (p.splits > 1 && p.colstats != nullptr) {
     const int row0 = p.m_tile0 * PAIR_M;
-    dim3 grid((p.rows_window + 31) / 32, (p.N + 255) / 256);
+    dim3 grid((p.rows_window + 31) / 32, (p.N + 127) / 128);
     launch_pdl(splitk_reduce_stats_kernel, grid, 256, 0, stream, p.partial, p.splits, p.rows_window, p.N, p.M, p.bias,
                p.row_bias, p.rows_per_batch, p.ld_row_bias,
                p.residual ? p.residual + static_cast<size_t>(row0) * p.ldr : nullptr, p.ldr,

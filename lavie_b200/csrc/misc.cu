@@ -168,7 +168,7 @@ conv_in_kernel(const float* __restrict__ x, int B, int Cin, int F, int H, int W,
 // memory feeds 8 FMAs.  Zero padding applies to the ACTIVATED map, so out-of-image taps contribute 0.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int COUT_P = 4;
-template <int COUT>
+template <int COUT, bool TRIPLE>      // TRIPLE: check mode, x = hi + lo of a split-bf16 triple (lo lo_off columns further)
 __global__ void __launch_bounds__(256)
 conv_out_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ scale_shift, int B, int F,
                 int H, int W, int C, const float* __restrict__ w, const float* __restrict__ bias,
@@ -213,7 +213,7 @@ conv_out_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __res
           const int xx = xs - 1 + i;
           if (row_ok && xx >= 0 && xx < W) {
             float2 t2 = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(xp + i * ldx)));
-            if (lo_off) {            // check mode: x = hi + lo of the split-bf16 triple
+            if (TRIPLE) {            // check mode: x = hi + lo of the split-bf16 triple
               const float2 tl = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(xp + i * ldx + lo_off)));
               t2.x += tl.x;
               t2.y += tl.y;
@@ -404,14 +404,19 @@ int conv_out_impl(const void* x, int ldx, const float* scale_shift, int B, int F
   LAVIE_REQUIRE(al16(x) && al16(scale_shift), LAVIE_ERR_ALIGN, "conv_out: alignment");
   const int smem = Cout * 9 * C * static_cast<int>(sizeof(float));
   LAVIE_REQUIRE(smem <= 200 * 1024, LAVIE_ERR_SHAPE, "conv_out: weights do not fit shared memory");
-  static LavieSmemConfig configured;
-  const int rc_cfg = lavie_config_smem(conv_out_kernel<4>, smem, &configured, "conv_out_kernel");
+  static LavieSmemConfig configured, configured_t;
+  const int rc_cfg = lo_off ? lavie_config_smem(conv_out_kernel<4, true>, smem, &configured_t, "conv_out_kernel<check>")
+                            : lavie_config_smem(conv_out_kernel<4, false>, smem, &configured, "conv_out_kernel");
   if (rc_cfg) return rc_cfg;
   const long long total = static_cast<long long>(B) * F * H * ((W + COUT_P - 1) / COUT_P);
   long long blocks = (total + 7) / 8;
   if (blocks > 148 * 2) blocks = 148 * 2;        // 2 resident blocks per SM (registers): one wave, one weight fill each
-  launch_pdl(conv_out_kernel<4>, static_cast<int>(blocks), 256, smem, stream, static_cast<const __nv_bfloat16*>(x), ldx,
-             scale_shift, B, F, H, W, C, w, bias, out, lo_off);
+  if (lo_off)
+    launch_pdl(conv_out_kernel<4, true>, static_cast<int>(blocks), 256, smem, stream,
+               static_cast<const __nv_bfloat16*>(x), ldx, scale_shift, B, F, H, W, C, w, bias, out, lo_off);
+  else
+    launch_pdl(conv_out_kernel<4, false>, static_cast<int>(blocks), 256, smem, stream,
+               static_cast<const __nv_bfloat16*>(x), ldx, scale_shift, B, F, H, W, C, w, bias, out, lo_off);
   return lavie_check_launch("conv_out_kernel");
 }
 }  // namespace

@@ -15,7 +15,7 @@ def conv(NF, H, W, C, N):
     w = pack_conv3x3((torch.randn(N, C, 3, 3, device=dev) * (9 * C) ** -0.5))
     b = torch.randn(N, device=dev)
     for _ in range(3):
-        ops.conv3x3(x, NF, H, W, w, bias=b)
+        ops.conv3x3(x, NF, H, W, w, bias=b, stats=True)     # as in the step: the epilogue also emits the GroupNorm statistics
 
 
 def gemm(M, N, K, res=True):
