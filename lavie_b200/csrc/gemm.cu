@@ -416,7 +416,20 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (p.colstats != nullptr && col_out0 < p.N && wrow0 < p.M) {
+        if (lane == 0 && !(p.debug & 16)) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmap_out)),
+                       "r"(smem_u32(my_stage + k * EPI_CHUNK_BYTES)), "r"(col_out0), "r"(wrow0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      };
+
+      // GroupNorm statistics of the consumer from the staged bf16 chunks.  Runs AFTER the accumulator has been handed back
+      // to the MMA warp (it only needs the staging buffers, which stay valid until this warp's next tile), so it overlaps
+      // the next tile's main loop even for the single-accumulator 320-wide tiles.
+      auto chunk_stats = [&](int k, int col_out0) {
+        if (col_out0 < p.N && wrow0 < p.M) {
           // GroupNorm statistics of the consumer, from the staged bf16 chunk (exactly the values that reach memory).
           // lane = (row parity, column pair): 16 conflict-free LDS.32 walk the 32 rows and one shuffle folds the parities;
           // a segmented scan over the 16 column pairs then folds them into 10-channel MICRO-GROUPS (every GroupNorm of
@@ -457,13 +470,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
           if (par == 0 && last_of_piece && col < p.N)
             *reinterpret_cast<float2*>(p.colstats + ((static_cast<size_t>(wrow0 >> 5) * (p.N >> 5) + (col_out0 >> 5)) * 4 +
                                                      (dec - dec0)) * 2) = make_float2(s0, q0);
-        }
-        if (lane == 0 && !(p.debug & 16)) {
-          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                           reinterpret_cast<uint64_t>(&tmap_out)),
-                       "r"(smem_u32(my_stage + k * EPI_CHUNK_BYTES)), "r"(col_out0), "r"(wrow0)
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       };
 
@@ -545,6 +551,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
+      if (p.colstats != nullptr && staged && !p.geglu) {
+        int k = 0;
+        for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT, ++k) chunk_stats(k, n0 + c * 32);
+      }
       if (tl) tl_row[5] = clock64();
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
