@@ -260,6 +260,12 @@ int lavie_conv_in_scaled(const float* x, const float* input_scale, int B, int Ci
 int lavie_conv_out(const void* x, int ldx, const float* scale_shift, int B, int F, int H, int W, int C,
                    const float* w, const float* bias, int Cout, float* out, lavie_stream_t stream);
 
+/* Last step of conv_out when the 3x3 conv itself ran on the tensor cores (lavie_conv3x3_bf16 with the Cout filters
+ * zero-padded to a 32-row weight matrix): y bf16 [B*F*H*W, ldy] channels-last -> fp32 [B, Cout, F, H, W], the layout
+ * base/models/unet.py:506 returns. */
+int lavie_unpack_nchw_f32(const void* y, int ldy, int B, int Cout, int F, int H, int W, float* out,
+                          lavie_stream_t stream);
+
 /* F.interpolate(scale_factor=(1,2,2), mode="nearest") of Upsample3D (resnet.py:59-62), channels-last. */
 int lavie_upsample_nearest2x(const void* x, int NF, int H, int W, int C, void* y, lavie_stream_t stream);
 

@@ -84,6 +84,7 @@ SIGNATURES = {
     "lavie_conv_in": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
     "lavie_conv_in_scaled": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
     "lavie_conv_out": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P]),
+    "lavie_unpack_nchw_f32": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_upsample_nearest2x": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_cfg_ddim_step": (c_int, [_P, _P, c_float, c_float, c_float, _P, _P, c_longlong, _P]),
     "lavie_cfg_linear_step": (c_int, [_P, _P, c_float, c_float, c_float, c_float, _P, _P, _P, c_longlong, _P]),

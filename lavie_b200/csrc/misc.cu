@@ -292,6 +292,30 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int NF, int H, int W, int
   }
 }
 
+// conv_out on the tensor cores: the 3x3 conv runs as an implicit GEMM with the Cout = 4 filters zero-padded to a
+// 32-column weight tile (gemm.cu, conv mode); this kernel picks the real channels out of the channels-last bf16 rows and
+// writes the reference's fp32 [B, Cout, F, H, W] layout (base/models/unet.py:506).  One thread per pixel: 8-byte read,
+// Cout coalesced 4-byte writes.
+__global__ void __launch_bounds__(256)
+unpack_nchw_kernel(const __nv_bfloat16* __restrict__ y, int ldy, int B, int Cout, long long pix_per_sample,
+                   float* __restrict__ out) {
+  pdl_prologue();
+  const long long total = static_cast<long long>(B) * pix_per_sample;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / pix_per_sample, pix = i - b * pix_per_sample;
+    const __nv_bfloat16* row = y + i * ldy;
+    for (int c0 = 0; c0 < Cout; c0 += 4) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + c0));
+      const float2 v0 = unpack_bf16(v.x), v1 = unpack_bf16(v.y);
+      const float f[4] = {v0.x, v0.y, v1.x, v1.y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c0 + e < Cout) out[(b * Cout + c0 + e) * pix_per_sample + pix] = f[e];
+    }
+  }
+}
+
 __global__ void cfg_ddim_kernel(const float* __restrict__ nu, const float* __restrict__ nt, float g, float sa_t,
                                 float s1a_t, float sa_p, float s1a_p, const float* __restrict__ lat,
                                 float* __restrict__ out, long long n) {
@@ -451,6 +475,17 @@ extern "C" int lavie_upsample_nearest2x(const void* x, int NF, int H, int W, int
   launch_pdl(upsample2x_kernel, grid_for(total, 256), 256, 0, stream, static_cast<const __nv_bfloat16*>(x), NF, H, W, C,
                                                               static_cast<__nv_bfloat16*>(y));
   return lavie_check_launch("upsample2x_kernel");
+}
+
+extern "C" int lavie_unpack_nchw_f32(const void* y, int ldy, int B, int Cout, int F, int H, int W, float* out,
+                                     cudaStream_t stream) {
+  LAVIE_REQUIRE(B > 0 && Cout > 0 && F > 0 && H > 0 && W > 0, LAVIE_ERR_SHAPE, "unpack_nchw: empty problem");
+  LAVIE_REQUIRE(ldy % 4 == 0 && ldy >= ((Cout + 3) & ~3) && (reinterpret_cast<uintptr_t>(y) & 7) == 0, LAVIE_ERR_ALIGN,
+                "unpack_nchw: rows must be 8-byte aligned and hold Cout rounded up to 4 columns");
+  const long long pps = static_cast<long long>(F) * H * W;
+  launch_pdl(unpack_nchw_kernel, grid_for(B * pps, 256), 256, 0, stream, static_cast<const __nv_bfloat16*>(y), ldy, B,
+             Cout, pps, out);
+  return lavie_check_launch("unpack_nchw_kernel");
 }
 
 extern "C" int lavie_cfg_ddim_step(const float* noise_uncond, const float* noise_text, float guidance, float alpha_t,

@@ -183,8 +183,9 @@ def im2col3x3(x: torch.Tensor, NF: int, H: int, W: int, stride: int = 1) -> torc
 
 def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride: int = 1, bias=None, row_bias=None,
             rows_per_batch=1, residual=None, out: Optional[torch.Tensor] = None, block_n: int = 0,
-            force_im2col: bool = False, stats: bool = False):
-    """3x3 pad-1 InflatedConv3d on a contiguous channels-last map; w: bf16 [N, 9*C] in (kh, kw, c) order."""
+            force_im2col: bool = False, stats: bool = False, algo_n: int = 0):
+    """3x3 pad-1 InflatedConv3d on a contiguous channels-last map; w: bf16 [N, 9*C] in (kh, kw, c) order.  ``algo_n``:
+    real output channels when the weight rows are zero-padded (launch accounting only)."""
     lib = _lib.load()
     rows, C, ld = _rows2d(x)
     assert rows == NF * H * W and ld == C, "conv3x3 needs a contiguous channels-last input"
@@ -203,7 +204,8 @@ def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride
     cs = _new_colsums(m_out, N, x.device) if stats and FUSE_GN_STATS else None
     ep = _epilogue(bias, row_bias, rows_per_batch, residual, False, cs)
     ws = _workspace(x.device)
-    with _Launch("gemm_bf16_tcgen05", 2.0 * m_out * N * 9 * C, 2.0 * (rows * C + N * 9 * C + m_out * N),
+    n_alg = algo_n or N
+    with _Launch("gemm_bf16_tcgen05", 2.0 * m_out * n_alg * 9 * C, 2.0 * (rows * C + n_alg * 9 * C + m_out * n_alg),
                  f"conv3x3 M={m_out} N={N} K={9 * C} W={W} s={stride}"):
         rc = lib.lavie_conv3x3_bf16(x.data_ptr(), NF, H, W, C, stride, w.data_ptr(), out.data_ptr(), ldo, N,
                                     ctypes.byref(ep) if ep is not None else None, block_n, ws.data_ptr(),
@@ -504,6 +506,26 @@ def conv_out(x: torch.Tensor, scale_shift: torch.Tensor, B: int, Fr: int, H: int
     with _Launch("lavie_conv_out"):
         check(lib.lavie_conv_out(x.data_ptr(), ldx, scale_shift.data_ptr(), B, Fr, H, W, C, w.data_ptr(), bias.data_ptr(),
                                  Cout, out.data_ptr(), _stream()), "lavie_conv_out")
+    return out
+
+
+CONV_OUT_PAD = 32      # conv_out's Cout = 4 filters are zero-padded to one 32-column chunk of the GEMM epilogue
+
+
+def conv_out_tc(x: torch.Tensor, scale_shift: torch.Tensor, B: int, Fr: int, H: int, W: int, w_pad: torch.Tensor,
+                bias_pad: torch.Tensor, Cout: int):
+    """conv_norm_out -> SiLU -> conv_out (unet.py:504-506) with the conv on the tensor cores: GroupNorm apply + SiLU
+    (one pass, bf16), implicit-GEMM 3x3 conv against the zero-padded filters w_pad bf16 [32, 9*C], then the 4 real
+    channels are unpacked into fp32 [B, Cout, F, H, W].  Needs C % 64 == 0 (im2col-mode TMA)."""
+    lib = _lib.load()
+    rows, C, _ = _rows2d(x)
+    assert rows == B * Fr * H * W and w_pad.shape == (CONV_OUT_PAD, 9 * C) and Cout <= CONV_OUT_PAD
+    h = groupnorm_apply(x, scale_shift, B, Fr * H * W, True)
+    y = conv3x3(h, B * Fr, H, W, w_pad, bias=bias_pad, block_n=64, algo_n=Cout)
+    out = torch.empty((B, Cout, Fr, H, W), dtype=F32, device=x.device)
+    with _Launch("lavie_unpack_nchw_f32", 0.0, rows * (2.0 * CONV_OUT_PAD + 4.0 * Cout)):
+        check(lib.lavie_unpack_nchw_f32(y.data_ptr(), y.stride(0), B, Cout, Fr, H, W, out.data_ptr(), _stream()),
+              "lavie_unpack_nchw_f32")
     return out
 
 

@@ -361,9 +361,18 @@ class UNet3DConditionModel(nn.Module):
             P[f"up_blocks.{i}.upsamplers.0.conv"] = (
                 b16(pack_conv3x3_(sd[f"up_blocks.{i}.upsamplers.0.conv.weight"])),
                 f32(f"up_blocks.{i}.upsamplers.0.conv.bias"))
+        boc0 = self.cfg.block_out_channels[0]
         P["conv_in"] = (f32("conv_in.weight"), f32("conv_in.bias"))
         P["conv_out"] = (sd["conv_out.weight"].permute(0, 2, 3, 1).to(device=dev, dtype=F32).contiguous(),
                          f32("conv_out.bias"))
+        if not self.check_mode and boc0 % 64 == 0:
+            # bf16 path: conv_out runs on the tensor cores with its Cout filters zero-padded to one 32-column chunk
+            co = sd["conv_out.weight"].shape[0]
+            wp = torch.zeros((ops.CONV_OUT_PAD, 9 * boc0), dtype=F32)
+            wp[:co] = pack_conv3x3(sd["conv_out.weight"].float().cpu(), dtype=None)
+            bp = torch.zeros(ops.CONV_OUT_PAD, dtype=F32)
+            bp[:co] = sd["conv_out.bias"].float().cpu()
+            P["conv_out_tc"] = (wp.to(device=dev, dtype=BF16).contiguous(), bp.to(dev), co)
         P["norm_out"] = (f32("conv_norm_out.weight"), f32("conv_norm_out.bias"))
         P["time1"] = (K.weight_small(sd["time_embedding.linear_1.weight"], dev), f32("time_embedding.linear_1.bias"))
         P["time2"] = (K.weight_small(sd["time_embedding.linear_2.weight"], dev), f32("time_embedding.linear_2.bias"))
@@ -584,6 +593,9 @@ class UNet3DConditionModel(nn.Module):
                 x = K.conv3x3(x, B * Fr, h, w, wu, bias=bu, stats=True)
         tap("up_out", x, boc[0], h, w)
         ss = self._gn5_scale_shift(x, None, B, Fr * h * w, P["norm_out"][0], P["norm_out"][1], cfg.norm_eps)
+        if "conv_out_tc" in P:
+            wp, bp, co = P["conv_out_tc"]
+            return ops.conv_out_tc(x, ss, B, Fr, h, w, wp, bp, co)
         return K.conv_out(x, ss, B, Fr, h, w, P["conv_out"][0], P["conv_out"][1])
 
     # ------------------------------------------------------------------ public forward

@@ -40,3 +40,11 @@ class TimestepEmbedding(nn.Module):
 
     def forward(self, sample):
         return self.linear_2(self.act(self.linear_1(sample)))
+
+
+class ImagePositionalEmbeddings(nn.Module):
+    """Name-only stand-in: vsr/models/diffusers_attention.py imports it; the VSR UNet never instantiates it."""
+
+    def __init__(self, *a, **k):
+        super().__init__()
+        raise NotImplementedError

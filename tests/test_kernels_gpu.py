@@ -348,6 +348,16 @@ def test_conv_in_and_out(H, W):
     ref = ref.reshape(B, Fr, 4, H, W).permute(0, 2, 1, 3, 4)
     assert out.shape == (B, 4, Fr, H, W)
     assert rel_l2(out, ref) < 2e-3
+    # the tensor-core route of the same op (GroupNorm apply + SiLU, implicit-GEMM conv against zero-padded filters, unpack
+    # to [B, 4, F, H, W]): bf16 activations and bf16 output rows, hence the looser bound
+    from lavie_b200.packing import pack_conv3x3
+    wp = torch.zeros(ops.CONV_OUT_PAD, 9 * 320, device="cuda")
+    wp[:4] = pack_conv3x3(wo, dtype=None)
+    bp = torch.zeros(ops.CONV_OUT_PAD, device="cuda")
+    bp[:4] = bo
+    out_tc = ops.conv_out_tc(y, ss, B, Fr, H, W, wp.to(torch.bfloat16).contiguous(), bp, 4)
+    assert out_tc.shape == (B, 4, Fr, H, W)
+    assert rel_l2(out_tc, ref) < 8e-3
 
 
 def test_upsample_and_cfg_ddim():
