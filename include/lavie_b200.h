@@ -82,6 +82,14 @@ int lavie_gemm_bf16(const void* a0, int lda0, int k0, const void* a1, int lda1, 
                     int ldo, int M, int N, const lavie_epilogue* ep, int block_n, void* workspace,
                     size_t workspace_bytes, lavie_stream_t stream);
 
+/* nn.Conv3d with a (taps,1,1) kernel over FRAMES (vsr/models/resnet.py:253-254,269: ResnetBlock3DCNN conv1 / conv2) as
+ * an implicit GEMM with K = taps*C.  x points at a channels-last map of ONE batch item whose frame axis the caller has
+ * padded with taps/2 zero frames on both sides: rows_in = (F + taps - 1) * tap_rows rows of C channels (row stride ldx),
+ * tap_rows = H*W.  Output row m (M = F*H*W rows) = sum_t x[m + t*tap_rows, :] . w[:, t, :]; w is bf16 [N, taps, C]. */
+int lavie_frame_conv_bf16(const void* x, int ldx, long long rows_in, int C, int taps, int tap_rows, const void* w,
+                          void* out, int ldo, int M, int N, const lavie_epilogue* ep, int block_n, void* workspace,
+                          size_t workspace_bytes, lavie_stream_t stream);
+
 /* 3x3 pad-1 InflatedConv3d, stride 1 or 2 (resnet.py:13-21; Downsample3D :102-110) as implicit GEMM over a CONTIGUOUS
  * channels-last map x[NF, H, W, C]; w is [N, 3, 3, C]; out has NF*Ho*Wo rows.  The A operand is fetched with
  * im2col-mode TMA (the hardware walks the output pixels and zero-fills the halo), so any H, W works;
@@ -259,6 +267,11 @@ int lavie_conv_in_scaled(const float* x, const float* input_scale, int B, int Ci
  * lavie_groupnorm_finalize, w fp32 [Cout, 3, 3, C]; writes fp32 [B, Cout, F, H, W]. */
 int lavie_conv_out(const void* x, int ldx, const float* scale_shift, int B, int F, int H, int W, int C,
                    const float* w, const float* bias, int Cout, float* out, lavie_stream_t stream);
+
+/* emb[b, :] += table[labels[b], :]: the noise-level class embedding the VSR UNet adds to the time embedding
+ * (vsr/models/unet.py:180, 494-507).  emb fp32 [B, dim], table fp32 [rows, dim], labels int64 [B] (clamped to the table). */
+int lavie_embedding_add(float* emb, const float* table, const long long* labels, int B, int dim, int rows,
+                        lavie_stream_t stream);
 
 /* Last step of conv_out when the 3x3 conv itself ran on the tensor cores (lavie_conv3x3_bf16 with the Cout filters
  * zero-padded to a 32-row weight matrix): y bf16 [B*F*H*W, ldy] channels-last -> fp32 [B, Cout, F, H, W], the layout

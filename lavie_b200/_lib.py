@@ -84,6 +84,9 @@ SIGNATURES = {
     "lavie_conv_in": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
     "lavie_conv_in_scaled": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
     "lavie_conv_out": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P]),
+    "lavie_embedding_add": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "lavie_frame_conv_bf16": (c_int, [_P, c_int, c_longlong, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int,
+                                      POINTER(Epilogue), c_int, _P, c_size_t, _P]),
     "lavie_unpack_nchw_f32": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_upsample_nearest2x": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_cfg_ddim_step": (c_int, [_P, _P, c_float, c_float, c_float, _P, _P, c_longlong, _P]),

@@ -31,6 +31,9 @@
 //   conv  : A is the channels-last feature map [NF, H, W, C]; K = 9*C ordered (kh, kw, c); every K block is one
 //           (tap, 64-channel) slab of 128 consecutive OUTPUT pixels fetched by ONE im2col-mode TMA request (the
 //           hardware walks the pixels, applies the stride and zero-fills the halo = the conv's zero padding).
+//   frame : nn.Conv3d with a (k,1,1) kernel (vsr/models/resnet.py:253-254,269) on a map whose frame axis is padded
+//           with k/2 zero frames on both sides: K = k*C ordered (tap, c), tap t of output row m is input row
+//           m + t * (pixels per frame) -- the same 2-D TMA box, shifted by whole frames.
 #include "common.cuh"
 
 namespace {
@@ -55,9 +58,10 @@ struct GemmParams {
   int rows_window;           // rows covered by the window (stride of the split-K partial planes)
   int splits, kb_per_split;  // split-K
   // conv3 mode
-  int conv;                  // 0 plain GEMM, 1 implicit-GEMM 3x3 conv (im2col-mode TMA)
+  int conv;                  // 0 plain GEMM, 1 implicit-GEMM 3x3 conv (im2col-mode TMA), 2 frame conv (k,1,1)
   int c_blocks;              // Cin / 64
-  int out_h, out_w, conv_stride;   // im2col-mode conv (conv == 2): output geometry and stride
+  int out_h, out_w, conv_stride;   // im2col-mode conv (conv == 1): output geometry and stride
+  int tap_rows;              // frame conv (conv == 2): rows between consecutive taps = pixels per frame
   // epilogue
   const float* bias;         // [N] or null
   const float* row_bias;     // [M / rows_per_batch, ld_row_bias] or null  (time embedding add, resnet.py:187-190)
@@ -267,7 +271,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
             if (rank == 0) mbar_arrive(&full_bar[stage]);
           } else {
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);   // bytes landing in both CTAs
-            if (p.conv) {
+            if (p.conv == 2) {
+              // (k,1,1) conv over frames on a frame-padded map: tap t of output row m is input row m + t * tap_rows
+              const int tap = kb / p.c_blocks;
+              tma2_load_2d(a_dst, &tmap_a0, full_leader, (kb - tap * p.c_blocks) * BLOCK_K,
+                           m_cta * BLOCK_M + tap * p.tap_rows);
+            } else if (p.conv) {
               // one request: 128 consecutive output pixels x 64 channels of filter tap (r, s)
               const int tap = kb / p.c_blocks;
               const int c0 = (kb - tap * p.c_blocks) * BLOCK_K;
@@ -1068,6 +1077,51 @@ extern "C" int lavie_check_gemm(const void* a0, int lda0, int k0, const void* a1
                                 void* out, int ldo, int M, int N, const lavie_epilogue* ep, void* workspace,
                                 size_t workspace_bytes, cudaStream_t stream) {
   return gemm_impl(a0, lda0, k0, a1, lda1, k1, w, out, ldo, M, N, ep, 0, workspace, workspace_bytes, 1, stream);
+}
+
+namespace {
+int frame_conv_impl(const void* x, int ldx, long long rows_in, int C, int taps, int tap_rows, const void* w, void* out,
+                    int ldo, int M, int N, const lavie_epilogue* ep, int block_n, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream) {
+  LAVIE_REQUIRE(M > 0 && N > 0 && taps >= 1 && taps <= 9 && tap_rows > 0, LAVIE_ERR_SHAPE,
+                "frame_conv: empty problem M=%d N=%d taps=%d tap_rows=%d", M, N, taps, tap_rows);
+  LAVIE_REQUIRE(C % BLOCK_K == 0 && N % 8 == 0 && ldx % 8 == 0, LAVIE_ERR_SHAPE,
+                "frame_conv: C=%d must be a multiple of 64, N and ldx multiples of 8", C);
+  LAVIE_REQUIRE(rows_in >= static_cast<long long>(M) + static_cast<long long>(taps - 1) * tap_rows, LAVIE_ERR_SHAPE,
+                "frame_conv: the padded input holds %lld rows, M + (taps-1)*tap_rows = %lld needed", rows_in,
+                static_cast<long long>(M) + static_cast<long long>(taps - 1) * tap_rows);
+  LAVIE_REQUIRE(aligned16(x) && aligned16(w), LAVIE_ERR_ALIGN, "frame_conv: alignment");
+  LAVIE_REQUIRE(workspace == nullptr || aligned16(workspace), LAVIE_ERR_ALIGN, "frame_conv: workspace alignment");
+  LAVIE_REQUIRE(!(ep && ep->geglu), LAVIE_ERR_SHAPE, "frame_conv: GEGLU epilogue not supported");
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = taps * C;
+  p.num_k_blocks = taps * (C / BLOCK_K);
+  p.k_split_blocks = p.num_k_blocks;
+  p.c_blocks = C / BLOCK_K;
+  p.tap_rows = tap_rows;
+  p.conv = 2;
+  p.check = 0;
+  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, false, false, workspace ? workspace_bytes : 0);
+  apply_plan(p, plan, workspace);
+  int rc = fill_epilogue(p, ep, N, out, ldo);
+  if (rc) return rc;
+  CUtensorMap ma, mb;
+  const uint64_t dims[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(rows_in)};
+  const uint64_t strides[1] = {static_cast<uint64_t>(ldx) * 2};
+  const uint32_t box[2] = {BLOCK_K, BLOCK_M};
+  rc = lavie_make_tmap(&ma, x, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_weight_map(&mb, w, N, taps * C, plan.bn);
+  if (rc) return rc;
+  return dispatch(plan, ma, ma, mb, p, stream);
+}
+}  // namespace
+
+extern "C" int lavie_frame_conv_bf16(const void* x, int ldx, long long rows_in, int C, int taps, int tap_rows,
+                                     const void* w, void* out, int ldo, int M, int N, const lavie_epilogue* ep,
+                                     int block_n, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return frame_conv_impl(x, ldx, rows_in, C, taps, tap_rows, w, out, ldo, M, N, ep, block_n, workspace, workspace_bytes,
+                         stream);
 }
 
 extern "C" int lavie_conv3x3_supported(int H, int W, int C) {

@@ -316,6 +316,18 @@ unpack_nchw_kernel(const __nv_bfloat16* __restrict__ y, int ldy, int B, int Cout
   }
 }
 
+// emb[b, :] += table[labels[b], :]   (the VSR UNet's noise-level class embedding, vsr/models/unet.py:494-507)
+__global__ void embedding_add_kernel(float* __restrict__ emb, const float* __restrict__ table,
+                                     const long long* __restrict__ labels, int B, int dim, int rows) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * dim) return;
+  const int b = i / dim, c = i - b * dim;
+  long long l = labels[b];
+  l = l < 0 ? 0 : (l >= rows ? rows - 1 : l);         // the reference raises on out-of-range levels; clamp, never fault
+  emb[i] += table[l * dim + c];
+}
+
 __global__ void cfg_ddim_kernel(const float* __restrict__ nu, const float* __restrict__ nt, float g, float sa_t,
                                 float s1a_t, float sa_p, float s1a_p, const float* __restrict__ lat,
                                 float* __restrict__ out, long long n) {
@@ -486,6 +498,13 @@ extern "C" int lavie_unpack_nchw_f32(const void* y, int ldy, int B, int Cout, in
   launch_pdl(unpack_nchw_kernel, grid_for(B * pps, 256), 256, 0, stream, static_cast<const __nv_bfloat16*>(y), ldy, B,
              Cout, pps, out);
   return lavie_check_launch("unpack_nchw_kernel");
+}
+
+extern "C" int lavie_embedding_add(float* emb, const float* table, const long long* labels, int B, int dim, int rows,
+                                   cudaStream_t stream) {
+  LAVIE_REQUIRE(emb && table && labels && B > 0 && dim > 0 && rows > 0, LAVIE_ERR_SHAPE, "embedding_add: bad arguments");
+  launch_pdl(embedding_add_kernel, (B * dim + 255) / 256, 256, 0, stream, emb, table, labels, B, dim, rows);
+  return lavie_check_launch("embedding_add_kernel");
 }
 
 extern "C" int lavie_cfg_ddim_step(const float* noise_uncond, const float* noise_text, float guidance, float alpha_t,

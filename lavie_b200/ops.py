@@ -216,6 +216,47 @@ def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride
     return out
 
 
+def frame_conv(xpad: torch.Tensor, taps: int, tap_rows: int, w: torch.Tensor, *, bias=None, row_bias=None,
+               rows_per_batch=1, residual=None, out: Optional[torch.Tensor] = None, block_n: int = 0,
+               stats: bool = False):
+    """nn.Conv3d (taps,1,1) over frames (vsr/models/resnet.py:253-254,269) for ONE batch item.  xpad: bf16
+    [(F + taps - 1) * tap_rows, C], the item's channels-last map with taps//2 zero frames on both sides;
+    w: bf16 [N, taps*C] in (tap, c) order.  Returns [F * tap_rows, N]."""
+    lib = _lib.load()
+    rows_in, C, ld = _rows2d(xpad)
+    M = rows_in - (taps - 1) * tap_rows
+    N = w.shape[0]
+    assert M > 0 and w.dtype == BF16 and w.is_contiguous() and w.shape[1] == taps * C, (w.shape, taps, C)
+    if out is None:
+        out = torch.empty((M, N), dtype=BF16, device=xpad.device)
+    Mo, No, ldo = _rows2d(out)
+    assert Mo == M and No == N
+    cs = _new_colsums(M, N, xpad.device) if stats and FUSE_GN_STATS else None
+    ep = _epilogue(bias, row_bias, rows_per_batch, residual, False, cs)
+    ws = _workspace(xpad.device)
+    with _Launch("gemm_bf16_tcgen05", 2.0 * M * N * taps * C, 2.0 * (rows_in * C + N * taps * C + M * N),
+                 f"frame_conv M={M} N={N} K={taps * C} taps={taps}"):
+        rc = lib.lavie_frame_conv_bf16(xpad.data_ptr(), ld, rows_in, C, taps, tap_rows, w.data_ptr(), out.data_ptr(), ldo,
+                                       M, N, ctypes.byref(ep) if ep is not None else None, block_n, ws.data_ptr(),
+                                       ws.numel(), _stream())
+    check(rc, "lavie_frame_conv_bf16")
+    if cs is not None:
+        out._gn_colsums = cs
+    return out
+
+
+def embedding_add(emb: torch.Tensor, table: torch.Tensor, labels: torch.Tensor):
+    """emb[b] += table[labels[b]] in place (vsr/models/unet.py:494-507); emb fp32 [B, dim], labels int64 [B]."""
+    lib = _lib.load()
+    B, dim = emb.shape
+    assert emb.dtype == F32 and emb.is_contiguous() and table.dtype == F32 and table.is_contiguous()
+    assert table.shape[1] == dim and labels.dtype == torch.int64 and labels.numel() == B and labels.is_cuda
+    with _Launch("lavie_embedding_add"):
+        check(lib.lavie_embedding_add(emb.data_ptr(), table.data_ptr(), labels.data_ptr(), B, dim, table.shape[0],
+                                      _stream()), "lavie_embedding_add")
+    return emb
+
+
 def _new_colsums(M: int, N: int, device) -> Optional[torch.Tensor]:
     """[slabs of 32 rows, 32-column chunks, 4 decade pieces, (sum, sumsq)] -- see lavie_epilogue.col_stats."""
     if N % 32 or N % 10:

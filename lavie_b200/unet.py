@@ -68,14 +68,16 @@ def _leaf_for(key_prefix: str, names: Dict[str, Tuple[int, ...]]) -> nn.Module:
     last = key_prefix.rsplit(".", 1)[-1]
     if "freqs" in names:
         return _RotaryFreqs(names["freqs"][0])
-    if last == "relative_attention_bias":
+    if last in ("relative_attention_bias", "class_embedding"):
         return torch.nn.utils.skip_init(nn.Embedding, w[0], w[1])
+    if len(w) == 5:                      # the VSR UNet's (k,1,1) frame convolutions (vsr/models/resnet.py:253-254,269)
+        return torch.nn.utils.skip_init(nn.Conv3d, w[1], w[0], tuple(w[2:]), padding=(w[2] // 2, 0, 0), bias=has_bias)
     if len(w) == 4:
         k = w[2]
         return torch.nn.utils.skip_init(nn.Conv2d, w[1], w[0], k, padding=k // 2, bias=has_bias)
     if len(w) == 2:
         return torch.nn.utils.skip_init(nn.Linear, w[1], w[0], bias=has_bias)
-    if last in ("norm1", "norm2", "norm3", "norm_temp") and ".transformer_blocks." in key_prefix:
+    if last in ("norm1", "norm2", "norm3", "norm_temp", "norm_temporal") and ".transformer_blocks." in key_prefix:
         return nn.LayerNorm(w[0])
     return nn.GroupNorm(32, w[0])
 
@@ -95,15 +97,18 @@ def _install(root: nn.Module, path: str, leaf: nn.Module) -> None:
 class UNet3DConditionModel(nn.Module):
     """B200-native LaVie base denoiser.  ``use_cuda_graph`` replays the whole step from one captured CUDA graph per
     input geometry (the reference launches ~1.9k kernels per step from Python)."""
+    _VARIANTS = ("base", "interp")
 
     def __init__(self, config: UNetConfig = BASE_CONFIG, use_cuda_graph: bool = True, check_mode: bool = False):
         """``check_mode=True``: the fp32-accumulate check mode of BASELINE's north star (rel-L2 <= 1e-3 vs the reference
         fp32 forward): same launch sequence, activations as split-bf16 triples through the same tcgen05 GEMM / conv
         mainloops with fp32 epilogues, fp32 norms and attention (lavie_b200/check.py).  For parity attribution, not speed."""
         super().__init__()
-        if getattr(config, "variant", "base") not in ("base", "interp"):
-            raise NotImplementedError(f"UNet variant {config.variant!r}: the base T2V denoiser and the frame-interpolation "
-                                      "denoiser have a B200 path")
+        if getattr(config, "variant", "base") not in self._VARIANTS:
+            raise NotImplementedError(f"UNet variant {config.variant!r} is not served by {type(self).__name__} "
+                                      f"(variants: {self._VARIANTS}; the VSR denoiser is lavie_b200.vsr.UNet3DVSRModel)")
+        if check_mode and config.variant == "vsr":
+            raise NotImplementedError("check mode covers the base and interpolation denoisers")
         self.cfg = config
         self.config = _Config(**config.to_dict())
         self.sample_size = config.sample_size
@@ -405,7 +410,7 @@ class UNet3DConditionModel(nn.Module):
         K = self._k
         r = self._packed[p]
         NF, rps = B * Fr, Fr * H * W
-        eps = self.cfg.norm_eps
+        eps = r.get("eps", self.cfg.norm_eps)
         h = self._gn5(x, x2, B, rps, r["g1"], r["b1"], eps, True)
         off, cout = self._packed["temb_slices"][p]
         # stats=True: the conv's epilogue also emits the column sums the NEXT GroupNorm needs (no second read of h)

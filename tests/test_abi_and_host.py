@@ -138,3 +138,23 @@ def test_ddim_schedule_matches_oracle():
     assert s.timesteps == ts.tolist() and s.ratio == ratio
     assert torch.equal(s.alphas_cumprod, acp)
     assert s.alphas(1) == (float(acp[1]), float(acp[0]))
+
+
+def test_vsr_module_keeps_the_reference_state_dict_layout():
+    """UNet3DVSRModel holds exactly the 1158 keys of the reference VSR UNet (shapes from lavie_b200.config, proven against
+    the reference in tests/golden/make_golden_vsr.py) and refuses to run without CUDA."""
+    import pytest
+    import torch
+    from lavie_b200.config import VSR_CONFIG, param_spec
+    from lavie_b200.vsr import UNet3DVSRModel, pack_frame_conv
+    m = UNet3DVSRModel()
+    spec = param_spec(VSR_CONFIG)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(spec.keys()) or set(sd.keys()) == set(spec.keys())
+    assert all(tuple(sd[k].shape) == tuple(v) for k, v in spec.items())
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 2, 8, 8), 1, torch.zeros(1, 3, 2, 8, 8), encoder_hidden_states=torch.zeros(1, 4, 1024))
+    # frame-conv weight packing: K ordered (tap, cin)
+    w = torch.arange(2 * 3 * 5, dtype=torch.float32).reshape(2, 3, 5, 1, 1)
+    p = pack_frame_conv(w)
+    assert p.shape == (2, 15) and float(p[1, 2 * 3 + 1]) == float(w[1, 1, 2, 0, 0])

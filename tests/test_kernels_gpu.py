@@ -245,7 +245,9 @@ def _padded(rows, heads, d, pitch, seed):
 @pytest.mark.parametrize("batch,Sq,Sk,d,pitch,div", [
     (4, 256, 256, 40, 48, 1), (2, 640, 640, 80, 80, 1), (2, 160, 160, 160, 160, 1), (3, 40, 40, 160, 160, 1),
     (4, 200, 77, 40, 48, 2), (4, 160, 77, 80, 80, 2), (4, 40, 77, 160, 160, 4), (1, 2560, 2560, 40, 48, 1),
-    (2, 64, 154, 40, 48, 1)])
+    (2, 64, 154, 40, 48, 1),
+    # head dims of the VSR denoiser (512 / 8 and 1024 / 8 channels per head)
+    (2, 320, 320, 64, 64, 1), (4, 256, 77, 64, 64, 2), (2, 200, 200, 128, 128, 1), (4, 96, 77, 128, 128, 4)])
 def test_attention(batch, Sq, Sk, d, pitch, div):
     ops = _ops()
     heads = 8
@@ -269,7 +271,7 @@ def test_attention_fused_qkv_views():
     assert rel_l2(out.float(), ref) < 1e-2
 
 
-@pytest.mark.parametrize("Fr,d,pitch", [(16, 40, 48), (16, 80, 80), (5, 160, 160)])
+@pytest.mark.parametrize("Fr,d,pitch", [(16, 40, 48), (16, 80, 80), (5, 160, 160), (16, 64, 64), (8, 128, 128)])
 def test_temporal_attention(Fr, d, pitch):
     ops = _ops()
     from lavie_b200.packing import rope_table
