@@ -641,20 +641,165 @@ def run_interp(args):
         os._exit(0)
 
 
+# ----------------------------------------------------------------------------------------------- config 5 (N2)
+VSR_WORKLOAD = "VSR x4-upscaler UNet3D, 1280x2048x{f} output (latent 4+3 ch x {f} x {h} x {w}), CFG batch 2, 77 text tokens, DDIM"
+
+
+def run_vsr(args):
+    """BASELINE config 5 on ONE GPU (python bench.py --workload vsr): a step = the VSR UNet forward on the CFG batch
+    ([2,4,F,320,512] latent + [2,3,F,320,512] noised low-res frames, noise level 50, the reference pipeline's call
+    vsr/models/pipeline_stable_diffusion_upscale_video_3d.py:712-727) + guidance + DDIM update.  Frame sharding of this
+    model is not built (its frame convolutions need a halo exchange), so N > 1 is refused.  Parity + CPU baseline: a bounded
+    sample (2 frames, 80x128 crop = 1/128 of the pixels; the model is convolutional apart from its 40x64-level
+    self-attention) against the unmodified reference on the host cores."""
+    from lavie_b200 import ops
+    from lavie_b200.config import VSR_CONFIG
+    from lavie_b200.pipeline import DDIMSchedule
+    from lavie_b200.synthetic import synthetic_state_dict
+    from lavie_b200.vsr import UNet3DVSRModel
+    from oracle import reference_loader as R
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1 or args.gpus != 1:
+        raise SystemExit("--workload vsr runs on one GPU (frame sharding of the VSR denoiser is not built)")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    Fr, H, W = args.vsr_frames, args.vsr_height, args.vsr_width
+    sd = synthetic_state_dict(VSR_CONFIG, seed=0)
+    unet = UNet3DVSRModel()
+    unet.load_state_dict(sd, strict=True)
+    unet = unet.to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(1, 4, Fr, H, W, generator=g)
+    low = torch.randn(2, 3, Fr, H, W, generator=g)
+    low[1] = low[0]
+    text = torch.randn(2, 77, 1024, generator=g)
+    labels = torch.tensor([50, 50])
+    sched = DDIMSchedule(50)
+    ts = sched.timesteps
+    x, lowd, txt = lat.to(dev), low.to(dev), text.to(dev)
+
+    def one_step(x, lowd, txt, i):
+        t = ts[i % len(ts)]
+        eps = unet(torch.cat([x, x]), t, lowd, encoder_hidden_states=txt, class_labels=labels).sample
+        a_t, a_prev = sched.alphas(t)
+        return ops.cfg_ddim_step(eps[:1].contiguous(), eps[1:].contiguous(), 5.0, a_t, a_prev, x)
+
+    for i in range(max(args.warmup, 3)):
+        x = one_step(x, lowd, txt, i)
+    torch.cuda.synchronize()
+    per_step = unet.launches_per_step() + 1
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(args.steps):
+            x = one_step(x, lowd, txt, i)
+        ev1.record()
+        torch.cuda.synchronize()
+    ms_per_step = ev0.elapsed_time(ev1) / args.steps
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    # e2e: latents + low-res frames + text from pinned host buffers every step, new latents back
+    xh = [lat.clone().pin_memory(), torch.empty_like(lat).pin_memory()]
+    lh, th = low.clone().pin_memory(), text.clone().pin_memory()
+    done = torch.cuda.Event()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        new = one_step(xh[i & 1].to(dev, non_blocking=True), lh.to(dev, non_blocking=True),
+                       th.to(dev, non_blocking=True), i)
+        xh[(i + 1) & 1].copy_(new, non_blocking=True)
+        done.record()
+        done.synchronize()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    # per-kernel CUDA-event profile of one eager forward
+    unet.use_cuda_graph = False
+    m_in = torch.cat([x, x])
+    unet(m_in, 500, lowd, encoder_hidden_states=txt, class_labels=labels)
+    ops.PROFILE = []
+    torch.cuda._sleep(300_000_000)
+    unet(m_in, 500, lowd, encoder_hidden_states=txt, class_labels=labels)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    unet.use_cuda_graph = True
+    agg = {}
+    for name, flops, nbytes, e0, e1, _tag in prof:
+        a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
+        a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += flops; a[3] += nbytes
+    total_ms = sum(a[1] for a in agg.values())
+    kernels = {k: {"launches": a[0], "ms": round(a[1], 3), "share": round(a[1] / total_ms, 4),
+                   "gflop": round(a[2] / 1e9, 1), "tflops": round(a[2] / (a[1] * 1e-3) / 1e12, 1) if a[2] else None,
+                   "gbs": round(a[3] / (a[1] * 1e-3) / 1e9, 1) if a[3] else None}
+               for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+    step_gflop = sum(a[2] for a in agg.values()) / 1e9
+    peaks = measured_peaks()
+    d = agg["gemm_bf16_tcgen05"]
+    achieved = d[2] / (d[1] * 1e-3) / 1e12
+    roofline = {"kernel": "gemm_bf16_tcgen05", "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                "launches_per_step": d[0], "avg_launch_ms": d[1] / d[0], "share_of_step": d[1] / total_ms,
+                "algorithmic_gflop_per_launch": d[2] / d[0] / 1e9, "peak_source": peaks["source"]}
+    parity, cpu = None, None
+    if not args.no_cpu_baseline:
+        f, hh, ww = min(2, Fr), min(80, H), min(128, W)
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        s_lat = torch.cat([lat, lat])[:, :, :f, :hh, :ww].contiguous()
+        s_low = low[:, :, :f, :hh, :ww].contiguous()
+        if R.available("vsr"):
+            ref = R.load_reference_unet("vsr", sd)
+            kind = "reference"
+            fwd = lambda: ref(s_lat, 500, s_low, encoder_hidden_states=text, class_labels=labels).sample
+        else:
+            from oracle import vsr_oracle as V
+            kind = "port"
+            fwd = lambda: V.unet_forward(sd, s_lat, 500, s_low, text, labels)
+        with torch.no_grad():
+            t0 = time.time()
+            ref_out = fwd()
+            dt = time.time() - t0
+        out_s = unet(s_lat.to(dev), 500, s_low.to(dev), encoder_hidden_states=txt, class_labels=labels).sample.cpu()
+        err = rel_l2(out_s, ref_out)
+        frac = (f * hh * ww) / (Fr * H * W)
+        parity = {"rel_l2": err, "tolerance": 2e-2, "shape": [2, 7, f, hh, ww],
+                  "vs": f"{'unmodified reference UNet3DVSRModel (baseline/_ref)' if kind == 'reference' else 'CPU oracle port'}, fp32"}
+        cpu = {"value": frac / dt, "unit": "steps/s", "cores": threads, "kind": kind,
+               "sample": f"1 forward on {f} frames x {hh}x{ww} of {Fr} x {H}x{W} ({frac:.5f} of a step's pixels) = {dt:.2f} s"}
+        if not err <= 2e-2:
+            raise SystemExit(f"vsr parity FAILED: {err:.3e}")
+    line = {"metric": "denoise steps/s (VSR 320x512 latent, CFG)", "value": 1e3 / ms_per_step, "unit": "steps/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": VSR_WORKLOAD.format(f=Fr, h=H, w=W), "weights": "random-init (seeded), 691.0 M params"},
+            "setup": {"parallelism": "single", "cuda_graph": True, "launches_per_step_per_rank": per_step,
+                      "peak_mem_gb": round(peak_mem, 1)},
+            "parity": parity, "step_gflop": step_gflop, "step_tflops": step_gflop / ms_per_step,
+            "clocks": clocks.summary(),
+            "e2e": {"value": args.steps / e2e_s, "unit": "steps/s",
+                    "h2d_bytes_per_step": (xh[0].numel() + lh.numel() + th.numel()) * 4,
+                    "d2h_bytes_per_step": xh[0].numel() * 4},
+            "gpu_launches": per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="base", choices=["base", "interp"],
-                    help="base = BASELINE config 1-3 (the headline); interp = config 4 on one GPU")
+    ap.add_argument("--workload", default="base", choices=["base", "interp", "vsr"],
+                    help="base = BASELINE config 1-3 (the headline); interp = config 4; vsr = config 5 on one GPU")
+    ap.add_argument("--vsr-frames", type=int, default=16)
+    ap.add_argument("--vsr-height", type=int, default=320)
+    ap.add_argument("--vsr-width", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "interp":
         run_interp(args)
+    elif args.workload == "vsr":
+        run_vsr(args)
     else:
         run_b200(args)
 

@@ -24,6 +24,8 @@ REF_FILES = {
              "models/resnet.py"],
     "interpolation": ["models/__init__.py", "models/unet.py", "models/unet_blocks.py", "models/attention.py",
                       "models/resnet.py", "models/utils.py", "models/clip.py"],
+    "vsr": ["models/__init__.py", "models/unet.py", "models/unet_blocks.py", "models/attention.py", "models/resnet.py",
+            "models/temporal_module.py", "models/diffusers_attention.py", "configs/unet_3d_config.json"],
 }
 
 
@@ -49,9 +51,10 @@ def available(tree: str = "base") -> bool:
 
 
 def load_reference_unet(variant: str = "base", state_dict=None):
-    """Build the reference's UNet3DConditionModel (eval, CPU fp32) for ``variant`` in {"base", "interp"} and load
-    ``state_dict`` with strict=True.  Raises FileNotFoundError when baseline/_ref is missing."""
-    tree = "base" if variant == "base" else "interpolation"
+    """Build the reference's UNet3DConditionModel (eval, CPU fp32) for ``variant`` in {"base", "interp"} -- or its
+    UNet3DVSRModel for "vsr", from the reference's own vsr/configs/unet_3d_config.json -- and load ``state_dict`` with
+    strict=True.  Raises FileNotFoundError when baseline/_ref is missing."""
+    tree = {"base": "base", "interp": "interpolation", "vsr": "vsr"}[variant]
     if not available(tree):
         raise FileNotFoundError(f"{REF_DIR}/{tree} not found: run __graft_entry__.build() in the build container")
     for p in (SHIMS, os.path.join(REF_DIR, tree)):
@@ -62,6 +65,13 @@ def load_reference_unet(variant: str = "base", state_dict=None):
         del sys.modules[name]                      # the two trees use the same package name
     mod = importlib.import_module("models.unet")
     from lavie_b200.config import BASE_CONFIG, INTERP_CONFIG
+    if variant == "vsr":
+        import json
+        with open(os.path.join(REF_DIR, "vsr", "configs", "unet_3d_config.json")) as f:
+            ref = mod.UNet3DVSRModel.from_config(json.load(f)).eval()
+        if state_dict is not None:
+            ref.load_state_dict(state_dict, strict=True)
+        return ref
     if variant == "base":
         cfg = BASE_CONFIG.to_dict()
     else:
