@@ -57,12 +57,13 @@ typedef struct {
   const void* residual;  /* bf16 [M, ld_residual] or NULL */
   int ld_residual;
   int geglu;
-  float* col_stats;      /* NULL or fp32 [ceil(M / 32), N / 32, 4, 2] (N % 32 == 0): per 32-row slab and 10-channel micro-group,
-                            (sum, sum of squares) of the bf16-rounded outputs; entry [slab][chunk][piece] covers the part of
-                            decade (chunk * 32) / 10 + piece that lies inside columns [chunk * 32, chunk * 32 + 32).  This is
-                            the statistics pass of the GroupNorm that consumes the output (resnet.py:180,191;
-                            attention.py:369; every group of the model is a whole number of decades), emitted by the
-                            producer's epilogue instead of a second read of the tensor; fold with
+  float* col_stats;      /* NULL or fp32 [ceil(M / 32), N / 32, 4, 2] (N % 32 == 0): per 32-row slab and micro-group of
+                            mg channels, (sum, sum of squares) of the bf16-rounded outputs; mg = 10 when N % 10 == 0 (base /
+                            interpolation model: every GroupNorm group is a whole number of decades), else 8 (VSR model:
+                            groups of 8..64 channels).  Entry [slab][chunk][piece] covers the part of micro-group
+                            (chunk * 32) / mg + piece that lies inside columns [chunk * 32, chunk * 32 + 32).  This is the
+                            statistics pass of the GroupNorm that consumes the output (resnet.py:180,191; attention.py:369),
+                            emitted by the producer's epilogue instead of a second read of the tensor; fold with
                             lavie_groupnorm_finalize_colsums.  Not in check mode. */
 } lavie_epilogue;
 

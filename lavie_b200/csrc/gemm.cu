@@ -76,6 +76,7 @@ struct GemmParams {
   float* colstats;           // [M / 32, N / 32, 4, 2] or null: per 32-row slab and 10-channel micro-group (stored per
                              // 32-column chunk and decade piece), (sum, sum of squares) of the bf16-rounded outputs: the
                              // GroupNorm statistics of the NEXT layer, emitted by the producer
+  int mg8;                   // micro-group width of colstats: 0 = 10 channels (N % 10 == 0), 1 = 8 channels (otherwise)
   int check;                 // fp32-accumulate check mode: accumulators ALWAYS leave as fp32 partials (even with
                              // splits == 1); bias / residual / GEGLU run in fp32 on split-bf16 triples (check reduce)
   int k_rot;                 // K-sweep rotation stride per M tile (0 = off)
@@ -461,8 +462,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
           s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
           q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
           const int col = col_out0 + 2 * c2;                         // even; a pair never straddles a decade
-          const int dec = (col * 6554) >> 16;                        // col / 10 for col < 16384
-          const int dec0 = (col_out0 * 6554) >> 16;
+          // micro-group index: col / 10 (col < 16384), or col / 8 for models whose groups are multiples of 8 only (VSR)
+          const int dec = p.mg8 ? (col >> 3) : ((col * 6554) >> 16);
+          const int dec0 = p.mg8 ? (col_out0 >> 3) : ((col_out0 * 6554) >> 16);
           // segmented inclusive scan over lanes 0..15 of each half (segments = equal decade, contiguous lanes)
 #pragma unroll
           for (int o = 1; o < 16; o <<= 1) {
@@ -620,7 +622,7 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_stats_kernel(const float* __restrict__ partial, int splits, int M, int N, int M_total,
                            const float* __restrict__ bias, const float* __restrict__ row_bias, int rows_per_batch,
                            int ld_row_bias, const __nv_bfloat16* __restrict__ residual, int ldr,
-                           __nv_bfloat16* __restrict__ out, int ldo, int row0, float* __restrict__ colstats) {
+                           __nv_bfloat16* __restrict__ out, int ldo, int row0, float* __restrict__ colstats, int mg) {
   pdl_prologue();
   constexpr int R = 4;                                 // rows per thread
   __shared__ float s_cs[8][128][2];                    // [row group][column][sum, sumsq]
@@ -685,8 +687,8 @@ splitk_reduce_stats_kernel(const float* __restrict__ partial, int splits, int M,
     const int cl = threadIdx.x >> 2, piece = threadIdx.x & 3;
     const int c0 = cbase + cl * 32;
     if (c0 < N) {
-      const int dec = ((c0 * 6554) >> 16) + piece;
-      const int lo = max(c0, dec * 10), hi = min(min(c0 + 32, dec * 10 + 10), N);
+      const int dec = c0 / mg + piece;
+      const int lo = max(c0, dec * mg), hi = min(min(c0 + 32, dec * mg + mg), N);
       if (lo < hi) {
         float a = 0.f, b = 0.f;
         for (int c = lo; c < hi; ++c)
@@ -774,7 +776,7 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     launch_pdl(splitk_reduce_stats_kernel, grid, 256, 0, stream, p.partial, p.splits, p.rows_window, p.N, p.M, p.bias,
                p.row_bias, p.rows_per_batch, p.ld_row_bias,
                p.residual ? p.residual + static_cast<size_t>(row0) * p.ldr : nullptr, p.ldr,
-               p.out + static_cast<size_t>(row0) * p.ldo, p.ldo, row0, p.colstats);
+               p.out + static_cast<size_t>(row0) * p.ldo, p.ldo, row0, p.colstats, p.mg8 ? 8 : 10);
     rc = lavie_check_launch("splitk_reduce_stats_kernel");
   } else if (p.splits > 1) {
     const int row0 = p.m_tile0 * PAIR_M;
@@ -943,6 +945,7 @@ int fill_epilogue(GemmParams& p, const lavie_epilogue* ep, int N, void* out, int
   p.bias = nullptr; p.row_bias = nullptr; p.rows_per_batch = 1; p.ld_row_bias = N; p.residual = nullptr; p.ldr = 0;
   p.geglu = 0;
   p.colstats = nullptr;
+  p.mg8 = (N % 10 != 0) ? 1 : 0;
   if (ep) {
     p.colstats = ep->col_stats;
     LAVIE_REQUIRE(!p.colstats || (aligned16(p.colstats) && !ep->geglu && N % 32 == 0 && N <= 8192), LAVIE_ERR_SHAPE,

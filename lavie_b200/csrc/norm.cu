@@ -659,18 +659,19 @@ namespace {
 // (sum, sumsq) per (sample, group) (frame-sharded exchange).
 __global__ void __launch_bounds__(256)
 gn_colsums_kernel(const float* __restrict__ cs0, int c0, const float* __restrict__ cs1, int c1, int slabs_per_sample,
-                  int groups, double inv_count, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                  float* __restrict__ scale_shift, double* __restrict__ sums) {
+                  int groups, int mg, double inv_count, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float eps, float* __restrict__ scale_shift, double* __restrict__ sums) {
   pdl_prologue();
   const int g = blockIdx.x, sample = blockIdx.y;
   const int C = c0 + c1, cpg = C / groups;
   const int ch0 = g * cpg;
-  const int decs = cpg / 10;
+  const int decs = cpg / mg;                                   // micro-groups (mg = 10 or 8 channels) per group
   const long long total = static_cast<long long>(slabs_per_sample) * decs;
   double a = 0.0, b = 0.0;
-  for (long long i = threadIdx.x; i < total; i += 256) {
+  auto load = [&](long long i) -> float2 {
+    if (i >= total) return make_float2(0.f, 0.f);
     const long long slab = static_cast<long long>(sample) * slabs_per_sample + i / decs;
-    int ch = ch0 + static_cast<int>(i % decs) * 10;            // first channel of the decade in the concat
+    int ch = ch0 + static_cast<int>(i % decs) * mg;            // first channel of the micro-group in the concat
     const float* cs = cs0;
     int cn = c0;
     if (ch >= c0) {
@@ -678,17 +679,26 @@ gn_colsums_kernel(const float* __restrict__ cs0, int c0, const float* __restrict
       cs = cs1;
       cn = c1;
     }
-    const int dec = ch / 10;
-    const int k_lo = ch >> 5, k_hi = (ch + 9) >> 5;            // the chunk(s) the decade touches
+    const int dec = ch / mg;
+    const int k_lo = ch >> 5, k_hi = (ch + mg - 1) >> 5;       // the chunk(s) the micro-group touches
     const float* row = cs + slab * (cn >> 5) * 8;
-    float2 v = __ldg(reinterpret_cast<const float2*>(row + (k_lo * 4 + (dec - (k_lo * 32) / 10)) * 2));
+    float2 v = __ldg(reinterpret_cast<const float2*>(row + (k_lo * 4 + (dec - (k_lo * 32) / mg)) * 2));
     if (k_hi != k_lo) {
-      const float2 w = __ldg(reinterpret_cast<const float2*>(row + (k_hi * 4 + (dec - (k_hi * 32) / 10)) * 2));
+      const float2 w = __ldg(reinterpret_cast<const float2*>(row + (k_hi * 4 + (dec - (k_hi * 32) / mg)) * 2));
       v.x += w.x;
       v.y += w.y;
     }
-    a += v.x;
-    b += v.y;
+    return v;
+  };
+  for (long long i = threadIdx.x; i < total; i += 256 * 8) {   // 8 independent loads in flight, summed in a fixed order
+    float2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = load(i + 256LL * u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a += v[u].x;
+      b += v[u].y;
+    }
   }
   __shared__ double sa[256], sb[256];
   sa[threadIdx.x] = a;
@@ -725,13 +735,17 @@ int colsums_impl(const float* cs0, int c0, const float* cs1, int c1, int samples
                  cudaStream_t stream) {
   const int C = c0 + c1;
   LAVIE_REQUIRE(samples > 0 && rows_per_sample > 0 && rows_per_sample % 32 == 0 && groups > 0 && C % groups == 0 &&
-                    (C / groups) % 10 == 0 && c0 > 0 && c0 % 32 == 0 && c1 % 32 == 0 && c0 % 10 == 0,
-                LAVIE_ERR_SHAPE,
-                "groupnorm colsums: rows_per_sample=%d must be a multiple of 32, C=%d / groups=%d a multiple of 10, "
-                "sources multiples of 32 channels", rows_per_sample, C, groups);
+                    c0 > 0 && c0 % 32 == 0 && c1 % 32 == 0, LAVIE_ERR_SHAPE,
+                "groupnorm colsums: rows_per_sample=%d must be a multiple of 32, C=%d %% groups=%d == 0, sources multiples "
+                "of 32 channels", rows_per_sample, C, groups);
+  // micro-group width the PRODUCERS used (gemm.cu fill_epilogue): 10 channels when their N is a multiple of 10, else 8
+  const int mg = (c0 % 10 == 0) ? 10 : 8;
+  LAVIE_REQUIRE((c1 == 0 || ((c1 % 10 == 0) == (mg == 10))) && (C / groups) % mg == 0 && c0 % mg == 0, LAVIE_ERR_SHAPE,
+                "groupnorm colsums: sources c0=%d c1=%d with groups of %d channels do not share a micro-group width", c0,
+                c1, C / groups);
   LAVIE_REQUIRE(cs0 != nullptr && (c1 == 0 || cs1 != nullptr), LAVIE_ERR_SHAPE, "groupnorm colsums: null statistics");
   dim3 grid(groups, samples);
-  launch_pdl(gn_colsums_kernel, grid, 256, 0, stream, cs0, c0, cs1, c1, rows_per_sample / 32, groups,
+  launch_pdl(gn_colsums_kernel, grid, 256, 0, stream, cs0, c0, cs1, c1, rows_per_sample / 32, groups, mg,
              1.0 / (static_cast<double>(rows_per_sample) * (C / groups)), gamma, beta, eps, scale_shift, sums);
   return lavie_check_launch("gn_colsums_kernel");
 }

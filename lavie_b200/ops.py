@@ -218,10 +218,11 @@ def conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w: torch.Tensor, *, stride
 
 def frame_conv(xpad: torch.Tensor, taps: int, tap_rows: int, w: torch.Tensor, *, bias=None, row_bias=None,
                rows_per_batch=1, residual=None, out: Optional[torch.Tensor] = None, block_n: int = 0,
-               stats: bool = False):
+               stats: bool = False, colsums_out: Optional[torch.Tensor] = None):
     """nn.Conv3d (taps,1,1) over frames (vsr/models/resnet.py:253-254,269) for ONE batch item.  xpad: bf16
     [(F + taps - 1) * tap_rows, C], the item's channels-last map with taps//2 zero frames on both sides;
-    w: bf16 [N, taps*C] in (tap, c) order.  Returns [F * tap_rows, N]."""
+    w: bf16 [N, taps*C] in (tap, c) order.  Returns [F * tap_rows, N].  ``colsums_out``: this item's slab range of a
+    column-statistics buffer that spans several items (see `_new_colsums`)."""
     lib = _lib.load()
     rows_in, C, ld = _rows2d(xpad)
     M = rows_in - (taps - 1) * tap_rows
@@ -231,7 +232,7 @@ def frame_conv(xpad: torch.Tensor, taps: int, tap_rows: int, w: torch.Tensor, *,
         out = torch.empty((M, N), dtype=BF16, device=xpad.device)
     Mo, No, ldo = _rows2d(out)
     assert Mo == M and No == N
-    cs = _new_colsums(M, N, xpad.device) if stats and FUSE_GN_STATS else None
+    cs = colsums_out if colsums_out is not None else (_new_colsums(M, N, xpad.device) if stats and FUSE_GN_STATS else None)
     ep = _epilogue(bias, row_bias, rows_per_batch, residual, False, cs)
     ws = _workspace(xpad.device)
     with _Launch("gemm_bf16_tcgen05", 2.0 * M * N * taps * C, 2.0 * (rows_in * C + N * taps * C + M * N),
@@ -259,7 +260,7 @@ def embedding_add(emb: torch.Tensor, table: torch.Tensor, labels: torch.Tensor):
 
 def _new_colsums(M: int, N: int, device) -> Optional[torch.Tensor]:
     """[slabs of 32 rows, 32-column chunks, 4 decade pieces, (sum, sumsq)] -- see lavie_epilogue.col_stats."""
-    if N % 32 or N % 10:
+    if N % 32:
         return None
     return torch.empty(((M + 31) // 32, N // 32, 4, 2), dtype=F32, device=device)
 
@@ -273,8 +274,12 @@ def colsums(x: torch.Tensor, rows_per_sample: int, x2: Optional[torch.Tensor] = 
     cs1 = getattr(x2, "_gn_colsums", None) if x2 is not None else None
     if cs0 is None or (x2 is not None and cs1 is None):
         return None
-    C = x.shape[1] + (x2.shape[1] if x2 is not None else 0)
-    if (C // 32) % 10:
+    # micro-group width the producers used: 10 channels when their N is a multiple of 10 (base / interpolation model),
+    # else 8 (VSR model); all sources and the consumer's 32 groups must agree on it
+    c0 = x.shape[1]
+    c1 = x2.shape[1] if x2 is not None else 0
+    mg = 10 if c0 % 10 == 0 else 8
+    if (c1 and (c1 % 10 == 0) != (mg == 10)) or ((c0 + c1) // 32) % mg or c0 % mg:
         return None
     return cs0, cs1
 

@@ -201,11 +201,16 @@ class UNet3DVSRModel(UNet3DConditionModel):
         buf = self._padbuf(k, B, Fr, HW, C, x.device)
         lo = (k // 2) * HW
         out = torch.empty((B * rps, w.shape[0]), dtype=BF16, device=x.device)
+        # the consumer's GroupNorm statistics come out of the conv's epilogue (one buffer, each item fills its slabs)
+        cs = ops._new_colsums(B * rps, w.shape[0], x.device) if (ops.FUSE_GN_STATS and rps % 32 == 0) else None
         for b in range(B):
             rows = slice(b * rps, (b + 1) * rps)
             ops.groupnorm_apply(x[rows], ss[b:b + 1], 1, rps, True, out=buf[b, lo:lo + rps])
             ops.frame_conv(buf[b], k, HW, w, bias=bias, row_bias=None if row_bias is None else row_bias[b:b + 1],
-                           rows_per_batch=rps, residual=None if residual is None else residual[rows], out=out[rows])
+                           rows_per_batch=rps, residual=None if residual is None else residual[rows], out=out[rows],
+                           colsums_out=None if cs is None else cs[b * rps // 32:(b + 1) * rps // 32])
+        if cs is not None:
+            out._gn_colsums = cs
         return out
 
     def _resnet_cnn(self, p, x, temb_all, B, Fr, HW):

@@ -497,6 +497,41 @@ def test_conv_column_sums_feed_groupnorm(NF, H, W, C, N, stride):
     assert rel_l2(ss, ss_ref) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K,splits", [(2048, 256, 256, 0), (1000, 512, 1536, 0), (640, 1024, 4608, 4)])
+def test_column_sums_with_octet_micro_groups(M, N, K, splits):
+    """Outputs whose width is not a multiple of 10 (the VSR model: 256 / 512 / 1024 channels, GroupNorm groups of
+    8 .. 64 channels) carry statistics per 8-channel micro-group: [slab][chunk][piece] = octet chunk*4 + piece.  They
+    must equal the sums of the stored bf16 values and feed the GroupNorm finalize exactly like the stand-alone pass,
+    also for a two-source concat whose groups straddle the seam (1024 + 512 channels: groups of 48)."""
+    ops = _ops()
+    from lavie_b200 import _lib
+    lib = _lib.load()
+    a = _bf(_rand(M, K))
+    w = _bf(_rand(N, K, scale=K ** -0.5))
+    lib.lavie_debug_set(1, splits)
+    try:
+        out = ops.gemm(a, w, bias=_rand(N, seed=1), stats=True)
+    finally:
+        lib.lavie_debug_set(1, 0)
+    slabs = (M + 31) // 32
+    pad = torch.zeros(slabs * 32, N, device=DEV)
+    pad[:M] = out.float()
+    v = pad.reshape(slabs, 32, N // 8, 8)
+    ref = torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], dim=-1)
+    got = out._gn_colsums.reshape(slabs, N // 8, 2)                  # [slab][chunk][piece] is octet-major already
+    assert rel_l2(got, ref) < 1e-5
+    if M % 32 == 0:
+        gamma, beta = _rand(N, seed=4) * 0.1 + 1, _rand(N, seed=5) * 0.1
+        ss = ops.groupnorm_scale_shift(out, 2, M // 2, gamma, beta, 1e-6)
+        ss_ref = ops.groupnorm_scale_shift(out.clone(), 2, M // 2, gamma, beta, 1e-6)
+        assert rel_l2(ss, ss_ref) < 1e-5
+        y2 = ops.gemm(_bf(_rand(M, 64, seed=9)), _bf(_rand(N // 2, 64, seed=10, scale=0.1)), stats=True)
+        g2, b2 = _rand(N + N // 2, seed=6) * 0.1 + 1, _rand(N + N // 2, seed=7) * 0.1
+        ss = ops.groupnorm_scale_shift(out, 1, M, g2, b2, 1e-5, x2=y2)
+        ss_ref = ops.groupnorm_scale_shift(out.clone(), 1, M, g2, b2, 1e-5, x2=y2.clone())
+        assert rel_l2(ss, ss_ref) < 1e-5
+
+
 def test_out_of_bounds_canaries():
     """compute-sanitizer is closed on this GPU pool (profiles/r2_compute_sanitizer_closed.txt), so the memory-safety
     evidence is canaries: every output lives inside a larger poisoned allocation and the bytes around it must survive
