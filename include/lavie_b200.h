@@ -301,6 +301,32 @@ int lavie_cfg_combine(const float* cond, const float* uncond, float scale, float
                       lavie_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Once-per-video encoders / decoders around the denoiser.  The heavy parts reuse lavie_gemm_bf16,
+ * lavie_conv3x3_bf16, the GroupNorm and LayerNorm entries above; these are the pieces only they need.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* CLIPTextEmbeddings.forward (transformers CLIPTextModel, called at base/pipelines/pipeline_videogen.py:337-348):
+ * out[row, :] = bf16(token_embedding[ids[row], :] + position_embedding[row % L, :]); tables fp32, ids int64 [rows]. */
+int lavie_clip_embed(const long long* ids, const float* token_embedding, const float* position_embedding, int rows, int L,
+                     int C, int vocab, void* out, lavie_stream_t stream);
+/* CLIPAttention core under the causal mask of CLIPTextTransformer: qkv bf16 [B*L, ld] = (q | k | v) x heads x d,
+ * out bf16 [B*L, heads*d]; L <= 128, d = 64 or 128; softmax(scale * q k^T + causal mask) v per (batch item, head). */
+int lavie_causal_attention_small(const void* qkv, int ld, int B, int L, int heads, int d, float scale, void* out, int ldo,
+                                 lavie_stream_t stream);
+/* in place on n bf16 values: kind 0 = quick_gelu x * sigmoid(1.702 x) (CLIP ViT-L text MLP), 1 = erf GELU. */
+int lavie_activation_bf16(void* x, long long n, int kind, lavie_stream_t stream);
+/* in place: every row of s (bf16 [rows, ld], n <= 4096 columns used) becomes softmax(scale * row) -- the attention
+ * probabilities of the VAE decoder's single-head mid-block attention (diffusers AttentionBlock), whose Q K^T and P V
+ * products are plain GEMMs. */
+int lavie_softmax_rows_bf16(void* s, int ld, long long rows, int n, float scale, lavie_stream_t stream);
+/* AutoencoderKL.post_quant_conv (1x1, 4 -> 4; mirror vsr/models/autoencoder_kl.py:183) on an fp32 [N, Cin, pixels] map,
+ * with decode_latents' 1/0.18215 folded in: out[n, co, p] = bias[co] + sum_ci w[co, ci] * scale * x[n, ci, p]. */
+int lavie_pointwise_conv_nchw_f32(const float* x, const float* w, const float* bias, float scale, int N, int Cin, int Cout,
+                                  long long pixels, float* out, lavie_stream_t stream);
+/* decode_latents post-processing (pipeline_videogen.py:426-428): out[pixel, 0..2] = uint8(clamp((y[pixel, 0..2] / 2 + 0.5)
+ * * 255 + 0.5, 0, 255)); y bf16 channels-last rows of >= 4 columns. */
+int lavie_image_to_uint8(const void* y, int ld, long long pixels, unsigned char* out, lavie_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * fp32-accumulate CHECK MODE (BASELINE north star: noise-prediction rel-L2 <= 1e-3 against the reference fp32 forward).
  * Activations are "split-bf16 triples": a row of C channels is stored as [hi | lo | hi] (3C bf16, hi = bf16(x),
  * lo = bf16(x - hi), ~16 mantissa bits).  With weights repacked by the caller as W' = [Wh | Wh | Wl] along K the

@@ -87,6 +87,12 @@ SIGNATURES = {
     "lavie_embedding_add": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "lavie_frame_conv_bf16": (c_int, [_P, c_int, c_longlong, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int,
                                       POINTER(Epilogue), c_int, _P, c_size_t, _P]),
+    "lavie_clip_embed": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "lavie_causal_attention_small": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_float, _P, c_int, _P]),
+    "lavie_activation_bf16": (c_int, [_P, c_longlong, c_int, _P]),
+    "lavie_softmax_rows_bf16": (c_int, [_P, c_int, c_longlong, c_int, c_float, _P]),
+    "lavie_image_to_uint8": (c_int, [_P, c_int, c_longlong, _P, _P]),
+    "lavie_pointwise_conv_nchw_f32": (c_int, [_P, _P, _P, c_float, c_int, c_int, c_int, c_longlong, _P, _P]),
     "lavie_unpack_nchw_f32": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_upsample_nearest2x": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_cfg_ddim_step": (c_int, [_P, _P, c_float, c_float, c_float, _P, _P, c_longlong, _P]),

@@ -626,3 +626,54 @@ def cfg_combine(cond, uncond, scale: float, duplicate: bool = True):
         check(lib.lavie_cfg_combine(cond.data_ptr(), uncond.data_ptr(), float(scale), out.data_ptr(), _ptr(second), n,
                                     _stream()), "lavie_cfg_combine")
     return out
+
+
+# ---- once-per-video encoders / decoders: CLIP text encoder and VAE decoder pieces ----
+def clip_embed(ids: torch.Tensor, tok: torch.Tensor, pos: torch.Tensor, L: int) -> torch.Tensor:
+    """ids int64 [rows]; tok fp32 [V, C]; pos fp32 [>= L, C] -> bf16 [rows, C] (token + position embedding)."""
+    lib = _lib.load()
+    assert ids.dtype == torch.int64 and ids.is_cuda and ids.is_contiguous() and tok.dtype == F32 and pos.dtype == F32
+    rows, C = ids.numel(), tok.shape[1]
+    out = torch.empty((rows, C), dtype=BF16, device=ids.device)
+    with _Launch("lavie_clip_embed"):
+        check(lib.lavie_clip_embed(ids.data_ptr(), tok.data_ptr(), pos.data_ptr(), rows, L, C, tok.shape[0], out.data_ptr(),
+                                   _stream()), "lavie_clip_embed")
+    return out
+
+
+def causal_attention_small(qkv: torch.Tensor, B: int, L: int, heads: int, d: int) -> torch.Tensor:
+    lib = _lib.load()
+    rows, cols, ld = _rows2d(qkv)
+    assert rows == B * L and cols == 3 * heads * d
+    out = torch.empty((rows, heads * d), dtype=BF16, device=qkv.device)
+    with _Launch("lavie_causal_attention_small", 4.0 * B * heads * L * L * d / 2):
+        check(lib.lavie_causal_attention_small(qkv.data_ptr(), ld, B, L, heads, d, d ** -0.5, out.data_ptr(), heads * d,
+                                               _stream()), "lavie_causal_attention_small")
+    return out
+
+
+def activation_(x: torch.Tensor, kind: str) -> torch.Tensor:
+    lib = _lib.load()
+    assert x.dtype == BF16 and x.is_contiguous() and x.is_cuda
+    with _Launch("lavie_activation_bf16", 0.0, 4.0 * x.numel()):
+        check(lib.lavie_activation_bf16(x.data_ptr(), x.numel(), {"quick_gelu": 0, "gelu": 1}[kind], _stream()),
+              "lavie_activation_bf16")
+    return x
+
+
+def softmax_rows_(s: torch.Tensor, scale: float) -> torch.Tensor:
+    lib = _lib.load()
+    rows, n, ld = _rows2d(s)
+    with _Launch("lavie_softmax_rows_bf16", 0.0, 4.0 * rows * n):
+        check(lib.lavie_softmax_rows_bf16(s.data_ptr(), ld, rows, n, float(scale), _stream()), "lavie_softmax_rows_bf16")
+    return s
+
+
+def image_to_uint8(y: torch.Tensor) -> torch.Tensor:
+    """y bf16 [pixels, >= 4] channels-last (columns 0..2 = RGB in [-1, 1]) -> uint8 [pixels, 3]."""
+    lib = _lib.load()
+    rows, _, ld = _rows2d(y)
+    out = torch.empty((rows, 3), dtype=torch.uint8, device=y.device)
+    with _Launch("lavie_image_to_uint8"):
+        check(lib.lavie_image_to_uint8(y.data_ptr(), ld, rows, out.data_ptr(), _stream()), "lavie_image_to_uint8")
+    return out
