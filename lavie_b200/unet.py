@@ -136,6 +136,7 @@ class UNet3DConditionModel(nn.Module):
         self._scale_one = None
         self._graphs: Dict[tuple, dict] = {}
         self._tables: Dict[tuple, tuple] = {}
+        self._text_seen = None        # (tensor, version, graph key) whose K/V projections sit in that graph's buffer
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     # ------------------------------------------------------------------ reference-compatible helpers
@@ -170,6 +171,7 @@ class UNet3DConditionModel(nn.Module):
         self._param_list = None
         self._graphs.clear()
         self._tables.clear()
+        self._text_seen = None
 
     def _weights_fingerprint(self):
         # version counters of the parameters seen at packing time (~0.1 ms for 830 tensors); module surgery after the
@@ -528,9 +530,11 @@ class UNet3DConditionModel(nn.Module):
         return K.gemm(tok, t["w_out"], bias=t["b_out"], residual=x, stats=True)
 
     def _step(self, sample: torch.Tensor, t: torch.Tensor, text: torch.Tensor, taps: Optional[dict] = None,
-              input_scale: Optional[torch.Tensor] = None):
+              input_scale: Optional[torch.Tensor] = None, kv_all: Optional[torch.Tensor] = None):
         """One denoiser evaluation.  sample fp32 [B,C,F,H,W], t fp32 [B], text [B*L, ctx] (bf16; fp32 in check mode)
-        -> fp32 [B,Co,F,H,W]."""
+        -> fp32 [B,Co,F,H,W].  ``kv_all``: the text K/V projections when the caller already holds them (graph path: they
+        are computed once per prompt, not once per step -- the reference re-projects them in every attn2 call,
+        attention.py:364)."""
         K = self._k
         P = self._packed
         cfg = self.cfg
@@ -560,7 +564,8 @@ class UNet3DConditionModel(nn.Module):
         if taps is not None:
             taps["emb"] = emb.clone()
         # all 16 cross-attention K/V projections of the text in one GEMM
-        kv_all = K.gemm(text, P["kv_w"])
+        if kv_all is None:
+            kv_all = K.gemm(text, P["kv_w"])
 
         x = K.conv_in(sample, P["conv_in"][0], P["conv_in"][1], input_scale)
         tap("conv_in", x, boc[0], H, W)
@@ -653,7 +658,7 @@ class UNet3DConditionModel(nn.Module):
         else:
             scale = torch.full((1,), float(input_scale), dtype=F32, device=dev)
         if self.use_cuda_graph and taps is None:
-            out = self._graph_step(x, t, txt, scale)
+            out = self._graph_step(x, t, txt, scale, encoder_hidden_states)
         else:
             out = self._step(x, t, txt, taps, scale)
         out = out.to(out_dtype) if out_dtype != F32 else out.clone()   # never hand out the graph's static buffer
@@ -681,7 +686,7 @@ class UNet3DConditionModel(nn.Module):
         g = ops.cfg_combine(eps[:n], eps[n:], cfg_scale).to(out.dtype)
         return g if out.shape[1] == co else torch.cat([g, out[:, co:]], dim=1)
 
-    def _graph_step(self, x, t, txt, scale):
+    def _graph_step(self, x, t, txt, scale, text_src=None):
         key = (tuple(x.shape), tuple(txt.shape))
         g = self._graphs.get(key)
         if g is None:
@@ -689,21 +694,33 @@ class UNet3DConditionModel(nn.Module):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):          # warm-up run: sets kernel attributes, fills table caches
-                self._step(g["x"], g["t"], g["txt"], None, g["scale"])
+                g["kv"] = ops.gemm(g["txt"], self._packed["kv_w"])
+                self._step(g["x"], g["t"], g["txt"], None, g["scale"], kv_all=g["kv"])
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             before = ops.LAUNCHES
             # with frame sharding the NCCL collectives of the step are captured too (same sequence on every rank)
             with torch.cuda.graph(graph):
-                g["out"] = self._step(g["x"], g["t"], g["txt"], None, g["scale"])
+                g["out"] = self._step(g["x"], g["t"], g["txt"], None, g["scale"], kv_all=g["kv"])
             g["launches"] = ops.LAUNCHES - before      # kernel nodes of ours in the captured step
             g["graph"] = graph
             self._graphs[key] = g
-        self._last_graph_launches = g["launches"]
         g["x"].copy_(x, non_blocking=True)
         g["t"].copy_(t, non_blocking=True)
-        g["txt"].copy_(txt, non_blocking=True)
         g["scale"].copy_(scale, non_blocking=True)
+        # text K/V projections: once per prompt tensor, outside the captured step.  A caller that passes the SAME tensor
+        # object, unmodified (version counter), step after step -- every pipeline of the reference does -- pays for the
+        # projection GEMM only on the first step.
+        seen = self._text_seen
+        hit = (text_src is not None and seen is not None and seen[0] is text_src and seen[1] == text_src._version
+               and seen[2] == key)
+        extra = 0
+        if not hit:
+            g["txt"].copy_(txt, non_blocking=True)
+            ops.gemm(g["txt"], self._packed["kv_w"], out=g["kv"])
+            extra = 1
+            self._text_seen = (text_src, text_src._version, key) if text_src is not None else None
+        self._last_graph_launches = g["launches"] + extra
         g["graph"].replay()
         return g["out"]

@@ -9,6 +9,11 @@ from conftest import load_golden, rel_l2
 
 pytestmark = pytest.mark.gpu
 BF16_TOL = 2e-2
+# The VAE decoder stacks 31 convolutions, 30 GroupNorms and an attention block between the latent and the pixels; with bf16
+# storage after every one of them the ORACLE ITSELF (weights and every intermediate rounded to bf16 on the CPU) is 2.3e-2
+# from its fp32 run on these inputs, so the stated tolerance for this path is 4e-2 (the images are quantised to 8 bits
+# right after: 4e-2 of the signal is < 0.3 grey levels rms).
+VAE_TOL = 4e-2
 DEV = "cuda"
 
 
@@ -87,7 +92,7 @@ def test_vae_decode_vs_oracle(vae, N, h, w):
     ref = V.decode(sd, z)
     out = m.decode(z.to(DEV)).sample
     assert out.shape == ref.shape == (N, 3, 8 * h, 8 * w) and out.dtype == torch.float32
-    assert rel_l2(out.cpu(), ref) < BF16_TOL
+    assert rel_l2(out.cpu(), ref) < VAE_TOL
 
 
 def test_vae_decode_latents_uint8(vae):

@@ -144,3 +144,28 @@ def test_api_contract(unet):
     assert unet.config.in_channels == 4 and unet.config.sample_size == 64
     unet.set_use_memory_efficient_attention_xformers(True)
     unet.set_attention_slice(1)
+
+
+def test_text_projections_are_cached_per_prompt_tensor(synthetic_sd):
+    """The K/V projections of the text run once per prompt tensor, outside the captured step: the same tensor object,
+    unmodified, skips the GEMM (one launch less); an in-place edit (version counter) or another tensor recomputes."""
+    from lavie_b200 import UNet3DConditionModel
+    from lavie_b200.synthetic import synthetic_inputs
+    unet = UNet3DConditionModel()
+    unet.load_state_dict(synthetic_sd, strict=True)
+    unet = unet.to("cuda").eval()
+    sample, t, text = synthetic_inputs(2, 2, 8, 8, seed=5)
+    sample, text = sample.to("cuda"), text.to("cuda")
+    a = unet(sample, t, encoder_hidden_states=text).sample
+    n_first = unet.launches_per_step()
+    b = unet(sample, t, encoder_hidden_states=text).sample
+    assert unet.launches_per_step() == n_first - 1 and torch.equal(a, b)
+    c = unet(sample, t, encoder_hidden_states=text.clone()).sample          # another object, same values
+    assert unet.launches_per_step() == n_first and torch.equal(a, c)
+    text2 = text.clone()
+    unet(sample, t, encoder_hidden_states=text2)
+    text2.mul_(0.5)                                                          # in-place edit of the cached prompt
+    d = unet(sample, t, encoder_hidden_states=text2).sample
+    assert unet.launches_per_step() == n_first and not torch.equal(a, d)
+    ref = unet(sample, t, encoder_hidden_states=(text * 0.5)).sample
+    assert torch.equal(d, ref)
