@@ -781,13 +781,121 @@ def run_vsr(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------- N4: encoders
+def run_encoders(args):
+    """SURVEY 8f row N4 (python bench.py --workload encoders): the two once-per-video stages around the denoiser on ONE
+    GPU.  A step = decode_latents of one 16-frame video (latents [1,4,16,40,64] -> uint8 [1,16,320,512,3],
+    pipeline_videogen.py:422-429) + the text encoding of its [negative, positive] prompt pair (CLIP ViT-L/14 text tower,
+    [2,77] ids, pipeline_videogen.py:337-348, 395-406).  value = videos/s with the latents resident; e2e = latents and ids
+    from pinned host buffers, uint8 frames and embeddings back on the host.  CPU baseline: the oracle ports on a bounded
+    sample (2 frames for the VAE).  The VAE oracle is parity-unpinned (no diffusers offline), the CLIP oracle is pinned to
+    transformers."""
+    from lavie_b200 import ops
+    from lavie_b200.clip import SD14_TEXT, CLIPTextEncoder, clip_synthetic_state_dict
+    from lavie_b200.vae import VAEDecoder, vae_synthetic_state_dict
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1 or args.gpus != 1:
+        raise SystemExit("--workload encoders runs on one GPU (replicas only: nothing to shard in a once-per-video stage)")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    vsd, csd = vae_synthetic_state_dict(0), clip_synthetic_state_dict(SD14_TEXT, 0)
+    vae = VAEDecoder(); vae.load_state_dict(vsd, strict=True); vae = vae.to(dev).eval()
+    clip = CLIPTextEncoder(); clip.load_state_dict(csd, strict=True); clip = clip.to(dev).eval()
+    g = torch.Generator().manual_seed(6)
+    lat = 0.18215 * torch.randn(1, 4, FRAMES, LAT_H, LAT_W, generator=g)
+    ids = torch.randint(0, 49408, (2, 77), generator=g)
+    latd, idsd = lat.to(dev), ids.to(dev)
+
+    def one_step(l, i):
+        z = l.permute(0, 2, 1, 3, 4).reshape(FRAMES, 4, LAT_H, LAT_W)
+        return vae.decode(z, scale=1.0 / 0.18215, as_uint8=True), clip(i)[0]
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(latd, idsd)
+    torch.cuda.synchronize()
+    l0 = ops.LAUNCHES
+    one_step(latd, idsd)
+    per_step = ops.LAUNCHES - l0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.steps):
+            one_step(latd, idsd)
+        ev1.record()
+        torch.cuda.synchronize()
+    ms_per_step = ev0.elapsed_time(ev1) / args.steps
+    lh, ih = lat.clone().pin_memory(), ids.clone().pin_memory()
+    vid_h = torch.empty((FRAMES, 8 * LAT_H, 8 * LAT_W, 3), dtype=torch.uint8).pin_memory()
+    emb_h = torch.empty((2, 77, 768), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, e = one_step(lh.to(dev, non_blocking=True), ih.to(dev, non_blocking=True))
+        vid_h.copy_(v, non_blocking=True)
+        emb_h.copy_(e, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    ops.PROFILE = []
+    torch.cuda._sleep(100_000_000)
+    one_step(latd, idsd)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    agg = {}
+    for name, flops, nbytes, e0, e1, _tag in prof:
+        a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
+        a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += flops; a[3] += nbytes
+    total_ms = sum(a[1] for a in agg.values())
+    kernels = {k: {"launches": a[0], "ms": round(a[1], 3), "share": round(a[1] / total_ms, 4),
+                   "gflop": round(a[2] / 1e9, 1), "tflops": round(a[2] / (a[1] * 1e-3) / 1e12, 1) if a[2] else None,
+                   "gbs": round(a[3] / (a[1] * 1e-3) / 1e9, 1) if a[3] else None}
+               for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+    peaks = measured_peaks()
+    d = agg["gemm_bf16_tcgen05"]
+    achieved = d[2] / (d[1] * 1e-3) / 1e12
+    roofline = {"kernel": "gemm_bf16_tcgen05", "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None, "launches_per_step": d[0],
+                "avg_launch_ms": d[1] / d[0], "share_of_step": d[1] / total_ms,
+                "algorithmic_gflop_per_launch": d[2] / d[0] / 1e9, "peak_source": peaks["source"]}
+    parity, cpu = None, None
+    if not args.no_cpu_baseline:
+        from oracle import clip_oracle as CO, vae_oracle as VO
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        f = 2
+        t0 = time.time()
+        ref_img = VO.decode(vsd, (lat / 0.18215)[0, :, :f].permute(1, 0, 2, 3).contiguous())
+        ref_emb = CO.clip_text_forward(csd, ids, 12)
+        dt = time.time() - t0
+        z = (latd / 0.18215)[0, :, :f].permute(1, 0, 2, 3).contiguous()
+        err_v = rel_l2(vae.decode(z).sample.cpu(), ref_img)
+        err_c = rel_l2(clip(idsd)[0].cpu(), ref_emb)
+        parity = {"vae_rel_l2": err_v, "vae_tolerance": 4e-2, "clip_rel_l2": err_c, "clip_tolerance": 2e-2,
+                  "vs": "CPU oracle ports, fp32 (VAE: restatement of the diffusers decoder, parity unpinned; CLIP: pinned "
+                        "to transformers.CLIPTextModel)", "shape": [f, 4, LAT_H, LAT_W]}
+        cpu = {"value": (f / FRAMES) / dt, "unit": "videos/s", "cores": threads, "kind": "port",
+               "sample": f"VAE decode of {f} of {FRAMES} frames + the full 2-prompt text encoding = {dt:.2f} s"}
+        if not (err_v <= 4e-2 and err_c <= 2e-2):
+            raise SystemExit(f"encoder parity FAILED: vae {err_v:.3e}, clip {err_c:.3e}")
+    line = {"metric": "videos/s (VAE decode 16 x 320x512 + CLIP encode of the prompt pair)", "value": 1e3 / ms_per_step,
+            "unit": "videos/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "decode_latents [1,4,16,40,64] -> uint8 [1,16,320,512,3] + CLIP ViT-L/14 text tower on "
+                                   "[2,77] ids", "weights": "random-init (seeded), 49.5 M + 123.1 M params"},
+            "setup": {"parallelism": "single", "cuda_graph": False, "launches_per_step_per_rank": per_step},
+            "parity": parity, "clocks": clocks.summary(),
+            "e2e": {"value": args.steps / e2e_s, "unit": "videos/s", "h2d_bytes_per_step": lh.numel() * 4 + ih.numel() * 8,
+                    "d2h_bytes_per_step": vid_h.numel() + emb_h.numel() * 4},
+            "gpu_launches": per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="base", choices=["base", "interp", "vsr"],
+    ap.add_argument("--workload", default="base", choices=["base", "interp", "vsr", "encoders"],
                     help="base = BASELINE config 1-3 (the headline); interp = config 4; vsr = config 5 on one GPU")
     ap.add_argument("--vsr-frames", type=int, default=16)
     ap.add_argument("--vsr-height", type=int, default=320)
@@ -800,6 +908,8 @@ def main():
         run_interp(args)
     elif args.workload == "vsr":
         run_vsr(args)
+    elif args.workload == "encoders":
+        run_encoders(args)
     else:
         run_b200(args)
 
