@@ -93,6 +93,10 @@ SIGNATURES = {
     "lavie_softmax_rows_bf16": (c_int, [_P, c_int, c_longlong, c_int, c_float, _P]),
     "lavie_image_to_uint8": (c_int, [_P, c_int, c_longlong, _P, _P]),
     "lavie_pointwise_conv_nchw_f32": (c_int, [_P, _P, _P, c_float, c_int, c_int, c_int, c_longlong, _P, _P]),
+    "lavie_groupnorm_finalize_colsums_seg": (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
+                                                     c_float, _P, _P]),
+    "lavie_upsample_conv3x3_supported": (c_int, [c_int, c_int, c_int]),
+    "lavie_upsample_conv3x3_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, POINTER(Epilogue), c_int, _P]),
     "lavie_unpack_nchw_f32": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_upsample_nearest2x": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_cfg_ddim_step": (c_int, [_P, _P, c_float, c_float, c_float, _P, _P, c_longlong, _P]),

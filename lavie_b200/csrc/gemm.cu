@@ -62,6 +62,10 @@ struct GemmParams {
   int c_blocks;              // Cin / 64
   int out_h, out_w, conv_stride;   // im2col-mode conv (conv == 1): output geometry and stride
   int tap_rows;              // frame conv (conv == 2): rows between consecutive taps = pixels per frame
+  int phases;                // 4: nearest-2x upsample + 3x3 conv as four 2x2 "phase" convs on the LOW-resolution map
+                             // (conv == 3; item = (m, n, phase); output pixel (2y + py, 2x + px)); else 1
+  int lowres_w;              // conv == 3: W of the low-resolution map (5-D output box coordinates)
+  int slabs_total;           // conv == 3: 32-row slabs per phase (stride of the phase segments of colstats)
   // epilogue
   const float* bias;         // [N] or null
   const float* row_bias;     // [M / rows_per_batch, ld_row_bias] or null  (time embedding add, resnet.py:187-190)
@@ -174,12 +178,17 @@ __device__ __forceinline__ void epi_bar_sync() {
 }
 
 struct Item {
-  int m_blk, n_blk, kb_begin, kb_end;
+  int m_blk, n_blk, kb_begin, kb_end, phase;
 };
 __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
   Item it;
   const int split = item % p.splits;
-  const int rest = item / p.splits;
+  int rest = item / p.splits;
+  it.phase = 0;
+  if (p.phases > 1) {                        // the four phases of one tile run back to back: they read the same pixels
+    it.phase = rest % p.phases;
+    rest /= p.phases;
+  }
   it.n_blk = rest % p.n_tiles;
   it.m_blk = rest / p.n_tiles + p.m_tile0;
   it.kb_begin = split * p.kb_per_split;
@@ -190,6 +199,7 @@ __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_a3,
                   const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
                   const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
   pdl_launch_dependents();
@@ -217,11 +227,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  const int num_items = p.m_tiles * p.n_tiles * p.splits;
+  const int num_items = p.m_tiles * p.n_tiles * p.splits * p.phases;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a0);
     tma_prefetch_desc(&tmap_a1);
+    if (p.phases > 1) {
+      tma_prefetch_desc(&tmap_a2);
+      tma_prefetch_desc(&tmap_a3);
+    }
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_out);
     tma_prefetch_desc(&tmap_res);
@@ -272,7 +286,22 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
             if (rank == 0) mbar_arrive(&full_bar[stage]);
           } else {
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);   // bytes landing in both CTAs
-            if (p.conv == 2) {
+            if (p.conv == 3) {
+              // nearest-2x upsample + 3x3 conv == four 2x2 convs on the low-resolution map, one per output-pixel parity
+              // (py, px): taps (a, b) read source pixel (y + py - 1 + a, x + px - 1 + b); the tap weights were summed on
+              // the host.  One im2col request per (tap, 64 channels) like the 3x3 mode; the bounding-box corners differ
+              // per phase, hence one tensor map per phase.
+              const int tap = kb / p.c_blocks;
+              const int c0 = (kb - tap * p.c_blocks) * BLOCK_K;
+              const int m0 = m_cta * BLOCK_M;
+              const int img = m0 / (p.out_h * p.out_w);
+              const int rem = m0 - img * (p.out_h * p.out_w);
+              const int oy = rem / p.out_w, ox = rem - oy * p.out_w;
+              const int px = it.phase & 1, py = it.phase >> 1;
+              const CUtensorMap* am = it.phase == 0 ? &tmap_a0 : it.phase == 1 ? &tmap_a1 : it.phase == 2 ? &tmap_a2 : &tmap_a3;
+              tma2_load_im2col(a_dst, am, full_leader, c0, ox + px - 1, oy + py - 1, img, static_cast<uint16_t>(tap & 1),
+                               static_cast<uint16_t>(tap >> 1));
+            } else if (p.conv == 2) {
               // (k,1,1) conv over frames on a frame-padded map: tap t of output row m is input row m + t * tap_rows
               const int tap = kb / p.c_blocks;
               tma2_load_2d(a_dst, &tmap_a0, full_leader, (kb - tap * p.c_blocks) * BLOCK_K,
@@ -295,7 +324,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
 #pragma unroll
             for (int h = 0; h < L::N_MMA; ++h)       // this CTA's half of each MMA's weight rows
               tma2_load_2d(b_dst + h * L::B_HALF_BYTES, &tmap_b, full_leader, kb * BLOCK_K,
-                           it.n_blk * BLOCK_N + h * L::UMMA_N + static_cast<int>(rank) * (L::UMMA_N / 2));
+                           it.phase * p.N + it.n_blk * BLOCK_N + h * L::UMMA_N + static_cast<int>(rank) * (L::UMMA_N / 2));
           }
         }
         __syncwarp();
@@ -427,10 +456,20 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && !(p.debug & 16)) {
-          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                           reinterpret_cast<uint64_t>(&tmap_out)),
-                       "r"(smem_u32(my_stage + k * EPI_CHUNK_BYTES)), "r"(col_out0), "r"(wrow0)
-                       : "memory");
+          if (p.phases > 1) {
+            // output pixel (2y + py, 2x + px) of the high-resolution map: 5-D box (c, px, x, py, n*H + y)
+            const int ny0 = wrow0 / p.lowres_w, x0 = wrow0 - ny0 * p.lowres_w;
+            asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmap_out)),
+                         "r"(smem_u32(my_stage + k * EPI_CHUNK_BYTES)), "r"(col_out0), "r"(it.phase & 1), "r"(x0),
+                         "r"(it.phase >> 1), "r"(ny0)
+                         : "memory");
+          } else {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmap_out)),
+                         "r"(smem_u32(my_stage + k * EPI_CHUNK_BYTES)), "r"(col_out0), "r"(wrow0)
+                         : "memory");
+          }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       };
@@ -479,8 +518,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
           const int dec_next = __shfl_down_sync(0xffffffffu, dec, 1);
           const bool last_of_piece = (c2 == 15) || (dec_next != dec) || (col + 2 >= p.N);
           if (par == 0 && last_of_piece && col < p.N)
-            *reinterpret_cast<float2*>(p.colstats + ((static_cast<size_t>(wrow0 >> 5) * (p.N >> 5) + (col_out0 >> 5)) * 4 +
-                                                     (dec - dec0)) * 2) = make_float2(s0, q0);
+            *reinterpret_cast<float2*>(p.colstats + ((static_cast<size_t>(it.phase * p.slabs_total + (wrow0 >> 5)) * (p.N >> 5) +
+                                                      (col_out0 >> 5)) * 4 + (dec - dec0)) * 2) = make_float2(s0, q0);
         }
       };
 
@@ -747,17 +786,17 @@ splitk_reduce_check_kernel(const float* __restrict__ partial, int splits, int M,
 }
 
 template <int BLOCK_N>
-int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& mo,
-                const CUtensorMap& mr, const GemmParams& p,
+int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& a3,
+                const CUtensorMap& b, const CUtensorMap& mo, const CUtensorMap& mr, const GemmParams& p,
                 int num_sms, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N>;
   static LavieSmemConfig configured;
   int rc = lavie_config_smem(gemm_bf16_tcgen05<BLOCK_N>, L::TOTAL, &configured, "gemm_bf16_tcgen05");
   if (rc) return rc;
-  const int items = p.m_tiles * p.n_tiles * p.splits;
+  const int items = p.m_tiles * p.n_tiles * p.splits * p.phases;
   int pairs = num_sms / 2;
   if (items < pairs) pairs = items;
-  launch_pdl(gemm_bf16_tcgen05<BLOCK_N>, 2 * pairs, NUM_THREADS, L::TOTAL, stream, a0, a1, b, mo, mr, p);
+  launch_pdl(gemm_bf16_tcgen05<BLOCK_N>, 2 * pairs, NUM_THREADS, L::TOTAL, stream, a0, a1, a2, a3, b, mo, mr, p);
   rc = lavie_check_launch("gemm_bf16_tcgen05");
   if (rc) return rc;
   if (p.check) {
@@ -843,14 +882,15 @@ double best_split(int m_tiles, int n_tiles, int bn, int num_k_blocks, int max_sp
 // Tile shape / split-K / tail choice.  Per K block a CTA pays the larger of the MMA time (2*bn cycles) and the L2
 // feed time of its stage bytes.  A launch whose last wave is mostly empty can instead run as two launches: full waves
 // over the leading tile rows, then the remaining rows split along K so that they fill the machine once more.
-Plan make_plan(int M, int N, int num_k_blocks, int forced_bn, bool geglu, bool conv, size_t ws_bytes) {
+Plan make_plan(int M, int N, int num_k_blocks, int forced_bn, bool geglu, bool conv, size_t ws_bytes,
+               bool no_split = false) {
   const int pairs = num_sms() / 2;
   const int m_tiles = (M + PAIR_M - 1) / PAIR_M;
   const int cands[6] = {320, 256, 192, 160, 128, 64};
   Plan best{128, 1, num_k_blocks, 0, 1, num_k_blocks};
   double best_cost = 1e30;
-  const int max_splits = geglu ? 1 : 16;
-  const int forced_s = geglu ? 0 : g_force_splits;
+  const int max_splits = (geglu || no_split) ? 1 : 16;
+  const int forced_s = (geglu || no_split) ? 0 : g_force_splits;
   for (int i = 0; i < 6; ++i) {
     const int bn = cands[i];
     if (forced_bn && bn != forced_bn) continue;
@@ -869,7 +909,7 @@ Plan make_plan(int M, int N, int num_k_blocks, int forced_bn, bool geglu, bool c
     }
     // main window (no split) + split-K tail; only when the single launch needs more than one wave
     const long tiles = static_cast<long>(m_tiles) * n_tiles;
-    if (geglu || forced_s || g_no_tail || tiles <= pairs || num_k_blocks < 16) continue;
+    if (geglu || no_split || forced_s || g_no_tail || tiles <= pairs || num_k_blocks < 16) continue;
     for (int tail = 1; tail < m_tiles && tail <= 16; ++tail) {
       const int main_tiles = m_tiles - tail;
       const long main_items = static_cast<long>(main_tiles) * n_tiles;
@@ -903,32 +943,45 @@ int make_epilogue_maps(const GemmParams& p, CUtensorMap* mo, CUtensorMap* mr) {
   return LAVIE_OK;
 }
 
-int launch_window(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& mo,
-                  const CUtensorMap& mr, const GemmParams& p, cudaStream_t stream) {
+int launch_window(int bn, const CUtensorMap* a, const CUtensorMap& b, const CUtensorMap& mo, const CUtensorMap& mr,
+                  const GemmParams& p, cudaStream_t stream) {
   switch (bn) {
-    case 64: return launch_gemm<64>(a0, a1, b, mo, mr, p, num_sms(), stream);
-    case 128: return launch_gemm<128>(a0, a1, b, mo, mr, p, num_sms(), stream);
-    case 160: return launch_gemm<160>(a0, a1, b, mo, mr, p, num_sms(), stream);
-    case 192: return launch_gemm<192>(a0, a1, b, mo, mr, p, num_sms(), stream);
-    case 256: return launch_gemm<256>(a0, a1, b, mo, mr, p, num_sms(), stream);
-    case 320: return launch_gemm<320>(a0, a1, b, mo, mr, p, num_sms(), stream);
+    case 64: return launch_gemm<64>(a[0], a[1], a[2], a[3], b, mo, mr, p, num_sms(), stream);
+    case 128: return launch_gemm<128>(a[0], a[1], a[2], a[3], b, mo, mr, p, num_sms(), stream);
+    case 160: return launch_gemm<160>(a[0], a[1], a[2], a[3], b, mo, mr, p, num_sms(), stream);
+    case 192: return launch_gemm<192>(a[0], a[1], a[2], a[3], b, mo, mr, p, num_sms(), stream);
+    case 256: return launch_gemm<256>(a[0], a[1], a[2], a[3], b, mo, mr, p, num_sms(), stream);
+    case 320: return launch_gemm<320>(a[0], a[1], a[2], a[3], b, mo, mr, p, num_sms(), stream);
     default: lavie_set_error("unsupported BLOCK_N %d", bn); return LAVIE_ERR_SHAPE;
   }
 }
 
 void set_window(GemmParams& p, int m_tile0, int m_tiles, int splits, int kbps);
 
-int dispatch(const Plan& plan, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, GemmParams& p,
-             cudaStream_t stream) {
+int make_phase_output_map(const GemmParams& p, CUtensorMap* mo);
+
+int dispatch_maps(const Plan& plan, const CUtensorMap* a, const CUtensorMap& b, GemmParams& p, cudaStream_t stream) {
   CUtensorMap mo, mr;
-  int rc = make_epilogue_maps(p, &mo, &mr);
+  int rc;
+  if (p.phases > 1) {
+    rc = make_phase_output_map(p, &mo);
+    mr = mo;
+  } else {
+    rc = make_epilogue_maps(p, &mo, &mr);
+  }
   if (rc) return rc;
   const int m_tiles = (p.M + PAIR_M - 1) / PAIR_M;
   set_window(p, 0, m_tiles - plan.tail_tiles, plan.splits, plan.kb_per_split);
-  rc = launch_window(plan.bn, a0, a1, b, mo, mr, p, stream);
+  rc = launch_window(plan.bn, a, b, mo, mr, p, stream);
   if (rc || plan.tail_tiles == 0) return rc;
   set_window(p, m_tiles - plan.tail_tiles, plan.tail_tiles, plan.tail_splits, plan.tail_kb_per_split);
-  return launch_window(plan.bn, a0, a1, b, mo, mr, p, stream);
+  return launch_window(plan.bn, a, b, mo, mr, p, stream);
+}
+
+int dispatch(const Plan& plan, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, GemmParams& p,
+             cudaStream_t stream) {
+  const CUtensorMap a[4] = {a0, a1, a0, a0};
+  return dispatch_maps(plan, a, b, p, stream);
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -972,6 +1025,7 @@ int fill_epilogue(GemmParams& p, const lavie_epilogue* ep, int N, void* out, int
 }
 
 void apply_plan(GemmParams& p, const Plan& plan, void* workspace) {
+  if (p.phases < 1) p.phases = 1;
   p.n_tiles = (p.N + plan.bn - 1) / plan.bn;
   p.partial = static_cast<float*>(workspace);
   p.debug = g_debug;
@@ -1125,6 +1179,69 @@ extern "C" int lavie_frame_conv_bf16(const void* x, int ldx, long long rows_in, 
                                      int block_n, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   return frame_conv_impl(x, ldx, rows_in, C, taps, tap_rows, w, out, ldo, M, N, ep, block_n, workspace, workspace_bytes,
                          stream);
+}
+
+namespace {
+// 5-D view of the contiguous high-resolution output [NF, 2H, 2W, N]: (c, px, x, py, n*H + y); one epilogue chunk = 32
+// consecutive low-resolution pixels x 32 channels = a box of (32 / by) x by pixels of one phase.
+int make_phase_output_map(const GemmParams& p, CUtensorMap* mo) {
+  const int W = p.lowres_w;
+  const uint32_t bx = W >= 32 ? 32u : static_cast<uint32_t>(W);
+  const uint32_t by = 32u / bx;
+  const uint64_t N = static_cast<uint64_t>(p.N);
+  const uint64_t dims[5] = {N, 2, static_cast<uint64_t>(W), 2, static_cast<uint64_t>(p.M / W)};
+  const uint64_t strides[4] = {N * 2, 2 * N * 2, 2 * static_cast<uint64_t>(W) * N * 2, 4 * static_cast<uint64_t>(W) * N * 2};
+  const uint32_t box[5] = {32, 1, bx, 1, by};
+  return lavie_make_tmap(mo, p.out, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+}  // namespace
+
+extern "C" int lavie_upsample_conv3x3_supported(int H, int W, int C) {
+  (void)H;
+  return (C % BLOCK_K == 0 && W > 0 && (W % 32 == 0 || 32 % W == 0)) ? 1 : 0;
+}
+
+extern "C" int lavie_upsample_conv3x3_bf16(const void* x, int NF, int H, int W, int C, const void* w_phases, void* out,
+                                           int N, const lavie_epilogue* ep, int block_n, cudaStream_t stream) {
+  LAVIE_REQUIRE(lavie_upsample_conv3x3_supported(H, W, C), LAVIE_ERR_SHAPE,
+                "upsample_conv3x3: C=%d must be a multiple of 64 and W=%d a divisor or a multiple of 32", C, W);
+  LAVIE_REQUIRE(N % 8 == 0 && aligned16(x) && aligned16(w_phases) && aligned16(out), LAVIE_ERR_ALIGN,
+                "upsample_conv3x3: alignment");
+  LAVIE_REQUIRE(!(ep && (ep->geglu || ep->residual || ep->row_bias)), LAVIE_ERR_SHAPE,
+                "upsample_conv3x3: only bias and col_stats are supported in the epilogue");
+  const int M = NF * H * W;                       // low-resolution pixels; every one produces 2 x 2 output pixels
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = 4 * C;
+  p.num_k_blocks = 4 * (C / BLOCK_K);
+  p.k_split_blocks = p.num_k_blocks;
+  p.c_blocks = C / BLOCK_K;
+  p.out_h = H; p.out_w = W; p.conv_stride = 1;
+  p.conv = 3;
+  p.phases = 4;
+  p.lowres_w = W;
+  p.slabs_total = (M + 31) / 32;
+  p.check = 0;
+  // the four phases multiply the work items: plan as if M were 4x as tall; no split-K (the partial planes are per phase)
+  const Plan plan = make_plan(4 * M, N, p.num_k_blocks, block_n, false, true, 0, true);
+  apply_plan(p, plan, nullptr);
+  int rc = fill_epilogue(p, ep, N, out, N);
+  if (rc) return rc;
+  CUtensorMap ma[4], mb;
+  for (int ph = 0; ph < 4; ++ph) {
+    rc = lavie_make_tmap_im2col(&ma[ph], x, NF, H, W, C, BLOCK_K, BLOCK_M, 1, (ph & 1) - 1, (ph >> 1) - 1);
+    if (rc) return rc;
+  }
+  // weights [4 phases * N, 4 * C]: phase-major rows, K ordered (a, b, c)
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(4 * C), static_cast<uint64_t>(4) * N};
+    const uint64_t strides[1] = {static_cast<uint64_t>(4 * C) * 2};
+    const uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>((plan.bn > 256 ? plan.bn / 2 : plan.bn) / 2)};
+    rc = lavie_make_tmap(&mb, w_phases, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  Plan single = plan;
+  single.splits = 1; single.kb_per_split = p.num_k_blocks; single.tail_tiles = 0;
+  return dispatch_maps(single, ma, mb, p, stream);
 }
 
 extern "C" int lavie_conv3x3_supported(int H, int W, int C) {

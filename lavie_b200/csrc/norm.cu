@@ -659,7 +659,7 @@ namespace {
 // (sum, sumsq) per (sample, group) (frame-sharded exchange).
 __global__ void __launch_bounds__(256)
 gn_colsums_kernel(const float* __restrict__ cs0, int c0, const float* __restrict__ cs1, int c1, int slabs_per_sample,
-                  int groups, int mg, double inv_count, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  int groups, int mg, int segs0, int segs1, double inv_count, const float* __restrict__ gamma, const float* __restrict__ beta,
                   float eps, float* __restrict__ scale_shift, double* __restrict__ sums) {
   pdl_prologue();
   const int g = blockIdx.x, sample = blockIdx.y;
@@ -670,14 +670,25 @@ gn_colsums_kernel(const float* __restrict__ cs0, int c0, const float* __restrict
   double a = 0.0, b = 0.0;
   auto load = [&](long long i) -> float2 {
     if (i >= total) return make_float2(0.f, 0.f);
-    const long long slab = static_cast<long long>(sample) * slabs_per_sample + i / decs;
+    const long long sl = i / decs;                             // slab of this sample, in row order
     int ch = ch0 + static_cast<int>(i % decs) * mg;            // first channel of the micro-group in the concat
     const float* cs = cs0;
-    int cn = c0;
+    int cn = c0, segs = segs0;
     if (ch >= c0) {
       ch -= c0;
       cs = cs1;
       cn = c1;
+      segs = segs1;
+    }
+    // a source written by the fused upsample conv (gemm.cu conv == 3) keeps its slabs in `segs` = 4 phase segments, each
+    // holding 1 / segs of every sample's slabs; any order works for a sum as long as it is fixed
+    long long slab;
+    if (segs > 1) {
+      const long long sps = slabs_per_sample / segs;
+      const long long seg = sl / sps;
+      slab = seg * (static_cast<long long>(gridDim.y) * sps) + static_cast<long long>(sample) * sps + (sl - seg * sps);
+    } else {
+      slab = static_cast<long long>(sample) * slabs_per_sample + sl;
     }
     const int dec = ch / mg;
     const int k_lo = ch >> 5, k_hi = (ch + mg - 1) >> 5;       // the chunk(s) the micro-group touches
@@ -732,8 +743,11 @@ gn_colsums_kernel(const float* __restrict__ cs0, int c0, const float* __restrict
 
 int colsums_impl(const float* cs0, int c0, const float* cs1, int c1, int samples, int rows_per_sample, int groups,
                  const float* gamma, const float* beta, float eps, float* scale_shift, double* sums,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, int segs0 = 1, int segs1 = 1) {
   const int C = c0 + c1;
+  LAVIE_REQUIRE(segs0 >= 1 && segs1 >= 1 && (rows_per_sample / 32) % segs0 == 0 && (rows_per_sample / 32) % segs1 == 0,
+                LAVIE_ERR_SHAPE, "groupnorm colsums: %d slabs per sample do not split into %d / %d phase segments",
+                rows_per_sample / 32, segs0, segs1);
   LAVIE_REQUIRE(samples > 0 && rows_per_sample > 0 && rows_per_sample % 32 == 0 && groups > 0 && C % groups == 0 &&
                     c0 > 0 && c0 % 32 == 0 && c1 % 32 == 0, LAVIE_ERR_SHAPE,
                 "groupnorm colsums: rows_per_sample=%d must be a multiple of 32, C=%d %% groups=%d == 0, sources multiples "
@@ -745,7 +759,7 @@ int colsums_impl(const float* cs0, int c0, const float* cs1, int c1, int samples
                 c1, C / groups);
   LAVIE_REQUIRE(cs0 != nullptr && (c1 == 0 || cs1 != nullptr), LAVIE_ERR_SHAPE, "groupnorm colsums: null statistics");
   dim3 grid(groups, samples);
-  launch_pdl(gn_colsums_kernel, grid, 256, 0, stream, cs0, c0, cs1, c1, rows_per_sample / 32, groups, mg,
+  launch_pdl(gn_colsums_kernel, grid, 256, 0, stream, cs0, c0, cs1, c1, rows_per_sample / 32, groups, mg, segs0, segs1,
              1.0 / (static_cast<double>(rows_per_sample) * (C / groups)), gamma, beta, eps, scale_shift, sums);
   return lavie_check_launch("gn_colsums_kernel");
 }
@@ -756,6 +770,15 @@ extern "C" int lavie_groupnorm_finalize_colsums(const float* cs0, int c0, const 
                                                 float eps, float* scale_shift, cudaStream_t stream) {
   LAVIE_REQUIRE(scale_shift != nullptr && gamma != nullptr && beta != nullptr, LAVIE_ERR_SHAPE, "groupnorm colsums: null");
   return colsums_impl(cs0, c0, cs1, c1, samples, rows_per_sample, groups, gamma, beta, eps, scale_shift, nullptr, stream);
+}
+
+extern "C" int lavie_groupnorm_finalize_colsums_seg(const float* cs0, int c0, int segs0, const float* cs1, int c1,
+                                                    int segs1, int samples, int rows_per_sample, int groups,
+                                                    const float* gamma, const float* beta, float eps, float* scale_shift,
+                                                    cudaStream_t stream) {
+  LAVIE_REQUIRE(scale_shift != nullptr && gamma != nullptr && beta != nullptr, LAVIE_ERR_SHAPE, "groupnorm colsums: null");
+  return colsums_impl(cs0, c0, cs1, c1, samples, rows_per_sample, groups, gamma, beta, eps, scale_shift, nullptr, stream,
+                      segs0, segs1 > 0 ? segs1 : 1);
 }
 
 extern "C" int lavie_groupnorm_reduce_colsums(const float* cs0, int c0, const float* cs1, int c1, int samples,

@@ -258,6 +258,37 @@ def embedding_add(emb: torch.Tensor, table: torch.Tensor, labels: torch.Tensor):
     return emb
 
 
+def upsample_conv3x3_supported(H: int, W: int, C: int) -> bool:
+    return bool(_lib.load().lavie_upsample_conv3x3_supported(H, W, C))
+
+
+def upsample_conv3x3(x: torch.Tensor, NF: int, H: int, W: int, w_phases: torch.Tensor, *, bias=None,
+                     stats: bool = False, block_n: int = 0):
+    """Upsample3D (nearest x2 in H and W, then 3x3 conv; resnet.py:44-76) without the upsampled copy: four 2x2 phase
+    convs on the low-resolution map x [NF*H*W, C]; w_phases from packing.pack_upsample_conv3x3.  Returns the
+    high-resolution map [NF*2H*2W, N]."""
+    lib = _lib.load()
+    rows, C, ld = _rows2d(x)
+    assert rows == NF * H * W and ld == C, "upsample_conv3x3 needs a contiguous channels-last input"
+    N = w_phases.shape[0] // 4
+    assert w_phases.dtype == BF16 and w_phases.is_contiguous() and tuple(w_phases.shape) == (4 * N, 4 * C)
+    out = torch.empty((4 * rows, N), dtype=BF16, device=x.device)
+    cs = None
+    if stats and FUSE_GN_STATS and N % 32 == 0 and rows % 32 == 0:
+        cs = torch.empty((4 * (rows // 32), N // 32, 4, 2), dtype=F32, device=x.device)     # 4 phase segments
+    ep = _epilogue(bias, None, 1, None, False, cs)
+    # algorithmic work = the reference's op: a 3x3 conv on the 4x map
+    with _Launch("gemm_bf16_tcgen05", 2.0 * 4 * rows * N * 9 * C, 2.0 * (rows * C + N * 9 * C + 4 * rows * N),
+                 f"upsample_conv3x3 M={4 * rows} N={N} K={9 * C} W={2 * W} (16 tap-GEMMs on the low-res map)"):
+        rc = lib.lavie_upsample_conv3x3_bf16(x.data_ptr(), NF, H, W, C, w_phases.data_ptr(), out.data_ptr(), N,
+                                             ctypes.byref(ep) if ep is not None else None, block_n, _stream())
+    check(rc, "lavie_upsample_conv3x3_bf16")
+    if cs is not None:
+        out._gn_colsums = cs
+        out._gn_segs = 4
+    return out
+
+
 def _new_colsums(M: int, N: int, device) -> Optional[torch.Tensor]:
     """[slabs of 32 rows, 32-column chunks, 4 decade pieces, (sum, sumsq)] -- see lavie_epilogue.col_stats."""
     if N % 32:
@@ -265,15 +296,20 @@ def _new_colsums(M: int, N: int, device) -> Optional[torch.Tensor]:
     return torch.empty(((M + 31) // 32, N // 32, 4, 2), dtype=F32, device=device)
 
 
-def colsums(x: torch.Tensor, rows_per_sample: int, x2: Optional[torch.Tensor] = None):
+def colsums(x: torch.Tensor, rows_per_sample: int, x2: Optional[torch.Tensor] = None, allow_segments: bool = False):
     """The producers' column statistics of (x, x2) when every source carries them and slabs do not straddle samples;
-    else None (the caller runs the stand-alone statistics pass)."""
+    else None (the caller runs the stand-alone statistics pass).  Statistics written by the fused upsample conv come in
+    4 phase segments (`_gn_segs`); only callers that can fold those (allow_segments) get them."""
     if rows_per_sample % 32:
         return None
     cs0 = getattr(x, "_gn_colsums", None)
     cs1 = getattr(x2, "_gn_colsums", None) if x2 is not None else None
     if cs0 is None or (x2 is not None and cs1 is None):
         return None
+    for t in (x, x2):
+        segs = getattr(t, "_gn_segs", 1) if t is not None else 1
+        if segs > 1 and (not allow_segments or (rows_per_sample // 32) % segs):
+            return None
     # micro-group width the producers used: 10 channels when their N is a multiple of 10 (base / interpolation model),
     # else 8 (VSR model); all sources and the consumer's 32 groups must agree on it
     c0 = x.shape[1]
@@ -299,14 +335,16 @@ def groupnorm_scale_shift(x: torch.Tensor, samples: int, rows_per_sample: int, g
     C = c0 + c1
     ss = torch.empty((samples, C, 2), dtype=F32, device=x.device)
     assert gamma.dtype == F32 and beta.dtype == F32 and gamma.numel() == C
-    cs = colsums(x, rows_per_sample, x2) if fused else None
+    cs = colsums(x, rows_per_sample, x2, allow_segments=True) if fused else None
     if cs is not None:
         # the statistics pass already happened in the producers' epilogues: fold their column sums (one small launch)
+        s0 = getattr(x, "_gn_segs", 1)
+        s1 = getattr(x2, "_gn_segs", 1) if x2 is not None else 1
         with _Launch("lavie_groupnorm_finalize_colsums", 0.0, 1.0 * (rows // 32) * C,
                      f"gn_colsums rows={rows} C={C} samples={samples}"):
-            check(lib.lavie_groupnorm_finalize_colsums(cs[0].data_ptr(), c0, _ptr(cs[1]), c1, samples, rows_per_sample,
-                                                       groups, gamma.data_ptr(), beta.data_ptr(), eps, ss.data_ptr(),
-                                                       _stream()), "lavie_groupnorm_finalize_colsums")
+            check(lib.lavie_groupnorm_finalize_colsums_seg(cs[0].data_ptr(), c0, s0, _ptr(cs[1]), c1, s1, samples,
+                                                           rows_per_sample, groups, gamma.data_ptr(), beta.data_ptr(), eps,
+                                                           ss.data_ptr(), _stream()), "lavie_groupnorm_finalize_colsums_seg")
         return ss
     chunks = lib.lavie_groupnorm_chunks(samples, rows_per_sample)
     partial = torch.empty((samples, chunks, groups, 2), dtype=F32, device=x.device)

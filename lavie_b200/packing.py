@@ -78,3 +78,26 @@ def rel_pos_bias_table(emb: torch.Tensor, frames: int, num_buckets: int = 32, ma
     large = torch.minimum(large, torch.full_like(large, half - 1))
     bucket = ret + torch.where(n < max_exact, n, large)
     return emb.float()[bucket].permute(2, 0, 1).contiguous()
+
+
+def pack_upsample_conv3x3(w: torch.Tensor, dtype=BF16) -> torch.Tensor:
+    """Upsample3D's conv [Cout, Cin, 3, 3] -> [4*Cout, 4*Cin] for lavie_upsample_conv3x3_bf16: rows phase (py*2+px)-major,
+    K ordered (a, b, cin).  A 3x3 conv on the nearest-2x upsampled map is, per output parity, a 2x2 conv on the source map:
+    upsampled row 2y + py + kh - 1 is source row y + floor((py + kh - 1) / 2), so the taps that land on the same source
+    pixel are summed (in fp32, before rounding)."""
+    co, ci, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    taps = {0: ([0], [1, 2]), 1: ([0, 1], [2])}          # parity -> (original taps of a = 0, of a = 1)
+    wf = w.float()
+    out = torch.empty((2, 2, co, 2, 2, ci), dtype=torch.float32, device=w.device)
+    for py in range(2):
+        for px in range(2):
+            for a in range(2):
+                for b in range(2):
+                    acc = 0
+                    for r in taps[py][a]:
+                        for c in taps[px][b]:
+                            acc = acc + wf[:, :, r, c]
+                    out[py, px, :, a, b, :] = acc
+    out = out.reshape(4 * co, 4 * ci)
+    return (out if dtype is None else out.to(dtype)).contiguous()

@@ -19,7 +19,7 @@ import torch
 from torch import nn
 
 from . import _lib, ops
-from .packing import pack_conv1x1, pack_conv3x3
+from .packing import pack_conv1x1, pack_conv3x3, pack_upsample_conv3x3
 from .synthetic import _gen
 
 BF16 = torch.bfloat16
@@ -157,7 +157,7 @@ class VAEDecoder(nn.Module):
                 P[p] = r
             if key.endswith(".upsamplers.0.conv.weight"):
                 p = key[: -len(".weight")]
-                P[p] = (b16(pack_conv3x3(sd[key], dtype=None)), f32(f"{p}.bias"))
+                P[p] = (b16(pack_conv3x3(sd[key], dtype=None)), f32(f"{p}.bias"), pack_upsample_conv3x3(sd[key]).to(dev))
         a = "decoder.mid_block.attentions.0"
         C = 512
         s = C ** -0.5                                   # folded into the query projection: scores leave the GEMM scaled
@@ -232,10 +232,14 @@ class VAEDecoder(nn.Module):
             for j in range(3):
                 x = self._resnet(f"decoder.up_blocks.{i}.resnets.{j}", x, N, H, W)
             if i != len(UP_CHANNELS) - 1:
-                wu, bu = P[f"decoder.up_blocks.{i}.upsamplers.0.conv"]
-                x = ops.upsample_nearest2x(x, N, H, W)
-                H, W = 2 * H, 2 * W
-                x = ops.conv3x3(x, N, H, W, wu, bias=bu, stats=True)
+                wu, bu, w4 = P[f"decoder.up_blocks.{i}.upsamplers.0.conv"]
+                if ops.upsample_conv3x3_supported(H, W, x.shape[1]):          # Upsample2D without the 4x copy
+                    x = ops.upsample_conv3x3(x, N, H, W, w4, bias=bu, stats=True)
+                    H, W = 2 * H, 2 * W
+                else:
+                    x = ops.upsample_nearest2x(x, N, H, W)
+                    H, W = 2 * H, 2 * W
+                    x = ops.conv3x3(x, N, H, W, wu, bias=bu, stats=True)
         ss = ops.groupnorm_scale_shift(x, N, H * W, P["norm_out"][0], P["norm_out"][1], 1e-6)
         if as_uint8:
             hact = ops.groupnorm_apply(x, ss, N, H * W, True)

@@ -23,7 +23,7 @@ import torch
 
 from . import ops
 from .config import VSR_CONFIG, UNetConfig, param_spec
-from .packing import head_pitch, interleave_geglu, pack_conv1x1, pack_conv3x3, pad_heads
+from .packing import head_pitch, interleave_geglu, pack_conv1x1, pack_conv3x3, pack_upsample_conv3x3, pad_heads
 from .unet import BF16, F32, UNet3DConditionModel, UNet3DConditionOutput
 
 
@@ -154,6 +154,8 @@ class UNet3DVSRModel(UNet3DConditionModel):
             for side, name in (("down_blocks", "downsamplers"), ("up_blocks", "upsamplers")):
                 q = f"{side}.{i}.{name}.0.conv"
                 P[q] = (b16(pack_conv3x3(sd[f"{q}.weight"], dtype=None)), f32(f"{q}.bias"))
+                if name == "upsamplers":
+                    P[f"{q}4"] = pack_upsample_conv3x3(sd[f"{q}.weight"]).to(dev)
         boc0 = self.cfg.block_out_channels[0]
         P["conv_in"] = (f32("conv_in.weight"), f32("conv_in.bias"))
         co = sd["conv_out.weight"].shape[0]
@@ -318,10 +320,8 @@ class UNet3DVSRModel(UNet3DConditionModel):
                 if kind == "CrossAttnUpBlock3D":
                     x = self._transformer_vsr(f"up_blocks.{i}.attentions.{j}", x, kv_all, B, Fr, h, w, text_len)
             if i != n_levels - 1:
-                wu, bu = P[f"up_blocks.{i}.upsamplers.0.conv"]
-                x = ops.upsample_nearest2x(x, B * Fr, h, w)
+                x = self._upsample(f"up_blocks.{i}.upsamplers.0", x, B * Fr, h, w)
                 h, w = 2 * h, 2 * w
-                x = ops.conv3x3(x, B * Fr, h, w, wu, bias=bu, stats=True)
             x = self._temporal_module(f"up_temporal_blocks.{i}", x, temb_all, B, Fr, h, w)
         ss = ops.groupnorm_scale_shift(x, B, Fr * h * w, P["norm_out"][0], P["norm_out"][1], cfg.norm_eps)
         wp, bp, co = P["conv_out_tc"]

@@ -532,6 +532,32 @@ def test_column_sums_with_octet_micro_groups(M, N, K, splits):
         assert rel_l2(ss, ss_ref) < 1e-5
 
 
+@pytest.mark.parametrize("NF,H,W,C,N", [(2, 5, 8, 128, 128), (3, 10, 16, 64, 320), (2, 20, 32, 640, 640), (1, 8, 64, 64, 256),
+                                         (4, 4, 4, 128, 72), (1, 3, 2, 64, 64)])
+def test_upsample_conv3x3_phase_convs(NF, H, W, C, N):
+    """Upsample3D without the 4x copy: four 2x2 phase convs on the low-resolution map == nearest x2 + 3x3 conv (incl.
+    borders, tile tails across images, N tails), and the statistics it emits (4 phase segments) feed the next GroupNorm
+    like a stand-alone pass."""
+    ops = _ops()
+    from lavie_b200.packing import pack_upsample_conv3x3
+    assert ops.upsample_conv3x3_supported(H, W, C)
+    x = _bf(_rand(NF * H * W, C))
+    w = _rand(N, C, 3, 3, scale=(9 * C) ** -0.5)
+    bias = _rand(N, seed=2)
+    y = ops.upsample_conv3x3(x, NF, H, W, pack_upsample_conv3x3(w).to(DEV), bias=bias, stats=True)
+    up = F.interpolate(x.float().reshape(NF, H, W, C).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, _bf(w).float(), bias, padding=1).permute(0, 2, 3, 1).reshape(NF * 4 * H * W, N)
+    assert y.shape == ref.shape
+    assert rel_l2(y.float(), ref) < 6e-3                      # tap sums are rounded to bf16 once more than the taps
+    rows = NF * 4 * H * W
+    gamma, beta = _rand(N, seed=4) * 0.1 + 1, _rand(N, seed=5) * 0.1
+    for samples in (1, NF):                                   # 5-D statistics and per-frame statistics
+        ss = ops.groupnorm_scale_shift(y, samples, rows // samples, gamma, beta, 1e-5)      # phase-segment sums if usable
+        ss_ref = ops.groupnorm_scale_shift(y.clone(), samples, rows // samples, gamma, beta, 1e-5)   # stand-alone pass
+        assert rel_l2(ss, ss_ref) < 1e-5
+    assert not ops.upsample_conv3x3_supported(5, 24, 64) and not ops.upsample_conv3x3_supported(5, 8, 40)
+
+
 def test_out_of_bounds_canaries():
     """compute-sanitizer is closed on this GPU pool (profiles/r2_compute_sanitizer_closed.txt), so the memory-safety
     evidence is canaries: every output lives inside a larger poisoned allocation and the bytes around it must survive
