@@ -551,7 +551,7 @@ def test_upsample_conv3x3_phase_convs(NF, H, W, C, N):
     assert rel_l2(y.float(), ref) < 6e-3                      # tap sums are rounded to bf16 once more than the taps
     rows = NF * 4 * H * W
     gamma, beta = _rand(N, seed=4) * 0.1 + 1, _rand(N, seed=5) * 0.1
-    for samples in (1, NF):                                   # 5-D statistics and per-frame statistics
+    for samples in ((1, NF) if N % 32 == 0 else ()):          # 5-D statistics and per-frame statistics (32 groups)
         ss = ops.groupnorm_scale_shift(y, samples, rows // samples, gamma, beta, 1e-5)      # phase-segment sums if usable
         ss_ref = ops.groupnorm_scale_shift(y.clone(), samples, rows // samples, gamma, beta, 1e-5)   # stand-alone pass
         assert rel_l2(ss, ss_ref) < 1e-5
