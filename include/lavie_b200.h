@@ -72,7 +72,10 @@ typedef struct {
  * resnet.py:202-203 conv_shortcut.  Replaces attention.py:95-104 (to_q/k/v/out), :328,356 (proj_in/out),
  * diffusers FeedForward (mirror vsr/models/diffusers_attention.py:734-822).  block_n = 0 lets the library choose.
  * workspace (optional, caller-owned, fp32) enables deterministic split-K on small-M / large-K problems: the library
- * uses at most workspace_bytes and picks splits <= workspace_bytes / (4*M*N). */
+ * uses at most workspace_bytes and picks splits <= workspace_bytes / (4*M*N).  When workspace_bytes > 256 KiB its LAST
+ * 64 KiB hold the tickets of the in-kernel reduction (the CTA whose partial block arrives last sums the planes in split
+ * order and runs the fused epilogue: deterministic, no reduction launch): that tail must be ZERO before the first call and
+ * the library leaves it zero; the same workspace must not be used by two GEMMs running concurrently. */
 /* Host-only query: the launch plan the library would choose for a GEMM (conv = 0) or a 3x3 conv (conv = 1, K = 9*Cin)
  * on the current device (148 SMs assumed when no device is present): tile width, split-K factor of the main window,
  * number of 256-row tile rows issued as a second split-K "tail window" launch (0 = single launch) and its split-K

@@ -77,6 +77,9 @@ struct GemmParams {
   __nv_bfloat16* out;
   int ldo;
   float* partial;            // split-K workspace [splits, M, N] fp32 (splits > 1)
+  int* tickets;              // in-kernel split-K reduction: one zeroed counter per (128-row block, n tile); the CTA whose
+                             // partial arrives LAST sums all planes in split order and runs the fused epilogue (no
+                             // reduction launch).  nullptr: the separate reduction kernel does it.
   float* colstats;           // [M / 32, N / 32, 4, 2] or null: per 32-row slab and 10-channel micro-group (stored per
                              // 32-column chunk and decade piece), (sum, sum of squares) of the bf16-rounded outputs: the
                              // GroupNorm statistics of the NEXT layer, emitted by the producer
@@ -221,6 +224,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
   uint64_t* tmem_empty = tmem_full + 2;         // [2]  (only the leader's are waited on)
   uint64_t* res_bar = tmem_empty + 2;           // [NUM_EPI_WARPS] residual-prefetch barriers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + NUM_EPI_WARPS);
+  volatile uint32_t* s_last = tmem_slot + 1;          // in-kernel split-K: "this CTA finishes the tile" flag
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -404,14 +408,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       const bool row_ok = row < p.M;
       const int n0 = it.n_blk * BLOCK_N;
       const bool staged = p.splits == 1 && !p.check;
+      const bool fixup = p.splits > 1 && !p.check && p.tickets != nullptr;     // in-kernel split-K reduction
       const bool has_res = staged && p.residual != nullptr;
       const bool tl = (p.debug & 512) && blockIdx.x == 0 && ew == 0 && lane == 0;
       long long* tl_row = reinterpret_cast<long long*>(p.partial) + ((item - pair) / num_pairs) * 8;
       if (tl) tl_row[0] = clock64();
-      if (staged) {
+      if (staged || fixup) {
         // buffers are free once the previous tile's stores have finished READING them
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
+      }
+      if (staged) {
         if (has_res && lane == 0 && !(p.debug & 64)) {
           int nch = 0;
           for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT) ++nch;
@@ -601,7 +608,69 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
-      if (p.colstats != nullptr && staged && !p.geglu) {
+      bool finished_here = staged;
+      if (fixup) {
+        // In-kernel split-K reduction.  Every epilogue thread has stored its share of this CTA's partial block; publish
+        // it (fence), count this CTA's arrival on the block's ticket, and let the LAST arrival finish the block: it sums
+        // the planes in split order 0..S-1 (so the result does not depend on who is last), then runs the same epilogue
+        // as an unsplit tile.  The ticket is left at zero for the next launch.
+        __threadfence();
+        epi_bar_sync();
+        if (ew == 0 && lane == 0) {
+          int* tk = p.tickets + (it.m_blk * 2 + static_cast<int>(rank)) * p.n_tiles + it.n_blk;
+          const int last = atomicAdd(tk, 1) == p.splits - 1;
+          if (last) *tk = 0;
+          *s_last = static_cast<uint32_t>(last);
+        }
+        epi_bar_sync();
+        if (*s_last) {
+          __threadfence();
+          finished_here = true;
+          const size_t plane = static_cast<size_t>(p.rows_window) * p.N;
+          const float* src_row = p.partial + static_cast<size_t>(row - p.m_tile0 * PAIR_M) * p.N;
+          int k = 0;
+#pragma unroll 1
+          for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT, ++k) {
+            const int col0 = n0 + c * 32;
+            float f[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = 0.f;
+            if (row_ok && col0 < p.N) {
+              for (int sp = 0; sp < p.splits; ++sp) {
+                const float* src = src_row + sp * plane + col0;
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                  if (col0 + e < p.N) {
+                    const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + e));
+                    f[e] += v4.x; f[e + 1] += v4.y; f[e + 2] += v4.z; f[e + 3] += v4.w;
+                  }
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                if (col0 + e < p.N) {
+                  if (p.bias) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + e));
+                    f[e] += b4.x; f[e + 1] += b4.y; f[e + 2] += b4.z; f[e + 3] += b4.w;
+                  }
+                  if (rb_row) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb_row + col0 + e));
+                    f[e] += b4.x; f[e + 1] += b4.y; f[e + 2] += b4.z; f[e + 3] += b4.w;
+                  }
+                  if (p.residual) {
+                    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p.residual + static_cast<size_t>(row) * p.ldr +
+                                                                          col0 + e));
+                    const float2 r0 = unpack_bf16(r.x), r1 = unpack_bf16(r.y);
+                    f[e] += r0.x; f[e + 1] += r0.y; f[e + 2] += r1.x; f[e + 3] += r1.y;
+                  }
+                }
+              }
+            }
+            stage_and_store(f, k, col0, false);
+          }
+        }
+      }
+      if (p.colstats != nullptr && finished_here && !p.check && !p.geglu) {
         int k = 0;
         for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT, ++k) chunk_stats(k, n0 + c * 32);
       }
@@ -809,6 +878,8 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
                p.residual ? p.residual + static_cast<size_t>(row0) * p.ldr : nullptr, p.ldr, p.geglu,
                p.out + static_cast<size_t>(row0) * p.ldo, p.ldo, row0);
     rc = lavie_check_launch("splitk_reduce_check_kernel");
+  } else if (p.splits > 1 && p.tickets != nullptr) {
+    // the last-arriving CTA of every block already reduced and stored it (and emitted the statistics)
   } else if (p.splits > 1 && p.colstats != nullptr) {
     const int row0 = p.m_tile0 * PAIR_M;
     dim3 grid((p.rows_window + 31) / 32, (p.N + 127) / 128);
@@ -835,6 +906,8 @@ int g_force_splits = 0;
 int g_debug = 0;
 int g_k_rot = 0;   // measured: no effect on B200 (profiles/r1_notes.md), kept as a tuning hook only
 int g_no_tail = 0; // lavie_debug_set(5, 1): never split a GEMM into main + tail launches (A/B timing)
+int g_inkernel_reduce = 1;   // lavie_debug_set(7, 0): split-K partials are summed by the separate reduction kernel (A/B)
+constexpr size_t TICKET_BYTES = 64 * 1024;   // tail of the caller's workspace: zero before first use, left zero
 int num_sms() { return lavie_num_sms(); }
 
 // Tile-shape / split-K choice: minimise  waves x (K blocks per item x per-block time + per-item overhead), where the
@@ -1024,9 +1097,22 @@ int fill_epilogue(GemmParams& p, const lavie_epilogue* ep, int N, void* out, int
   return LAVIE_OK;
 }
 
-void apply_plan(GemmParams& p, const Plan& plan, void* workspace) {
+// bytes of the caller's workspace the planner may use for partial planes: the tail holds the split-K tickets
+size_t plan_ws_bytes(const void* workspace, size_t workspace_bytes, int check) {
+  if (workspace == nullptr) return 0;
+  if (g_inkernel_reduce && !check && workspace_bytes > 4 * TICKET_BYTES) return workspace_bytes - TICKET_BYTES;
+  return workspace_bytes;
+}
+
+void apply_plan(GemmParams& p, const Plan& plan, void* workspace, size_t workspace_bytes = 0) {
   if (p.phases < 1) p.phases = 1;
   p.n_tiles = (p.N + plan.bn - 1) / plan.bn;
+  p.tickets = nullptr;
+  if (workspace != nullptr && plan_ws_bytes(workspace, workspace_bytes, p.check) != workspace_bytes) {
+    const size_t blocks = static_cast<size_t>((p.M + PAIR_M - 1) / PAIR_M) * 2 * p.n_tiles;
+    if (blocks * sizeof(int) <= TICKET_BYTES)
+      p.tickets = reinterpret_cast<int*>(static_cast<char*>(workspace) + workspace_bytes - TICKET_BYTES);
+  }
   p.partial = static_cast<float*>(workspace);
   p.debug = g_debug;
   p.k_rot = g_k_rot;
@@ -1053,6 +1139,7 @@ extern "C" int lavie_debug_set(int what, int value) {
   if (what == 4) g_lavie_attn_poly = value;
   if (what == 5) g_no_tail = value;
   if (what == 6 && value > 0) g_lavie_gn_target_ctas = value;
+  if (what == 7) g_inkernel_reduce = value ? 1 : 0;
   return 0;
 }
 
@@ -1097,8 +1184,8 @@ int gemm_impl(const void* a0, int lda0, int k0, const void* a1, int lda1, int k1
   p.check = check;
   int rc = check_workspace(check, M, N, workspace, workspace_bytes);
   if (rc) return rc;
-  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, geglu, false, workspace ? workspace_bytes : 0);
-  apply_plan(p, plan, workspace);
+  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, geglu, false, plan_ws_bytes(workspace, workspace_bytes, check));
+  apply_plan(p, plan, workspace, workspace_bytes);
   rc = fill_epilogue(p, ep, N, out, ldo);
   if (rc) return rc;
   CUtensorMap ma0, ma1, mb;
@@ -1158,8 +1245,8 @@ int frame_conv_impl(const void* x, int ldx, long long rows_in, int C, int taps, 
   p.tap_rows = tap_rows;
   p.conv = 2;
   p.check = 0;
-  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, false, false, workspace ? workspace_bytes : 0);
-  apply_plan(p, plan, workspace);
+  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, false, false, plan_ws_bytes(workspace, workspace_bytes, 0));
+  apply_plan(p, plan, workspace, workspace_bytes);
   int rc = fill_epilogue(p, ep, N, out, ldo);
   if (rc) return rc;
   CUtensorMap ma, mb;
@@ -1270,8 +1357,8 @@ int conv3x3_impl(const void* x, int NF, int H, int W, int C, int stride, const v
   p.check = check;
   int rc = check_workspace(check, M, N, workspace, workspace_bytes);
   if (rc) return rc;
-  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, false, true, workspace ? workspace_bytes : 0);
-  apply_plan(p, plan, workspace);
+  const Plan plan = make_plan(M, N, p.num_k_blocks, block_n, false, true, plan_ws_bytes(workspace, workspace_bytes, check));
+  apply_plan(p, plan, workspace, workspace_bytes);
   rc = fill_epilogue(p, ep, N, out, ldo);
   if (rc) return rc;
   CUtensorMap ma, mb;

@@ -72,7 +72,9 @@ def _workspace(device) -> torch.Tensor:
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     ws = _workspaces.get(key)
     if ws is None:
-        ws = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+        # zero-initialised: the last 64 KiB are the tickets of the in-kernel split-K reduction (lavie_gemm_bf16 contract:
+        # zero before the first call, the library leaves them zero)
+        ws = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
 
