@@ -626,47 +626,42 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         if (*s_last) {
           __threadfence();
           finished_here = true;
+          // Coalesced sweep: for this part of the epilogue a lane owns a COLUMN, so every load instruction reads 128
+          // consecutive bytes of one partial row; the bf16 results go straight into the (swizzled) staging chunk the TMA
+          // store and the statistics read.  Same summation order as the reduction kernel: planes 0..S-1, bias, time bias,
+          // residual.
           const size_t plane = static_cast<size_t>(p.rows_window) * p.N;
-          const float* src_row = p.partial + static_cast<size_t>(row - p.m_tile0 * PAIR_M) * p.N;
           int k = 0;
 #pragma unroll 1
           for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT, ++k) {
             const int col0 = n0 + c * 32;
-            float f[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) f[e] = 0.f;
-            if (row_ok && col0 < p.N) {
-              for (int sp = 0; sp < p.splits; ++sp) {
-                const float* src = src_row + sp * plane + col0;
-#pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                  if (col0 + e < p.N) {
-                    const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + e));
-                    f[e] += v4.x; f[e + 1] += v4.y; f[e + 2] += v4.z; f[e + 3] += v4.w;
-                  }
-                }
+            const int col = col0 + lane;
+            const bool col_ok = col < p.N;
+            uint8_t* chunk = my_stage + k * EPI_CHUNK_BYTES;
+            const float bias_c = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const int grow = wrow0 + r;
+              float a = 0.f;
+              if (grow < p.M && col_ok) {
+                const float* src = p.partial + static_cast<size_t>(grow - p.m_tile0 * PAIR_M) * p.N + col;
+                for (int sp = 0; sp < p.splits; ++sp) a += __ldcg(src + sp * plane);
+                a += bias_c;
+                if (p.row_bias) a += __ldg(p.row_bias + static_cast<size_t>(grow / p.rows_per_batch) * p.ld_row_bias + col);
+                if (p.residual) a += __bfloat162float(p.residual[static_cast<size_t>(grow) * p.ldr + col]);
               }
-#pragma unroll
-              for (int e = 0; e < 32; e += 4) {
-                if (col0 + e < p.N) {
-                  if (p.bias) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + e));
-                    f[e] += b4.x; f[e + 1] += b4.y; f[e + 2] += b4.z; f[e + 3] += b4.w;
-                  }
-                  if (rb_row) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb_row + col0 + e));
-                    f[e] += b4.x; f[e + 1] += b4.y; f[e + 2] += b4.z; f[e + 3] += b4.w;
-                  }
-                  if (p.residual) {
-                    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p.residual + static_cast<size_t>(row) * p.ldr +
-                                                                          col0 + e));
-                    const float2 r0 = unpack_bf16(r.x), r1 = unpack_bf16(r.y);
-                    f[e] += r0.x; f[e + 1] += r0.y; f[e + 2] += r1.x; f[e + 3] += r1.y;
-                  }
-                }
-              }
+              *reinterpret_cast<__nv_bfloat16*>(chunk + r * 64 + ((((lane >> 3) ^ ((r >> 1) & 3)) << 4) + (lane & 7) * 2)) =
+                  __float2bfloat16_rn(a);
             }
-            stage_and_store(f, k, col0, false);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmap_out)),
+                           "r"(smem_u32(chunk)), "r"(col0), "r"(wrow0)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
           }
         }
       }
