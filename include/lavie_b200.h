@@ -42,7 +42,8 @@ const char* lavie_last_error(void);
 int lavie_abi_version(void);
 /* Tuning hooks for tests/benchmarks (never needed for correct results): what = 1 forces the split-K factor of the
  * GEMM (0 = automatic); 2 = debug bit mask (512: GEMM per-tile clock64 timeline into the workspace); 3 = programmatic
- * dependent launch on/off; 4 = attention: every n-th exp2 on the FMA pipe (0 = all on the MUFU). */
+ * dependent launch on/off; 4 = attention: every n-th exp2 on the FMA pipe (0 = all on the MUFU); 5 = no split-K tail
+ * windows; 7 = in-kernel split-K reduction on/off (default off). */
 int lavie_debug_set(int what, int value);
 /* Device scratch (>= 64 KB) that the attention kernel fills with a per-tile clock64 timeline of one CTA; NULL = off. */
 int lavie_debug_buffer(void* device_ptr);
@@ -72,10 +73,10 @@ typedef struct {
  * resnet.py:202-203 conv_shortcut.  Replaces attention.py:95-104 (to_q/k/v/out), :328,356 (proj_in/out),
  * diffusers FeedForward (mirror vsr/models/diffusers_attention.py:734-822).  block_n = 0 lets the library choose.
  * workspace (optional, caller-owned, fp32) enables deterministic split-K on small-M / large-K problems: the library
- * uses at most workspace_bytes and picks splits <= workspace_bytes / (4*M*N).  When workspace_bytes > 256 KiB its LAST
- * 64 KiB hold the tickets of the in-kernel reduction (the CTA whose partial block arrives last sums the planes in split
- * order and runs the fused epilogue: deterministic, no reduction launch): that tail must be ZERO before the first call and
- * the library leaves it zero; the same workspace must not be used by two GEMMs running concurrently. */
+ * uses at most workspace_bytes and picks splits <= workspace_bytes / (4*M*N).  Only with lavie_debug_set(7, 1) (in-kernel
+ * reduction: the CTA whose partial block arrives last sums the planes in split order and runs the fused epilogue; same
+ * bits, no reduction launch, measured slower and therefore off by default) and workspace_bytes > 256 KiB, the LAST 64 KiB
+ * hold its tickets: that tail must be ZERO before the first call and the library leaves it zero. */
 /* Host-only query: the launch plan the library would choose for a GEMM (conv = 0) or a 3x3 conv (conv = 1, K = 9*Cin)
  * on the current device (148 SMs assumed when no device is present): tile width, split-K factor of the main window,
  * number of 256-row tile rows issued as a second split-K "tail window" launch (0 = single launch) and its split-K

@@ -136,8 +136,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if os.environ.get("LAVIE_INKERNEL_SPLITK", "1") == "0":      # A/B switch: separate split-K reduction kernels
-        lib.lavie_debug_set(7, 0)
+    if os.environ.get("LAVIE_INKERNEL_SPLITK", "0") == "1":      # A/B switch: in-kernel split-K reduction (slower, off)
+        lib.lavie_debug_set(7, 1)
     _lib = lib
     return lib
 

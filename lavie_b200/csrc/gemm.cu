@@ -639,19 +639,33 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
             const bool col_ok = col < p.N;
             uint8_t* chunk = my_stage + k * EPI_CHUNK_BYTES;
             const float bias_c = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.f;
-#pragma unroll 8
+            // 32 independent loads in flight per lane and plane (one per row of the slab)
+            float a[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) a[r] = 0.f;
+            const int rows_here = min(32, p.M - wrow0);                 // <= 0: slab entirely beyond M
+            const float* src0 = p.partial + static_cast<size_t>(wrow0 - p.m_tile0 * PAIR_M) * p.N + col;
+            if (col_ok) {
+              for (int sp = 0; sp < p.splits; ++sp) {
+                const float* src = src0 + sp * plane;
+#pragma unroll
+                for (int r = 0; r < 32; ++r)
+                  if (r < rows_here) a[r] += __ldcg(src + static_cast<size_t>(r) * p.N);
+              }
+            }
+#pragma unroll
             for (int r = 0; r < 32; ++r) {
               const int grow = wrow0 + r;
-              float a = 0.f;
-              if (grow < p.M && col_ok) {
-                const float* src = p.partial + static_cast<size_t>(grow - p.m_tile0 * PAIR_M) * p.N + col;
-                for (int sp = 0; sp < p.splits; ++sp) a += __ldcg(src + sp * plane);
-                a += bias_c;
-                if (p.row_bias) a += __ldg(p.row_bias + static_cast<size_t>(grow / p.rows_per_batch) * p.ld_row_bias + col);
-                if (p.residual) a += __bfloat162float(p.residual[static_cast<size_t>(grow) * p.ldr + col]);
+              float v = a[r];
+              if (r < rows_here && col_ok) {
+                v += bias_c;
+                if (p.row_bias) v += __ldg(p.row_bias + static_cast<size_t>(grow / p.rows_per_batch) * p.ld_row_bias + col);
+                if (p.residual) v += __bfloat162float(p.residual[static_cast<size_t>(grow) * p.ldr + col]);
+              } else {
+                v = 0.f;
               }
               *reinterpret_cast<__nv_bfloat16*>(chunk + r * 64 + ((((lane >> 3) ^ ((r >> 1) & 3)) << 4) + (lane & 7) * 2)) =
-                  __float2bfloat16_rn(a);
+                  __float2bfloat16_rn(v);
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -901,7 +915,9 @@ int g_force_splits = 0;
 int g_debug = 0;
 int g_k_rot = 0;   // measured: no effect on B200 (profiles/r1_notes.md), kept as a tuning hook only
 int g_no_tail = 0; // lavie_debug_set(5, 1): never split a GEMM into main + tail launches (A/B timing)
-int g_inkernel_reduce = 1;   // lavie_debug_set(7, 0): split-K partials are summed by the separate reduction kernel (A/B)
+int g_inkernel_reduce = 0;   // lavie_debug_set(7, 1): the last-arriving CTA of a block sums the split-K planes in the kernel
+                             // instead of the separate reduction kernel.  Correct (same bits), but measured SLOWER on the
+                             // full step (profiles/r2_ab_inkernel_splitk.txt): off by default, kept for A/B.
 constexpr size_t TICKET_BYTES = 64 * 1024;   // tail of the caller's workspace: zero before first use, left zero
 int num_sms() { return lavie_num_sms(); }
 
