@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblavie_b200.so")
+LIB_PATH = os.environ.get("LAVIE_LIB_PATH") or os.path.join(_HERE, "liblavie_b200.so")   # override: A/B of two builds
 
 
 class LavieError(RuntimeError):
