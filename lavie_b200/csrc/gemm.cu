@@ -394,26 +394,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
     const int chalf = ew >> 2;                     // which share of the 32-column chunks this warp drains
     const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     uint8_t* my_stage = s_epi + ew * (L::EPI_CHUNKS * EPI_CHUNK_BYTES);
+    uint64_t* my_res_bar = &res_bar[ew];
+    uint32_t res_phase = 0;
     const int swz = (lane >> 1) & 3;               // 64-byte swizzle: 16-byte unit j of row r lives at unit j ^ ((r>>1)&3)
     int acc = 0;
     uint32_t acc_phase = 0;
-    // Residual operand: every lane keeps the 64 bytes of ITS row for the NEXT chunk in registers, loaded one chunk (or
-    // one tile) ahead with plain read-only loads, so the L2 latency hides behind the chunk in flight.  (The TMA prefetch
-    // into the staging buffers it replaces could only be issued once the previous tile's stores had left those buffers:
-    // 1300-3000 exposed cycles per tile on the K = C projections, tools/gemm_timeline.py.)
-    uint4 rnext[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-    auto res_load = [&](int row_, int col0_) {
-      const __nv_bfloat16* src = p.residual + static_cast<size_t>(row_) * p.ldr + col0_;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        rnext[j] = (row_ < p.M && col0_ + 8 * j < p.N) ? __ldg(reinterpret_cast<const uint4*>(src + 8 * j))
-                                                       : make_uint4(0, 0, 0, 0);
-    };
-    const bool res_mode = p.splits == 1 && !p.check && !p.geglu && p.residual != nullptr && !(p.debug & 64);
-    if (res_mode && pair < num_items) {
-      const Item it0 = decode_item(p, pair);
-      res_load((it0.m_blk * 2 + static_cast<int>(rank)) * BLOCK_M + q * 32 + lane, it0.n_blk * BLOCK_N + chalf * 32);
-    }
     for (int item = pair; item < num_items; item += num_pairs) {
       const Item it = decode_item(p, item);
       const int split = item % p.splits;
@@ -433,12 +418,26 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
       }
+      if (staged) {
+        if (has_res && lane == 0 && !(p.debug & 64)) {
+          int nch = 0;
+          for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT) ++nch;
+          mbar_expect_tx(my_res_bar, nch * EPI_CHUNK_BYTES);
+          int k = 0;
+          for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT, ++k)
+            tma_load_2d(my_stage + k * EPI_CHUNK_BYTES, &tmap_res, my_res_bar, n0 + c * 32, wrow0);
+        }
+      }
 
       if (tl) tl_row[1] = clock64();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (tl) tl_row[2] = clock64();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      if (has_res && !(p.debug & 64)) {
+        mbar_wait(my_res_bar, res_phase);
+        res_phase ^= 1;
+      }
       const float* rb_row = (p.row_bias && row_ok) ? p.row_bias + static_cast<size_t>(row / p.rows_per_batch) * p.ld_row_bias
                                                     : nullptr;
 
@@ -553,18 +552,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         for (int c = chalf; c < BLOCK_N / 32; c += EPI_SPLIT, ++k) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c * 32, v);
-          uint4 rcur[4];
-          if (res_mode) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-            // prefetch the next chunk of this tile, or the first chunk of this CTA's next tile
-            if (c + EPI_SPLIT < BLOCK_N / 32) {
-              res_load(row, n0 + (c + EPI_SPLIT) * 32);
-            } else if (item + num_pairs < num_items) {
-              const Item nx = decode_item(p, item + num_pairs);
-              res_load((nx.m_blk * 2 + static_cast<int>(rank)) * BLOCK_M + q * 32 + lane, nx.n_blk * BLOCK_N + chalf * 32);
-            }
-          }
           tmem_wait_ld();
           if (tl && k == 0) tl_row[3] = clock64();
           const int col0 = n0 + c * 32;
@@ -587,16 +574,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
               }
             }
           }
-          if (res_mode) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 r0 = unpack_bf16(rcur[j].x), r1 = unpack_bf16(rcur[j].y), r2 = unpack_bf16(rcur[j].z),
-                           r3 = unpack_bf16(rcur[j].w);
-              f[8 * j] += r0.x; f[8 * j + 1] += r0.y; f[8 * j + 2] += r1.x; f[8 * j + 3] += r1.y;
-              f[8 * j + 4] += r2.x; f[8 * j + 5] += r2.y; f[8 * j + 6] += r3.x; f[8 * j + 7] += r3.y;
-            }
-          }
-          stage_and_store(f, k, col0, false);
+          stage_and_store(f, k, col0, has_res && !(p.debug & 64));
         }
       } else {
         // GEGLU: value columns [0, BN/2), gate columns [BN/2, BN) of the same tile (weights interleaved on the
