@@ -658,10 +658,17 @@ def run_vsr(args):
     from lavie_b200.synthetic import synthetic_state_dict
     from lavie_b200.vsr import UNet3DVSRModel
     from oracle import reference_loader as R
-    if int(os.environ.get("WORLD_SIZE", "1")) != 1 or args.gpus != 1:
-        raise SystemExit("--workload vsr runs on one GPU (frame sharding of the VSR denoiser is not built)")
-    dev = torch.device("cuda", 0)
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world not in (1, 2) or args.gpus != world:
+        raise SystemExit("--workload vsr runs on 1 GPU or on 2 (CFG halves on separate GPUs); frame sharding of the VSR "
+                         "denoiser is not built")
+    dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    if world == 2:
+        dist.init_process_group("nccl", device_id=dev)
     Fr, H, W = args.vsr_frames, args.vsr_height, args.vsr_width
     sd = synthetic_state_dict(VSR_CONFIG, seed=0)
     unet = UNet3DVSRModel()
@@ -677,25 +684,55 @@ def run_vsr(args):
     ts = sched.timesteps
     x, lowd, txt = lat.to(dev), low.to(dev), text.to(dev)
 
+    gather = [torch.empty((1, 4, Fr, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
+
     def one_step(x, lowd, txt, i):
         t = ts[i % len(ts)]
-        eps = unet(torch.cat([x, x]), t, lowd, encoder_hidden_states=txt, class_labels=labels).sample
         a_t, a_prev = sched.alphas(t)
-        return ops.cfg_ddim_step(eps[:1].contiguous(), eps[1:].contiguous(), 5.0, a_t, a_prev, x)
+        if world == 1:
+            eps = unet(torch.cat([x, x]), t, lowd, encoder_hidden_states=txt, class_labels=labels).sample
+            return ops.cfg_ddim_step(eps[:1].contiguous(), eps[1:].contiguous(), 5.0, a_t, a_prev, x)
+        # CFG split: rank r evaluates batch item r (its own prompt), the two noise predictions are exchanged
+        eps = unet(x, t, lowd[rank:rank + 1], encoder_hidden_states=txt[rank:rank + 1], class_labels=labels[rank:rank + 1]).sample
+        dist.all_gather(gather, eps.contiguous())
+        return ops.cfg_ddim_step(gather[0], gather[1], 5.0, a_t, a_prev, x)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    parity2 = None
+    if world == 2:
+        # every rank: its half alone against the same half inside the batch-2 forward on its own GPU
+        both = unet(torch.cat([x, x]), 500, lowd, encoder_hidden_states=txt, class_labels=labels).sample
+        mine = unet(x, 500, lowd[rank:rank + 1], encoder_hidden_states=txt[rank:rank + 1], class_labels=labels[rank:rank + 1]).sample
+        err = rel_l2(mine, both[rank:rank + 1])
+        errs = [None, None]
+        dist.all_gather_object(errs, err)
+        parity2 = {"rel_l2": max(errs), "per_rank": [round(e, 6) for e in errs], "tolerance": 2e-2,
+                   "vs": "the same CFG half inside the batch-2 forward on the rank's own GPU"}
+        del both, mine
+        unet._graphs.clear()
+        torch.cuda.empty_cache()
     for i in range(max(args.warmup, 3)):
         x = one_step(x, lowd, txt, i)
-    torch.cuda.synchronize()
+    barrier()
     per_step = unet.launches_per_step() + 1
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(0) as clocks:
-        torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clocks:
+        barrier()
         ev0.record()
         for i in range(args.steps):
             x = one_step(x, lowd, txt, i)
         ev1.record()
-        torch.cuda.synchronize()
-    ms_per_step = ev0.elapsed_time(ev1) / args.steps
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax)
+    ms_per_step = ms / args.steps
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
     # e2e: latents + low-res frames + text from pinned host buffers every step, new latents back
     xh = [lat.clone().pin_memory(), torch.empty_like(lat).pin_memory()]
@@ -709,15 +746,22 @@ def run_vsr(args):
         xh[(i + 1) & 1].copy_(new, non_blocking=True)
         done.record()
         done.synchronize()
-    torch.cuda.synchronize()
+    barrier()
     e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax)
     # per-kernel CUDA-event profile of one eager forward
     unet.use_cuda_graph = False
-    m_in = torch.cat([x, x])
-    unet(m_in, 500, lowd, encoder_hidden_states=txt, class_labels=labels)
+    if world == 1:
+        m_in, l_in, t_in, c_in = torch.cat([x, x]), lowd, txt, labels
+    else:
+        m_in, l_in, t_in, c_in = x, lowd[rank:rank + 1], txt[rank:rank + 1], labels[rank:rank + 1]
+    unet(m_in, 500, l_in, encoder_hidden_states=t_in, class_labels=c_in)
     ops.PROFILE = []
     torch.cuda._sleep(300_000_000)
-    unet(m_in, 500, lowd, encoder_hidden_states=txt, class_labels=labels)
+    unet(m_in, 500, l_in, encoder_hidden_states=t_in, class_labels=c_in)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     unet.use_cuda_graph = True
@@ -730,7 +774,7 @@ def run_vsr(args):
                    "gflop": round(a[2] / 1e9, 1), "tflops": round(a[2] / (a[1] * 1e-3) / 1e12, 1) if a[2] else None,
                    "gbs": round(a[3] / (a[1] * 1e-3) / 1e9, 1) if a[3] else None}
                for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
-    step_gflop = sum(a[2] for a in agg.values()) / 1e9
+    step_gflop = sum(a[2] for a in agg.values()) / 1e9 * world
     peaks = measured_peaks()
     d = agg["gemm_bf16_tcgen05"]
     achieved = d[2] / (d[1] * 1e-3) / 1e12
@@ -738,8 +782,14 @@ def run_vsr(args):
                 "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None,
                 "launches_per_step": d[0], "avg_launch_ms": d[1] / d[0], "share_of_step": d[1] / total_ms,
                 "algorithmic_gflop_per_launch": d[2] / d[0] / 1e9, "peak_source": peaks["source"]}
-    parity, cpu = None, None
-    if not args.no_cpu_baseline:
+    parity, cpu = parity2, None
+    if world > 1 and parity2["rel_l2"] > 2e-2:
+        raise SystemExit(f"vsr CFG-split parity FAILED: {parity2['rel_l2']:.3e}")
+    if rank != 0:
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
+    if world == 1 and not args.no_cpu_baseline:
         f, hh, ww = min(2, Fr), min(80, H), min(128, W)
         threads = os.cpu_count() or 1
         torch.set_num_threads(threads)
@@ -767,10 +817,11 @@ def run_vsr(args):
         if not err <= 2e-2:
             raise SystemExit(f"vsr parity FAILED: {err:.3e}")
     line = {"metric": "denoise steps/s (VSR 320x512 latent, CFG)", "value": 1e3 / ms_per_step, "unit": "steps/s",
-            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": VSR_WORKLOAD.format(f=Fr, h=H, w=W), "weights": "random-init (seeded), 691.0 M params"},
-            "setup": {"parallelism": "single", "cuda_graph": True, "launches_per_step_per_rank": per_step,
+            "setup": {"parallelism": "single" if world == 1 else "cfg2", "cuda_graph": True,
+                      "launches_per_step_per_rank": per_step,
                       "peak_mem_gb": round(peak_mem, 1)},
             "parity": parity, "step_gflop": step_gflop, "step_tflops": step_gflop / ms_per_step,
             "clocks": clocks.summary(),
@@ -779,6 +830,11 @@ def run_vsr(args):
                     "d2h_bytes_per_step": xh[0].numel() * 4},
             "gpu_launches": per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 # ----------------------------------------------------------------------------------------------- N4: encoders

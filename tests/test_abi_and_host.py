@@ -158,3 +158,27 @@ def test_vsr_module_keeps_the_reference_state_dict_layout():
     w = torch.arange(2 * 3 * 5, dtype=torch.float32).reshape(2, 3, 5, 1, 1)
     p = pack_frame_conv(w)
     assert p.shape == (2, 15) and float(p[1, 2 * 3 + 1]) == float(w[1, 1, 2, 0, 0])
+
+
+def test_upsample_conv_weight_packing_is_the_subpixel_identity():
+    """packing.pack_upsample_conv3x3: a 3x3 conv on the nearest-2x upsampled map == four 2x2 phase convs on the source map
+    with summed taps (what lavie_upsample_conv3x3_bf16 computes), borders included.  CPU, fp32."""
+    import torch
+    import torch.nn.functional as F
+    from lavie_b200.packing import pack_upsample_conv3x3
+    g = torch.Generator().manual_seed(0)
+    co, ci, H, W = 5, 3, 4, 6
+    w = torch.randn(co, ci, 3, 3, generator=g)
+    x = torch.randn(2, ci, H, W, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    wp = pack_upsample_conv3x3(w, dtype=None).reshape(2, 2, co, 2, 2, ci)        # [py, px, n, a, b, c]
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for py in range(2):
+        for px in range(2):
+            acc = torch.zeros(2, co, H, W)
+            for a in range(2):
+                for b in range(2):                                              # source pixel (y + py - 1 + a, x + px - 1 + b)
+                    acc += torch.einsum("nchw,oc->nohw", xp[:, :, py + a:py + a + H, px + b:px + b + W], wp[py, px, :, a, b, :])
+            out[:, :, py::2, px::2] = acc
+    assert float((out - ref).abs().max()) < 1e-5
