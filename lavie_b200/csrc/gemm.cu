@@ -614,17 +614,21 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         // it (fence), count this CTA's arrival on the block's ticket, and let the LAST arrival finish the block: it sums
         // the planes in split order 0..S-1 (so the result does not depend on who is last), then runs the same epilogue
         // as an unsplit tile.  The ticket is left at zero for the next launch.
-        __threadfence();
+        // (one device-scope fence by the ticket thread, cumulative over the CTA barrier -- the grid-sync pattern; a fence
+        // in every thread cost tens of microseconds with the strided partial stores in flight)
         epi_bar_sync();
         if (ew == 0 && lane == 0) {
+          __threadfence();
           int* tk = p.tickets + (it.m_blk * 2 + static_cast<int>(rank)) * p.n_tiles + it.n_blk;
           const int last = atomicAdd(tk, 1) == p.splits - 1;
-          if (last) *tk = 0;
+          if (last) {
+            *tk = 0;
+            __threadfence();
+          }
           *s_last = static_cast<uint32_t>(last);
         }
         epi_bar_sync();
         if (*s_last) {
-          __threadfence();
           finished_here = true;
           // Coalesced sweep: for this part of the epilogue a lane owns a COLUMN, so every load instruction reads 128
           // consecutive bytes of one partial row; the bf16 results go straight into the (swizzled) staging chunk the TMA
