@@ -662,14 +662,29 @@ def run_vsr(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world not in (1, 2) or args.gpus != world:
-        raise SystemExit("--workload vsr runs on 1 GPU or on 2 (CFG halves on separate GPUs); frame sharding of the VSR "
-                         "denoiser is not built")
+    if world not in (1, 2, 4, 8) or args.gpus != world or (world > 2 and args.vsr_frames % (world // 2)):
+        raise SystemExit("--workload vsr runs on 1, 2, 4 or 8 GPUs (CFG halves x frame shards)")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    if world == 2:
+    if world >= 2:
         dist.init_process_group("nccl", device_id=dev)
     Fr, H, W = args.vsr_frames, args.vsr_height, args.vsr_width
+    # N >= 2: rank = half * P + shard; the CFG halves go to the two halves of the ranks, each half shards the frames over
+    # P = N / 2 GPUs (halo exchange of the frame convs, all-reduced GroupNorm sums, all-to-all around temporal attention)
+    P = max(world // 2, 1)
+    half, shard_idx = (rank // P, rank % P) if world >= 2 else (0, 0)
+    frame_group = pair_group = None
+    if world >= 2:
+        for hh in range(2):
+            gg = dist.new_group(list(range(hh * P, hh * P + P)))
+            if hh == half:
+                frame_group = gg
+        for ss in range(P):
+            gg = dist.new_group([ss, P + ss])
+            if ss == shard_idx:
+                pair_group = gg
+    fl = Fr // P
+    fsl = slice(shard_idx * fl, (shard_idx + 1) * fl)
     sd = synthetic_state_dict(VSR_CONFIG, seed=0)
     unet = UNet3DVSRModel()
     unet.load_state_dict(sd, strict=True)
@@ -683,8 +698,10 @@ def run_vsr(args):
     sched = DDIMSchedule(50)
     ts = sched.timesteps
     x, lowd, txt = lat.to(dev), low.to(dev), text.to(dev)
+    if world >= 2:
+        x, lowd = x[:, :, fsl].contiguous(), lowd[:, :, fsl].contiguous()
 
-    gather = [torch.empty((1, 4, Fr, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
+    gather = [torch.empty((1, 4, fl, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
 
     def one_step(x, lowd, txt, i):
         t = ts[i % len(ts)]
@@ -692,9 +709,10 @@ def run_vsr(args):
         if world == 1:
             eps = unet(torch.cat([x, x]), t, lowd, encoder_hidden_states=txt, class_labels=labels).sample
             return ops.cfg_ddim_step(eps[:1].contiguous(), eps[1:].contiguous(), 5.0, a_t, a_prev, x)
-        # CFG split: rank r evaluates batch item r (its own prompt), the two noise predictions are exchanged
-        eps = unet(x, t, lowd[rank:rank + 1], encoder_hidden_states=txt[rank:rank + 1], class_labels=labels[rank:rank + 1]).sample
-        dist.all_gather(gather, eps.contiguous())
+        # CFG split: the ranks of half h evaluate batch item h (its own prompt) on their frames; the two noise predictions
+        # of the same frames are exchanged between the pair
+        eps = unet(x, t, lowd[half:half + 1], encoder_hidden_states=txt[half:half + 1], class_labels=labels[half:half + 1]).sample
+        dist.all_gather(gather, eps.contiguous(), group=pair_group)
         return ops.cfg_ddim_step(gather[0], gather[1], 5.0, a_t, a_prev, x)
 
     def barrier():
@@ -703,22 +721,32 @@ def run_vsr(args):
         torch.cuda.synchronize()
 
     parity2 = None
-    if world == 2:
-        # every rank: its half alone against the same half inside the batch-2 forward on its own GPU
-        both = unet(torch.cat([x, x]), 500, lowd, encoder_hidden_states=txt, class_labels=labels).sample
-        mine = unet(x, 500, lowd[rank:rank + 1], encoder_hidden_states=txt[rank:rank + 1], class_labels=labels[rank:rank + 1]).sample
-        err = rel_l2(mine, both[rank:rank + 1])
-        errs = [None, None]
+    if world >= 2:
+        # every rank: its (half, frame shard) through the partitioned path against the un-sharded batch-1 forward of the
+        # same half on its own GPU (outside any timing)
+        xf, lf = lat.to(dev), low.to(dev)
+        full = unet(xf, 500, lf[half:half + 1], encoder_hidden_states=txt[half:half + 1], class_labels=labels[half:half + 1]).sample
+        unet._graphs.clear()
+        if P > 1:
+            unet.set_frame_sharding(frame_group)
+        mine = unet(x, 500, lowd[half:half + 1], encoder_hidden_states=txt[half:half + 1], class_labels=labels[half:half + 1]).sample
+        err = rel_l2(mine, full[:, :, fsl])
+        errs = [None] * world
         dist.all_gather_object(errs, err)
         parity2 = {"rel_l2": max(errs), "per_rank": [round(e, 6) for e in errs], "tolerance": 2e-2,
-                   "vs": "the same CFG half inside the batch-2 forward on the rank's own GPU"}
-        del both, mine
-        unet._graphs.clear()
+                   "vs": "un-sharded batch-1 forward of the same CFG half on the rank's own GPU", "shape": [1, 7, Fr, H, W]}
+        del full, mine, xf, lf
         torch.cuda.empty_cache()
     for i in range(max(args.warmup, 3)):
         x = one_step(x, lowd, txt, i)
     barrier()
-    per_step = unet.launches_per_step() + 1
+    if P > 1:                                    # sharded steps run eagerly: count the C-ABI calls of one step
+        l0 = ops.LAUNCHES
+        x = one_step(x, lowd, txt, 0)
+        per_step = ops.LAUNCHES - l0
+        barrier()
+    else:
+        per_step = unet.launches_per_step() + 1
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
@@ -735,8 +763,9 @@ def run_vsr(args):
     ms_per_step = ms / args.steps
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
     # e2e: latents + low-res frames + text from pinned host buffers every step, new latents back
-    xh = [lat.clone().pin_memory(), torch.empty_like(lat).pin_memory()]
-    lh, th = low.clone().pin_memory(), text.clone().pin_memory()
+    lat_s, low_s = (lat, low) if world == 1 else (lat[:, :, fsl].contiguous(), low[:, :, fsl].contiguous())
+    xh = [lat_s.clone().pin_memory(), torch.empty_like(lat_s).pin_memory()]
+    lh, th = low_s.clone().pin_memory(), text.clone().pin_memory()
     done = torch.cuda.Event()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -757,7 +786,7 @@ def run_vsr(args):
     if world == 1:
         m_in, l_in, t_in, c_in = torch.cat([x, x]), lowd, txt, labels
     else:
-        m_in, l_in, t_in, c_in = x, lowd[rank:rank + 1], txt[rank:rank + 1], labels[rank:rank + 1]
+        m_in, l_in, t_in, c_in = x, lowd[half:half + 1], txt[half:half + 1], labels[half:half + 1]
     unet(m_in, 500, l_in, encoder_hidden_states=t_in, class_labels=c_in)
     ops.PROFILE = []
     torch.cuda._sleep(300_000_000)
@@ -820,7 +849,8 @@ def run_vsr(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": VSR_WORKLOAD.format(f=Fr, h=H, w=W), "weights": "random-init (seeded), 691.0 M params"},
-            "setup": {"parallelism": "single" if world == 1 else "cfg2", "cuda_graph": True,
+            "setup": {"parallelism": "single" if world == 1 else ("cfg2" if P == 1 else f"cfg2 x frames{P}"),
+                      "cuda_graph": P == 1,
                       "launches_per_step_per_rank": per_step,
                       "peak_mem_gb": round(peak_mem, 1)},
             "parity": parity, "step_gflop": step_gflop, "step_tflops": step_gflop / ms_per_step,

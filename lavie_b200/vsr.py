@@ -40,12 +40,18 @@ class UNet3DVSRModel(UNet3DConditionModel):
     def __init__(self, config: UNetConfig = VSR_CONFIG, use_cuda_graph: bool = True):
         super().__init__(config, use_cuda_graph=use_cuda_graph, check_mode=False)
         self._padbufs: Dict[tuple, torch.Tensor] = {}
+        self._graph_ok = True
 
-    def set_frame_sharding(self, group=None, backend: str = "p2p", frame_counts=None):
-        if group is not None:
-            raise NotImplementedError("frame sharding of the VSR denoiser is not built: its (k,1,1) frame convolutions "
-                                      "need a k//2-frame halo exchange on top of the base model's exchanges")
-        super().set_frame_sharding(None)
+    def set_frame_sharding(self, group=None, backend: str = "nccl", frame_counts=None):
+        """Frame sharding of the VSR denoiser (BASELINE config 5): every rank of `group` holds F / P consecutive frames of
+        one CFG half.  Per-frame work is shard-local; the 5-D GroupNorm sums are all-reduced, the tokens go all-to-all
+        around every temporal attention (both as in the base model, NCCL back end), and every (k,1,1) frame convolution
+        first receives k//2 halo frames of its (GroupNorm-applied) input from each neighbour (NCCL send / recv).  The
+        peer-memory back end of the base model is not wired to this variant.  Sharded steps run eagerly (no step graph)."""
+        if group is not None and (backend != "nccl" or frame_counts is not None):
+            raise NotImplementedError("the VSR denoiser shards equal frame counts over the NCCL back end only")
+        super().set_frame_sharding(group, backend="nccl" if group is not None else "p2p")
+        self._graph_ok = self._shard is None
 
     def _invalidate(self):
         super()._invalidate()
@@ -208,6 +214,8 @@ class UNet3DVSRModel(UNet3DConditionModel):
         for b in range(B):
             rows = slice(b * rps, (b + 1) * rps)
             ops.groupnorm_apply(x[rows], ss[b:b + 1], 1, rps, True, out=buf[b, lo:lo + rps])
+            if self._shard is not None:
+                self._exchange_frame_halo(buf[b], k // 2, Fr, HW)
             ops.frame_conv(buf[b], k, HW, w, bias=bias, row_bias=None if row_bias is None else row_bias[b:b + 1],
                            rows_per_batch=rps, residual=None if residual is None else residual[rows], out=out[rows],
                            colsums_out=None if cs is None else cs[b * rps // 32:(b + 1) * rps // 32])
@@ -215,17 +223,37 @@ class UNet3DVSRModel(UNet3DConditionModel):
             out._gn_colsums = cs
         return out
 
+    def _exchange_frame_halo(self, buf, pad: int, Fr: int, HW: int):
+        """Frame-sharded (k,1,1) conv: the pad = k//2 frames in front of / behind this rank's frames are the LAST / FIRST
+        pad frames of the left / right neighbour (already normalised and activated); the video's ends keep their zeros."""
+        import torch.distributed as dist
+        group, P, idx = self._shard
+        if Fr < pad:
+            raise ValueError(f"frame sharding needs at least {pad} frames per rank for this frame convolution")
+        n = pad * HW
+        lo = n
+        ranks = dist.get_process_group_ranks(group)
+        reqs = []
+        if idx > 0:
+            reqs.append(dist.P2POp(dist.isend, buf[lo:lo + n], ranks[idx - 1], group))             # my first frames -> left
+            reqs.append(dist.P2POp(dist.irecv, buf[:lo], ranks[idx - 1], group))                   # left's last frames
+        if idx < P - 1:
+            reqs.append(dist.P2POp(dist.isend, buf[lo + (Fr - pad) * HW:lo + Fr * HW], ranks[idx + 1], group))
+            reqs.append(dist.P2POp(dist.irecv, buf[lo + Fr * HW:], ranks[idx + 1], group))
+        for r in dist.batch_isend_irecv(reqs):
+            r.wait()
+
     def _resnet_cnn(self, p, x, temb_all, B, Fr, HW):
         """ResnetBlock3DCNN.forward (vsr/models/resnet.py:284-316): both GroupNorms see the 5-D tensor (eps 1e-6)."""
         r = self._packed[p]
         rps = Fr * HW
-        ss = ops.groupnorm_scale_shift(x, B, rps, r["g1"], r["b1"], 1e-6)
+        ss = self._gn5_scale_shift(x, None, B, rps, r["g1"], r["b1"], 1e-6)
         rb = None
         if p in self._packed["temb_slices"]:
             off, cout = self._packed["temb_slices"][p]
             rb = temb_all[:, off:off + cout]
         h = self._frame_conv_block(x, ss, B, Fr, HW, r["k"], r["w1"], r["cb1"], rb, None)
-        ss = ops.groupnorm_scale_shift(h, B, rps, r["g2"], r["b2"], 1e-6)
+        ss = self._gn5_scale_shift(h, None, B, rps, r["g2"], r["b2"], 1e-6)
         return self._frame_conv_block(h, ss, B, Fr, HW, 3, r["w2"], r["cb2"], None, x)
 
     def _temporal_module(self, p, x, temb_all, B, Fr, H, W):
@@ -260,11 +288,28 @@ class UNet3DVSRModel(UNet3DConditionModel):
         a = ops.attention(q, kv_all[:, ko:ko + hp], kv_all[:, ko + hp:ko + 2 * hp], NF, heads, HW, text_len, d, pitch,
                           kv_batch_div=Fr)
         tok = ops.gemm(a, t["attn2_wo"], bias=t["attn2_bo"], residual=tok)
-        n = ops.layernorm(tok, t["norm_temporal_g"], t["norm_temporal_b"])
-        qkv = ops.gemm(n, t["attn_temporal_qkv"])
-        rope, bias = self._frame_tables(p, Fr)
-        a = ops.temporal_attention(qkv, B, Fr, HW, heads, d, pitch, rope, bias)
-        tok = ops.gemm(a, t["attn_temporal_wo"], bias=t["attn_temporal_bo"], residual=tok)
+        if self._shard is None:
+            n = ops.layernorm(tok, t["norm_temporal_g"], t["norm_temporal_b"])
+            qkv = ops.gemm(n, t["attn_temporal_qkv"])
+            rope, bias = self._frame_tables(p, Fr)
+            a = ops.temporal_attention(qkv, B, Fr, HW, heads, d, pitch, rope, bias)
+            tok = ops.gemm(a, t["attn_temporal_wo"], bias=t["attn_temporal_bo"], residual=tok)
+        else:
+            # frame-sharded: all-to-all to pixel sharding (every rank gets ALL frames of HW/P pixels), attend, and back
+            import torch.distributed as dist
+            group, P, _ = self._shard
+            assert B == 1 and HW % P == 0, "frame sharding runs one CFG half per rank and needs H*W divisible by P"
+            hwp = HW // P
+            send = ops.layernorm_scatter(tok, t["norm_temporal_g"], t["norm_temporal_b"], HW, hwp)   # [P, F_loc, hwp, C]
+            recv = torch.empty_like(send)                                                             # [F, hwp, C]
+            dist.all_to_all_single(recv, send, group=group)
+            qkv = ops.gemm(recv, t["attn_temporal_qkv"])
+            rope, bias = self._frame_tables(p, Fr * P)
+            a = ops.temporal_attention(qkv, 1, Fr * P, hwp, heads, d, pitch, rope, bias)
+            y = ops.gemm(a, t["attn_temporal_wo"], bias=t["attn_temporal_bo"])                        # [F, hwp, C]
+            back = torch.empty_like(y)                                                                # [P, F_loc, hwp, C]
+            dist.all_to_all_single(back, y, group=group)
+            tok = ops.add_gathered(tok, back, HW, hwp)
         n = ops.layernorm(tok, t["norm3_g"], t["norm3_b"])
         g = ops.gemm(n, t["ff1_w"], bias=t["ff1_b"], geglu=True)
         tok = ops.gemm(g, t["ff2_w"], bias=t["ff2_b"], residual=tok)
@@ -323,7 +368,7 @@ class UNet3DVSRModel(UNet3DConditionModel):
                 x = self._upsample(f"up_blocks.{i}.upsamplers.0", x, B * Fr, h, w)
                 h, w = 2 * h, 2 * w
             x = self._temporal_module(f"up_temporal_blocks.{i}", x, temb_all, B, Fr, h, w)
-        ss = ops.groupnorm_scale_shift(x, B, Fr * h * w, P["norm_out"][0], P["norm_out"][1], cfg.norm_eps)
+        ss = self._gn5_scale_shift(x, None, B, Fr * h * w, P["norm_out"][0], P["norm_out"][1], cfg.norm_eps)
         wp, bp, co = P["conv_out_tc"]
         return ops.conv_out_tc(x, ss, B, Fr, h, w, wp, bp, co)
 
@@ -371,7 +416,7 @@ class UNet3DVSRModel(UNet3DConditionModel):
             x = 2 * x - 1.0
         txt = encoder_hidden_states.to(device=dev, dtype=BF16, non_blocking=True).reshape(
             -1, self.cfg.cross_attention_dim).contiguous()
-        if self.use_cuda_graph and taps is None:
+        if self.use_cuda_graph and self._graph_ok and taps is None:
             out = self._graph_step_vsr(x, t, txt, labels)
         else:
             out = self._step_vsr(x, t, txt, labels, taps)

@@ -172,3 +172,56 @@ def test_two_gpu_frame_sharding_matches_single_gpu():
     for rank, errs in sorted(got):
         print(f"rank {rank}: " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
         assert max(errs.values()) < 2e-2, errs
+
+
+def _vsr_two_gpu_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from lavie_b200.config import VSR_CONFIG
+    from lavie_b200.synthetic import synthetic_state_dict
+    from lavie_b200.vsr import UNet3DVSRModel
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
+    try:
+        unet = UNet3DVSRModel()
+        unet.load_state_dict(synthetic_state_dict(VSR_CONFIG, seed=0), strict=True)
+        unet = unet.to(dev).eval()
+        frames = 8
+        g = torch.Generator().manual_seed(21)
+        sample, low = torch.randn(1, 4, frames, 16, 32, generator=g).to(dev), torch.randn(1, 3, frames, 16, 32, generator=g).to(dev)
+        text = torch.randn(1, 77, 1024, generator=g).to(dev)
+        labels = torch.tensor([40])
+        ref = unet(sample, 300, low, encoder_hidden_states=text, class_labels=labels).sample
+        unet.set_frame_sharding(dist.group.WORLD)
+        fl = frames // world
+        sl = slice(rank * fl, (rank + 1) * fl)
+        errs = {}
+        for i in range(2):
+            out = unet(sample[:, :, sl].contiguous(), 300, low[:, :, sl].contiguous(), encoder_hidden_states=text,
+                       class_labels=labels).sample
+            errs[f"vsr/frames{world}/call{i}"] = rel_l2(out, ref[:, :, sl])
+        q.put((rank, errs))
+        torch.cuda.synchronize()
+        dist.barrier()
+    finally:
+        os._exit(0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpu_vsr_frame_sharding_matches_single_gpu():
+    """VSR denoiser, 8 frames over 2 ranks (4 each: enough for the 2-frame halo of the (5,1,1) convolutions): halo
+    exchange of the frame convs, all-reduced GroupNorm sums, all-to-all around the temporal attention."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_vsr_two_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, errs in sorted(got):
+        print(f"rank {rank}: " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+        assert max(errs.values()) < 2e-2, errs
