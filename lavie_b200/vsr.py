@@ -224,24 +224,10 @@ class UNet3DVSRModel(UNet3DConditionModel):
         return out
 
     def _exchange_frame_halo(self, buf, pad: int, Fr: int, HW: int):
-        """Frame-sharded (k,1,1) conv: the pad = k//2 frames in front of / behind this rank's frames are the LAST / FIRST
-        pad frames of the left / right neighbour (already normalised and activated); the video's ends keep their zeros."""
-        import torch.distributed as dist
+        """Frame-sharded (k,1,1) conv: fill the pad frames from the neighbours (lavie_b200.sharding.exchange_frame_halo)."""
+        from .sharding import exchange_frame_halo
         group, P, idx = self._shard
-        if Fr < pad:
-            raise ValueError(f"frame sharding needs at least {pad} frames per rank for this frame convolution")
-        n = pad * HW
-        lo = n
-        ranks = dist.get_process_group_ranks(group)
-        reqs = []
-        if idx > 0:
-            reqs.append(dist.P2POp(dist.isend, buf[lo:lo + n], ranks[idx - 1], group))             # my first frames -> left
-            reqs.append(dist.P2POp(dist.irecv, buf[:lo], ranks[idx - 1], group))                   # left's last frames
-        if idx < P - 1:
-            reqs.append(dist.P2POp(dist.isend, buf[lo + (Fr - pad) * HW:lo + Fr * HW], ranks[idx + 1], group))
-            reqs.append(dist.P2POp(dist.irecv, buf[lo + Fr * HW:], ranks[idx + 1], group))
-        for r in dist.batch_isend_irecv(reqs):
-            r.wait()
+        exchange_frame_halo(buf, pad, Fr, HW, group, P, idx)
 
     def _resnet_cnn(self, p, x, temb_all, B, Fr, HW):
         """ResnetBlock3DCNN.forward (vsr/models/resnet.py:284-316): both GroupNorms see the 5-D tensor (eps 1e-6)."""

@@ -73,3 +73,36 @@ def test_scatter_rows_is_a_permutation_with_the_expected_blocks():
 def test_rank_layout():
     p, frame_groups, pair_groups = frame_shard_ranks(8)
     assert p == 4 and frame_groups == [[0, 1, 2, 3], [4, 5, 6, 7]] and pair_groups[2] == [2, 6]
+
+
+def _halo_worker(rank, world, port, result):
+    """Frame-sharded (k,1,1) convolution of the VSR denoiser: pad-frame halo exchange + local conv == the conv on the
+    whole video (zero padding at the video's ends only)."""
+    import torch.nn.functional as F
+    from lavie_b200.sharding import exchange_frame_halo
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    frames, hw, C = 8, 6, 4
+    x = torch.randn(frames, hw, C, dtype=torch.float64)
+    ok = 0
+    for k in (3, 5):
+        pad = k // 2
+        w = torch.randn(C, C, k, 1, 1, dtype=torch.float64)
+        want = F.conv3d(x.permute(2, 0, 1)[None, :, :, :, None], w, padding=(pad, 0, 0))[0, :, :, :, 0].permute(1, 2, 0)
+        f_loc = frames // world
+        buf = torch.zeros((f_loc + 2 * pad) * hw, C, dtype=torch.float64)
+        buf[pad * hw:(pad + f_loc) * hw] = x[rank * f_loc:(rank + 1) * f_loc].reshape(f_loc * hw, C)
+        exchange_frame_halo(buf, pad, f_loc, hw, dist.group.WORLD, world, rank)
+        local = buf.reshape(f_loc + 2 * pad, hw, C)
+        got = F.conv3d(local.permute(2, 0, 1)[None, :, :, :, None], w)[0, :, :, :, 0].permute(1, 2, 0)   # "valid" over frames
+        ok += int(torch.allclose(got, want[rank * f_loc:(rank + 1) * f_loc], atol=1e-12))
+    result[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_frame_conv_halo_exchange_world2():
+    world = 2
+    result = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_halo_worker, args=(world, _free_port(), result), nprocs=world, join=True)
+    assert dict(result) == {0: 2, 1: 2}
