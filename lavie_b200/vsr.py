@@ -52,6 +52,7 @@ class UNet3DVSRModel(UNet3DConditionModel):
             raise NotImplementedError("the VSR denoiser shards equal frame counts over the NCCL back end only")
         super().set_frame_sharding(group, backend="nccl" if group is not None else "p2p")
         self._graph_ok = self._shard is None
+        self._padbufs = {}          # pad frames that held halos must not be mistaken for the zero padding of an un-sharded run
 
     def _invalidate(self):
         super()._invalidate()
