@@ -11,6 +11,14 @@ int g_lavie_gn_apply_ctas = 148 * 8;       // apply
 
 namespace {
 
+// Streaming (multi-wave, non-persistent) kernels: A/B switch for WHEN the dependent grid may start.  Default: at our start
+// (its prologue overlaps our whole run); -DLAVIE_PDL_LATE_NORMS: only when we exit.
+#ifdef LAVIE_PDL_LATE_NORMS
+#define PDL_STREAM_PROLOGUE() pdl_wait()
+#else
+#define PDL_STREAM_PROLOGUE() pdl_prologue()
+#endif
+
 constexpr int GN_THREADS = 256;
 constexpr int GN_MIN_ROWS_PER_CHUNK = 16;
 
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __nv_bfloat16* __restrict__ x1, int ld1,
                 int c1, int rows_per_sample, int rows_per_chunk, int groups, int chunks, float* __restrict__ partial,
                 const GnFused fused) {
-  pdl_prologue();
+  PDL_STREAM_PROLOGUE();
   extern __shared__ float sm[];          // [row_lanes][2][C]  (one private slot per row lane: deterministic)
   const int C = c0 + c1;
   const int sample = blockIdx.y;
@@ -189,7 +197,7 @@ __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int ld0, int c0, const __nv_bfloat16* __restrict__ x1, int ld1,
                 int c1, int rows_per_sample, int rows_per_chunk, const float* __restrict__ scale_shift, int silu,
                 __nv_bfloat16* __restrict__ y, int ldy) {
-  pdl_prologue();
+  PDL_STREAM_PROLOGUE();
   const int C = c0 + c1;
   const int vec_per_row = C >> 3;
   const int sample = blockIdx.y;
@@ -263,7 +271,7 @@ __global__ void __launch_bounds__(256)
 layernorm_grouped_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gamma,
                          const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy, int rows,
                          int perm_hw, int perm_hwp) {
-  pdl_prologue();
+  PDL_STREAM_PROLOGUE();
   constexpr int VPL = 5;
   constexpr int C = 40 * L;
   constexpr int RPW = 32 / L;
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy, int rows, int C,
                  int perm_hw, int perm_hwp) {
-  pdl_prologue();
+  PDL_STREAM_PROLOGUE();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
