@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Headline benchmark: LaVie base T2V denoise steps/s at 320x512x16 with classifier-free guidance (BASELINE.json).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path (one process per GPU)
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path (one process per GPU; N > 1 under
+                                                             # torch.distributed.run: CFG halves x frame shards)
+    python bench.py --impl reference --steps K --warmup W    # the UNMODIFIED reference forward on the host CPU cores
+    python bench.py --workload interp|vsr|encoders           # BASELINE configs 4 / 5 and the once-per-video stages
 
 A "step" is one CFG denoising step of VideoGenPipeline's loop (pipeline_videogen.py:664-689): the UNet forward on
 [2,4,16,40,64] (uncond + cond), the guidance combine and the DDIM update.  Weights are deterministic random-init of
@@ -11,7 +13,9 @@ the architecture (no checkpoint offline), inputs synthetic.
 Prints ONE JSON line (rank 0).  `value` = steps/s with the latents resident in HBM; `e2e` = the same step driven
 through the public module API from pinned HOST buffers (H2D of latents + text, D2H of the new latents, every step);
 `roofline` = the dominant kernel (tcgen05 implicit-GEMM conv / GEMM) timed per launch with CUDA events;
-`cpu_baseline` = the CPU oracle (a port of the reference forward) timed on this box's cores on a bounded sample.
+`cpu_baseline` = the unmodified reference model (baseline/_ref, copied there by __graft_entry__.build(); the CPU oracle
+port when it is absent) timed on this box's cores; `parity` = the product's forward at the headline shape against that
+CPU forward (N = 1), or every rank's partitioned forward against the un-sharded one on its own GPU (N > 1).
 """
 from __future__ import annotations
 
