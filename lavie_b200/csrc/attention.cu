@@ -792,6 +792,187 @@ temporal_attn_mma_kernel(const TempParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Cross-attention against a SHORT key sequence (the text: Sk <= 80 keys, attention.py:364-366 / vsr attn1 + attn2) in a
+// single pass: no online softmax, no TMEM, no tile loop.  K and V of one (text, head) live in shared memory; a warp owns
+// 16 query rows at a time: S[16 x 80] = Q K^T on mma.sync m16n8k16 (Q straight from global memory into the A fragments
+// with the same contraction-index permutation as the temporal kernel, K fragments by 16-byte shared loads), softmax in
+// registers (a row lives in one lane quad), the exp(S) registers are the A operand of P.V (V through ldmatrix.trans).
+// A block serves one (text, head) and strides over that group's query tiles, so K / V are staged once per block.  The op
+// is bound by streaming Q in and O out once; the tcgen05 kernel it replaces for these shapes spent its time in per-CTA
+// set-up for two mostly padded 64-key tiles (64 us at 81920 queries x 8 heads, 115 TFLOP/s).
+// ------------------------------------------------------------------------------------------------------------
+struct XAttnParams {
+  const __nv_bfloat16* q;
+  const __nv_bfloat16* k;
+  const __nv_bfloat16* v;
+  __nv_bfloat16* o;
+  long long q_seq, q_batch, kv_seq, kv_batch, o_seq, o_batch;   // strides in elements
+  int Sq, Sk, heads, d, head_pitch, kv_div, tiles_per_batch, blocks_per_group;
+  float scale_log2;
+};
+
+constexpr int XATT_KEYS = 80;          // 10 n-tiles of 8 keys
+constexpr int XATT_NT = XATT_KEYS / 8;
+
+template <int DP>
+__global__ void __launch_bounds__(128)
+cross_attn_mma_kernel(const XAttnParams p) {
+  pdl_prologue();
+  constexpr int KP = DP + 8;                      // smem row pitch (elements) of K and V
+  constexpr int NB32 = DP / 32;
+  constexpr bool TAIL16 = (DP % 32) != 0;
+  extern __shared__ __align__(16) unsigned char xsm[];
+  __nv_bfloat16* sk = reinterpret_cast<__nv_bfloat16*>(xsm);
+  __nv_bfloat16* sv = sk + XATT_KEYS * KP;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int group = blockIdx.x / p.blocks_per_group;          // (kv batch, head)
+  const int part = blockIdx.x - group * p.blocks_per_group;
+  const int kvb = group / p.heads, h = group - kvb * p.heads;
+  // ---- stage K and V of this (text, head): rows >= Sk are zero ----
+  {
+    const __nv_bfloat16* kb = p.k + static_cast<size_t>(kvb) * p.kv_batch + h * p.head_pitch;
+    const __nv_bfloat16* vb = p.v + static_cast<size_t>(kvb) * p.kv_batch + h * p.head_pitch;
+    constexpr int VEC = DP / 8;
+    for (int i = threadIdx.x; i < XATT_KEYS * VEC; i += blockDim.x) {
+      const int r = i / VEC, c = i - r * VEC;
+      uint4 kk = make_uint4(0, 0, 0, 0), vv = kk;
+      if (r < p.Sk) {
+        kk = __ldg(reinterpret_cast<const uint4*>(kb + static_cast<size_t>(r) * p.kv_seq + c * 8));
+        vv = __ldg(reinterpret_cast<const uint4*>(vb + static_cast<size_t>(r) * p.kv_seq + c * 8));
+      }
+      *reinterpret_cast<uint4*>(sk + r * KP + c * 8) = kk;
+      *reinterpret_cast<uint4*>(sv + r * KP + c * 8) = vv;
+    }
+  }
+  __syncthreads();
+  const long long tiles = static_cast<long long>(p.kv_div) * p.tiles_per_batch;     // query tiles of this group
+  const uint32_t sv_addr = smem_u32(sv) + ((lane & 15) * KP) * 2;
+  for (long long tile = static_cast<long long>(part) * 4 + wib; tile < tiles; tile += static_cast<long long>(p.blocks_per_group) * 4) {
+    const int bl = static_cast<int>(tile / p.tiles_per_batch);
+    const int r0 = static_cast<int>(tile - static_cast<long long>(bl) * p.tiles_per_batch) * 16;
+    const long long b = static_cast<long long>(kvb) * p.kv_div + bl;
+    const bool lo_ok = r0 + g < p.Sq, hi_ok = r0 + g + 8 < p.Sq;
+    const __nv_bfloat16* q_lo_p = p.q + b * p.q_batch + static_cast<long long>(r0 + g) * p.q_seq + h * p.head_pitch;
+    const __nv_bfloat16* q_hi_p = q_lo_p + 8 * p.q_seq;
+    // ---- all Q loads of the tile first ----
+    uint4 pq_lo[NB32 > 0 ? NB32 : 1], pq_hi[NB32 > 0 ? NB32 : 1];
+    uint2 tq_lo = make_uint2(0, 0), tq_hi = tq_lo;
+#pragma unroll
+    for (int blk = 0; blk < NB32; ++blk) {
+      pq_lo[blk] = lo_ok ? __ldg(reinterpret_cast<const uint4*>(q_lo_p + blk * 32 + t * 8)) : make_uint4(0, 0, 0, 0);
+      pq_hi[blk] = hi_ok ? __ldg(reinterpret_cast<const uint4*>(q_hi_p + blk * 32 + t * 8)) : make_uint4(0, 0, 0, 0);
+    }
+    if (TAIL16) {
+      if (lo_ok) tq_lo = __ldg(reinterpret_cast<const uint2*>(q_lo_p + NB32 * 32 + t * 4));
+      if (hi_ok) tq_hi = __ldg(reinterpret_cast<const uint2*>(q_hi_p + NB32 * 32 + t * 4));
+    }
+    // ---- S = Q K^T ----
+    float s[XATT_NT][4];
+#pragma unroll
+    for (int nt = 0; nt < XATT_NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[nt][e] = 0.f;
+#pragma unroll
+    for (int blk = 0; blk < NB32; ++blk) {
+      const uint32_t a_first[4] = {pq_lo[blk].x, pq_hi[blk].x, pq_lo[blk].y, pq_hi[blk].y};
+      const uint32_t a_second[4] = {pq_lo[blk].z, pq_hi[blk].z, pq_lo[blk].w, pq_hi[blk].w};
+#pragma unroll
+      for (int nt = 0; nt < XATT_NT; ++nt) {
+        const uint4 kk = *reinterpret_cast<const uint4*>(sk + (nt * 8 + g) * KP + blk * 32 + t * 8);
+        mma_bf16_16816(s[nt], a_first, kk.x, kk.y);
+        mma_bf16_16816(s[nt], a_second, kk.z, kk.w);
+      }
+    }
+    if (TAIL16) {
+      const uint32_t a_tail[4] = {tq_lo.x, tq_hi.x, tq_lo.y, tq_hi.y};
+#pragma unroll
+      for (int nt = 0; nt < XATT_NT; ++nt) {
+        const uint2 kk = *reinterpret_cast<const uint2*>(sk + (nt * 8 + g) * KP + NB32 * 32 + t * 4);
+        mma_bf16_16816(s[nt], a_tail, kk.x, kk.y);
+      }
+    }
+    // ---- softmax over the keys (row g: elements 0,1; row g+8: elements 2,3 of every n-tile) ----
+    float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < XATT_NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool key_ok = nt * 8 + 2 * t + e < p.Sk;
+        s[nt][e] = key_ok ? s[nt][e] * p.scale_log2 : -INFINITY;
+        s[nt][2 + e] = key_ok ? s[nt][2 + e] * p.scale_log2 : -INFINITY;
+        mx_lo = fmaxf(mx_lo, s[nt][e]);
+        mx_hi = fmaxf(mx_hi, s[nt][2 + e]);
+      }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < XATT_NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[nt][e] = fast_exp2(s[nt][e] - mx_lo);
+        s[nt][2 + e] = fast_exp2(s[nt][2 + e] - mx_hi);
+        sum_lo += s[nt][e];
+        sum_hi += s[nt][2 + e];
+      }
+    sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
+    sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+    sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
+    sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+    const float inv_lo = 1.f / sum_lo, inv_hi = 1.f / sum_hi;
+    // ---- O = P V: the probabilities (unnormalised, bf16) are the A fragments; 1 / sum is applied to the fp32 result ----
+    uint32_t pa[XATT_NT / 2][4];
+#pragma unroll
+    for (int j = 0; j < XATT_NT / 2; ++j) {
+      pa[j][0] = pack_bf16(s[2 * j][0], s[2 * j][1]);
+      pa[j][1] = pack_bf16(s[2 * j][2], s[2 * j][3]);
+      pa[j][2] = pack_bf16(s[2 * j + 1][0], s[2 * j + 1][1]);
+      pa[j][3] = pack_bf16(s[2 * j + 1][2], s[2 * j + 1][3]);
+    }
+    __nv_bfloat16* o_lo = p.o + b * p.o_batch + static_cast<long long>(r0 + g) * p.o_seq + h * p.d;
+    __nv_bfloat16* o_hi = o_lo + 8 * p.o_seq;
+#pragma unroll
+    for (int c = 0; c < DP / 8; ++c) {
+      if (c * 8 < p.d) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < XATT_NT / 2; ++j) {
+          uint32_t b0, b1;
+          ldmatrix_x2_trans(b0, b1, sv_addr + (j * 16 * KP + c * 8) * 2);
+          mma_bf16_16816(o, pa[j], b0, b1);
+        }
+        const int col = c * 8 + 2 * t;
+        if (lo_ok) *reinterpret_cast<uint32_t*>(o_lo + col) = pack_bf16(o[0] * inv_lo, o[1] * inv_lo);
+        if (hi_ok) *reinterpret_cast<uint32_t*>(o_hi + col) = pack_bf16(o[2] * inv_hi, o[3] * inv_hi);
+      }
+    }
+  }
+}
+
+template <int DP>
+int launch_cross_attn(const XAttnParams& p0, int kv_batches, cudaStream_t stream) {
+  XAttnParams p = p0;
+  constexpr int KP = DP + 8;
+  const int smem = 2 * XATT_KEYS * KP * 2;
+  static LavieSmemConfig configured;
+  int rc = lavie_config_smem(cross_attn_mma_kernel<DP>, smem, &configured, "cross_attn_mma_kernel");
+  if (rc) return rc;
+  const int groups = kv_batches * p.heads;
+  const long long tiles = static_cast<long long>(p.kv_div) * p.tiles_per_batch;
+  // ~4 blocks of 4 warps per SM, at least 2 tiles per warp, K / V staged once per block
+  long long per_group = (static_cast<long long>(lavie_num_sms()) * 4 + groups - 1) / groups;
+  const long long max_per_group = (tiles + 7) / 8;
+  if (per_group > max_per_group) per_group = max_per_group;
+  if (per_group < 1) per_group = 1;
+  p.blocks_per_group = static_cast<int>(per_group);
+  launch_pdl(cross_attn_mma_kernel<DP>, static_cast<int>(groups * per_group), 128, smem, stream, p);
+  return lavie_check_launch("cross_attn_mma_kernel");
+}
+
 template <int DP>
 int launch_temporal_mma(const TempParams& p, cudaStream_t stream) {
   long long blocks = (p.items + 3) / 4;
@@ -839,6 +1020,28 @@ extern "C" int lavie_attention_strided_bf16(const void* q, long long q_seq_strid
   p.scale_log2 = scale * 1.4426950408889634f;
   p.o = static_cast<__nv_bfloat16*>(o);
   p.timeline = static_cast<long long*>(g_lavie_debug_buf);
+  if (Sk <= XATT_KEYS && sparse_causal_frames == 0 && g_lavie_xattn && q_batch_stride >= q_seq_stride &&
+      kv_batch_stride >= kv_seq_stride) {
+    // short key sequence (text cross-attention): the single-pass mma.sync kernel
+    XAttnParams x;
+    x.q = static_cast<const __nv_bfloat16*>(q); x.k = static_cast<const __nv_bfloat16*>(k);
+    x.v = static_cast<const __nv_bfloat16*>(v); x.o = static_cast<__nv_bfloat16*>(o);
+    x.q_seq = q_seq_stride; x.q_batch = q_batch_stride; x.kv_seq = kv_seq_stride; x.kv_batch = kv_batch_stride;
+    x.o_seq = o_seq_stride; x.o_batch = o_batch_stride;
+    x.Sq = Sq; x.Sk = Sk; x.heads = heads; x.d = d; x.head_pitch = head_pitch; x.kv_div = kv_batch_div;
+    x.tiles_per_batch = (Sq + 15) / 16; x.blocks_per_group = 1;
+    x.scale_log2 = scale * 1.4426950408889634f;
+    const int kvb = batch / kv_batch_div;
+    switch (dk) {
+      case 48: return launch_cross_attn<48>(x, kvb, stream);
+      case 64: return launch_cross_attn<64>(x, kvb, stream);
+      case 80: return launch_cross_attn<80>(x, kvb, stream);
+      case 96: return launch_cross_attn<96>(x, kvb, stream);
+      case 128: return launch_cross_attn<128>(x, kvb, stream);
+      case 160: return launch_cross_attn<160>(x, kvb, stream);
+      default: break;
+    }
+  }
   CUtensorMap mq, mk, mv;
   const int cols = heads * head_pitch;
   const bool swap = q_batch_stride < q_seq_stride;

@@ -41,6 +41,7 @@ int lavie_make_tmap_im2col(CUtensorMap* map, const void* base, int N, int H, int
 // ---------------------------------------------------------------------------------------------
 extern int g_lavie_pdl;       // 1 = on (default); lavie_debug_set(3, 0) turns it off for A/B timing
 extern void* g_lavie_debug_buf; // device scratch for the clock64 timelines (lavie_debug_buffer), nullptr = off
+extern int g_lavie_xattn;     // attention: single-pass kernel for Sk <= 80 on/off; lavie_debug_set(8, v)
 extern int g_lavie_attn_poly; // attention: every n-th exp2 on the FMA pipe (0 = none); lavie_debug_set(4, n)
 
 // Per-DEVICE lazily configured kernel attributes.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the

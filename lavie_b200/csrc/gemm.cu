@@ -1155,6 +1155,7 @@ extern "C" int lavie_debug_set(int what, int value) {
   if (what == 5) g_no_tail = value;
   if (what == 6 && value > 0) g_lavie_gn_target_ctas = value;
   if (what == 7) g_inkernel_reduce = value ? 1 : 0;
+  if (what == 8) g_lavie_xattn = value ? 1 : 0;
   return 0;
 }
 
