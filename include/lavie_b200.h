@@ -43,8 +43,8 @@ int lavie_abi_version(void);
 /* Tuning hooks for tests/benchmarks (never needed for correct results): what = 1 forces the split-K factor of the
  * GEMM (0 = automatic); 2 = debug bit mask (512: GEMM per-tile clock64 timeline into the workspace); 3 = programmatic
  * dependent launch on/off; 4 = attention: every n-th exp2 on the FMA pipe (0 = all on the MUFU); 5 = no split-K tail
- * windows; 7 = in-kernel split-K reduction on/off (default off); 8 = single-pass attention kernel for short key sequences
- * (Sk <= 80: the text cross-attentions) on/off (default on). */
+ * windows; 7 = in-kernel split-K reduction on/off (default off); 8 = single-pass mma.sync attention kernel for short key
+ * sequences (Sk <= 80: the text cross-attentions) on/off (default off: bound by the legacy HMMA rate, not faster). */
 int lavie_debug_set(int what, int value);
 /* Device scratch (>= 64 KB) that the attention kernel fills with a per-tile clock64 timeline of one CTA; NULL = off. */
 int lavie_debug_buffer(void* device_ptr);

@@ -138,8 +138,8 @@ def load() -> ctypes.CDLL:
         fn.argtypes = args
     if os.environ.get("LAVIE_INKERNEL_SPLITK", "0") == "1":      # A/B switch: in-kernel split-K reduction (slower, off)
         lib.lavie_debug_set(7, 1)
-    if os.environ.get("LAVIE_XATTN", "1") == "0":                # A/B switch: text cross-attention on the tcgen05 flash kernel
-        lib.lavie_debug_set(8, 0)
+    if os.environ.get("LAVIE_XATTN", "0") == "1":                # A/B switch: text cross-attention on the mma.sync kernel
+        lib.lavie_debug_set(8, 1)
     _lib = lib
     return lib
 

@@ -156,7 +156,9 @@ int lavie_config_smem_impl(const void* func, int bytes, LavieSmemConfig* st, con
 }
 
 int g_lavie_pdl = 1;
-int g_lavie_xattn = 1;         // 1: short key sequences (Sk <= 80) run on the single-pass mma.sync kernel; lavie_debug_set(8, 0): off
+int g_lavie_xattn = 0;         // lavie_debug_set(8, 1): short key sequences (Sk <= 80) run on the single-pass mma.sync kernel.
+                               // Correct, but bound by the legacy HMMA issue rate (~150 TFLOP/s on B200): 85 vs 64 us at the
+                               // 40x64 level, 30.5 vs 33 us at 20x32 -> off by default (profiles/r2_notes.md)
 int g_lavie_attn_poly = -1;    // -1: per-shape default, 0: all exponentials on the MUFU, 4: every 4th on the FMA pipe
 void* g_lavie_debug_buf = nullptr;
 
