@@ -16,7 +16,24 @@ import torch  # noqa: E402
 
 from lavie_b200.config import BASE_CONFIG, INTERP_CONFIG  # noqa: E402
 from lavie_b200.synthetic import synthetic_state_dict  # noqa: E402
-from oracle.reference_loader import load_reference_unet  # noqa: E402
+
+
+def load_reference_unet(variant, state_dict):
+    """The unmodified reference model from baseline/_ref (copied there by __graft_entry__.build()) with the stand-ins for
+    its two un-vendored dependencies -- a local copy of what bench.py's reference arm does, so that this tool does not
+    import the test-only oracle package."""
+    import importlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tree = "base" if variant == "base" else "interpolation"
+    for pth in (os.path.join(root, "tests", "golden", "shims"), os.path.join(root, "baseline", "_ref", tree)):
+        sys.path.insert(0, pth)
+    mod = importlib.import_module("models.unet")
+    cfg = (BASE_CONFIG if variant == "base" else INTERP_CONFIG).to_dict()
+    if variant != "base":
+        cfg["use_first_frame"] = True
+    ref = mod.UNet3DConditionModel.from_config(cfg).eval()
+    ref.load_state_dict(state_dict, strict=True)
+    return ref
 
 
 def main():
