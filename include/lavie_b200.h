@@ -296,6 +296,12 @@ int lavie_conv_out(const void* x, int ldx, const float* scale_shift, int B, int 
 int lavie_embedding_add(float* emb, const float* table, const long long* labels, int B, int dim, int rows,
                         lavie_stream_t stream);
 
+/* conv_in (unet.py:454) on the tensor cores: explicit im2col of the fp32 [B, Cin, F, H, W] input (scaled by
+ * *input_scale when given) into bf16 rows col[B*F*H*W, kpad], K index = c*9 + kh*3 + kw, zeros beyond 9*Cin and outside
+ * the image; the conv is then lavie_gemm_bf16 against the [Cout, kpad] zero-padded filters. */
+int lavie_im2col_input_bf16(const float* x, const float* input_scale, int B, int Cin, int F, int H, int W, int kpad,
+                            void* col, lavie_stream_t stream);
+
 /* Last step of conv_out when the 3x3 conv itself ran on the tensor cores (lavie_conv3x3_bf16 with the Cout filters
  * zero-padded to a 32-row weight matrix): y bf16 [B*F*H*W, ldy] channels-last -> fp32 [B, Cout, F, H, W], the layout
  * base/models/unet.py:506 returns. */

@@ -97,6 +97,7 @@ SIGNATURES = {
                                                      c_float, _P, _P]),
     "lavie_upsample_conv3x3_supported": (c_int, [c_int, c_int, c_int]),
     "lavie_upsample_conv3x3_bf16": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, POINTER(Epilogue), c_int, _P]),
+    "lavie_im2col_input_bf16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_unpack_nchw_f32": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_upsample_nearest2x": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "lavie_cfg_ddim_step": (c_int, [_P, _P, c_float, c_float, c_float, _P, _P, c_longlong, _P]),

@@ -580,6 +580,35 @@ def conv_in(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, input_scale: O
     return out
 
 
+def conv_in_kpad(cin: int) -> int:
+    """K of the conv_in GEMM: 9 * Cin rounded up to the GEMM's 64-deep K block."""
+    return (9 * cin + 63) // 64 * 64
+
+
+def conv_in_tc(x: torch.Tensor, w_pad: torch.Tensor, bias: torch.Tensor, input_scale: Optional[torch.Tensor] = None):
+    """conv_in on the tensor cores: x fp32 [B,Cin,F,H,W] -> im2col rows [B*F*H*W, kpad] (bf16, scaled by input_scale) ->
+    one GEMM against w_pad bf16 [Cout, kpad] (filters in (c, kh, kw) order, zero-padded) + bias -> bf16 [rows, Cout]."""
+    lib = _lib.load()
+    assert x.dtype == F32 and x.is_contiguous() and x.dim() == 5
+    B, Cin, Fr, H, W = x.shape
+    kpad = w_pad.shape[1]
+    assert kpad == conv_in_kpad(Cin) and w_pad.dtype == BF16 and w_pad.is_contiguous()
+    col = torch.empty((B * Fr * H * W, kpad), dtype=BF16, device=x.device)
+    with _Launch("lavie_im2col_input_bf16", 0.0, 4.0 * x.numel() + 2.0 * col.numel()):
+        assert input_scale is None or (input_scale.dtype == F32 and input_scale.is_cuda and input_scale.numel() == 1)
+        check(lib.lavie_im2col_input_bf16(x.data_ptr(), _ptr(input_scale), B, Cin, Fr, H, W, kpad, col.data_ptr(),
+                                          _stream()), "lavie_im2col_input_bf16")
+    return gemm(col, w_pad, bias=bias)
+
+
+def pack_conv_in(w: torch.Tensor, device) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> bf16 [Cout, kpad] in (c, kh, kw) order, zero-padded (conv_in_tc)."""
+    co, ci = w.shape[:2]
+    out = torch.zeros((co, conv_in_kpad(ci)), dtype=F32)
+    out[:, :9 * ci] = w.detach().float().cpu().reshape(co, 9 * ci)
+    return out.to(device=device, dtype=BF16).contiguous()
+
+
 def conv_out(x: torch.Tensor, scale_shift: torch.Tensor, B: int, Fr: int, H: int, W: int, w: torch.Tensor,
              bias: torch.Tensor):
     """x bf16 [B*F*H*W, C] raw; w fp32 [Cout, 3, 3, C]; returns fp32 [B, Cout, F, H, W]."""

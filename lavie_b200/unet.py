@@ -373,6 +373,8 @@ class UNet3DConditionModel(nn.Module):
                     sd[f"up_blocks.{i}.upsamplers.0.conv.weight"]).to(dev)
         boc0 = self.cfg.block_out_channels[0]
         P["conv_in"] = (f32("conv_in.weight"), f32("conv_in.bias"))
+        if not self.check_mode:          # bf16 path: explicit im2col of the few input channels + one GEMM
+            P["conv_in_tc"] = (ops.pack_conv_in(sd["conv_in.weight"], dev), f32("conv_in.bias"))
         P["conv_out"] = (sd["conv_out.weight"].permute(0, 2, 3, 1).to(device=dev, dtype=F32).contiguous(),
                          f32("conv_out.bias"))
         if not self.check_mode and boc0 % 64 == 0:
@@ -584,7 +586,10 @@ class UNet3DConditionModel(nn.Module):
         if kv_all is None:
             kv_all = K.gemm(text, P["kv_w"])
 
-        x = K.conv_in(sample, P["conv_in"][0], P["conv_in"][1], input_scale)
+        if "conv_in_tc" in P:
+            x = ops.conv_in_tc(sample, P["conv_in_tc"][0], P["conv_in_tc"][1], input_scale)
+        else:
+            x = K.conv_in(sample, P["conv_in"][0], P["conv_in"][1], input_scale)
         tap("conv_in", x, boc[0], H, W)
         skips = [(x, boc[0])]
         h, w = H, W

@@ -165,6 +165,7 @@ class UNet3DVSRModel(UNet3DConditionModel):
                     P[f"{q}4"] = pack_upsample_conv3x3(sd[f"{q}.weight"]).to(dev)
         boc0 = self.cfg.block_out_channels[0]
         P["conv_in"] = (f32("conv_in.weight"), f32("conv_in.bias"))
+        P["conv_in_tc"] = (ops.pack_conv_in(sd["conv_in.weight"], dev), f32("conv_in.bias"))
         co = sd["conv_out.weight"].shape[0]
         wp = torch.zeros((ops.CONV_OUT_PAD, 9 * boc0), dtype=F32)
         wp[:co] = pack_conv3x3(sd["conv_out.weight"].float().cpu(), dtype=None)
@@ -323,7 +324,7 @@ class UNet3DVSRModel(UNet3DConditionModel):
         temb_all = ops.linear_smallm(emb, P["temb_w"], P["temb_b"], silu_in=True)
         kv_all = ops.gemm(text, P["kv_w"])
 
-        x = ops.conv_in(sample7, P["conv_in"][0], P["conv_in"][1], None)
+        x = ops.conv_in_tc(sample7, P["conv_in_tc"][0], P["conv_in_tc"][1], None)
         skips = [x]
         h, w = H, W
         for i, kind in enumerate(cfg.down_block_types):

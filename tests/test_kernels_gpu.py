@@ -368,6 +368,16 @@ def test_conv_in_and_out(H, W):
     y = ops.conv_in(x, w, b)
     ref = F.conv2d(x.permute(0, 2, 1, 3, 4).reshape(B * Fr, 4, H, W), w, b, padding=1).permute(0, 2, 3, 1).reshape(-1, 320)
     assert rel_l2(y.float(), ref) < 4e-3
+    # the tensor-core route of conv_in: explicit im2col of the 4 input channels + one GEMM (bf16 inputs and filters)
+    y_tc = ops.conv_in_tc(x, ops.pack_conv_in(w, DEV), b)
+    assert y_tc.shape == y.shape and rel_l2(y_tc.float(), ref) < 6e-3
+    sc = torch.full((1,), 0.37, device=DEV)
+    assert rel_l2(ops.conv_in_tc(x, ops.pack_conv_in(w, DEV), b, sc).float(),
+                  F.conv2d(0.37 * x.permute(0, 2, 1, 3, 4).reshape(B * Fr, 4, H, W), w, b, padding=1).permute(0, 2, 3, 1)
+                  .reshape(-1, 320)) < 6e-3
+    x7, w7 = _rand(B, 7, Fr, H, W, seed=8), _rand(256, 7, 3, 3, seed=9, scale=1 / 8.0)      # the VSR model's 7 channels
+    ref7 = F.conv2d(x7.permute(0, 2, 1, 3, 4).reshape(B * Fr, 7, H, W), w7, None, padding=1).permute(0, 2, 3, 1).reshape(-1, 256)
+    assert rel_l2(ops.conv_in_tc(x7, ops.pack_conv_in(w7, DEV), torch.zeros(256, device=DEV)).float(), ref7) < 6e-3
     # conv_norm_out + SiLU + conv_out
     gamma = _rand(320, seed=2) * 0.1 + 1
     beta = _rand(320, seed=3) * 0.1
