@@ -652,7 +652,9 @@ VSR_WORKLOAD = "VSR x4-upscaler UNet3D, 1280x2048x{f} output (latent 4+3 ch x {f
 def run_vsr(args):
     """BASELINE config 5 on ONE GPU (python bench.py --workload vsr): a step = the VSR UNet forward on the CFG batch
     ([2,4,F,320,512] latent + [2,3,F,320,512] noised low-res frames, noise level 50, the reference pipeline's call
-    vsr/models/pipeline_stable_diffusion_upscale_video_3d.py:712-727) + guidance + DDIM update.  Frame sharding of this
+    vsr/models/pipeline_stable_diffusion_upscale_video_3d.py:712-727) + guidance + DDIM update.  The reference's sample.py
+    feeds 16 frames as two independent 8-frame chunks (vsr/sample.py:100-118); the default here runs the 16 frames as ONE
+    video (same FLOPs, temporal attention / frame convs over 16 frames), --vsr-frames 8 runs one chunk.  Frame sharding of this
     model is not built (its frame convolutions need a halo exchange), so N > 1 is refused.  Parity + CPU baseline: a bounded
     sample (2 frames, 80x128 crop = 1/128 of the pixels; the model is convolutional apart from its 40x64-level
     self-attention) against the unmodified reference on the host cores."""
